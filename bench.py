@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — contrast-loss fwd+bwd throughput on synthetic Cityscapes-shaped batches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--workload s1|s2]
+
+Workload s1 = BASELINE configs[1]: HRNet-W48 pixel-contrast (no bank), 1024x512 input -> 256x128 embedding,
+19 classes, batch 8 PER GPU (weak scaling; the no-bank loss has no cross-rank exchange).
+Workload s2 = configs[2] shape per rank (bank 19x(5000+5000)x256, one image per rank, bank merge allgather).
+A "step" = one pass of the hot path over one batch: label/argmax/key scan, anchor selection + gather, InfoNCE
+forward, InfoNCE backward and the dense embedding-gradient write (+ bank enqueue for s2).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+S1 = dict(B=8, D=256, h=128, w=256, K=19, stride=4, block=32, T=0.1, bT=0.07, max_samples=1024, max_views=100)
+S2 = dict(B=1, D=256, h=128, w=256, K=19, stride=4, block=32, T=0.07, bT=0.07, max_samples=1024, max_views=100,
+          M=5000, F=10, net_stride=4)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        self.lines = [l for l in out.splitlines() if l.strip()]
+
+    def summary(self):
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = max(smax, float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(cfg, seed, device=None, bank=False):
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    d = make_contrast_batch(B=cfg["B"], D=cfg["D"], h=cfg["h"], w=cfg["w"], num_classes=cfg["K"],
+                            img_stride=cfg["stride"], block=cfg["block"], seed=seed)
+    out = dict(embed=d["embed"], seg=d["seg"], target=d["target"])
+    if bank:
+        out.update(make_bank(cfg["K"], cfg["M"], cfg["D"], seed + 1000))
+    if device is not None:
+        out = {k: v.to(device) for k, v in out.items()}
+    return out
+
+
+def engine_configer(cfg, bank=False):
+    import contrastiveseg_b200 as cs
+    d = {"data": {"num_classes": cfg["K"]}, "network": {"stride": cfg.get("net_stride", 4)},
+         "loss": {"params": {"ce_ignore_index": -1, "ce_reduction": "elementwise_mean"}},
+         "contrast": {"temperature": cfg["T"], "base_temperature": cfg["bT"], "max_samples": cfg["max_samples"],
+                      "max_views": cfg["max_views"], "loss_weight": 0.1, "use_rmi": False, "rng": "device"}}
+    if bank:
+        d["contrast"].update(with_memory=True, memory_size=cfg["M"], pixel_update_freq=cfg["F"])
+    return cs.Configer(d)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores (the reference is Python and cannot
+# travel to the GPU box; oracle/ref_port.py restates it op for op and is pinned to it by golden vectors)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_step(inp, cfg, bank=False):
+    from oracle import ref_port as P
+    embed = inp["embed"].clone().requires_grad_(True)
+    predict = inp["seg"].argmax(1)
+    queue = torch.cat((inp["segment_queue"], inp["pixel_queue"]), 1) if bank else None
+    loss = P.pixel_contrast_loss(embed, inp["target"], predict, temperature=cfg["T"], base_temperature=cfg["bT"],
+                                 max_samples=cfg["max_samples"], max_views=cfg["max_views"], queue=queue,
+                                 per_pair_gather=True)
+    loss.backward()
+    if bank:
+        P.dequeue_and_enqueue(inp["embed"], inp["target"], inp["segment_queue"], inp["segment_queue_ptr"],
+                              inp["pixel_queue"], inp["pixel_queue_ptr"], network_stride=cfg["net_stride"],
+                              memory_size=cfg["M"], pixel_update_freq=cfg["F"])
+    return float(loss.item())
+
+
+def run_reference(args, cfg, bank, rank):
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    total = args.steps + args.warmup
+    B_ref = cfg["B"] if total <= 20 else max(1, cfg["B"] // 2) if total <= 60 else max(1, cfg["B"] // 4)
+    c = dict(cfg); c["B"] = B_ref
+    inp = make_inputs(c, 304, None, bank)
+    for _ in range(args.warmup):
+        cpu_port_step(inp, c, bank)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(inp, c, bank)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    val = B_ref * args.steps / dt
+    sample = (f"{args.steps} steps of the full workload geometry at batch {B_ref} (of {cfg['B']}) on {cores} host threads, "
+              "fp32 torch CPU, per-(image,class) gather + autograd backward like the reference")
+    return {"impl": "reference", "metric": "contrast-loss fwd+bwd throughput", "value": val, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, bank, B_ref),
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def workload_config(cfg, bank, B=None):
+    name = ("HRNet-W48 pixel-contrast + pixel/region memory bank" if bank else "HRNet-W48 pixel-contrast (no memory bank)")
+    return {"workload": f"{name}, synthetic Cityscapes 1024x512 19-class -> embed {cfg['D']}x{cfg['h']}x{cfg['w']}, "
+                        f"batch {B or cfg['B']} per GPU, max_samples {cfg['max_samples']}, max_views {cfg['max_views']}",
+            "per_gpu_batch": B or cfg["B"], "parallelism": "dp (images sharded, no data-path collective)" if not bank
+            else "dp + one NCCL all_gather of the bank enqueue packet per step",
+            "l2": "inputs larger than L2 (embed 268 MB + grad 268 MB per step vs 126 MB L2)" if (B or cfg["B"]) >= 4
+            else "L2 flushed between iterations"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# engine arm
+# ---------------------------------------------------------------------------------------------------
+def stage_timings(cfg, inp, dev, iters=20):
+    """CUDA-event time of every C-ABI stage on the launching stream (dominant-kernel roofline)."""
+    import ctypes as C
+    from contrastiveseg_b200 import _abi, functional as Fn
+    lib = _abi.load()
+    geom = _abi.Geom(cfg["B"], cfg["D"], cfg["h"], cfg["w"], inp["target"].shape[1], inp["target"].shape[2], cfg["K"],
+                     cfg["max_samples"], cfg["max_views"], -1)
+    ws = Fn.ContrastWorkspace(dev, geom, 0, 0, 0, 0)
+    d = ws.desc
+    d.embed, d.labels, d.seg = inp["embed"].data_ptr(), inp["target"].data_ptr(), inp["seg"].data_ptr()
+    d.temperature, d.base_temperature, d.seed = cfg["T"], cfg["bT"], 12345
+    grad = torch.empty_like(inp["embed"])
+    d.grad_embed = grad.data_ptr()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sw = _abi.SweepDesc()
+    ms_ = cfg["max_samples"]
+    sw.anchors, sw.anchor_cls = ws.anchors_f32.data_ptr(), ws.anchor_meta.data_ptr() + 8 * ms_
+    sw.diag_col, sw.plan = ws.anchor_meta.data_ptr() + 12 * ms_, ws.plan.data_ptr()
+    sw.a_rows, sw.D, sw.mode = ms_, cfg["D"], 0
+    sw.temperature, sw.base_temperature = cfg["T"], cfg["bT"]
+    g = C.byref(geom)
+    stages = {
+        "class_stats": lambda: lib.pcl_class_stats(g, d.labels, d.seg, None, d.keys, d.chunk_pref, stream),
+        "plan_anchors": lambda: lib.pcl_plan_anchors(g, d.chunk_pref, d.counts, d.plan, stream),
+        "select_gather": lambda: lib.pcl_select_gather(g, d.embed, d.keys, d.chunk_pref, d.plan, None, 12345, 0,
+                                                       d.anchor_meta, d.anchors_f32, d.anchors_bf16, d.inv_norm,
+                                                       d.norm_max, stream),
+        "infonce_fwd": lambda: lib.pcl_infonce_fwd(C.byref(sw), d.partials, d.rowstats, d.loss, stream),
+        "infonce_bwd": lambda: lib.pcl_infonce_bwd(C.byref(sw), d.rowstats, None, d.dpartials, d.dA, stream),
+        "scatter_grad": lambda: lib.pcl_scatter_grad(g, d.plan, d.anchor_meta, d.dA, d.anchors_f32, d.inv_norm, 0,
+                                                     d.grad_embed, stream),
+    }
+    out = {}
+    acc = {k: 0.0 for k in stages}
+    for it in range(iters + 2):
+        flush.zero_()
+        for name, fn in stages.items():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st = fn()
+            e1.record()
+            _abi.check(st, name)
+            torch.cuda.synchronize(dev)
+            if it >= 2:
+                acc[name] += e0.elapsed_time(e1)
+    for k in acc:
+        out[k] = acc[k] / iters
+    A = int(ws.plan[2].item())
+    return out, A
+
+
+def run_engine(args, cfg, bank, rank, world, dev):
+    import contrastiveseg_b200 as cs
+    from contrastiveseg_b200 import _abi
+    _abi.load()
+    peaks = load_peaks()
+    inp_h = make_inputs(cfg, 304 + rank, None, bank)
+    inp = {k: v.to(dev) for k, v in inp_h.items()}
+    cfgr = engine_configer(cfg, bank)
+    crit = cs.PixelContrastLoss(cfgr)
+    mbank = None
+    if bank:
+        mbank = cs.MemoryBank(cfg["K"], cfg["M"], cfg["D"]).to(dev)
+        mbank.segment_queue.copy_(inp["segment_queue"]); mbank.pixel_queue.copy_(inp["pixel_queue"])
+    embed = inp["embed"].clone().requires_grad_(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if cfg["B"] < 4 else None
+
+    def step(e, tgt, seg):
+        e.grad = None
+        queue = (mbank.segment_queue, mbank.pixel_queue) if bank else None
+        loss = crit(e, tgt, seg=seg, queue=queue)
+        if bank:
+            mbank.enqueue(e.detach(), tgt, network_stride=cfg["net_stride"], pixel_update_freq=cfg["F"])
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step(embed, inp["target"], inp["seg"])
+    sampler = ClockSampler(dev.index)
+    barrier()
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    per_step = []
+    barrier()
+    ev[0].record()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        step(embed, inp["target"], inp["seg"])
+    ev[1].record()
+    barrier()
+    sampler.stop()
+    t_ms = ev[0].elapsed_time(ev[1])
+    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    t_ms = float(tt.item())
+    value = world * cfg["B"] * args.steps / (t_ms / 1e3)
+
+    # ---- e2e: host (pinned) buffers in, loss scalar out, every step ----
+    pin = {k: inp_h[k].pin_memory() for k in ("embed", "seg", "target")}
+    dbuf = {k: torch.empty_like(inp[k]) for k in ("embed", "seg", "target")}
+    h2d = sum(pin[k].numel() * pin[k].element_size() for k in pin)
+
+    def e2e_step():
+        for k in pin:
+            dbuf[k].copy_(pin[k], non_blocking=True)
+        e = dbuf["embed"].requires_grad_(True)
+        loss = step(e, dbuf["target"], dbuf["seg"])
+        dbuf["embed"] = e.detach()
+        return loss.item()                          # D2H read of the step's result
+    e_steps = max(3, min(args.steps, 50))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    barrier()
+    e_dt = time.perf_counter() - t0
+    et = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(et, op=torch.distributed.ReduceOp.MAX)
+    e2e_val = world * cfg["B"] * e_steps / float(et.item())
+
+    if rank != 0:
+        return None
+    # ---- per-stage times + roofline of the dominant stage (rank 0, N-independent) ----
+    roof = None
+    stages = {}
+    if not bank:
+        stages, A = stage_timings(cfg, inp, dev)
+        dom = max(stages, key=stages.get)
+        BDHW4 = cfg["B"] * cfg["D"] * cfg["h"] * cfg["w"] * 4
+        alg_bytes = {
+            "scatter_grad": BDHW4 + 2 * A * cfg["D"] * 4,
+            "class_stats": cfg["B"] * cfg["h"] * cfg["w"] * (cfg["K"] * 4 + 8 + 2),
+            "select_gather": A * cfg["D"] * (4 + 4 + 2) + cfg["B"] * cfg["h"] * cfg["w"] * 2,
+        }
+        if dom in alg_bytes:
+            ach = alg_bytes[dom] / (stages[dom] * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "algorithmic_bytes": alg_bytes[dom]}
+        else:
+            flops = 2.0 * A * A * cfg["D"] * (2 if dom == "infonce_fwd" else 2)
+            ach = flops / (stages[dom] * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "note": "exact fp32 SIMT sweep at A=N<=1024 (latency-bound regime, SURVEY §8d); tensor path is for bank/sweep sizes"}
+    # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_port_step(inp_h, cfg, bank)
+        n_cpu = 2
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            cpu_port_step(inp_h, cfg, bank)
+        cdt = time.perf_counter() - t0
+        cpu = {"value": cfg["B"] * n_cpu / cdt, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} full steps (batch {cfg['B']}) after 1 warm-up, fp32 torch CPU, {cdt / n_cpu * 1e3:.0f} ms/step"}
+    launches_per_step = 10 + (4 if bank else 0)
+    return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, bank), "clocks": sampler.summary(),
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e_steps},
+            "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
+            "stage_ms": stages, "impl": "engine"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="s1", choices=["s1", "s2"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = dict(S1 if args.workload == "s1" else S2)
+    bank = args.workload == "s2"
+    if args.impl == "reference":
+        if args.steps == 200 and args.warmup == 10:      # defaults are sized for the GPU arm
+            args.steps, args.warmup = 3, 1
+        res = run_reference(args, cfg, bank, rank)
+        if res is not None:
+            print(json.dumps(res), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl engine needs a CUDA device (the engine has no CPU path)")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    res = run_engine(args, cfg, bank, rank, world, dev)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

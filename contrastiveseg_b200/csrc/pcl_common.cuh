@@ -1,0 +1,88 @@
+// Shared helpers for the pixel-contrast engine kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pcl.h"
+
+namespace pcl {
+
+// ---- error plumbing -----------------------------------------------------------------------------
+void set_cuda_error(cudaError_t e, const char* file, int line);
+
+#define PCL_CUDA(expr)                                                  \
+  do {                                                                  \
+    cudaError_t e__ = (expr);                                           \
+    if (e__ != cudaSuccess) {                                           \
+      ::pcl::set_cuda_error(e__, __FILE__, __LINE__);                   \
+      return PCL_ERR_CUDA;                                              \
+    }                                                                   \
+  } while (0)
+
+#define PCL_LAUNCH_CHECK() PCL_CUDA(cudaGetLastError())
+
+#define PCL_REQUIRE(cond)                 \
+  do {                                    \
+    if (!(cond)) return PCL_ERR_ARG;      \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Class rank used for the sorted anchor layout: 1,2,...,K-1,0  (class 0 last: in bank mode its
+// positives are the analytic zero tail, Q3).
+__device__ __host__ __forceinline__ int class_rank(int c, int K) { return c == 0 ? K - 1 : c - 1; }
+
+// ATen nearest-neighbour source index (UpSampleNearest: min(int(floorf(dst*scale)), in-1), scale=in/out in fp32).
+__device__ __host__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+
+// Keyed bijection on [0, n): multiply/xorshift rounds on the next power of two with cycle walking.
+// Used when no permutation table is injected: view j of a group takes element perm(j), so distinct
+// j give distinct elements without any sequential state (replaces torch.randperm(n)[:k]).
+__device__ __forceinline__ uint32_t keyed_perm(uint32_t j, uint32_t n, uint64_t key) {
+  if (n <= 1) return 0;
+  int bits = 32 - __clz(n - 1);
+  uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  int sh = bits > 1 ? bits / 2 : 1;
+  uint32_t x = j;
+  do {
+    x = (x * 0x9E3779B1u + k0) & mask;  x ^= x >> sh;
+    x = (x * 0x85EBCA6Bu + k1) & mask;  x ^= x >> sh;
+    x = (x * 0xC2B2AE35u + (k0 ^ 0x27D4EB2Fu)) & mask;  x ^= x >> sh;
+    x = (x * 0x165667B1u + (k1 ^ 0x9E3779B9u)) & mask;  x ^= x >> sh;
+  } while (x >= n);
+  return x;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace pcl

@@ -1,0 +1,512 @@
+// Exact-fp32 InfoNCE sweep — SIMT tiles, no A x N temporaries.
+//
+// Replaces lib/loss/loss_contrast.py:91-128 and lib/loss/loss_contrast_mem.py:91-152 (the dense
+// A x N matmul and ~12 dense A x N temporaries, and the 194.6 MB torch.cat + _sample_negative copies:
+// the two queues are read in place, the all-zero tail of the flattened bank is handled analytically).
+//
+// Three sweeps over (row tile 64) x (column tile 64) logit tiles, column range split across CTAs:
+//   NEG  per-row running (max, sum of exp over negatives)            -> partial (m, neg) per split
+//   POS  per-row sum over positives of log-prob, of 1/(e+Neg), count -> partial per split
+//   BWD  recompute logits, form the gradient tile G (closed form), dA += G . C
+// Row statistics are combined in fixed split order, so results are bit-reproducible.
+// This is the exact path (fp32 FMA); the bf16 tcgen05 path lives in pcl_infonce_tc.cu.
+#include "pcl_common.cuh"
+#include <math_constants.h>
+
+namespace pcl {
+
+constexpr int TM = 64, TN = 64, LDT = 68;     // tile rows/cols, padded leading dim of transposed tiles
+constexpr int SWEEP_THREADS = 256;
+constexpr int QMAX = 16;                      // D/16 accumulators per row in BWD (D <= 256)
+
+struct SweepArgs {
+  const float* anchors; const int32_t* acls; const int32_t* diag; const int32_t* plan;
+  int a_rows, D, mode;
+  const float* segq; const float* pixq; int K, M0, M1, R;
+  const float* contrast; const int32_t* ccls;
+  int64_t n_cols;          // upper bound of streamed columns (self mode: a_rows)
+  int tail_count;          // analytic all-zero columns with label 0 (bank mode: R)
+  float inv_T, T_over_bT;
+  int nan_safe;
+  int row_tiles, splits, a_pad, col_tiles;
+};
+
+__device__ __forceinline__ int live_rows(const SweepArgs& a) {
+  int A = a.plan ? a.plan[PCL_PLAN_A] : a.a_rows;
+  return A < a.a_rows ? A : a.a_rows;
+}
+
+__device__ __forceinline__ const float* col_row(const SweepArgs& a, int64_t n, int& label) {
+  if (a.mode == 1) {
+    int c = (int)(n / a.R);
+    int q = (int)(n - (int64_t)c * a.R);
+    label = c + 1;
+    return q < a.M0 ? a.segq + ((int64_t)(c + 1) * a.M0 + q) * a.D
+                    : a.pixq + ((int64_t)(c + 1) * a.M1 + (q - a.M0)) * a.D;
+  }
+  if (a.mode == 0) { label = a.acls[n]; return a.anchors + n * a.D; }
+  label = a.ccls[n];
+  return a.contrast + n * a.D;
+}
+
+// Load a 64 x D row-major block (row pointers in s_ptr, nullptr = zero row) transposed into dst[k*LDT + r].
+__device__ __forceinline__ void load_tile_T(float* __restrict__ dst, const float* const* s_ptr, int D) {
+  const int r = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  const float* src = s_ptr[r];
+  for (int kk = kq * 8; kk < D; kk += 32) {
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (src != nullptr) {
+      v0 = *reinterpret_cast<const float4*>(src + kk);
+      v1 = *reinterpret_cast<const float4*>(src + kk + 4);
+    }
+    dst[(kk + 0) * LDT + r] = v0.x; dst[(kk + 1) * LDT + r] = v0.y;
+    dst[(kk + 2) * LDT + r] = v0.z; dst[(kk + 3) * LDT + r] = v0.w;
+    dst[(kk + 4) * LDT + r] = v1.x; dst[(kk + 5) * LDT + r] = v1.y;
+    dst[(kk + 6) * LDT + r] = v1.z; dst[(kk + 7) * LDT + r] = v1.w;
+  }
+}
+
+enum { MODE_NEG = 0, MODE_POS = 1, MODE_BWD = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+k_sweep(SweepArgs a, float* __restrict__ partials, const float* __restrict__ rowstats, float* __restrict__ dpartials) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = a.D;
+  float* As_t = smem;                         // [D][LDT]
+  float* Ct = As_t + D * LDT;                 // [D][LDT]
+  float* Gs = Ct + D * LDT;                   // [TM][LDT]   (BWD only)
+  float* s_extra = Gs + (MODE == MODE_BWD ? TM * LDT : 0);
+  const float** s_ptr = reinterpret_cast<const float**>(s_extra);                  // [64]
+  int* s_rcls = reinterpret_cast<int*>(s_ptr + 64);                                // [64]
+  int* s_rdiag = s_rcls + 64;                                                      // [64]
+  int* s_clab = s_rdiag + 64;                                                      // [64] (-2 = invalid column)
+  float* s_rm = reinterpret_cast<float*>(s_clab + 64);                             // [64]
+  float* s_rneg = s_rm + 64;
+  float* s_rs = s_rneg + 64;
+  float* s_rc = s_rs + 64;
+  float* s_cm = s_rc + 64;                                                         // column stats (self BWD)
+  float* s_cneg = s_cm + 64;
+  float* s_cs = s_cneg + 64;
+  float* s_cc = s_cs + 64;
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int rt = blockIdx.x, split = blockIdx.y;
+  const int A = live_rows(a);
+  const int row0 = rt * TM;
+  if (row0 >= A) return;
+  const int64_t ncols = a.mode == 0 ? (int64_t)A : a.n_cols;
+  const float rs_scale = a.T_over_bT / (float)A;
+
+  // ---- row tile: pointers, labels, stats ----
+  if (tid < 64) {
+    int r = row0 + tid;
+    bool ok = r < A;
+    s_ptr[tid] = ok ? a.anchors + (int64_t)r * D : nullptr;
+    s_rcls[tid] = ok ? a.acls[r] : -1;
+    s_rdiag[tid] = ok ? (a.mode == 0 ? r : (a.diag ? a.diag[r] : -1)) : -1;
+    if (MODE != MODE_NEG) {
+      const float* st = rowstats;
+      s_rm[tid] = ok ? st[r] : 0.f;
+      s_rneg[tid] = ok ? st[a.a_rows + r] : 1.f;
+      if (MODE == MODE_BWD) {
+        s_rs[tid] = ok ? st[3 * a.a_rows + r] : 0.f;
+        float np = ok ? st[4 * a.a_rows + r] : 1.f;
+        float c = rs_scale / np;
+        if (a.nan_safe && !(np > 0.f)) c = 0.f;
+        s_rc[tid] = ok ? c : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  load_tile_T(As_t, s_ptr, D);
+
+  // ---- column tile range of this CTA ----
+  int t_lo = 0, t_hi = (int)((ncols + TN - 1) / TN);
+  if (MODE == MODE_POS && a.mode == 1) {
+    // rows are sorted by class rank 1..K-1,0; real positive columns exist for ranks <= K-2
+    int last = (A - 1 - row0 < TM - 1) ? (A - 1 - row0) : (TM - 1);
+    int rk_f = class_rank(s_rcls[0], a.K), rk_l = class_rank(s_rcls[last], a.K);
+    if (rk_l > a.K - 2) rk_l = a.K - 2;
+    if (rk_f > rk_l) { t_lo = 0; t_hi = 0; }
+    else {
+      t_lo = (int)(((int64_t)rk_f * a.R) / TN);
+      t_hi = (int)((((int64_t)(rk_l + 1) * a.R) + TN - 1) / TN);
+    }
+  }
+  const int span = t_hi - t_lo;
+  const int per = (span + a.splits - 1) / a.splits;
+  const int my_lo = t_lo + split * per;
+  const int my_hi = min(t_hi, my_lo + per);
+
+  float run_m[4], run_a[4], run_b[4];          // NEG: (max, sum) ; POS: (possum, s, count in run_m)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { run_m[i] = MODE == MODE_NEG ? -CUDART_INF_F : 0.f; run_a[i] = 0.f; run_b[i] = 0.f; }
+  float dacc[4][QMAX];
+  if (MODE == MODE_BWD) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < QMAX; ++q) dacc[i][q] = 0.f;
+  }
+  const int nq = D / 16;
+
+  for (int ct = my_lo; ct < my_hi; ++ct) {
+    __syncthreads();                          // previous tile fully consumed (Ct, Gs, column arrays)
+    if (tid < 64) {
+      int64_t n = (int64_t)ct * TN + tid;
+      int lab = -2;
+      const float* p = nullptr;
+      if (n < ncols) p = col_row(a, n, lab);
+      s_ptr[tid] = p;
+      s_clab[tid] = lab;
+      if (MODE == MODE_BWD && a.mode == 0) {
+        bool ok = n < ncols;
+        s_cm[tid] = ok ? rowstats[n] : 0.f;
+        s_cneg[tid] = ok ? rowstats[a.a_rows + n] : 1.f;
+        s_cs[tid] = ok ? rowstats[3 * a.a_rows + n] : 0.f;
+        float np = ok ? rowstats[4 * a.a_rows + n] : 1.f;
+        float c = rs_scale / np;
+        if (a.nan_safe && !(np > 0.f)) c = 0.f;
+        s_cc[tid] = ok ? c : 0.f;
+      }
+    }
+    __syncthreads();
+    load_tile_T(Ct, s_ptr, D);
+    __syncthreads();
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) {
+      float4 av = *reinterpret_cast<const float4*>(As_t + k * LDT + ty * 4);
+      float4 bv = *reinterpret_cast<const float4*>(Ct + k * LDT + tx * 4);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+
+    const int64_t col_base = (int64_t)ct * TN + tx * 4;
+    if (MODE == MODE_NEG) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rcls = s_rcls[ty * 4 + i];
+        float tmax = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (s_clab[tx * 4 + j] != -2) tmax = fmaxf(tmax, acc[i][j] * a.inv_T);
+        if (tmax > run_m[i]) {
+          run_a[i] = (run_m[i] == -CUDART_INF_F) ? 0.f : run_a[i] * expf(run_m[i] - tmax);
+          run_m[i] = tmax;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int lab = s_clab[tx * 4 + j];
+          if (lab != -2 && lab != rcls) run_a[i] += expf(acc[i][j] * a.inv_T - run_m[i]);
+        }
+      }
+    } else if (MODE == MODE_POS) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+        const int rcls = s_rcls[r], rdiag = s_rdiag[r];
+        const float m = s_rm[r], neg = s_rneg[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int lab = s_clab[tx * 4 + j];
+          if (lab == rcls && rcls >= 0 && (col_base + j) != (int64_t)rdiag) {
+            float lm = acc[i][j] * a.inv_T - m;
+            float t = expf(lm) + neg;
+            run_a[i] += lm - logf(t);
+            run_b[i] += 1.f / t;
+            run_m[i] += 1.f;
+          }
+        }
+      }
+    } else {
+      // gradient tile G (closed form)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+        const int rcls = s_rcls[r], rdiag = s_rdiag[r];
+        const float m = s_rm[r], neg = s_rneg[r], S = s_rs[r], c = s_rc[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cj = tx * 4 + j;
+          const int lab = s_clab[cj];
+          float gval = 0.f;
+          if (lab != -2 && rcls >= 0) {
+            const float l = acc[i][j] * a.inv_T;
+            const float e = expf(l - m);
+            if (lab == rcls) {
+              if ((col_base + j) != (int64_t)rdiag) gval = -c * (1.f - e / (e + neg));
+            } else {
+              gval = c * e * S;
+            }
+            if (a.mode == 0) {               // + G_ji: the column is an anchor too (self-contrast)
+              const float e2 = expf(l - s_cm[cj]);
+              if (lab == rcls) {
+                if ((col_base + j) != (int64_t)rdiag) gval += -s_cc[cj] * (1.f - e2 / (e2 + s_cneg[cj]));
+              } else {
+                gval += s_cc[cj] * e2 * s_cs[cj];
+              }
+            }
+          }
+          Gs[r * LDT + cj] = gval;
+        }
+      }
+      __syncthreads();
+      // dA[r][d] += sum_j G[r][j] * C[j][d],  C[j][d] = Ct[d*LDT + j]
+#pragma unroll 4
+      for (int j4 = 0; j4 < TN; j4 += 4) {
+        float4 gv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gv[i] = *reinterpret_cast<const float4*>(Gs + (ty * 4 + i) * LDT + j4);
+#pragma unroll
+        for (int q = 0; q < QMAX; ++q) {
+          if (q < nq) {
+            float4 cv = *reinterpret_cast<const float4*>(Ct + (tx + 16 * q) * LDT + j4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dacc[i][q] += gv[i].x * cv.x + gv[i].y * cv.y + gv[i].z * cv.z + gv[i].w * cv.w;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- write partials ----
+  if (MODE == MODE_NEG) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m = run_m[i], n = run_a[i];
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        float om = __shfl_xor_sync(0xffffffffu, m, o), on = __shfl_xor_sync(0xffffffffu, n, o);
+        float nm = fmaxf(m, om);
+        float s0 = (m == -CUDART_INF_F) ? 0.f : n * expf(m - nm);
+        float s1 = (om == -CUDART_INF_F) ? 0.f : on * expf(om - nm);
+        n = s0 + s1; m = nm;
+      }
+      if (tx == 0) {
+        int r = row0 + ty * 4 + i;
+        partials[((int64_t)0 * a.splits + split) * a.a_pad + r] = m;
+        partials[((int64_t)1 * a.splits + split) * a.a_pad + r] = n;
+      }
+    }
+  } else if (MODE == MODE_POS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float p = run_a[i], s = run_b[i], c = run_m[i];
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) {
+        p += __shfl_xor_sync(0xffffffffu, p, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+      }
+      if (tx == 0) {
+        int r = row0 + ty * 4 + i;
+        partials[((int64_t)2 * a.splits + split) * a.a_pad + r] = p;
+        partials[((int64_t)3 * a.splits + split) * a.a_pad + r] = s;
+        partials[((int64_t)4 * a.splits + split) * a.a_pad + r] = c;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int r = row0 + ty * 4 + i;
+      float* dst = dpartials + ((int64_t)split * a.a_pad + r) * D;
+#pragma unroll
+      for (int q = 0; q < QMAX; ++q)
+        if (q < nq) dst[tx + 16 * q] = dacc[i][q];
+    }
+  }
+}
+
+// Combine the NEG partials of all splits (fixed order) and add the analytic zero tail (Q3).
+__global__ void k_combine_neg(SweepArgs a, const float* __restrict__ partials, float* __restrict__ rowstats) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int A = live_rows(a);
+  if (r >= a.a_rows) return;
+  if (r >= A) { rowstats[r] = 0.f; rowstats[a.a_rows + r] = 0.f; return; }
+  float m = -CUDART_INF_F;
+  for (int p = 0; p < a.splits; ++p) m = fmaxf(m, partials[((int64_t)0 * a.splits + p) * a.a_pad + r]);
+  if (a.tail_count > 0) m = fmaxf(m, 0.f);
+  float n = 0.f;
+  for (int p = 0; p < a.splits; ++p) {
+    float pm = partials[((int64_t)0 * a.splits + p) * a.a_pad + r];
+    if (pm != -CUDART_INF_F) n += partials[((int64_t)1 * a.splits + p) * a.a_pad + r] * expf(pm - m);
+  }
+  if (a.tail_count > 0 && a.acls[r] != 0) n += (float)a.tail_count * expf(-m);
+  rowstats[r] = m;
+  rowstats[a.a_rows + r] = n;
+}
+
+// Combine the POS partials, add the zero-tail positives of class-0 anchors, row losses and the mean.
+__global__ void __launch_bounds__(1024)
+k_finalize(SweepArgs a, const float* __restrict__ partials, float* __restrict__ rowstats, float* __restrict__ loss) {
+  __shared__ float s_red[1024];
+  const int A = live_rows(a);
+  float acc = 0.f;
+  for (int r = threadIdx.x; r < a.a_rows; r += blockDim.x) {
+    float ps = 0.f, s = 0.f, c = 0.f, rl = 0.f;
+    if (r < A) {
+      for (int p = 0; p < a.splits; ++p) {
+        ps += partials[((int64_t)2 * a.splits + p) * a.a_pad + r];
+        s += partials[((int64_t)3 * a.splits + p) * a.a_pad + r];
+        c += partials[((int64_t)4 * a.splits + p) * a.a_pad + r];
+      }
+      if (a.tail_count > 0 && a.acls[r] == 0) {
+        const float m = rowstats[r], neg = rowstats[a.a_rows + r];
+        const float t = expf(-m) + neg;
+        // the masked (i,i) entry can fall inside the zero tail when A > (K-1)*R (Q1)
+        const int dg = a.diag ? a.diag[r] : -1;
+        const float tc = (float)(a.tail_count - ((dg >= a.n_cols && dg < a.n_cols + a.tail_count) ? 1 : 0));
+        ps += tc * (-m - logf(t));
+        s += tc / t;
+        c += tc;
+      }
+      rl = -a.T_over_bT * ps / c;
+      if (a.nan_safe && !(c > 0.f)) rl = 0.f;
+      acc += rl;
+    }
+    rowstats[2 * a.a_rows + r] = ps;
+    rowstats[3 * a.a_rows + r] = s;
+    rowstats[4 * a.a_rows + r] = c;
+    rowstats[5 * a.a_rows + r] = rl;
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = A > 0 ? s_red[0] / (float)A : 0.f;
+}
+
+__global__ void k_reduce_dA(SweepArgs a, const float* __restrict__ dpartials, const float* __restrict__ grad_loss,
+                            float* __restrict__ dA) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)a.a_rows * a.D;
+  if (idx >= total) return;
+  const int r = (int)(idx / a.D);
+  const int A = live_rows(a);
+  float v = 0.f;
+  if (r < A) {
+    for (int p = 0; p < a.splits; ++p) v += dpartials[((int64_t)p * a.a_pad) * a.D + idx];
+    v *= a.inv_T * (grad_loss ? *grad_loss : 1.f);
+  }
+  dA[idx] = v;
+}
+
+}  // namespace pcl
+
+using namespace pcl;
+
+static int make_args(const pcl_sweep_desc* d, SweepArgs* a) {
+  if (!d || !d->anchors || !d->anchor_cls) return PCL_ERR_ARG;
+  if (d->a_rows <= 0 || d->D <= 0) return PCL_ERR_ARG;
+  if (d->D % 32 != 0 || d->D > 256) return PCL_ERR_UNSUPPORTED;
+  if (!(d->temperature > 0.f) || !(d->base_temperature > 0.f)) return PCL_ERR_ARG;
+  memset(a, 0, sizeof(*a));
+  a->anchors = d->anchors; a->acls = d->anchor_cls; a->diag = d->diag_col; a->plan = d->plan;
+  a->a_rows = d->a_rows; a->D = d->D; a->mode = d->mode;
+  if (d->mode == 0) {
+    a->n_cols = d->a_rows; a->tail_count = 0;
+  } else if (d->mode == 1) {
+    if (!d->segment_queue || d->bank_K < 1 || d->bank_M0 < 1 || d->bank_M1 < 0) return PCL_ERR_ARG;
+    if (d->bank_M1 > 0 && !d->pixel_queue) return PCL_ERR_ARG;
+    a->segq = d->segment_queue; a->pixq = d->pixel_queue; a->K = d->bank_K; a->M0 = d->bank_M0; a->M1 = d->bank_M1;
+    a->R = d->bank_M0 + d->bank_M1;
+    a->n_cols = (int64_t)(d->bank_K - 1) * a->R; a->tail_count = a->R;
+  } else if (d->mode == 2) {
+    if (!d->contrast || !d->contrast_cls || d->n_cols <= 0) return PCL_ERR_ARG;
+    a->contrast = d->contrast; a->ccls = d->contrast_cls; a->n_cols = d->n_cols; a->tail_count = 0;
+  } else {
+    return PCL_ERR_ARG;
+  }
+  a->inv_T = 1.f / d->temperature;
+  a->T_over_bT = d->temperature / d->base_temperature;
+  a->nan_safe = d->nan_safe;
+  a->row_tiles = ceil_div(d->a_rows, TM);
+  a->a_pad = a->row_tiles * TM;
+  a->col_tiles = (int)ceil_div64(a->n_cols > 0 ? a->n_cols : 1, TN);
+  int splits = 296 / a->row_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > a->col_tiles) splits = a->col_tiles;
+  if (splits > 148) splits = 148;
+  a->splits = splits;
+  return PCL_OK;
+}
+
+static size_t sweep_smem(int D, bool bwd) {
+  return (size_t)(2 * D * LDT + (bwd ? TM * LDT : 0)) * sizeof(float) + 64 * sizeof(void*) + 64 * 3 * sizeof(int) +
+         64 * 8 * sizeof(float);
+}
+
+extern "C" int pcl_sweep_sizes(const pcl_sweep_desc* d, pcl_sweep_sizes_t* out) {
+  SweepArgs a;
+  // pointers are not needed to size the buffers: validate the shape fields only
+  pcl_sweep_desc tmp = *d;
+  static const float dummy_f = 0.f;
+  static const int32_t dummy_i = 0;
+  tmp.anchors = &dummy_f; tmp.anchor_cls = &dummy_i;
+  if (tmp.mode == 1) { tmp.segment_queue = &dummy_f; tmp.pixel_queue = &dummy_f; }
+  if (tmp.mode == 2) { tmp.contrast = &dummy_f; tmp.contrast_cls = &dummy_i; }
+  int st = make_args(&tmp, &a);
+  if (st != PCL_OK || !out) return st != PCL_OK ? st : PCL_ERR_ARG;
+  out->n_real_cols = a.n_cols;
+  out->row_tiles = a.row_tiles;
+  out->splits = a.splits;
+  out->partial_f32 = (int64_t)a.splits * a.a_pad;
+  out->rowstat_f32 = a.a_rows;
+  out->dpartial_f32 = (int64_t)a.splits * a.a_pad * a.D;
+  return PCL_OK;
+}
+
+extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream) {
+  SweepArgs a;
+  int st = make_args(d, &a);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(partials && rowstats && loss);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = sweep_smem(a.D, false);
+  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // every (split, live row) slot is written by its CTA (empty column ranges write "nothing seen"),
+  // so the partial buffers need no initialisation
+  dim3 grid(a.row_tiles, a.splits);
+  k_sweep<MODE_NEG><<<grid, SWEEP_THREADS, smem, s>>>(a, partials, nullptr, nullptr);
+  PCL_LAUNCH_CHECK();
+  k_combine_neg<<<ceil_div(a.a_rows, 256), 256, 0, s>>>(a, partials, rowstats);
+  PCL_LAUNCH_CHECK();
+  k_sweep<MODE_POS><<<grid, SWEEP_THREADS, smem, s>>>(a, partials, rowstats, nullptr);
+  PCL_LAUNCH_CHECK();
+  k_finalize<<<1, 1024, 0, s>>>(a, partials, rowstats, loss);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_infonce_bwd(const pcl_sweep_desc* d, const float* rowstats, const float* grad_loss,
+                               float* dpartials, float* dA, void* stream) {
+  SweepArgs a;
+  int st = make_args(d, &a);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(rowstats && dpartials && dA);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = sweep_smem(a.D, true);
+  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(a.row_tiles, a.splits);
+  k_sweep<MODE_BWD><<<grid, SWEEP_THREADS, smem, s>>>(a, nullptr, rowstats, dpartials);
+  PCL_LAUNCH_CHECK();
+  const int64_t total = (int64_t)a.a_rows * a.D;
+  k_reduce_dA<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(a, dpartials, grad_loss, dA);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}

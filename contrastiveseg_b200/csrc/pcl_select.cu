@@ -1,0 +1,393 @@
+// Anchor selection and gather/scatter kernels (SURVEY §8 rows a3, a4 and the dense-gradient writer).
+//
+// Replaces lib/loss/loss_contrast.py:30-89 (_hard_anchor_sampling) and :131-142 without the per-(image,
+// class) Python loop, its ~5 host syncs per pair, and the 268 MB permute+contiguous copy:
+//   k_keys    one pass over labels/seg: nearest-neighbour label, argmax, 16-bit key per pixel, and a
+//             histogram of keys per 1024-pixel chunk (HBM-bound: reads B*K*h*w*4 B of seg once)
+//   k_plan    class filter, TC, V, hard/easy split, class-sorted row layout (one block, integer only)
+//   k_select  one warp per anchor: rank -> pixel (chunk prefix search + in-chunk ordered scan), gather
+//             of the pixel's D channels from NCHW, optional L2-normalise, fp32 + bf16 rows
+//   k_scatter dense-gradient writer (after a memset): one warp per anchor row
+#include "pcl_common.cuh"
+
+namespace pcl {
+
+// ------------------------------------------------------------------------------------------------
+// k_keys
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __restrict__ labels,
+       const float* __restrict__ seg, const int64_t* __restrict__ predict, uint16_t* __restrict__ keys,
+       int32_t* __restrict__ chunk_hist) {
+  extern __shared__ int s_hist[];                 // 2K+1 bins
+  const int K = g.K, NK = 2 * K;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int HW = g.h * g.w;
+  for (int i = threadIdx.x; i <= NK; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int64_t* lab_b = labels + (int64_t)b * g.Himg * g.Wimg;
+#pragma unroll
+  for (int j = 0; j < PCL_CHUNK / 256; ++j) {
+    int p = chunk * PCL_CHUNK + j * 256 + threadIdx.x;
+    if (p < HW) {
+      int py = p / g.w, px = p - py * g.w;
+      int sy = nearest_src(py, scale_h, g.Himg), sx = nearest_src(px, scale_w, g.Wimg);
+      int64_t lab = lab_b[(int64_t)sy * g.Wimg + sx];
+      int key = NK;
+      if (lab >= 0 && lab < K && lab != (int64_t)g.ignore_label) {
+        int pred;
+        if (seg != nullptr) {
+          const float* sp = seg + (int64_t)b * K * HW + p;
+          float best = sp[0];
+          pred = 0;
+          for (int c = 1; c < K; ++c) {
+            float v = sp[(int64_t)c * HW];
+            if (v > best) { best = v; pred = c; }
+          }
+        } else {
+          int64_t pv = predict[(int64_t)b * HW + p];
+          pred = (pv >= 0 && pv < K) ? (int)pv : -1;
+        }
+        key = 2 * (int)lab + (pred == (int)lab ? 1 : 0);
+      }
+      keys[(int64_t)b * HW + p] = (uint16_t)key;
+      atomicAdd(&s_hist[key], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NK; i += blockDim.x)
+    chunk_hist[((int64_t)b * NK + i) * nchunk + chunk] = s_hist[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_plan (single block)
+// plan layout: [0..16) header, then 8 int32 per pair: img, cls, n_hard, n_easy, keep_hard, keep_easy,
+//              sorted_base (first class-sorted row of the pair), reserved
+// ------------------------------------------------------------------------------------------------
+constexpr int PLAN_THREADS = 256;
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_plan(pcl_geom g, int nchunk, int32_t* __restrict__ chunk_pref, int32_t* __restrict__ counts,
+       int32_t* __restrict__ plan) {
+  __shared__ int s_scan[PLAN_THREADS];
+  __shared__ int s_cls_cnt[PCL_MAX_CLASSES];
+  __shared__ int s_cls_start[PCL_MAX_CLASSES];
+  __shared__ int s_TC, s_V;
+  const int K = g.K, NK = 2 * K, B = g.B;
+  const int tid = threadIdx.x;
+
+  // 1. per (image,key): exclusive prefix over chunks, total into counts
+  for (int row = tid; row < B * NK; row += PLAN_THREADS) {
+    int32_t* p = chunk_pref + (int64_t)row * nchunk;
+    int run = 0;
+    for (int c = 0; c < nchunk; ++c) { int v = p[c]; p[c] = run; run += v; }
+    counts[row] = run;
+  }
+  for (int c = tid; c < K; c += PLAN_THREADS) s_cls_cnt[c] = 0;
+  __syncthreads();
+
+  // 2. compact kept (image,class) pairs in (image asc, class asc) order
+  const int E = B * K;
+  const int per = (E + PLAN_THREADS - 1) / PLAN_THREADS;
+  const int e0 = tid * per, e1 = min(E, e0 + per);
+  int local = 0;
+  for (int e = e0; e < e1; ++e) {
+    int b = e / K, c = e - b * K;
+    int n = counts[b * NK + 2 * c] + counts[b * NK + 2 * c + 1];
+    local += (n > g.max_views) ? 1 : 0;
+  }
+  s_scan[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int i = 0; i < PLAN_THREADS; ++i) { int v = s_scan[i]; s_scan[i] = run; run += v; }
+    s_TC = run;
+    s_V = run > 0 ? min(g.max_samples / run, g.max_views) : 0;
+  }
+  __syncthreads();
+  const int TC = s_TC, V = s_V;
+  int32_t* pairs = plan + PCL_PLAN_HEADER;
+  int t = s_scan[tid];
+  int split_err = 0;
+  for (int e = e0; e < e1; ++e) {
+    int b = e / K, c = e - b * K;
+    int nh = counts[b * NK + 2 * c], ne = counts[b * NK + 2 * c + 1];
+    if (nh + ne > g.max_views) {
+      int kh, ke;
+      // loss_contrast.py:66-77   (num >= n_view / 2  <=>  2*num >= n_view)
+      if (2 * nh >= V && 2 * ne >= V) { kh = V / 2; ke = V - kh; }
+      else if (2 * nh >= V)           { ke = ne;    kh = V - ke; }
+      else if (2 * ne >= V)           { kh = nh;    ke = V - kh; }
+      else                            { kh = 0; ke = 0; split_err = 1; }
+      int32_t* q = pairs + (int64_t)t * 8;
+      q[0] = b; q[1] = c; q[2] = nh; q[3] = ne; q[4] = kh; q[5] = ke; q[6] = 0; q[7] = 0;
+      atomicAdd(&s_cls_cnt[c], 1);
+      ++t;
+    }
+  }
+  if (split_err) atomicOr(&plan[PCL_PLAN_FLAGS], PCL_FLAG_SPLIT_ERROR);
+  __syncthreads();
+  if (tid == 0) {
+    // class-sorted start rows, rank order 1,2,...,K-1,0
+    int run = 0;
+    for (int r = 0; r < K; ++r) {
+      int c = (r == K - 1) ? 0 : r + 1;
+      s_cls_start[c] = run;
+      run += s_cls_cnt[c];
+    }
+    plan[PCL_PLAN_TC] = TC;
+    plan[PCL_PLAN_V] = V;
+    plan[PCL_PLAN_A] = TC * V;
+    int f = 0;
+    if (TC == 0) f |= PCL_FLAG_NO_CLASS;
+    if (TC > 0 && V == 0) f |= PCL_FLAG_ZERO_VIEWS;
+    atomicOr(&plan[PCL_PLAN_FLAGS], f);
+    plan[PCL_PLAN_NPAIR_MAX] = E;
+  }
+  __syncthreads();
+  // 3. sorted base per pair: V * (class start + number of earlier images that kept the class)
+  for (int p = tid; p < TC; p += PLAN_THREADS) {
+    int32_t* q = pairs + (int64_t)p * 8;
+    int b = q[0], c = q[1];
+    int before = 0;
+    for (int bb = 0; bb < b; ++bb) {
+      int n = counts[bb * NK + 2 * c] + counts[bb * NK + 2 * c + 1];
+      before += (n > g.max_views) ? 1 : 0;
+    }
+    q[6] = V * (s_cls_start[c] + before);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_select: one warp per anchor row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t* __restrict__ keys,
+         const int32_t* __restrict__ chunk_pref, const int32_t* __restrict__ plan,
+         const int32_t* __restrict__ ranks, uint64_t seed, int normalize, int32_t* __restrict__ meta,
+         float* __restrict__ anchors, __nv_bfloat16* __restrict__ anchors_bf16, float* __restrict__ inv_norm,
+         float* __restrict__ norm_max) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int TC = plan[PCL_PLAN_TC], V = plan[PCL_PLAN_V];
+  if (V <= 0 || i >= TC * V) return;
+  const int t = i / V, v = i - t * V;
+  const int32_t* q = plan + PCL_PLAN_HEADER + (int64_t)t * 8;
+  const int b = q[0], c = q[1], nh = q[2], ne = q[3], kh = q[4], base = q[6];
+  const int K = g.K, NK = 2 * K, HW = g.h * g.w, D = g.D;
+  const bool easy = v >= kh;
+  const int j = easy ? v - kh : v;
+  const int n = easy ? ne : nh;
+  const int key = 2 * c + (easy ? 1 : 0);
+  int rank;
+  if (ranks != nullptr) rank = ranks[(int64_t)t * V + v];
+  else rank = (int)keyed_perm((uint32_t)j, (uint32_t)n, mix64(seed ^ ((uint64_t)(b * K + c) << 1 | (easy ? 1u : 0u))));
+  if (rank < 0) rank = 0;
+  if (rank >= n) rank = n - 1;               // defensive: malformed injected table
+
+  // chunk that holds the rank-th pixel of this key
+  const int32_t* pref = chunk_pref + ((int64_t)b * NK + key) * nchunk;
+  int chunk = -1;
+  for (int c0 = 0; c0 < nchunk; c0 += 32) {
+    int ch = c0 + lane;
+    bool ok = false;
+    if (ch < nchunk) {
+      int lo = pref[ch];
+      ok = lo <= rank && (ch + 1 == nchunk || pref[ch + 1] > rank);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) { chunk = c0 + __ffs(m) - 1; break; }
+  }
+  if (chunk < 0) return;                       // cannot happen for a consistent table
+  const int local = rank - pref[chunk];
+
+  // ordered scan of the chunk: lane L owns pixels [32L, 32L+32)
+  const int p0 = chunk * PCL_CHUNK + lane * 32;
+  const uint16_t* kb = keys + (int64_t)b * HW;
+  int cnt = 0;
+  for (int u = 0; u < 32; ++u) {
+    int p = p0 + u;
+    cnt += (p < HW && kb[p] == (uint16_t)key) ? 1 : 0;
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int excl = incl - cnt;
+  int pix = -1;
+  if (local >= excl && local < incl) {
+    int need = local - excl;
+    for (int u = 0; u < 32; ++u) {
+      int p = p0 + u;
+      if (p < HW && kb[p] == (uint16_t)key) {
+        if (need == 0) { pix = p; break; }
+        --need;
+      }
+    }
+  }
+  unsigned owner = __ballot_sync(0xffffffffu, pix >= 0);
+  if (!owner) return;
+  pix = __shfl_sync(0xffffffffu, pix, __ffs(owner) - 1);
+
+  // gather the D channels of (b, pix)
+  const int s = base + v;
+  const float* src = embed + (int64_t)b * D * HW + pix;
+  float* dst = anchors + (int64_t)s * D;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float x = src[(int64_t)d * HW];
+    ss += x * x;
+    dst[d] = x;
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float inv = normalize ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
+  for (int d = lane; d < D; d += 32) {
+    float y = dst[d] * inv;
+    if (normalize) dst[d] = y;
+    if (anchors_bf16 != nullptr) anchors_bf16[(int64_t)s * D + d] = __float2bfloat16(y);
+  }
+  if (lane == 0) {
+    const int ms = g.max_samples;
+    meta[s] = pix;
+    meta[ms + s] = b;
+    meta[2 * ms + s] = c;
+    meta[3 * ms + s] = v * TC + t;
+    inv_norm[s] = inv;
+    atomicMax(reinterpret_cast<int*>(norm_max), __float_as_int(nrm * inv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scatter: dA rows -> dense NCHW gradient (buffer is zeroed by a memset first)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_scatter(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restrict__ meta,
+          const float* __restrict__ dA, const float* __restrict__ anchors, const float* __restrict__ inv_norm,
+          int normalize, float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int A = plan[PCL_PLAN_A];
+  if (s >= A) return;
+  const int ms = g.max_samples, D = g.D;
+  const int64_t HW = (int64_t)g.h * g.w;
+  const int pix = meta[s], b = meta[ms + s];
+  const float* ga = dA + (int64_t)s * D;
+  float dot = 0.f, inv = 1.f;
+  if (normalize) {
+    const float* y = anchors + (int64_t)s * D;
+    for (int d = lane; d < D; d += 32) dot += y[d] * ga[d];
+    dot = warp_sum(dot);
+    inv = inv_norm[s];
+  }
+  float* dst = grad + (int64_t)b * D * HW + pix;
+  for (int d = lane; d < D; d += 32) {
+    float v = ga[d];
+    if (normalize) v = (v - anchors[(int64_t)s * D + d] * dot) * inv;
+    dst[(int64_t)d * HW] = v;
+  }
+}
+
+}  // namespace pcl
+
+using namespace pcl;
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+static int check_geom(const pcl_geom* g) {
+  if (!g) return PCL_ERR_ARG;
+  if (g->B <= 0 || g->D <= 0 || g->h <= 0 || g->w <= 0 || g->Himg <= 0 || g->Wimg <= 0) return PCL_ERR_ARG;
+  if (g->K <= 0 || g->K > PCL_MAX_CLASSES) return PCL_ERR_ARG;
+  if (g->max_samples <= 0 || g->max_views <= 0) return PCL_ERR_ARG;
+  if ((int64_t)g->B * g->K > (1 << 20)) return PCL_ERR_ARG;
+  return PCL_OK;
+}
+
+extern "C" int pcl_select_sizes(const pcl_geom* g, pcl_select_sizes_t* out) {
+  int st = check_geom(g);
+  if (st != PCL_OK || !out) return PCL_ERR_ARG;
+  const int64_t HW = (int64_t)g->h * g->w;
+  out->nchunk = (int32_t)ceil_div64(HW, PCL_CHUNK);
+  out->max_pairs = g->B * g->K;
+  out->keys_u16 = (int64_t)g->B * HW;
+  out->chunk_pref_i32 = (int64_t)g->B * 2 * g->K * out->nchunk;
+  out->counts_i32 = (int64_t)g->B * 2 * g->K;
+  out->plan_i32 = PCL_PLAN_HEADER + 8 * (int64_t)out->max_pairs;
+  out->anchor_meta_i32 = 4 * (int64_t)g->max_samples;
+  return PCL_OK;
+}
+
+extern "C" int pcl_class_stats(const pcl_geom* g, const int64_t* labels, const float* seg, const int64_t* predict,
+                               uint16_t* keys, int32_t* chunk_pref, void* stream) {
+  int st = check_geom(g);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(labels && keys && chunk_pref && (seg || predict));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t HW = (int64_t)g->h * g->w;
+  const int nchunk = (int)ceil_div64(HW, PCL_CHUNK);
+  const float scale_h = (float)g->Himg / (float)g->h, scale_w = (float)g->Wimg / (float)g->w;
+  dim3 grid(nchunk, g->B);
+  size_t smem = (2 * g->K + 1) * sizeof(int);
+  k_keys<<<grid, 256, smem, s>>>(*g, nchunk, scale_h, scale_w, labels, seg, predict, keys, chunk_pref);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_plan_anchors(const pcl_geom* g, int32_t* chunk_pref, int32_t* counts, int32_t* plan,
+                                void* stream) {
+  int st = check_geom(g);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(chunk_pref && counts && plan);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nchunk = (int)ceil_div64((int64_t)g->h * g->w, PCL_CHUNK);
+  PCL_CUDA(cudaMemsetAsync(plan, 0, PCL_PLAN_HEADER * sizeof(int32_t), s));
+  k_plan<<<1, PLAN_THREADS, 0, s>>>(*g, nchunk, chunk_pref, counts, plan);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_select_gather(const pcl_geom* g, const float* embed, const uint16_t* keys,
+                                 const int32_t* chunk_pref, const int32_t* plan, const int32_t* ranks,
+                                 uint64_t seed, int normalize, int32_t* anchor_meta, float* anchors_f32,
+                                 void* anchors_bf16, float* inv_norm, float* norm_max, void* stream) {
+  int st = check_geom(g);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(embed && keys && chunk_pref && plan && anchor_meta && anchors_f32 && inv_norm && norm_max);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ms = g->max_samples;
+  const int nchunk = (int)ceil_div64((int64_t)g->h * g->w, PCL_CHUNK);
+  PCL_CUDA(cudaMemsetAsync(anchor_meta, 0xFF, 4 * (size_t)ms * sizeof(int32_t), s));
+  PCL_CUDA(cudaMemsetAsync(anchors_f32, 0, (size_t)ms * g->D * sizeof(float), s));
+  if (anchors_bf16) {
+    size_t rows = (size_t)ceil_div(ms, 128) * 128;
+    PCL_CUDA(cudaMemsetAsync(anchors_bf16, 0, rows * g->D * sizeof(__nv_bfloat16), s));
+  }
+  PCL_CUDA(cudaMemsetAsync(inv_norm, 0, (size_t)ms * sizeof(float), s));
+  PCL_CUDA(cudaMemsetAsync(norm_max, 0, sizeof(float), s));
+  const int warps = 8;
+  k_select<<<ceil_div(ms, warps), warps * 32, 0, s>>>(*g, nchunk, embed, keys, chunk_pref, plan, ranks, seed,
+                                                     normalize, anchor_meta, anchors_f32,
+                                                     (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_scatter_grad(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
+                                const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed,
+                                void* stream) {
+  int st = check_geom(g);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(plan && anchor_meta && dA && grad_embed);
+  if (normalize) PCL_REQUIRE(anchors_f32 && inv_norm);
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t bytes = (size_t)g->B * g->D * g->h * g->w * sizeof(float);
+  PCL_CUDA(cudaMemsetAsync(grad_embed, 0, bytes, s));
+  const int warps = 8;
+  k_scatter<<<ceil_div(g->max_samples, warps), warps * 32, 0, s>>>(*g, plan, anchor_meta, dA, anchors_f32, inv_norm,
+                                                                  normalize, grad_embed);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}

@@ -1,0 +1,46 @@
+// One loss step chained on a stream behind a single descriptor (include/pcl.h: pcl_step_*).
+#include "pcl_common.cuh"
+
+static void fill_sweep(const pcl_step_desc* d, pcl_sweep_desc* w) {
+  memset(w, 0, sizeof(*w));
+  const int ms = d->g.max_samples;
+  w->anchors = d->anchors_f32;
+  w->anchor_cls = d->anchor_meta + 2 * (int64_t)ms;
+  w->diag_col = d->anchor_meta + 3 * (int64_t)ms;       // reference row index r = v*TC + t (Q1)
+  w->plan = d->plan;
+  w->a_rows = ms;
+  w->D = d->g.D;
+  w->mode = d->mode;
+  w->segment_queue = d->segment_queue;
+  w->pixel_queue = d->pixel_queue;
+  w->bank_K = d->bank_K; w->bank_M0 = d->bank_M0; w->bank_M1 = d->bank_M1;
+  w->temperature = d->temperature; w->base_temperature = d->base_temperature;
+  w->nan_safe = d->nan_safe;
+}
+
+extern "C" int pcl_step_stats(const pcl_step_desc* d, void* stream) {
+  if (!d) return PCL_ERR_ARG;
+  int st = pcl_class_stats(&d->g, d->labels, d->seg, d->predict, d->keys, d->chunk_pref, stream);
+  if (st != PCL_OK) return st;
+  return pcl_plan_anchors(&d->g, d->chunk_pref, d->counts, d->plan, stream);
+}
+
+extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {
+  if (!d) return PCL_ERR_ARG;
+  int st = pcl_select_gather(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
+                             d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, d->norm_max, stream);
+  if (st != PCL_OK) return st;
+  pcl_sweep_desc w;
+  fill_sweep(d, &w);
+  return pcl_infonce_fwd(&w, d->partials, d->rowstats, d->loss, stream);
+}
+
+extern "C" int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss, void* stream) {
+  if (!d) return PCL_ERR_ARG;
+  pcl_sweep_desc w;
+  fill_sweep(d, &w);
+  int st = pcl_infonce_bwd(&w, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
+  if (st != PCL_OK) return st;
+  return pcl_scatter_grad(&d->g, d->plan, d->anchor_meta, d->dA, d->anchors_f32, d->inv_norm, d->normalize,
+                          d->grad_embed, stream);
+}

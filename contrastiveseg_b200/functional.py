@@ -1,0 +1,320 @@
+"""Autograd entry points of the engine: thin Python over the C ABI (include/pcl.h).
+
+PyTorch is plumbing here (device memory, streams, autograd hand-off); all arithmetic of the path runs in
+the CUDA kernels of libpcl_b200.so.  No fallback: tensors must be CUDA tensors and the library must load.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import _abi
+from . import rng as _rng
+
+
+@dataclasses.dataclass
+class ContrastOptions:
+    temperature: float = 0.1
+    base_temperature: float = 0.07
+    max_samples: int = 1024
+    max_views: int = 100
+    ignore_label: int = -1
+    num_classes: Optional[int] = None      # class ids tracked; default: seg planes / bank classes / 256
+    normalize: bool = False                # True: `embed` is the raw projection, the engine normalises the sampled columns
+    nan_safe: bool = False                 # False reproduces the reference's NaN for rows without positives (Q8)
+    rng: str = "device"                    # "device" (no host sync) | "torch_cpu" (reference RNG stream)
+    perm_fn: Optional[Callable[[int], torch.Tensor]] = None   # injected permutations (parity tests)
+    seed: int = 304
+    precision: str = "fp32"                # "fp32" exact SIMT sweep | "bf16" tcgen05 sweep (bank / large problems)
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _abi.PclError(f"{name} must be a CUDA tensor: the engine has no CPU path")
+
+
+class ContrastWorkspace:
+    """Caller-owned scratch for one geometry (torch allocator owns the memory; the C side keeps no state)."""
+
+    def __init__(self, device: torch.device, geom: _abi.Geom, mode: int, bank_K: int, bank_M0: int, bank_M1: int):
+        lib = _abi.load()
+        self.device = device
+        self.geom = geom
+        sizes = _abi.SelectSizes()
+        _abi.check(lib.pcl_select_sizes(C.byref(geom), C.byref(sizes)), "pcl_select_sizes")
+        self.sizes = sizes
+        ms, D = geom.max_samples, geom.D
+        sw = _abi.SweepDesc()
+        sw.a_rows, sw.D, sw.mode = ms, D, mode
+        sw.bank_K, sw.bank_M0, sw.bank_M1 = bank_K, bank_M0, bank_M1
+        sw.temperature, sw.base_temperature = 1.0, 1.0
+        ss = _abi.SweepSizes()
+        _abi.check(lib.pcl_sweep_sizes(C.byref(sw), C.byref(ss)), "pcl_sweep_sizes")
+        self.sweep_sizes = ss
+        i32 = dict(dtype=torch.int32, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.keys = torch.empty(sizes.keys_u16, dtype=torch.int16, device=device)
+        self.chunk_pref = torch.empty(sizes.chunk_pref_i32, **i32)
+        self.counts = torch.empty(sizes.counts_i32, **i32)
+        self.plan = torch.zeros(sizes.plan_i32, **i32)
+        self.anchor_meta = torch.empty(sizes.anchor_meta_i32, **i32)
+        self.anchors_f32 = torch.empty((ms, D), **f32)
+        self.anchors_bf16 = torch.empty((-(-ms // 128) * 128, D), dtype=torch.bfloat16, device=device)
+        self.inv_norm = torch.empty(ms, **f32)
+        self.norm_max = torch.zeros(1, **f32)
+        self.partials = torch.empty(5 * ss.partial_f32, **f32)
+        self.rowstats = torch.empty(6 * ss.rowstat_f32, **f32)
+        self.dpartials = torch.empty(ss.dpartial_f32, **f32)
+        self.dA = torch.empty((ms, D), **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.ranks = torch.zeros(ms, **i32)
+        self.ranks_host = torch.zeros(ms, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+        self.busy = False
+        d = _abi.StepDesc()
+        d.g = geom
+        d.mode, d.bank_K, d.bank_M0, d.bank_M1 = mode, bank_K, bank_M0, bank_M1
+        for name in ("keys", "chunk_pref", "counts", "plan", "anchor_meta", "anchors_f32", "anchors_bf16", "inv_norm",
+                     "norm_max", "partials", "rowstats", "dpartials", "dA", "loss"):
+            setattr(d, name, getattr(self, name).data_ptr())
+        self.desc = d
+
+    # views used by tests / diagnostics
+    def plan_header(self):
+        return self.plan[:_abi.PLAN_HEADER].tolist()
+
+
+_WS_CACHE = {}
+
+
+def _get_workspace(device, key, geom, mode, bank_K, bank_M0, bank_M1) -> ContrastWorkspace:
+    lst = _WS_CACHE.setdefault((device.index, key), [])
+    for ws in lst:
+        if not ws.busy:
+            return ws
+    ws = ContrastWorkspace(device, geom, mode, bank_K, bank_M0, bank_M1)
+    lst.append(ws)
+    return ws
+
+
+def clear_workspaces() -> None:
+    _WS_CACHE.clear()
+
+
+_step_counter = [0]
+
+
+class _PixelContrastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, embed, labels, seg, predict, segq, pixq, opts: ContrastOptions):
+        lib = _abi.load()
+        _require_cuda(embed, "embed")
+        device = embed.device
+        if embed.dtype != torch.float32:
+            raise _abi.PclError("embed must be float32 (the reference trainer runs without AMP)")
+        embed_c = embed.contiguous()
+        labels_c = labels.to(device=device, dtype=torch.int64).contiguous()
+        B, D, h, w = embed_c.shape
+        if labels_c.dim() != 3 or labels_c.shape[0] != B:
+            raise _abi.PclError("labels must be (B, Himg, Wimg)")
+        seg_c = pred_c = None
+        if seg is not None:
+            seg_c = seg.detach().to(torch.float32).contiguous()
+            if seg_c.shape[0] != B or tuple(seg_c.shape[2:]) != (h, w):
+                raise _abi.PclError("seg must be (B, K, h, w) at the embedding resolution")
+        elif predict is not None:
+            pred_c = predict.to(device=device, dtype=torch.int64).contiguous()
+        else:
+            raise _abi.PclError("either seg or predict is required")
+        mode, bank_K, M0, M1 = 0, 0, 0, 0
+        segq_c = pixq_c = None
+        if segq is not None:
+            mode = 1
+            segq_c = segq.detach().to(torch.float32).contiguous()
+            bank_K, M0 = segq_c.shape[0], segq_c.shape[1]
+            if pixq is not None:
+                pixq_c = pixq.detach().to(torch.float32).contiguous()
+                M1 = pixq_c.shape[1]
+            if segq_c.shape[2] != D:
+                raise _abi.PclError("bank feature dim differs from the embedding dim")
+        K = opts.num_classes or (seg_c.shape[1] if seg_c is not None else (bank_K if mode == 1 else _abi.MAX_CLASSES))
+        if seg_c is not None and seg_c.shape[1] != K:
+            raise _abi.PclError("num_classes differs from the number of seg planes")
+        geom = _abi.Geom(B, D, h, w, labels_c.shape[1], labels_c.shape[2], K, opts.max_samples, opts.max_views,
+                         opts.ignore_label)
+        key = (B, D, h, w, labels_c.shape[1], labels_c.shape[2], K, opts.max_samples, opts.max_views,
+               opts.ignore_label, mode, bank_K, M0, M1)
+        ws = _get_workspace(device, key, geom, mode, bank_K, M0, M1)
+        d = ws.desc
+        d.embed, d.labels = embed_c.data_ptr(), labels_c.data_ptr()
+        d.seg = _abi.ptr(seg_c)
+        d.predict = _abi.ptr(pred_c)
+        d.segment_queue, d.pixel_queue = _abi.ptr(segq_c), _abi.ptr(pixq_c)
+        d.temperature, d.base_temperature = opts.temperature, opts.base_temperature
+        d.nan_safe = int(opts.nan_safe)
+        d.normalize = int(opts.normalize)
+        _step_counter[0] += 1
+        d.seed = (int(opts.seed) * 0x9E3779B97F4A7C15 + _step_counter[0]) & 0xFFFFFFFFFFFFFFFF
+        with torch.cuda.device(device):
+            stream = _stream_ptr(device)
+            _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
+            if opts.perm_fn is not None or opts.rng == "torch_cpu":
+                # reference RNG stream: one small D2H copy (B*2K int32), then randperm in the reference's order
+                counts = ws.counts.view(B, 2 * K).cpu().numpy()
+                pairs, TC, V = _rng.host_plan(counts, opts.max_samples, opts.max_views)
+                table = _rng.anchor_rank_table(pairs, V, opts.perm_fn or (lambda n: torch.randperm(n)))
+                flat = table[:max(TC, 1), :max(V, 1)].reshape(-1)
+                n = min(flat.numel(), ws.ranks.numel())
+                ws.ranks_host[:n].copy_(flat[:n])
+                ws.ranks[:n].copy_(ws.ranks_host[:n], non_blocking=True)
+                d.ranks = ws.ranks.data_ptr()
+            elif opts.rng == "device":
+                d.ranks = None
+            else:
+                raise _abi.PclError(f"unknown rng mode {opts.rng!r}")
+            _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
+        ctx.ws = ws
+        ctx.embed_shape = tuple(embed_c.shape)
+        ctx.keep = (embed_c, labels_c, seg_c, pred_c, segq_c, pixq_c)     # keep inputs alive until kernels ran
+        if embed.requires_grad and torch.is_grad_enabled():
+            ws.busy = True
+        return ws.loss[0].clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        lib = _abi.load()
+        ws = ctx.ws
+        device = ws.device
+        grad = torch.empty(ctx.embed_shape, dtype=torch.float32, device=device)
+        go = grad_out.detach().to(device=device, dtype=torch.float32).contiguous().view(1)
+        d = ws.desc
+        d.grad_embed = grad.data_ptr()
+        with torch.cuda.device(device):
+            _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
+        ws.busy = False
+        ctx.keep = None
+        return grad, None, None, None, None, None, None
+
+
+def pixel_contrast_loss(embed: torch.Tensor, labels: torch.Tensor, *, seg: Optional[torch.Tensor] = None,
+                        predict: Optional[torch.Tensor] = None, segment_queue: Optional[torch.Tensor] = None,
+                        pixel_queue: Optional[torch.Tensor] = None, options: Optional[ContrastOptions] = None):
+    """Pixel-contrast loss (lib/loss/loss_contrast.py:130-147 / loss_contrast_mem.py:154-171) on the GPU engine.
+
+    embed (B,D,h,w) fp32 CUDA; labels (B,Himg,Wimg) int64; either seg (B,K,h,w) logits (argmax fused) or
+    predict (B,h,w) int64; optional bank queues (K,M,D).  Returns a 0-dim tensor with autograd to embed."""
+    return _PixelContrastFn.apply(embed, labels, seg, predict, segment_queue, pixel_queue, options or ContrastOptions())
+
+
+def last_workspace(embed_device: torch.device):
+    """Most recently created workspace on a device (diagnostics / tests)."""
+    for (dev, _), lst in reversed(list(_WS_CACHE.items())):
+        if dev == embed_device.index and lst:
+            return lst[-1]
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# direct InfoNCE on explicit anchors / contrast rows (S4 sweeps, kernel tests)
+# ------------------------------------------------------------------------------------------------
+def infonce_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast: Optional[torch.Tensor] = None,
+                    contrast_cls: Optional[torch.Tensor] = None, queues: Optional[Tuple[torch.Tensor, ...]] = None,
+                    diag_col: Optional[torch.Tensor] = None, temperature: float = 0.1, base_temperature: float = 0.07,
+                    nan_safe: bool = False):
+    """Returns (loss (1,), rowstats (6, A), desc-state) for the exact fp32 sweep.
+    Modes: self-contrast (contrast None, queues None), explicit matrix (contrast given), bank (queues given)."""
+    lib = _abi.load()
+    _require_cuda(anchors, "anchors")
+    dev = anchors.device
+    a = anchors.detach().to(torch.float32).contiguous()
+    A, D = a.shape
+    cls = anchor_cls.to(device=dev, dtype=torch.int32).contiguous()
+    sw = _abi.SweepDesc()
+    sw.anchors, sw.anchor_cls = a.data_ptr(), cls.data_ptr()
+    dg = None
+    if diag_col is not None:
+        dg = diag_col.to(device=dev, dtype=torch.int32).contiguous()
+        sw.diag_col = dg.data_ptr()
+    sw.a_rows, sw.D = A, D
+    keep = [a, cls, dg]
+    if queues is not None:
+        sw.mode = 1
+        sq = queues[0].detach().to(torch.float32).contiguous()
+        pq = queues[1].detach().to(torch.float32).contiguous() if len(queues) > 1 and queues[1] is not None else None
+        sw.segment_queue, sw.pixel_queue = sq.data_ptr(), _abi.ptr(pq)
+        sw.bank_K, sw.bank_M0, sw.bank_M1 = sq.shape[0], sq.shape[1], (pq.shape[1] if pq is not None else 0)
+        keep += [sq, pq]
+    elif contrast is not None:
+        sw.mode = 2
+        c = contrast.detach().to(torch.float32).contiguous()
+        cc = contrast_cls.to(device=dev, dtype=torch.int32).contiguous()
+        sw.contrast, sw.contrast_cls, sw.n_cols = c.data_ptr(), cc.data_ptr(), c.shape[0]
+        keep += [c, cc]
+    else:
+        sw.mode = 0
+    sw.temperature, sw.base_temperature, sw.nan_safe = temperature, base_temperature, int(nan_safe)
+    ss = _abi.SweepSizes()
+    _abi.check(lib.pcl_sweep_sizes(C.byref(sw), C.byref(ss)), "pcl_sweep_sizes")
+    partials = torch.empty(5 * ss.partial_f32, dtype=torch.float32, device=dev)
+    rowstats = torch.empty(6 * ss.rowstat_f32, dtype=torch.float32, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(lib.pcl_infonce_fwd(C.byref(sw), partials.data_ptr(), rowstats.data_ptr(), loss.data_ptr(),
+                                       _stream_ptr(dev)), "pcl_infonce_fwd")
+    return loss, rowstats.view(6, A), (sw, ss, keep)
+
+
+def infonce_backward(state, rowstats: torch.Tensor, grad_loss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _abi.load()
+    sw, ss, keep = state
+    dev = keep[0].device
+    dpart = torch.empty(ss.dpartial_f32, dtype=torch.float32, device=dev)
+    dA = torch.empty((sw.a_rows, sw.D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(lib.pcl_infonce_bwd(C.byref(sw), rowstats.contiguous().data_ptr(), _abi.ptr(grad_loss),
+                                       dpart.data_ptr(), dA.data_ptr(), _stream_ptr(dev)), "pcl_infonce_bwd")
+    return dA
+
+
+# ------------------------------------------------------------------------------------------------
+# a1: projection-head normalise (lib/models/modules/projection.py:24)
+# ------------------------------------------------------------------------------------------------
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _abi.load()
+        _require_cuda(x, "x")
+        xc = x.to(torch.float32).contiguous()
+        B, D = xc.shape[0], xc.shape[1]
+        HW = xc.numel() // (B * D)
+        y = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _abi.check(lib.pcl_l2norm_fwd(xc.data_ptr(), y.data_ptr(), B, D, HW, _stream_ptr(xc.device)), "pcl_l2norm_fwd")
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        lib = _abi.load()
+        (xc,) = ctx.saved_tensors
+        B, D = xc.shape[0], xc.shape[1]
+        HW = xc.numel() // (B * D)
+        g = gy.to(torch.float32).contiguous()
+        gx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _abi.check(lib.pcl_l2norm_bwd(xc.data_ptr(), g.data_ptr(), gx.data_ptr(), B, D, HW, _stream_ptr(xc.device)),
+                       "pcl_l2norm_bwd")
+        return gx
+
+
+def l2_normalize(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=1) for (B, D, ...) CUDA tensors on the engine kernel."""
+    return _L2NormFn.apply(x)

@@ -1,0 +1,241 @@
+/*
+ * pcl.h — C ABI of the B200 pixel-contrast loss engine (libpcl_b200.so).
+ *
+ * The reference (tfzhou/ContrastiveSeg) has no FFI on this path: it is Python/ATen behind three
+ * nn.Module classes and one trainer method.  This header is the boundary a
+ * maintainer binds instead; each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name starts with h_;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, keeps no
+ *     global mutable state and never throws; the return value is 0 or a negative pcl_status;
+ *   - scratch comes from caller-provided buffers (sizes: pcl_select_sizes / pcl_sweep_sizes), so the
+ *     caller's allocator owns all memory and the sequence is CUDA-graph capturable;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns PCL_ERR_CUDA.
+ */
+#ifndef PCL_H_
+#define PCL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_VERSION 100          /* major*100 + minor */
+#define PCL_MAX_CLASSES 256      /* class ids tracked: [0, K), K <= 256 */
+#define PCL_CHUNK 1024           /* pixels per selection chunk */
+#define PCL_ROW_TILE 64          /* anchor rows per SIMT tile */
+#define PCL_PLAN_HEADER 16       /* int32 words at the start of the plan buffer */
+
+typedef enum {
+  PCL_OK = 0,
+  PCL_ERR_ARG = -1,        /* bad argument (null pointer, size out of range, unsupported D ...) */
+  PCL_ERR_CUDA = -2,       /* CUDA runtime error (see pcl_last_cuda_error) or no device */
+  PCL_ERR_UNSUPPORTED = -3,/* valid request the engine does not implement (e.g. tensor path with D != 256) */
+  PCL_ERR_SHAPE = -4       /* reference would raise an index error (e.g. Q6 label grid larger than feature map) */
+} pcl_status;
+
+/* plan buffer header words (int32), written by pcl_plan_anchors */
+enum { PCL_PLAN_TC = 0, PCL_PLAN_V = 1, PCL_PLAN_A = 2, PCL_PLAN_FLAGS = 3, PCL_PLAN_NPAIR_MAX = 4 };
+/* PCL_PLAN_FLAGS bits */
+enum { PCL_FLAG_NO_CLASS = 1, PCL_FLAG_ZERO_VIEWS = 2, PCL_FLAG_SPLIT_ERROR = 4 };
+
+int         pcl_version(void);
+const char* pcl_strerror(int status);
+const char* pcl_last_cuda_error(void);          /* text of the last CUDA error seen by this thread */
+int         pcl_device_count(void);             /* 0 without a usable CUDA device */
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry of one loss call (host struct, passed by pointer).
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct {
+  int32_t B, D, h, w;          /* embedding (B,D,h,w) fp32 NCHW                                  */
+  int32_t Himg, Wimg;          /* label map (B,Himg,Wimg) int64                                  */
+  int32_t K;                   /* number of class ids, labels outside [0,K) count as ignored     */
+  int32_t max_samples;         /* contrast.max_samples                                            */
+  int32_t max_views;           /* contrast.max_views                                              */
+  int32_t ignore_label;        /* loss.params.ce_ignore_index (default -1)                        */
+} pcl_geom;
+
+/* Element counts of the selection scratch buffers for a geometry. */
+typedef struct {
+  int64_t keys_u16;            /* B*h*w             uint16 pixel keys (2*label + easy, 2K = ignored) */
+  int64_t chunk_pref_i32;      /* B*2K*nchunk       exclusive per-chunk prefix of key counts        */
+  int64_t counts_i32;          /* B*2K              per-image key totals                            */
+  int64_t plan_i32;            /* header + 8 words per (image,class) pair                           */
+  int64_t anchor_meta_i32;     /* 4*max_samples     pixel, image, class, reference row              */
+  int32_t nchunk;
+  int32_t max_pairs;           /* B*K */
+} pcl_select_sizes_t;
+
+int pcl_select_sizes(const pcl_geom* g, pcl_select_sizes_t* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * a3 + a4 (first half): label down-sampling, argmax, hard/easy key per pixel, per-chunk histograms.
+ * Replaces lib/loss/loss_contrast.py:131-134 (nearest interpolation of the label map),
+ * :183 (torch.max(seg,1)) and the unique/nonzero scans of :37-39,:60-61.
+ *   labels   (B,Himg,Wimg) int64
+ *   seg      (B,K,h,w) fp32 or NULL      — if non-NULL, predict = argmax over the K planes
+ *   predict  (B,h,w) int64 or NULL       — used when seg is NULL
+ * ----------------------------------------------------------------------------------------------*/
+int pcl_class_stats(const pcl_geom* g, const int64_t* labels, const float* seg, const int64_t* predict,
+                    uint16_t* keys, int32_t* chunk_pref, void* stream);
+
+/* a4: class filter (count > max_views), TC, V = min(max_samples / TC, max_views), hard/easy split
+ * rule and the class-sorted anchor row layout.  Replaces lib/loss/loss_contrast.py:37-48,63-77.
+ * chunk_pref is turned into exclusive prefixes in place; counts and plan are written. */
+int pcl_plan_anchors(const pcl_geom* g, int32_t* chunk_pref, int32_t* counts, int32_t* plan, void* stream);
+
+/* a4 (second half) + gather: choose the pixels of every anchor row and gather their embeddings.
+ * Replaces lib/loss/loss_contrast.py:79-86 (randperm, index, X_[ptr] = X[ii, indices]) and the
+ * 268 MB permute+contiguous of :141-142 (never materialised here).
+ *   ranks     NULL -> device RNG (keyed Feistel permutation, `seed`), no host round trip;
+ *             else (TC,V) int32 table: ranks[t*V+v] = perm value used for view v of pair t
+ *             (hard ranks first, then easy ranks) — replay of the reference's torch.randperm draws.
+ *   normalize 0: embed is already L2-normalised (projection.py:24 ran upstream);
+ *             1: embed is the raw projection, only the gathered columns are normalised here.
+ * Outputs (row s = class-sorted anchor index, rows >= A are zero-filled):
+ *   anchor_meta (4,max_samples) int32: pixel, image, class, reference row r = v*TC + t
+ *   anchors_f32 (max_samples,D), anchors_bf16 (max_samples rounded up to 128, D) or NULL,
+ *   inv_norm (max_samples) fp32 (1/||x|| of the raw column; 1 when normalize == 0),
+ *   norm_max  1 float, max over anchors of ||a|| (stabiliser bound for the tensor path). */
+int pcl_select_gather(const pcl_geom* g, const float* embed, const uint16_t* keys, const int32_t* chunk_pref,
+                      const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize,
+                      int32_t* anchor_meta, float* anchors_f32, void* anchors_bf16, float* inv_norm,
+                      float* norm_max, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a5 + a6: the contrast set and the InfoNCE sweep.
+ * Replaces lib/loss/loss_contrast.py:91-128 and lib/loss/loss_contrast_mem.py:91-152.
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct {
+  /* anchors (rows); device scalar plan[PCL_PLAN_A] gives the live row count, a_rows its upper bound */
+  const float*   anchors;        /* (a_rows, D) fp32, class-sorted                                   */
+  const int32_t* anchor_cls;     /* (a_rows) int32                                                   */
+  const int32_t* diag_col;       /* (a_rows) int32 contrast column removed from the positives (Q1)   */
+  const int32_t* plan;           /* plan buffer or NULL (then a_live = a_rows)                       */
+  int32_t a_rows;
+  int32_t D;
+  /* contrast set.  mode 0: self-contrast (columns == anchors, loss_contrast.py:91-128)
+   *                mode 1: memory bank, read in place from the two queues (mem:91-105,221):
+   *                        column n = (c-1)*R + q, R = M0+M1, c = 1..K-1 (class 0 skipped, Q2), q < M0 -> segment
+   *                        row, else pixel row; plus `R` all-zero columns of label 0 handled analytically (Q3)
+   *                mode 2: explicit matrix `contrast` (n_cols, D) with labels `contrast_cls`           */
+  int32_t mode;
+  const float*   segment_queue;  /* (K, M0, D) fp32                                                  */
+  const float*   pixel_queue;    /* (K, M1, D) fp32, or NULL with bank_M1 == 0 (pre-concatenated queue
+                                    (K, R, D) passed as segment_queue with bank_M0 == R)             */
+  int32_t bank_K, bank_M0, bank_M1;
+  const float*   contrast;       /* mode 2                                                           */
+  const int32_t* contrast_cls;   /* mode 2                                                           */
+  int32_t n_cols;                /* mode 2                                                           */
+  float temperature, base_temperature;
+  int32_t nan_safe;              /* 0: rows without positives give NaN like the reference (Q8); 1: they give 0 */
+} pcl_sweep_desc;
+
+typedef struct {
+  int64_t n_real_cols;         /* streamed columns                                                  */
+  int32_t row_tiles, splits;   /* launch grid of the SIMT sweep                                     */
+  int64_t partial_f32;         /* splits * a_rows_padded floats, per partial statistic (5 of them)  */
+  int64_t rowstat_f32;         /* a_rows floats, per final statistic (6: m, neg, possum, s, npos, row_loss) */
+  int64_t dpartial_f32;        /* splits * a_rows_padded * D floats (backward partial dA)           */
+} pcl_sweep_sizes_t;
+
+int pcl_sweep_sizes(const pcl_sweep_desc* d, pcl_sweep_sizes_t* out);
+
+/* Forward: loss (1 float) and per-row statistics.  partials: 5 * partial_f32 floats of scratch;
+ * rowstats: 6 * rowstat_f32 floats (m, neg, possum, s, npos, row_loss), kept for the backward. */
+int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream);
+
+/* Backward: dA (a_rows, D) = d loss / d anchors (closed form), multiplied by the
+ * upstream gradient *grad_loss (device scalar, may be NULL = 1).  dpartials: scratch. */
+int pcl_infonce_bwd(const pcl_sweep_desc* d, const float* rowstats, const float* grad_loss, float* dpartials,
+                    float* dA, void* stream);
+
+/* dA -> dense NCHW gradient of the embedding (zero fill + scatter; with normalize == 1 the
+ * projection-normalise backward of the touched columns is fused in: dx = (g - y (y.g)) / ||x||).
+ * Replaces the autograd backward of loss_contrast.py:83-85,:141-142 (152 SelectBackward0 zero fills). */
+int pcl_scatter_grad(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
+                     const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a1: projection-head normalise, lib/models/modules/projection.py:24  (F.normalize(x, p=2, dim=1)).
+ * ----------------------------------------------------------------------------------------------*/
+int pcl_l2norm_fwd(const float* x, float* y, int32_t B, int32_t D, int64_t HW, void* stream);
+int pcl_l2norm_bwd(const float* x, const float* gy, float* gx, int32_t B, int32_t D, int64_t HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * a7 + a8: memory bank.  Replaces segmentor/trainer_contrastive.py:102-138 (_dequeue_and_enqueue).
+ * Step 1 (parallel): build this rank's enqueue packet.  Step 2 (ordered): apply the packets of all
+ * ranks in rank order — world 1 reproduces the reference exactly, world > 1 is the allgather merge
+ * (SURVEY §8e).  Packet layout per (image b, class c) slot, slot = b*K + c, `slot_f32` floats:
+ *   [0] n pixels of the class in the sub-sampled label map (0 = slot empty)   [1] K' = min(n, F)
+ *   [2 .. 2+D)            normalised segment mean          (trainer_contrastive.py:120-122)
+ *   [2+D .. 2+D+F*D)      K' normalised pixel rows         (trainer_contrastive.py:126-130)
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct {
+  int32_t B, D, h, w;          /* keys (B,D,h,w) fp32                                               */
+  int32_t Himg, Wimg;          /* labels (B,Himg,Wimg) int64                                        */
+  int32_t K, M;                /* queues (K,M,D)                                                    */
+  int32_t network_stride;      /* labels[:, ::s, ::s]  (Q6: flat index of that grid == feature column) */
+  int32_t pixel_update_freq;   /* F                                                                 */
+} pcl_bank_geom;
+
+int64_t pcl_bank_packet_floats(const pcl_bank_geom* g);    /* floats in one rank's packet           */
+int64_t pcl_bank_scratch_floats(const pcl_bank_geom* g);   /* floats of scratch for pcl_bank_packet */
+
+/* ranks: NULL -> device RNG with `seed`; else (B*K, F) int32 table of perm values per slot. */
+int pcl_bank_packet(const pcl_bank_geom* g, const float* keys, const int64_t* labels, const int32_t* ranks,
+                    uint64_t seed, float* scratch, float* packet, void* stream);
+
+/* Apply `world` packets (contiguous, rank-major) to the queues in place.  shadow_bf16 (optional,
+ * ((K-1)*2M rounded up to 256, D) bf16) is the engine's class-blocked bf16 copy used by the tensor path. */
+int pcl_bank_apply(const pcl_bank_geom* g, const float* packets, int32_t world, float* segment_queue,
+                   int64_t* segment_queue_ptr, float* pixel_queue, int64_t* pixel_queue_ptr,
+                   void* shadow_bf16, void* stream);
+
+/* Rebuild the bf16 shadow from the fp32 queues (after a checkpoint load / external write). */
+int pcl_bank_shadow_rebuild(const float* segment_queue, const float* pixel_queue, int32_t K, int32_t M,
+                            int32_t D, void* shadow_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One loss step = the calls above chained on one stream behind a single descriptor (what
+ * PixelContrastLoss.forward / its autograd backward bind; lib/loss/loss_contrast.py:130-147,
+ * lib/loss/loss_contrast_mem.py:154-171).  All scratch is caller-owned.
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct {
+  pcl_geom g;
+  /* inputs */
+  const float*   embed;          /* (B,D,h,w)                                                        */
+  const int64_t* labels;         /* (B,Himg,Wimg)                                                    */
+  const float*   seg;            /* (B,K,h,w) or NULL                                                */
+  const int64_t* predict;        /* (B,h,w) or NULL                                                  */
+  const int32_t* ranks;          /* injected permutation values or NULL (device RNG)                 */
+  uint64_t seed;
+  int32_t normalize;
+  /* contrast set: mode 0 self, 1 bank */
+  int32_t mode;
+  const float* segment_queue; const float* pixel_queue;
+  int32_t bank_K, bank_M0, bank_M1;
+  float temperature, base_temperature;
+  int32_t nan_safe;
+  /* scratch */
+  uint16_t* keys; int32_t* chunk_pref; int32_t* counts; int32_t* plan; int32_t* anchor_meta;
+  float* anchors_f32; void* anchors_bf16; float* inv_norm; float* norm_max;
+  float* partials; float* rowstats; float* dpartials; float* dA;
+  /* outputs */
+  float* loss;                   /* 1 float                                                          */
+  float* grad_embed;             /* (B,D,h,w), written by pcl_step_backward                          */
+} pcl_step_desc;
+
+int pcl_step_stats(const pcl_step_desc* d, void* stream);      /* pcl_class_stats + pcl_plan_anchors      */
+int pcl_step_forward(const pcl_step_desc* d, void* stream);    /* pcl_select_gather + pcl_infonce_fwd     */
+int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss, void* stream); /* bwd + scatter     */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCL_H_ */

@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/pcl.h declares (no compute calls: CPU-only)."""
+import os
+import re
+
+import pytest
+
+import contrastiveseg_b200 as cs
+from contrastiveseg_b200 import _abi, build
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pcl.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = build.build_library()
+    assert os.path.exists(path)
+    lib = _abi.load()
+    assert lib.pcl_version() == 100
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _abi.load(build_if_missing=True)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in pcl.h but not exported"
+        assert name in _abi.SIGNATURES, f"{name} has no ctypes signature"
+    for name in _abi.SIGNATURES:
+        assert name in syms, f"{name} bound in _abi.py but not declared in pcl.h"
+
+
+def test_status_strings():
+    lib = _abi.load(build_if_missing=True)
+    assert lib.pcl_strerror(0) == b"ok"
+    assert b"argument" in lib.pcl_strerror(-1)
+
+
+def test_struct_layout_matches_header():
+    # sizes of the host structs as laid out by the C compiler rules (natural alignment)
+    import ctypes as C
+    assert C.sizeof(_abi.Geom) == 40
+    assert C.sizeof(_abi.BankGeom) == 40
+    assert C.sizeof(_abi.SelectSizes) == 48
+    assert C.sizeof(_abi.SweepSizes) == 40
+
+
+def test_no_cpu_fallback():
+    import torch
+    with pytest.raises(_abi.PclError):
+        cs.pixel_contrast_loss(torch.zeros(1, 32, 4, 4), torch.zeros(1, 8, 8, dtype=torch.long),
+                               predict=torch.zeros(1, 4, 4, dtype=torch.long))
+    with pytest.raises(_abi.PclError):
+        cs.l2_normalize(torch.zeros(1, 32, 4, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "contrastiveseg_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference-generated golden
+vectors.  Tolerances (fp32 exact path): loss <= 2e-6 relative to the float64 oracle and <= 1e-5 relative to the
+fp32 reference golden (north_star bar: 1e-4); gradient <= 1e-5 * max|g|; sampled anchors, bank rows and pointers
+bit-exact (bank segment means: 1e-6, they are fp32 sums in the reference)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import contrastiveseg_b200 as cs
+from contrastiveseg_b200 import functional as Fn
+from oracle import ref_port as P
+from helpers import load_golden, unpack_perms, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+LOSS_CASES = ["nomem_small", "nomem_oddv", "nomem_mv1", "nomem_nondiv", "nomem_d256", "mem_small", "mem_d256"]
+
+
+def _cfg(T, bT, ms, mv, K, extra=None):
+    d = {"data": {"num_classes": int(K)},
+         "contrast": {"temperature": T, "base_temperature": bT, "max_samples": int(ms), "max_views": int(mv),
+                      "loss_weight": 0.1, "use_rmi": False, "use_lovasz": False},
+         "loss": {"params": {"ce_ignore_index": -1, "ce_reduction": "elementwise_mean"}},
+         "network": {"stride": 8}}
+    if extra:
+        d["contrast"].update(extra)
+    return cs.Configer(d)
+
+
+def _oracle(g, dtype=torch.float64):
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    embed = torch.from_numpy(g["embed"]).to(dtype).requires_grad_(True)
+    queue = None
+    if "segment_queue" in g:
+        queue = torch.cat((torch.from_numpy(g["segment_queue"]), torch.from_numpy(g["pixel_queue"])), 1)
+    loss, det = P.pixel_contrast_loss(embed, torch.from_numpy(g["target"]), torch.from_numpy(g["predict"]),
+                                      temperature=T, base_temperature=bT, max_samples=int(ms), max_views=int(mv),
+                                      ignore_label=int(ign), queue=queue,
+                                      perm_fn=P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"])),
+                                      return_details=True)
+    loss.backward()
+    return loss.item(), embed.grad, det
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_loss_and_grad_match_reference(name):
+    g = load_golden(name)
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    crit = cs.PixelContrastLoss(_cfg(T, bT, ms, mv, K))
+    crit.perm_fn = P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"]))
+    embed = torch.from_numpy(g["embed"]).to(DEV).requires_grad_(True)
+    target = torch.from_numpy(g["target"]).to(DEV)
+    predict = torch.from_numpy(g["predict"]).to(DEV)
+    queue = None
+    if "segment_queue" in g:
+        queue = (torch.from_numpy(g["segment_queue"]).to(DEV), torch.from_numpy(g["pixel_queue"]).to(DEV))
+    loss = crit(embed, target, predict, queue)
+    loss.backward()
+    torch.cuda.synchronize()
+    o_loss, o_grad, det = _oracle(g)
+    assert rel_err(loss.item(), o_loss) < 2e-6, (loss.item(), o_loss)
+    assert rel_err(loss.item(), g["loss"]) < 1e-5
+    gmax = o_grad.abs().max().item()
+    assert (embed.grad.cpu().double() - o_grad).abs().max().item() <= 1e-5 * gmax
+    assert (embed.grad.cpu() - torch.from_numpy(g["grad_embed"])).abs().max().item() <= 1e-5 * gmax
+    # the sampled anchors are the reference's, bit for bit
+    ws = Fn.last_workspace(embed.device)
+    hdr = ws.plan_header()
+    TC, V, A = hdr[0], hdr[1], hdr[2]
+    assert (TC, V) == tuple(g["X_"].shape[:2])
+    meta = ws.anchor_meta.view(4, -1)[:, :A].cpu()
+    ref_rows = meta[3].long()
+    X = torch.zeros((A, g["X_"].shape[2]))
+    X[ref_rows] = ws.anchors_f32[:A].cpu()
+    X_ = X.view(V, TC, -1).permute(1, 0, 2)
+    assert torch.equal(X_, torch.from_numpy(g["X_"]))
+    cls_by_ref = torch.zeros(A, dtype=torch.long)
+    cls_by_ref[ref_rows] = meta[2].long()
+    assert torch.equal(cls_by_ref[:TC].float(), torch.from_numpy(g["y_"]))
+
+
+@pytest.mark.parametrize("name", ["mem_small"])
+def test_concatenated_queue_tensor_is_accepted(name):
+    g = load_golden(name)
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    crit = cs.PixelContrastLoss(_cfg(T, bT, ms, mv, K))
+    crit.perm_fn = P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"]))
+    queue = torch.cat((torch.from_numpy(g["segment_queue"]), torch.from_numpy(g["pixel_queue"])), 1).to(DEV)
+    loss = crit(torch.from_numpy(g["embed"]).to(DEV), torch.from_numpy(g["target"]).to(DEV),
+                torch.from_numpy(g["predict"]).to(DEV), queue)
+    assert rel_err(loss.item(), g["loss"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,mem", [("wrapper_nomem_embed", False), ("wrapper_nomem_warmup", False),
+                                      ("wrapper_mem_embed", True)])
+def test_contrast_ce_wrapper(name, mem):
+    g = load_golden(name)
+    T, bT, ms, mv, K, ign, lw, with_embed, _ = g["params"].tolist()
+    cfg = _cfg(T, bT, ms, mv, K, {"loss_weight": lw})
+    crit = (cs.MemContrastCELoss if mem else cs.ContrastCELoss)(cfg).to(DEV)
+    crit.contrast_criterion.perm_fn = P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"]))
+    seg = torch.from_numpy(g["seg"]).to(DEV).requires_grad_(True)
+    embed = torch.from_numpy(g["embed"]).to(DEV).requires_grad_(True)
+    preds = {"seg": seg, "embed": embed}
+    if mem:
+        preds["segment_queue"] = torch.from_numpy(g["segment_queue"]).to(DEV)
+        preds["pixel_queue"] = torch.from_numpy(g["pixel_queue"]).to(DEV)
+    loss = crit(preds, torch.from_numpy(g["target"]).to(DEV), with_embed=bool(with_embed))
+    loss.backward()
+    assert rel_err(loss.item(), g["loss"]) < 1e-5
+    assert torch.allclose(seg.grad.cpu(), torch.from_numpy(g["grad_seg"]), rtol=1e-4, atol=1e-7)
+    gref = torch.from_numpy(g["grad_embed"])
+    assert (embed.grad.cpu() - gref).abs().max().item() <= 1e-5 * max(gref.abs().max().item(), 1e-12) + 1e-12
+
+
+@pytest.mark.parametrize("name", ["enqueue_aligned", "enqueue_q6"])
+def test_bank_enqueue_matches_reference(name):
+    g = load_golden(name)
+    net_stride, M, Fq, steps, K = g["params"].tolist()
+    sq, pq = torch.from_numpy(g["sq0"]).to(DEV), torch.from_numpy(g["pq0"]).to(DEV)
+    sp = torch.zeros(K, dtype=torch.long, device=DEV)
+    pp = torch.zeros(K, dtype=torch.long, device=DEV)
+    for s in range(steps):
+        replay = P.PermReplay(unpack_perms(g[f"perm_flat{s}"], g[f"perm_lens{s}"]))
+        cs.dequeue_and_enqueue(torch.from_numpy(g[f"keys{s}"]).to(DEV), torch.from_numpy(g[f"labels{s}"]).to(DEV),
+                               sq, sp, pq, pp, network_stride=net_stride, memory_size=M, pixel_update_freq=Fq,
+                               perm_fn=replay)
+        assert replay.pos == len(replay.draws)
+        assert torch.equal(sp.cpu(), torch.from_numpy(g[f"sp{s + 1}"]))
+        assert torch.equal(pp.cpu(), torch.from_numpy(g[f"pp{s + 1}"]))
+        assert torch.equal(pq.cpu(), torch.from_numpy(g[f"pq{s + 1}"]))
+        assert torch.allclose(sq.cpu(), torch.from_numpy(g[f"sq{s + 1}"]), rtol=0, atol=1e-6)
+
+
+def test_bank_enqueue_shape_error_like_reference():
+    # label grid larger than the feature map: the reference raises an index error, the engine PCL_ERR_SHAPE
+    bank = cs.MemoryBank(4, 8, 32).to(DEV)
+    keys = torch.randn(1, 32, 4, 4, device=DEV)
+    labels = torch.ones(1, 32, 32, dtype=torch.long, device=DEV)
+    with pytest.raises(Exception):
+        bank.enqueue(keys, labels, network_stride=2, pixel_update_freq=2)
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 16, 32), (1, 32, 7, 9), (3, 320, 5, 8)])
+def test_l2_normalize_matches_torch(shape):
+    torch.manual_seed(0)
+    x = torch.randn(shape, device=DEV, requires_grad=True)
+    y = cs.l2_normalize(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = F.normalize(x2, p=2, dim=1)
+    y2.backward(gy)
+    assert torch.allclose(y, y2, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(x.grad, x2.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_fused_normalize_path_equals_normalise_then_loss():
+    """normalize=True: raw projection in, only the sampled columns are normalised; gradient is w.r.t. raw."""
+    g = load_golden("nomem_small")
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    torch.manual_seed(1)
+    raw = torch.randn(g["embed"].shape, device=DEV) * 3.0
+    target = torch.from_numpy(g["target"]).to(DEV)
+    predict = torch.from_numpy(g["predict"]).to(DEV)
+    perms = []
+    rec = P.PermRecorder(torch.Generator().manual_seed(5))
+    crit = cs.PixelContrastLoss(_cfg(T, bT, ms, mv, K))
+    crit.perm_fn = rec
+    r1 = raw.clone().requires_grad_(True)
+    l1 = crit(r1, target, predict, normalize=True)
+    l1.backward()
+    crit.perm_fn = P.PermReplay(rec.draws)
+    r2 = raw.clone().requires_grad_(True)
+    l2 = crit(F.normalize(r2, p=2, dim=1), target, predict)
+    l2.backward()
+    assert rel_err(l1.item(), l2.item()) < 1e-6
+    assert (r1.grad - r2.grad).abs().max().item() <= 1e-5 * r2.grad.abs().max().item()
+
+
+def _check_device_sampling(ws, lab, prd, ms, mv):
+    hdr = ws.plan_header()
+    TC, V, A = hdr[0], hdr[1], hdr[2]
+    meta = ws.anchor_meta.view(4, -1)[:, :A].cpu().long()
+    pix, img, cls, ref = meta
+    # rows are a permutation of the reference rows, every (image,class) pair has V distinct pixels of its class
+    assert sorted(ref.tolist()) == list(range(A))
+    B = lab.shape[0]
+    kept = [(b, c) for b in range(B) for c in P.kept_classes(lab[b], -1, mv)]
+    assert TC == len(kept) and V == min(ms // TC, mv)
+    for t, (b, c) in enumerate(kept):
+        rows = ((ref % TC) == t).nonzero()[:, 0]
+        assert rows.numel() == V
+        assert (img[rows] == b).all() and (cls[rows] == c).all()
+        px = pix[rows]
+        assert px.unique().numel() == V
+        assert (lab[b][px] == c).all()
+        nh = int(((lab[b] == c) & (prd[b] != c)).sum()); ne = int(((lab[b] == c) & (prd[b] == c)).sum())
+        kh, ke = P.split_hard_easy(nh, ne, V)
+        assert int((prd[b][px] != c).sum()) == kh and int((prd[b][px] == c).sum()) == ke
+    return TC, V, A, meta
+
+
+@pytest.mark.parametrize("mem", [False, True])
+def test_device_rng_sampling_is_valid_and_loss_matches_oracle_on_same_indices(mem):
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    K, D, ms, mv = 7, 64, 200, 12
+    data = make_contrast_batch(B=3, D=D, h=24, w=40, num_classes=K, img_stride=4, block=16, seed=77)
+    bank = make_bank(K, 30, D, 78)
+    crit = cs.PixelContrastLoss(_cfg(0.1, 0.07, ms, mv, K))
+    embed = data["embed"].to(DEV).requires_grad_(True)
+    queue = (bank["segment_queue"].to(DEV), bank["pixel_queue"].to(DEV)) if mem else None
+    loss = crit(embed, data["target"].to(DEV), seg=data["seg"].to(DEV), queue=queue)
+    loss.backward()
+    ws = Fn.last_workspace(embed.device)
+    lab = P.downsample_labels(data["target"], 24, 40).reshape(3, -1)
+    prd = data["seg"].argmax(1).reshape(3, -1)
+    TC, V, A, meta = _check_device_sampling(ws, lab, prd, ms, mv)
+    pix, img, cls, ref = meta
+    # oracle on exactly these anchors (reference row order)
+    X = data["embed"].permute(0, 2, 3, 1).reshape(3, -1, D).double()
+    anchors = torch.zeros((A, D), dtype=torch.float64)
+    ya = torch.zeros(A, dtype=torch.long)
+    anchors[ref] = X[img, pix]
+    ya[ref] = cls
+    a = anchors.clone().requires_grad_(True)
+    if mem:
+        contrast, yc = P.flatten_queue(torch.cat((bank["segment_queue"], bank["pixel_queue"]), 1).double())
+        lo = P.infonce_dense(a, ya.double(), contrast, yc, 0.1, 0.07)
+    else:
+        lo = P.infonce_dense(a, ya.double(), a, ya.double(), 0.1, 0.07)
+    lo.backward()
+    assert rel_err(loss.item(), lo.item()) < 2e-6
+    gd = torch.zeros(3, 24 * 40, D, dtype=torch.float64)
+    gd[img, pix] = a.grad[ref]
+    gd = gd.view(3, 24, 40, D).permute(0, 3, 1, 2)
+    assert (embed.grad.cpu().double() - gd).abs().max().item() <= 1e-5 * gd.abs().max().item()
+
+
+def test_device_rng_changes_between_steps_and_is_seed_reproducible():
+    from contrastiveseg_b200.synth import make_contrast_batch
+    data = make_contrast_batch(B=2, D=32, h=24, w=24, num_classes=5, img_stride=2, block=8, seed=9)
+    crit = cs.PixelContrastLoss(_cfg(0.1, 0.07, 40, 6, 5))
+    e = data["embed"].to(DEV)
+    t, s = data["target"].to(DEV), data["seg"].to(DEV)
+    crit(e, t, seg=s)
+    ws = Fn.last_workspace(e.device)
+    p1 = ws.anchor_meta.view(4, -1)[0].clone()
+    crit(e, t, seg=s)
+    p2 = ws.anchor_meta.view(4, -1)[0].clone()
+    assert not torch.equal(p1, p2)
+
+
+def test_explicit_infonce_modes_and_nan_semantics():
+    from contrastiveseg_b200.synth import make_sweep_point
+    pt = make_sweep_point(200, 700, D=64, num_classes=6, seed=3, clustered=0.5)
+    a, ya, c, yc = pt["anchors"], pt["ya"], pt["contrast"], pt["yc"]
+    diag = torch.arange(200)
+    loss, st, state = Fn.infonce_forward(a.to(DEV), ya.to(DEV), contrast=c.to(DEV), contrast_cls=yc.to(DEV),
+                                         diag_col=diag.to(DEV), temperature=0.07, base_temperature=0.07)
+    dA = Fn.infonce_backward(state, st)
+    cf = P.infonce_closed_form(a.double(), ya, c.double(), yc, 0.07, 0.07, self_contrast=False)
+    assert rel_err(loss.item(), cf["loss"].item()) < 2e-6
+    assert (dA.cpu().double() - cf["dA"]).abs().max().item() <= 1e-5 * cf["dA"].abs().max().item()
+    assert torch.allclose(st[4].cpu().double(), cf["npos"])
+    # self-contrast
+    loss, st, state = Fn.infonce_forward(a.to(DEV), ya.to(DEV), temperature=0.1, base_temperature=0.07)
+    dA = Fn.infonce_backward(state, st)
+    cf = P.infonce_closed_form(a.double(), ya, a.double(), ya, 0.1, 0.07, self_contrast=True)
+    assert rel_err(loss.item(), cf["loss"].item()) < 2e-6
+    assert (dA.cpu().double() - cf["dA"]).abs().max().item() <= 1e-5 * cf["dA"].abs().max().item()
+    # a row without positives: NaN like the reference (Q8), 0 with nan_safe
+    ya2 = ya.clone(); ya2[0] = 17
+    loss, _, _ = Fn.infonce_forward(a.to(DEV), ya2.to(DEV), contrast=c.to(DEV), contrast_cls=yc.to(DEV),
+                                    temperature=0.1, base_temperature=0.07)
+    assert torch.isnan(loss).item()
+    loss, _, _ = Fn.infonce_forward(a.to(DEV), ya2.to(DEV), contrast=c.to(DEV), contrast_cls=yc.to(DEV),
+                                    temperature=0.1, base_temperature=0.07, nan_safe=True)
+    assert torch.isfinite(loss).item()
+
+
+def test_empty_inputs_give_zero_loss_not_a_crash():
+    # no class qualifies (everything ignored): the reference crashes (Q8); the engine returns 0 with a zero gradient
+    crit = cs.PixelContrastLoss(_cfg(0.1, 0.07, 64, 4, 5))
+    embed = F.normalize(torch.randn(2, 32, 8, 8, device=DEV), dim=1).requires_grad_(True)
+    target = torch.full((2, 16, 16), -1, dtype=torch.long, device=DEV)
+    loss = crit(embed, target, predict=torch.zeros(2, 8, 8, dtype=torch.long, device=DEV))
+    loss.backward()
+    assert loss.item() == 0.0 and embed.grad.abs().max().item() == 0.0
+
+
+def test_full_size_cityscapes_batch_properties():
+    """BASELINE config 2 (B=8, 256x128x256 embedding, 19 classes): size-independent checks — every anchor row is a
+    valid distinct pixel of its class, loss equals the float64 oracle on the same anchors, the dense gradient is zero
+    outside the sampled columns and sums to the per-anchor gradients."""
+    from contrastiveseg_b200.synth import make_contrast_batch
+    data = make_contrast_batch(B=8, D=256, h=128, w=256, num_classes=19, img_stride=4, block=32, seed=304)
+    crit = cs.PixelContrastLoss(_cfg(0.1, 0.07, 1024, 100, 19))
+    embed = data["embed"].to(DEV).requires_grad_(True)
+    loss = crit(embed, data["target"].to(DEV), seg=data["seg"].to(DEV))
+    loss.backward()
+    ws = Fn.last_workspace(embed.device)
+    lab = P.downsample_labels(data["target"], 128, 256).reshape(8, -1)
+    prd = data["seg"].argmax(1).reshape(8, -1)
+    TC, V, A, meta = _check_device_sampling(ws, lab, prd, 1024, 100)
+    pix, img, cls, ref = meta
+    X = data["embed"].permute(0, 2, 3, 1).reshape(8, -1, 256)
+    anchors = torch.zeros((A, 256), dtype=torch.float64)
+    ya = torch.zeros(A, dtype=torch.long)
+    anchors[ref] = X[img, pix].double()
+    ya[ref] = cls
+    cf = P.infonce_closed_form(anchors, ya, anchors, ya, 0.1, 0.07, self_contrast=True)
+    assert rel_err(loss.item(), cf["loss"].item()) < 2e-6
+    g = embed.grad
+    nz = (g != 0).any(dim=1).sum().item()
+    assert nz <= A and nz >= A - 2
+    got = g.permute(0, 2, 3, 1).reshape(8, -1, 256)[img.to(DEV), pix.to(DEV)].cpu().double()
+    assert (got - cf["dA"][ref]).abs().max().item() <= 1e-5 * cf["dA"].abs().max().item()
+    assert abs(g.double().sum().item() - cf["dA"].sum().item()) <= 1e-4 * cf["dA"].abs().sum().item()
