@@ -52,6 +52,14 @@ class BankGeom(C.Structure):
                 ("K", c_i32), ("M", c_i32), ("network_stride", c_i32), ("pixel_update_freq", c_i32)]
 
 
+class TcDesc(C.Structure):
+    _fields_ = [("anchors_f32", c_vp), ("anchors_bf16", c_vp), ("anchor_cls", c_vp), ("diag_col", c_vp), ("plan", c_vp),
+                ("a_rows", c_i32), ("D", c_i32), ("mode", c_i32),
+                ("contrast_bf16", c_vp), ("contrast_cls", c_vp), ("n_cols", c_i64), ("contrast_rows_alloc", c_i64),
+                ("bank_K", c_i32), ("bank_R", c_i32), ("sorted", c_i32), ("contrast_norm_bound", c_f32),
+                ("temperature", c_f32), ("base_temperature", c_f32), ("nan_safe", c_i32)]
+
+
 class StepDesc(C.Structure):
     _fields_ = [("g", Geom),
                 ("embed", c_vp), ("labels", c_vp), ("seg", c_vp), ("predict", c_vp), ("ranks", c_vp),
@@ -87,6 +95,10 @@ SIGNATURES = {
     "pcl_bank_packet": (c_i32, [C.POINTER(BankGeom), c_vp, c_vp, c_vp, c_u64, c_vp, c_vp, c_vp]),
     "pcl_bank_apply": (c_i32, [C.POINTER(BankGeom), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_bank_shadow_rebuild": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "pcl_tc_sizes": (c_i32, [C.POINTER(TcDesc), C.POINTER(SweepSizes)]),
+    "pcl_to_bf16": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "pcl_infonce_tc_fwd": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_tc_dump_logits": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp]),
     "pcl_step_stats": (c_i32, [C.POINTER(StepDesc), c_vp]),
     "pcl_step_forward": (c_i32, [C.POINTER(StepDesc), c_vp]),
     "pcl_step_backward": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp]),

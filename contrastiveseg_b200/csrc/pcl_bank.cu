@@ -111,10 +111,10 @@ k_bank_rows(BankDims d, const float* __restrict__ keys, const int32_t* __restric
         ss += m * m;
       }
       ss = warp_sum(ss);
-      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      const float den = fmaxf(sqrtf(ss), 1e-12f);          // F.normalize: x / max(||x||, eps)
       for (int dd = lane; dd < D; dd += 32) {
         float m = (float)((double)(long long)sm[dd] * FIX_INV / (double)n);
-        out[2 + dd] = m * inv;
+        out[2 + dd] = m / den;
       }
     } else {
       int col;
@@ -127,9 +127,9 @@ k_bank_rows(BankDims d, const float* __restrict__ keys, const int32_t* __restric
         ss += v * v;
       }
       ss = warp_sum(ss);
-      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      const float den = fmaxf(sqrtf(ss), 1e-12f);
       float* o = out + 2 + D + (int64_t)row * D;
-      for (int dd = lane; dd < D; dd += 32) o[dd] = kb[(int64_t)dd * d.HW + col] * inv;
+      for (int dd = lane; dd < D; dd += 32) o[dd] = kb[(int64_t)dd * d.HW + col] / den;
     }
   }
 }

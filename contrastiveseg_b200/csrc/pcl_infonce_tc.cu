@@ -1,0 +1,459 @@
+// Tensor-core InfoNCE sweep for sm_100a (north_star "anchor x memory-bank similarity as a dense
+// bf16 contraction on tcgen05 tensor cores fed by TMA staging").
+//
+// One CTA = one 128-row anchor tile x a contiguous range of 256-column contrast tiles, D = 256 (K-major bf16):
+//   warp 0   TMA producer   : anchor tile once (4 x [128 x 64] boxes, 64 KB), then a 4-stage ring of [256 x 64]
+//                             contrast boxes (32 KB each), SWIZZLE_128B
+//   warp 1   MMA issuer     : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, 16 MMAs per logit tile,
+//                             accumulators double-buffered in TMEM (2 x 256 columns = all 512)
+//   warps 2-9 epilogue      : tcgen05.ld 32x32b.x32 -> one FFMA + one ex2 per logit (scale 1/T and the row stabiliser
+//                             folded into the FFMA), class test only on tiles that straddle a class boundary,
+//                             row sums kept in registers; never materialises A x N
+// Sweeps: NEG (sum over negatives of exp(l - m)), POS (log-prob sums over the positive column range).  The row
+// stabiliser is the Cauchy-Schwarz bound m_i = |a_i| * max|c| / T (exact in real arithmetic; no running max needed).
+// Partials per (split, row) are combined in fixed order by the shared row-statistic kernels (pcl_sweep.cuh).
+#include "pcl_common.cuh"
+#include "pcl_sweep.cuh"
+#include "ptx_sm100.cuh"
+
+namespace pcl {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, NKB = 4, DDIM = 256;
+constexpr int STAGES = 4;
+constexpr int A_KB_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
+constexpr int NUM_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+struct TcArgs {
+  const int32_t* acls; const int32_t* diag; const int32_t* plan; const int32_t* ccls;
+  const float* row_m2;         // per-row stabiliser in log2 units
+  int a_rows, a_pad, mode, K, R, sorted;
+  int64_t n_cols;
+  float k1;                    // log2(e) / T
+  int splits;
+};
+
+struct SmemLayout {
+  uint8_t a[NKB * A_KB_BYTES];
+  uint8_t b[STAGES * B_STAGE_BYTES];
+  uint64_t full[STAGES], empty[STAGES], a_full, tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  float comb[3][2][BM];
+};
+
+__device__ __forceinline__ int col_label(const TcArgs& a, int64_t n) {
+  return a.ccls ? a.ccls[n] : (a.mode == 1 ? (int)(n / a.R) + 1 : a.acls[n]);
+}
+
+enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2 };   // DUMP: raw logit tiles to global (descriptor self-test)
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a,
+         float* __restrict__ partials, const float* __restrict__ rowstats) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = a.plan ? min(a.plan[PCL_PLAN_A], a.a_rows) : a.a_rows;
+  const int row0 = blockIdx.x * BM;
+  if (row0 >= A) return;
+  const int split = blockIdx.y;
+  const int64_t ncols = a.mode == 0 ? (int64_t)A : a.n_cols;
+
+  // ---- column-tile range of this CTA (identical in every warp) ----
+  int t_lo = 0, t_hi = (int)((ncols + BN - 1) / BN);
+  if (MODE == TC_POS && a.mode == 1) {
+    const int last = min(A - 1, row0 + BM - 1);
+    int rk_f = class_rank(a.acls[row0], a.K), rk_l = class_rank(a.acls[last], a.K);
+    if (rk_l > a.K - 2) rk_l = a.K - 2;
+    if (rk_f > rk_l) { t_lo = 0; t_hi = 0; }
+    else {
+      t_lo = (int)(((int64_t)rk_f * a.R) / BN);
+      t_hi = (int)((((int64_t)(rk_l + 1) * a.R) + BN - 1) / BN);
+    }
+  }
+  const int span = t_hi - t_lo;
+  const int per = (span + a.splits - 1) / a.splits;
+  const int my_lo = t_lo + split * per;
+  const int my_hi = min(t_hi, my_lo + per);
+  const int ntiles = my_hi > my_lo ? my_hi - my_lo : 0;
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&sm.full[s], 1); ptx::mbar_init(&sm.empty[s], 1); }
+    ptx::mbar_init(&sm.a_full, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.tmem_full[i], 1); ptx::mbar_init(&sm.tmem_empty[i], EPI_THREADS / 32); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(&sm.tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0 && ntiles > 0) {
+      ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * A_KB_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sm.a + kb * A_KB_BYTES, &tmA, &sm.a_full, kb * BK, row0);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < ntiles; ++it) {
+        const int ct = my_lo + it;
+        for (int kb = 0; kb < NKB; ++kb) {
+          ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&sm.full[stage], B_STAGE_BYTES);
+          ptx::tma_load_2d(sm.b + stage * B_STAGE_BYTES, &tmB, &sm.full[stage], kb * BK, ct * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+      ptx::mbar_wait(&sm.a_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t a_base = ptx::smem_u32(sm.a), b_base = ptx::smem_u32(sm.b);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < ntiles; ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < NKB; ++kb) {
+          ptx::mbar_wait(&sm.full[stage], phase);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
+            const uint64_t db = ptx::make_desc_kmajor_sw128(b_base + stage * B_STAGE_BYTES + k * 32);
+            ptx::mma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&sm.empty[stage]);          // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&sm.tmem_full[acc]);          // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                 // which 128 columns of the 256-column tile
+    const int r_in = quarter * 32 + lane;
+    const int row = row0 + r_in;
+    const bool valid = row < A;
+    const int rcls = valid ? a.acls[row] : -1;
+    const int rdiag = valid ? (a.mode == 0 ? row : (a.diag ? a.diag[row] : -1)) : -1;
+    const float m2 = valid ? a.row_m2[row] : 0.f;
+    float neg_i = 1.f;
+    if (MODE == TC_POS) neg_i = valid ? rowstats[a.a_rows + row] : 1.f;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;       // NEG: 4 partial sums; POS: possum2, s, cnt
+    for (int it = 0; it < ntiles; ++it) {
+      const int ct = my_lo + it;
+      const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
+      const int64_t col0 = (int64_t)ct * BN + half * (BN / 2);
+      // tile class: all 128 columns valid and of one class (sorted contrast set) -> no per-element test
+      bool uniform = false;
+      int ulab = -1;
+      if (a.sorted && col0 + BN / 2 <= ncols) {
+        ulab = col_label(a, col0);
+        uniform = ulab == col_label(a, col0 + BN / 2 - 1);
+      }
+      ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * BN + half * (BN / 2);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
+        ptx::tmem_ld_wait();
+        const int64_t cb = col0 + ch * 32;
+        if (MODE == TC_DUMP) {
+          // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * BN
+          const int64_t ld = (int64_t)((ncols + BN - 1) / BN) * BN;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) partials[(int64_t)row * ld + cb + j] = __uint_as_float(v[j]);
+        } else if (MODE == TC_NEG) {
+          if (uniform) {
+            if (valid && ulab != rcls) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), a.k1, -m2));
+                acc1 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), a.k1, -m2));
+                acc2 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), a.k1, -m2));
+                acc3 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = cb + j;
+              if (col < ncols) {
+                const int lab = col_label(a, col);
+                if (valid && lab != rcls) acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+              }
+            }
+          }
+        } else {
+          const bool all_pos = uniform && ulab == rcls && !(rdiag >= cb && rdiag < cb + 32);
+          if (uniform && ulab != rcls) {
+            // no positives of this row in the tile
+          } else if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = cb + j;
+              bool pos = all_pos;
+              if (!all_pos) pos = col < ncols && col_label(a, col) == rcls && col != (int64_t)rdiag;
+              if (pos) {
+                const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
+                const float t = ptx::ex2_approx(x) + neg_i;
+                acc0 += x - ptx::lg2_approx(t);
+                acc1 += ptx::rcp_approx(t);
+                acc2 += 1.f;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.tmem_empty[accb]);
+    }
+    // ---- combine the two column halves, write the partials of this split ----
+    if (MODE == TC_DUMP) {
+    } else if (MODE == TC_NEG) {
+      sm.comb[0][half][r_in] = (acc0 + acc1) + (acc2 + acc3);
+    } else {
+      sm.comb[0][half][r_in] = acc0 * LN2;
+      sm.comb[1][half][r_in] = acc1;
+      sm.comb[2][half][r_in] = acc2;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    if (half == 0 && MODE != TC_DUMP) {
+      const int64_t o = (int64_t)split * a.a_pad + row;
+      const int64_t stride = (int64_t)a.splits * a.a_pad;
+      if (MODE == TC_NEG) {
+        partials[0 * stride + o] = m2 * LN2;                               // stabiliser in natural-log units
+        partials[1 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+      } else {
+        partials[2 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+        partials[3 * stride + o] = sm.comb[1][0][r_in] + sm.comb[1][1][r_in];
+        partials[4 * stride + o] = sm.comb[2][0][r_in] + sm.comb[2][1][r_in];
+      }
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// anchors fp32 -> bf16 rows (optional) and the per-row stabiliser m2 = |bf16(a)| * cbound * log2(e)/T
+__global__ void k_tc_prep(const float* __restrict__ anchors, __nv_bfloat16* __restrict__ out_bf16,
+                          const __nv_bfloat16* __restrict__ in_bf16, int a_rows, int a_pad, float cbound, float k1,
+                          float* __restrict__ row_m2) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a_pad) return;
+  float ss = 0.f;
+  for (int d = lane; d < DDIM; d += 32) {
+    __nv_bfloat16 h;
+    if (out_bf16) {
+      h = __float2bfloat16(r < a_rows ? anchors[(int64_t)r * DDIM + d] : 0.f);
+      out_bf16[(int64_t)r * DDIM + d] = h;
+    } else {
+      h = in_bf16[(int64_t)r * DDIM + d];
+    }
+    const float f = __bfloat162float(h);
+    ss += f * f;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) row_m2[r] = sqrtf(ss) * cbound * k1 * 1.0001f;
+}
+
+__global__ void k_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n_real, int64_t n_total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(i < n_real ? src[i] : 0.f);
+}
+
+}  // namespace tc
+}  // namespace pcl
+
+using namespace pcl;
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmapEncodeTiled)p;
+  }
+  return fn;
+}
+
+// bf16 row-major (rows, 256) matrix, box = 64 columns (128 B) x box_rows, 128-byte swizzle, OOB rows read as zero
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return PCL_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)tc::DDIM, rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)tc::DDIM * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PCL_OK : PCL_ERR_CUDA;
+}
+
+struct TcPlan {
+  tc::TcArgs a;
+  SweepArgs sw;         // for the shared combine / finalize kernels
+  int row_tiles;
+};
+
+static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
+  if (!d || !d->anchor_cls || d->a_rows <= 0) return PCL_ERR_ARG;
+  if (d->D != tc::DDIM) return PCL_ERR_UNSUPPORTED;
+  if (!(d->temperature > 0.f) || !(d->base_temperature > 0.f)) return PCL_ERR_ARG;
+  memset(p, 0, sizeof(*p));
+  tc::TcArgs& a = p->a;
+  a.acls = d->anchor_cls; a.diag = d->diag_col; a.plan = d->plan; a.ccls = nullptr;
+  a.a_rows = d->a_rows; a.mode = d->mode;
+  p->row_tiles = ceil_div(d->a_rows, tc::BM);
+  a.a_pad = p->row_tiles * tc::BM;
+  int tail = 0;
+  if (d->mode == 0) {
+    a.n_cols = d->a_rows; a.sorted = 0; a.K = 0; a.R = 1;
+  } else if (d->mode == 1) {
+    if (d->bank_K < 1 || d->bank_R < 1) return PCL_ERR_ARG;
+    a.K = d->bank_K; a.R = d->bank_R; a.n_cols = (int64_t)(d->bank_K - 1) * d->bank_R; a.sorted = 1; tail = d->bank_R;
+  } else if (d->mode == 2) {
+    if (!d->contrast_cls || d->n_cols <= 0) return PCL_ERR_ARG;
+    a.ccls = d->contrast_cls; a.n_cols = d->n_cols; a.sorted = d->sorted ? 1 : 0; a.K = 0; a.R = 1;
+  } else {
+    return PCL_ERR_ARG;
+  }
+  a.k1 = tc::LOG2E / d->temperature;
+  const int col_tiles = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, tc::BN);
+  int splits = 148 / p->row_tiles;
+  if (splits < 1) splits = 1;
+  if (splits > col_tiles) splits = col_tiles;
+  a.splits = splits;
+  SweepArgs& s = p->sw;
+  s.acls = d->anchor_cls; s.diag = d->diag_col; s.plan = d->plan;
+  s.a_rows = d->a_rows; s.D = tc::DDIM; s.mode = d->mode;
+  s.n_cols = a.n_cols; s.tail_count = tail;
+  s.inv_T = 1.f / d->temperature; s.T_over_bT = d->temperature / d->base_temperature;
+  s.nan_safe = d->nan_safe; s.row_tiles = p->row_tiles; s.splits = splits; s.a_pad = a.a_pad; s.col_tiles = col_tiles;
+  return PCL_OK;
+}
+
+extern "C" int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out) {
+  pcl_tc_desc tmp = *d;
+  static const int32_t dummy = 0;
+  tmp.anchor_cls = &dummy;
+  if (tmp.mode == 2) tmp.contrast_cls = &dummy;
+  TcPlan p;
+  int st = make_tc_plan(&tmp, &p);
+  if (st != PCL_OK || !out) return st != PCL_OK ? st : PCL_ERR_ARG;
+  out->n_real_cols = p.a.n_cols;
+  out->row_tiles = p.row_tiles;
+  out->splits = p.a.splits;
+  out->partial_f32 = (int64_t)p.a.splits * p.a.a_pad;
+  out->rowstat_f32 = d->a_rows;
+  out->dpartial_f32 = (int64_t)p.a.splits * p.a.a_pad * tc::DDIM;
+  return PCL_OK;
+}
+
+extern "C" int pcl_to_bf16(const float* src, void* dst, int64_t n_real, int64_t n_total, void* stream) {
+  PCL_REQUIRE(src && dst && n_total >= n_real && n_real >= 0);
+  tc::k_to_bf16<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n_real, n_total);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
+                                  void* stream) {
+  TcPlan p;
+  int st = make_tc_plan(d, &p);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(row_m2 && partials && rowstats && loss && d->anchors_bf16);
+  if (d->mode != 0) PCL_REQUIRE(d->contrast_bf16);
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::TcArgs& a = p.a;
+  a.row_m2 = row_m2;
+  // 1. bf16 anchors (if fp32 given) + row stabilisers
+  const float cbound = d->contrast_norm_bound > 0.f ? d->contrast_norm_bound : 1.0f;
+  tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
+                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, cbound,
+                                                     a.k1, row_m2);
+  PCL_LAUNCH_CHECK();
+  // 2. tensor maps
+  CUtensorMap tmA, tmB;
+  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)a.a_pad, tc::BM);
+  if (st != PCL_OK) return st;
+  if (d->mode == 0) st = make_tmap(&tmB, d->anchors_bf16, (uint64_t)a.a_pad, tc::BN);
+  else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
+  if (st != PCL_OK) return st;
+  const size_t smem = sizeof(tc::SmemLayout) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(p.row_tiles, a.splits);
+  tc::k_tc_fwd<tc::TC_NEG><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  PCL_LAUNCH_CHECK();
+  k_combine_neg<<<ceil_div(d->a_rows, 256), 256, 0, s>>>(p.sw, partials, rowstats);
+  PCL_LAUNCH_CHECK();
+  tc::k_tc_fwd<tc::TC_POS><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
+  PCL_LAUNCH_CHECK();
+  k_finalize<<<1, 1024, 0, s>>>(p.sw, partials, rowstats, loss);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+// Descriptor / pipeline self-test: raw similarity tiles S = A . C^T (fp32 accumulate of bf16 operands) to `dump`
+// ((a_rows rounded up to 128) x (n_cols rounded up to 256) floats).
+extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* dump, void* stream) {
+  TcPlan p;
+  int st = make_tc_plan(d, &p);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(row_m2 && dump && d->anchors_bf16);
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::TcArgs& a = p.a;
+  a.row_m2 = row_m2;
+  tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
+                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, 1.f, a.k1,
+                                                     row_m2);
+  PCL_LAUNCH_CHECK();
+  CUtensorMap tmA, tmB;
+  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)a.a_pad, tc::BM);
+  if (st != PCL_OK) return st;
+  if (d->mode == 0) st = make_tmap(&tmB, d->anchors_bf16, (uint64_t)a.a_pad, tc::BN);
+  else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
+  if (st != PCL_OK) return st;
+  const size_t smem = sizeof(tc::SmemLayout) + 1024;
+  PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p.row_tiles, a.splits);
+  tc::k_tc_fwd<tc::TC_DUMP><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, dump, nullptr);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}

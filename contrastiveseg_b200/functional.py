@@ -318,3 +318,91 @@ class _L2NormFn(torch.autograd.Function):
 def l2_normalize(x: torch.Tensor) -> torch.Tensor:
     """F.normalize(x, p=2, dim=1) for (B, D, ...) CUDA tensors on the engine kernel."""
     return _L2NormFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) InfoNCE on explicit operands — D must be 256
+# ------------------------------------------------------------------------------------------------
+def to_bf16_rows(x: torch.Tensor, rows_alloc: int) -> torch.Tensor:
+    """fp32 (n, 256) -> bf16 (rows_alloc, 256) zero-padded copy on the engine's conversion kernel."""
+    lib = _abi.load()
+    xc = x.detach().to(torch.float32).contiguous()
+    out = torch.empty((rows_alloc, xc.shape[1]), dtype=torch.bfloat16, device=xc.device)
+    with torch.cuda.device(xc.device):
+        _abi.check(lib.pcl_to_bf16(xc.data_ptr(), out.data_ptr(), xc.numel(), out.numel(), _stream_ptr(xc.device)),
+                   "pcl_to_bf16")
+    return out
+
+
+def _tc_desc(anchors, anchor_cls, contrast_bf16, contrast_cls, n_cols, bank, diag_col, temperature, base_temperature,
+             nan_safe, sorted_cols, norm_bound):
+    dev = anchors.device
+    a = anchors.detach().to(torch.float32).contiguous()
+    A, D = a.shape
+    a_pad = -(-A // 128) * 128
+    a16 = torch.empty((a_pad, D), dtype=torch.bfloat16, device=dev)
+    cls = anchor_cls.to(device=dev, dtype=torch.int32).contiguous()
+    d = _abi.TcDesc()
+    d.anchors_f32, d.anchors_bf16, d.anchor_cls = a.data_ptr(), a16.data_ptr(), cls.data_ptr()
+    keep = [a, a16, cls]
+    if diag_col is not None:
+        dg = diag_col.to(device=dev, dtype=torch.int32).contiguous()
+        d.diag_col = dg.data_ptr()
+        keep.append(dg)
+    d.a_rows, d.D = A, D
+    if bank is not None:                       # (shadow bf16, K, R)
+        shadow, K, R = bank
+        d.mode, d.contrast_bf16, d.bank_K, d.bank_R = 1, shadow.data_ptr(), K, R
+        d.contrast_rows_alloc = shadow.shape[0]
+        keep.append(shadow)
+    elif contrast_bf16 is not None:
+        cc = contrast_cls.to(device=dev, dtype=torch.int32).contiguous()
+        d.mode, d.contrast_bf16, d.contrast_cls = 2, contrast_bf16.data_ptr(), cc.data_ptr()
+        d.n_cols, d.contrast_rows_alloc, d.sorted = n_cols, contrast_bf16.shape[0], int(sorted_cols)
+        keep += [contrast_bf16, cc]
+    else:
+        d.mode = 0
+    d.contrast_norm_bound = norm_bound
+    d.temperature, d.base_temperature, d.nan_safe = temperature, base_temperature, int(nan_safe)
+    return d, keep, a_pad
+
+
+def infonce_tc_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast_bf16: Optional[torch.Tensor] = None,
+                       contrast_cls: Optional[torch.Tensor] = None, n_cols: int = 0, bank=None,
+                       diag_col: Optional[torch.Tensor] = None, temperature: float = 0.1, base_temperature: float = 0.07,
+                       nan_safe: bool = False, sorted_cols: bool = True, norm_bound: float = 1.0):
+    """bf16 tcgen05 sweep.  Returns (loss (1,), rowstats (6, A), state)."""
+    lib = _abi.load()
+    _require_cuda(anchors, "anchors")
+    dev = anchors.device
+    d, keep, a_pad = _tc_desc(anchors, anchor_cls, contrast_bf16, contrast_cls, n_cols, bank, diag_col, temperature,
+                              base_temperature, nan_safe, sorted_cols, norm_bound)
+    ss = _abi.SweepSizes()
+    _abi.check(lib.pcl_tc_sizes(C.byref(d), C.byref(ss)), "pcl_tc_sizes")
+    row_m2 = torch.empty(a_pad, dtype=torch.float32, device=dev)
+    partials = torch.empty(5 * ss.partial_f32, dtype=torch.float32, device=dev)
+    rowstats = torch.empty(6 * ss.rowstat_f32, dtype=torch.float32, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(lib.pcl_infonce_tc_fwd(C.byref(d), row_m2.data_ptr(), partials.data_ptr(), rowstats.data_ptr(),
+                                          loss.data_ptr(), _stream_ptr(dev)), "pcl_infonce_tc_fwd")
+    return loss, rowstats.view(6, d.a_rows), (d, ss, keep, row_m2)
+
+
+def tc_dump_logits(anchors: torch.Tensor, contrast_bf16: Optional[torch.Tensor], n_cols: int) -> torch.Tensor:
+    """Raw S = A.C^T from the TMA/tcgen05 pipeline (self-test of descriptors and barriers)."""
+    lib = _abi.load()
+    dev = anchors.device
+    A = anchors.shape[0]
+    cls = torch.zeros(A, dtype=torch.int32, device=dev)
+    ccls = torch.zeros(max(n_cols, 1), dtype=torch.int32, device=dev)
+    d, keep, a_pad = _tc_desc(anchors, cls, contrast_bf16, ccls if contrast_bf16 is not None else None, n_cols, None,
+                              None, 1.0, 1.0, False, False, 1.0)
+    ncols = n_cols if contrast_bf16 is not None else A
+    ld = -(-ncols // 256) * 256
+    dump = torch.zeros((a_pad, ld), dtype=torch.float32, device=dev)
+    row_m2 = torch.empty(a_pad, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(lib.pcl_tc_dump_logits(C.byref(d), row_m2.data_ptr(), dump.data_ptr(), _stream_ptr(dev)),
+                   "pcl_tc_dump_logits")
+    return dump[:A, :ncols]

@@ -202,6 +202,39 @@ int pcl_bank_shadow_rebuild(const float* segment_queue, const float* pixel_queue
                             int32_t D, void* shadow_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * a6 on the tensor cores (tcgen05 + TMA, bf16 operands, fp32 accumulate in TMEM), D must be 256.
+ * Same semantics and row-statistic layout as pcl_infonce_fwd; operands are bf16 copies:
+ *   anchors_bf16   (a_rows rounded up to 128, 256) bf16 — written here from anchors_f32 when that is non-NULL
+ *   contrast_bf16  mode 1: the bank shadow ((K-1)*R rounded up to 256 rows, class-blocked, see pcl_bank_apply);
+ *                  mode 2: (contrast_rows_alloc, 256) rows with labels contrast_cls (sorted = labels are
+ *                  non-decreasing, enables the no-compare fast path); mode 0: ignored (columns == anchors)
+ *   contrast_norm_bound  upper bound of the contrast rows' L2 norm (1 for a normalised bank); only has to keep
+ *                  exp() in range — the loss does not depend on it
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct {
+  const float*   anchors_f32;    /* (a_rows, 256) or NULL when anchors_bf16 is already filled                */
+  void*          anchors_bf16;
+  const int32_t* anchor_cls; const int32_t* diag_col; const int32_t* plan;
+  int32_t a_rows, D;
+  int32_t mode;
+  const void*    contrast_bf16;
+  const int32_t* contrast_cls;
+  int64_t n_cols; int64_t contrast_rows_alloc;
+  int32_t bank_K, bank_R, sorted;
+  float contrast_norm_bound;
+  float temperature, base_temperature;
+  int32_t nan_safe;
+} pcl_tc_desc;
+
+int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out);
+int pcl_to_bf16(const float* src, void* dst_bf16, int64_t n_real, int64_t n_total, void* stream);
+/* row_m2: a_rows rounded up to 128 floats of scratch (per-row stabiliser, kept for the backward). */
+int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
+                       void* stream);
+/* Pipeline self-test: raw similarity tiles S = A.C^T into dump[(a_rows up to 128) x (n_cols up to 256)] fp32. */
+int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* dump, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * One loss step = the calls above chained on one stream behind a single descriptor (what
  * PixelContrastLoss.forward / its autograd backward bind; lib/loss/loss_contrast.py:130-147,
  * lib/loss/loss_contrast_mem.py:154-171).  All scratch is caller-owned.
