@@ -93,18 +93,24 @@ class ContrastWorkspace:
 _WS_CACHE = {}
 
 
+_LAST_WS = {}
+
+
 def _get_workspace(device, key, geom, mode, bank_K, bank_M0, bank_M1) -> ContrastWorkspace:
     lst = _WS_CACHE.setdefault((device.index, key), [])
     for ws in lst:
         if not ws.busy:
+            _LAST_WS[device.index] = ws
             return ws
     ws = ContrastWorkspace(device, geom, mode, bank_K, bank_M0, bank_M1)
     lst.append(ws)
+    _LAST_WS[device.index] = ws
     return ws
 
 
 def clear_workspaces() -> None:
     _WS_CACHE.clear()
+    _LAST_WS.clear()
 
 
 _step_counter = [0]
@@ -214,11 +220,8 @@ def pixel_contrast_loss(embed: torch.Tensor, labels: torch.Tensor, *, seg: Optio
 
 
 def last_workspace(embed_device: torch.device):
-    """Most recently created workspace on a device (diagnostics / tests)."""
-    for (dev, _), lst in reversed(list(_WS_CACHE.items())):
-        if dev == embed_device.index and lst:
-            return lst[-1]
-    return None
+    """Workspace used by the most recent loss call on a device (diagnostics / tests)."""
+    return _LAST_WS.get(embed_device.index)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,11 +6,13 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 python -c "import os; print(os.cpu_count())" > gpurun_out/cpus.txt
 timeout 300 python -m contrastiveseg_b200.build > gpurun_out/build.log 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 180 python tools/tc_selftest.py dump > gpurun_out/tc_dump.log 2>&1; echo "dump exit $?" >> gpurun_out/tc_dump.log
+timeout 300 python tools/tc_selftest.py fwd > gpurun_out/tc_fwd.log 2>&1; echo "fwd exit $?" >> gpurun_out/tc_fwd.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
 if [ "${1:-}" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 fi
-tail -5 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+cat gpurun_out/tc_dump.log gpurun_out/tc_fwd.log; tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
