@@ -98,6 +98,7 @@ SIGNATURES = {
     "pcl_tc_sizes": (c_i32, [C.POINTER(TcDesc), C.POINTER(SweepSizes)]),
     "pcl_to_bf16": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "pcl_infonce_tc_fwd": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_infonce_tc_bwd": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_tc_dump_logits": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp]),
     "pcl_step_stats": (c_i32, [C.POINTER(StepDesc), c_vp]),
     "pcl_step_forward": (c_i32, [C.POINTER(StepDesc), c_vp]),

@@ -255,6 +255,259 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// =====================================================================================================
+// Backward: dA = G . C / T with G formed on the fly (closed form) — FlashAttention-backward
+// shaped: MMA1 S = A.C^T (128 x 128 tile, K = 256) -> epilogue turns S into the bf16 gradient tile G in shared
+// memory (128B-swizzled K-major) -> MMA2 dA(128 x 256, TMEM-resident across the whole column sweep) += G . C,
+// where the SAME shared-memory contrast tile is re-read as an MN-major B operand.
+// TMEM: S double buffer = columns [0,256), dA accumulator = columns [256,512).
+// =====================================================================================================
+constexpr int BNB = 128;                          // columns per tile in the backward sweep
+constexpr int C_KB_BYTES = BNB * BK * 2;          // 16 KB: one [128 x 64] box
+constexpr int C_STAGE_BYTES = NKB * C_KB_BYTES;   // 64 KB: the full [128 x 256] tile
+constexpr int G_BYTES = BM * BNB * 2;             // 32 KB
+constexpr int BWD_STAGES = 2;
+
+struct SmemBwd {
+  uint8_t a[NKB * A_KB_BYTES];                    // 64 KB
+  uint8_t c[BWD_STAGES * C_STAGE_BYTES];          // 128 KB
+  uint8_t g[G_BYTES];                             // 32 KB
+  uint64_t a_full, c_full[BWD_STAGES], c_empty[BWD_STAGES], s_full[2], s_empty[2], g_full, g_empty, da_full;
+  uint32_t tmem_base;
+};
+
+struct TcBwdArgs {
+  TcArgs t;
+  const float* rowstats;       // m, neg, possum, s, npos, row_loss (a_rows each)
+  float rs_scale;              // (T / bT) / A_live is applied per row: c_i = rs_scale' / npos_i; here T/bT
+  int nan_safe;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, TcBwdArgs ba,
+         float* __restrict__ dpartials) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemBwd& sm = *reinterpret_cast<SmemBwd*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const TcArgs& a = ba.t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = a.plan ? min(a.plan[PCL_PLAN_A], a.a_rows) : a.a_rows;
+  const int row0 = blockIdx.x * BM;
+  if (row0 >= A) return;
+  const int split = blockIdx.y;
+  const int64_t ncols = a.mode == 0 ? (int64_t)A : a.n_cols;
+  const int t_hi = (int)((ncols + BNB - 1) / BNB);
+  const int per = (t_hi + a.splits - 1) / a.splits;
+  const int my_lo = split * per;
+  const int my_hi = min(t_hi, my_lo + per);
+  const int ntiles = my_hi > my_lo ? my_hi - my_lo : 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmC);
+    ptx::mbar_init(&sm.a_full, 1);
+    for (int s = 0; s < BWD_STAGES; ++s) { ptx::mbar_init(&sm.c_full[s], 1); ptx::mbar_init(&sm.c_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.s_full[i], 1); ptx::mbar_init(&sm.s_empty[i], EPI_THREADS / 32); }
+    ptx::mbar_init(&sm.g_full, EPI_THREADS / 32);
+    ptx::mbar_init(&sm.g_empty, 1);
+    ptx::mbar_init(&sm.da_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(&sm.tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  const uint32_t tmem_dA = tmem_base + 2 * BNB;
+
+  if (warp == 0) {
+    if (lane == 0 && ntiles > 0) {
+      ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * A_KB_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sm.a + kb * A_KB_BYTES, &tmA, &sm.a_full, kb * BK, row0);
+      for (int it = 0; it < ntiles; ++it) {
+        const int stage = it & 1, phase = (it >> 1) & 1;
+        ptx::mbar_wait(&sm.c_empty[stage], phase ^ 1);
+        ptx::mbar_arrive_expect_tx(&sm.c_full[stage], C_STAGE_BYTES);
+        for (int kb = 0; kb < NKB; ++kb)
+          ptx::tma_load_2d(sm.c + stage * C_STAGE_BYTES + kb * C_KB_BYTES, &tmC, &sm.c_full[stage], kb * BK,
+                           (my_lo + it) * BNB);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc1 = ptx::make_idesc_bf16(BM, BNB, 0, 0);     // S = A . C^T   (both K-major)
+      constexpr uint32_t idesc2 = ptx::make_idesc_bf16(BM, DDIM, 0, 1);    // dA += G . C   (B operand MN-major)
+      const uint32_t a_base = ptx::smem_u32(sm.a), c_base = ptx::smem_u32(sm.c), g_base = ptx::smem_u32(sm.g);
+      ptx::mbar_wait(&sm.a_full, 0);
+      ptx::tc_fence_after();
+      auto mma2 = [&](int t) {
+        const int stage = t & 1;
+        ptx::mbar_wait(&sm.g_full, t & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BNB / 16; ++k) {
+          // A operand: G tile, K-major, K = column index j: 2 blocks of 64 j, 32 B per 16-element K step
+          const uint64_t dg = ptx::make_desc_kmajor_sw128(g_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
+          // B operand: contrast tile read MN-major: N = feature d (4 chunks of 64 at 16 KB), K = j (16 rows = 2 KB per step)
+          const uint64_t dc = ptx::make_desc_mnmajor_sw128(c_base + stage * C_STAGE_BYTES + k * 2048, C_KB_BYTES, 1024);
+          ptx::mma_f16_ss(tmem_dA, dg, dc, idesc2, (t | k) != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(&sm.g_empty);
+        ptx::mma_commit(&sm.c_empty[stage]);
+      };
+      for (int it = 0; it < ntiles; ++it) {
+        const int stage = it & 1, phase = (it >> 1) & 1;
+        const uint32_t acc = it & 1;
+        ptx::mbar_wait(&sm.s_empty[acc], phase ^ 1);
+        ptx::mbar_wait(&sm.c_full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BNB;
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
+            const uint64_t dc = ptx::make_desc_kmajor_sw128(c_base + stage * C_STAGE_BYTES + kb * C_KB_BYTES + k * 32);
+            ptx::mma_f16_ss(d_tmem, da, dc, idesc1, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(&sm.s_full[acc]);
+        if (it > 0) mma2(it - 1);                 // deferred one tile: epilogue(it-1) overlaps MMA1(it)
+      }
+      mma2(ntiles - 1);
+      ptx::mma_commit(&sm.da_full);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;             // which 64 columns of the 128-column tile
+    const int r_in = quarter * 32 + lane;
+    const int row = row0 + r_in;
+    const bool valid = row < A;
+    const float* st = ba.rowstats;
+    const int rcls = valid ? a.acls[row] : -1;
+    const int rdiag = valid ? (a.mode == 0 ? row : (a.diag ? a.diag[row] : -1)) : -1;
+    const float m2 = valid ? a.row_m2[row] : 0.f;
+    const float neg_i = valid ? st[a.a_rows + row] : 1.f;
+    const float s_i = valid ? st[3 * a.a_rows + row] : 0.f;
+    float c_i = 0.f;
+    if (valid) {
+      const float np = st[4 * a.a_rows + row];
+      c_i = ba.rs_scale / ((float)A * np);
+      if (ba.nan_safe && !(np > 0.f)) c_i = 0.f;
+    }
+    const float cs_i = c_i * s_i;
+    const float cn_i = -c_i * neg_i;
+    uint8_t* g_row = sm.g + r_in * 128;           // + kblock * 16 KB + swizzled 16-byte chunk
+    for (int it = 0; it < ntiles; ++it) {
+      const int ct = my_lo + it;
+      const uint32_t acc = it & 1, phase = (it >> 1) & 1;
+      const int64_t col0 = (int64_t)ct * BNB + half * 64;
+      bool uniform = false;
+      int ulab = -1;
+      if (a.sorted && col0 + 64 <= ncols) {
+        ulab = col_label(a, col0);
+        uniform = ulab == col_label(a, col0 + 63);
+      }
+      ptx::mbar_wait(&sm.s_full[acc], phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BNB + half * 64;
+      uint32_t packed[2][16];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
+        ptx::tmem_ld_wait();
+        const int64_t cb = col0 + ch * 32;
+        float gv[32];
+        if (uniform && ulab != rcls) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gv[j] = cs_i * ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t col = cb + j;
+            float gval = 0.f;
+            if (valid && col < ncols) {
+              const int lab = uniform ? ulab : col_label(a, col);
+              const float x = __uint_as_float(v[j]) * a.k1;
+              const float e = ptx::ex2_approx(x - m2);
+              if (lab == rcls) {
+                if (col != (int64_t)rdiag) gval = cn_i * ptx::rcp_approx(e + neg_i);     // -c (1 - e/(e+Neg))
+              } else {
+                gval = cs_i * e;
+              }
+              if (a.mode == 0) {
+                // self-contrast: the column is an anchor too, add G_ji (its statistics, same logit)
+                const int cj = (int)col;
+                const float np_j = st[4 * a.a_rows + cj];
+                float c_j = ba.rs_scale / ((float)A * np_j);
+                if (ba.nan_safe && !(np_j > 0.f)) c_j = 0.f;
+                const float e2 = ptx::ex2_approx(x - a.row_m2[cj]);
+                const float neg_j = st[a.a_rows + cj];
+                if (lab == rcls) {
+                  if (col != (int64_t)rdiag) gval += -c_j * neg_j * ptx::rcp_approx(e2 + neg_j);
+                } else {
+                  gval += c_j * st[3 * a.a_rows + cj] * e2;
+                }
+              }
+            }
+            gv[j] = gval;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[ch][j] = pack_bf16x2(gv[2 * j], gv[2 * j + 1]);
+      }
+      // S fully read: hand the accumulator back before waiting for the G buffer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.s_empty[acc]);
+      // G buffer free once MMA2 of the previous tile retired
+      ptx::mbar_wait(&sm.g_empty, (it & 1) ^ 1);
+      // this thread's 64 columns = K-block `half` of the G tile, 8 chunks of 16 B, 128B-swizzled by row
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ch * 4 + q;
+          uint4 val = make_uint4(packed[ch][4 * q], packed[ch][4 * q + 1], packed[ch][4 * q + 2], packed[ch][4 * q + 3]);
+          *reinterpret_cast<uint4*>(g_row + half * (BM * 128) + ((chunk ^ (r_in & 7)) << 4)) = val;
+        }
+      }
+      ptx::fence_proxy_async();                   // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sm.g_full);
+    }
+    // ---- dA tile: TMEM -> global partial of this split ----
+    if (ntiles > 0) {
+      ptx::mbar_wait(&sm.da_full, 0);
+      ptx::tc_fence_after();
+    }
+    float* dst = dpartials + ((int64_t)split * a.a_pad + row) * DDIM + half * 128;
+    const uint32_t t_da = tmem_dA + ((uint32_t)(quarter * 32) << 16) + half * 128;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t v[32];
+      if (ntiles > 0) {
+        ptx::tmem_ld_32x32b_x32(t_da + ch * 32, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(dst + ch * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 // anchors fp32 -> bf16 rows (optional) and the per-row stabiliser m2 = |bf16(a)| * cbound * log2(e)/T
 __global__ void k_tc_prep(const float* __restrict__ anchors, __nv_bfloat16* __restrict__ out_bf16,
                           const __nv_bfloat16* __restrict__ in_bf16, int a_rows, int a_pad, float cbound, float k1,
@@ -454,6 +707,47 @@ extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* du
   PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.row_tiles, a.splits);
   tc::k_tc_fwd<tc::TC_DUMP><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, dump, nullptr);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
+                                  float* dpartials, float* dA, void* stream) {
+  TcPlan p;
+  int st = make_tc_plan(d, &p);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(row_m2 && rowstats && dpartials && dA && d->anchors_bf16);
+  if (d->mode != 0) PCL_REQUIRE(d->contrast_bf16);
+  cudaStream_t s = (cudaStream_t)stream;
+  tc::TcBwdArgs ba;
+  ba.t = p.a;
+  ba.t.row_m2 = row_m2;
+  ba.rowstats = rowstats;
+  ba.rs_scale = d->temperature / d->base_temperature;
+  ba.nan_safe = d->nan_safe;
+  // the backward sweeps 128-column tiles: recompute the split count for that tile width
+  const int col_tiles = (int)ceil_div64(ba.t.n_cols > 0 ? ba.t.n_cols : 1, tc::BNB);
+  int splits = ba.t.splits;
+  if (splits > col_tiles) splits = col_tiles;
+  ba.t.splits = splits;
+  p.sw.splits = splits;
+  CUtensorMap tmA, tmC;
+  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)ba.t.a_pad, tc::BM);
+  if (st != PCL_OK) return st;
+  if (d->mode == 0) st = make_tmap(&tmC, d->anchors_bf16, (uint64_t)ba.t.a_pad, tc::BNB);
+  else st = make_tmap(&tmC, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : ba.t.n_cols), tc::BNB);
+  if (st != PCL_OK) return st;
+  const size_t smem = sizeof(tc::SmemBwd) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid(p.row_tiles, splits);
+  tc::k_tc_bwd<<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmC, ba, dpartials);
+  PCL_LAUNCH_CHECK();
+  const int64_t total = (int64_t)d->a_rows * tc::DDIM;
+  k_reduce_dA<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(p.sw, dpartials, grad_loss, dA);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

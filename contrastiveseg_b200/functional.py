@@ -409,3 +409,17 @@ def tc_dump_logits(anchors: torch.Tensor, contrast_bf16: Optional[torch.Tensor],
         _abi.check(lib.pcl_tc_dump_logits(C.byref(d), row_m2.data_ptr(), dump.data_ptr(), _stream_ptr(dev)),
                    "pcl_tc_dump_logits")
     return dump[:A, :ncols]
+
+
+def infonce_tc_backward(state, rowstats: torch.Tensor, grad_loss: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dA (A, 256) fp32 from the tcgen05 backward sweep (recompute S, G tile in shared memory, dA += G.C)."""
+    lib = _abi.load()
+    d, ss, keep, row_m2 = state
+    dev = row_m2.device
+    dpart = torch.empty(ss.dpartial_f32, dtype=torch.float32, device=dev)
+    dA = torch.empty((d.a_rows, d.D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(lib.pcl_infonce_tc_bwd(C.byref(d), row_m2.data_ptr(), rowstats.contiguous().data_ptr(),
+                                          _abi.ptr(grad_loss), dpart.data_ptr(), dA.data_ptr(), _stream_ptr(dev)),
+                   "pcl_infonce_tc_bwd")
+    return dA

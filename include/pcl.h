@@ -231,6 +231,10 @@ int pcl_to_bf16(const float* src, void* dst_bf16, int64_t n_real, int64_t n_tota
 /* row_m2: a_rows rounded up to 128 floats of scratch (per-row stabiliser, kept for the backward). */
 int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
                        void* stream);
+/* Backward on the tensor cores: dA (a_rows, 256) fp32 = d loss / d anchors * (*grad_loss or 1).  row_m2 and rowstats
+ * come from pcl_infonce_tc_fwd; dpartials: pcl_tc_sizes().dpartial_f32 floats of scratch. */
+int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
+                       float* dpartials, float* dA, void* stream);
 /* Pipeline self-test: raw similarity tiles S = A.C^T into dump[(a_rows up to 128) x (n_cols up to 256)] fp32. */
 int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* dump, void* stream);
 

@@ -360,3 +360,22 @@ def test_tc_forward_matches_oracle(A, N, T, self_mode):
     assert torch.equal(st[4].cpu().double(), cf16["npos"])
     assert rel_err(loss.item(), cf16["loss"].item()) < 2e-5
     assert rel_err(loss.item(), cf32["loss"].item()) < 1e-4
+
+
+@pytest.mark.parametrize("A,N,T,self_mode", [(200, 1000, 0.1, False), (912, 912, 0.1, True), (1024, 20000, 0.07, False)])
+def test_tc_backward_matches_oracle(A, N, T, self_mode):
+    """Gradient tolerance of the bf16 path: 2e-3 * max|g| (bf16 gradient tile G)."""
+    from contrastiveseg_b200.synth import make_sweep_point
+    pt = make_sweep_point(A, N, D=256, num_classes=19, seed=A * 3 + N, clustered=0.5)
+    a, ya, c, yc = pt["anchors"], pt["ya"], pt["contrast"], pt["yc"]
+    if self_mode:
+        loss, st, state = Fn.infonce_tc_forward(a.to(DEV), ya.to(DEV), temperature=T, base_temperature=0.07)
+        cf = P.infonce_closed_form(a.double(), ya, a.double(), ya, T, 0.07, self_contrast=True)
+    else:
+        c16 = Fn.to_bf16_rows(c.to(DEV), -(-N // 256) * 256)
+        loss, st, state = Fn.infonce_tc_forward(a.to(DEV), ya.to(DEV), contrast_bf16=c16, contrast_cls=yc.to(DEV), n_cols=N,
+                                                diag_col=torch.arange(A).to(DEV), temperature=T, base_temperature=0.07)
+        cf = P.infonce_closed_form(a.double(), ya, c.double(), yc, T, 0.07, self_contrast=False)
+    dA = Fn.infonce_tc_backward(state, st).cpu().double()
+    assert (dA - cf["dA"]).abs().max().item() <= 2e-3 * cf["dA"].abs().max().item()
+    assert ((dA - cf["dA"]).norm() / cf["dA"].norm()).item() < 2e-3

@@ -56,6 +56,27 @@ def fwd_test(A, N, T=0.1, clustered=0.5, self_mode=False):
     return r16, r32
 
 
+def bwd_test(A, N, T=0.1, clustered=0.5, self_mode=False):
+    pt = make_sweep_point(A, N, D=256, num_classes=19, seed=A * 3 + N, clustered=clustered)
+    a, ya, c, yc = pt["anchors"], pt["ya"], pt["contrast"], pt["yc"]
+    if self_mode:
+        loss, st, state = Fn.infonce_tc_forward(a.to(dev), ya.to(dev), temperature=T, base_temperature=0.07)
+        cf = P.infonce_closed_form(bf(a).double(), ya, bf(a).double(), ya, T, 0.07, self_contrast=True)
+    else:
+        c16 = Fn.to_bf16_rows(c.to(dev), -(-N // 256) * 256)
+        loss, st, state = Fn.infonce_tc_forward(a.to(dev), ya.to(dev), contrast_bf16=c16, contrast_cls=yc.to(dev), n_cols=N,
+                                                diag_col=torch.arange(A).to(dev), temperature=T, base_temperature=0.07)
+        cf = P.infonce_closed_form(bf(a).double(), ya, bf(c).double(), yc, T, 0.07, self_contrast=False)
+    dA = Fn.infonce_tc_backward(state, st)
+    torch.cuda.synchronize()
+    ref = cf["dA"]
+    err = (dA.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+    fro = ((dA.cpu().double() - ref).norm() / ref.norm()).item()
+    print(f"bwd A={A} N={N} self={self_mode}: max-abs err / max|g| = {err:.2e}  rel-Frobenius = {fro:.2e}  "
+          f"(dA[0,:3]={dA[0,:3].tolist()} ref={ref[0,:3].tolist()})", flush=True)
+    return err
+
+
 if stage in ("all", "dump"):
     dump_test(128, 256)
     dump_test(200, 1000)
@@ -65,4 +86,9 @@ if stage in ("all", "fwd"):
     fwd_test(912, 912, self_mode=True)
     fwd_test(1024, 20000, T=0.07)
     fwd_test(300, 190000 // 10, T=0.07, clustered=1.0)
+if stage in ("all", "bwd"):
+    bwd_test(128, 128 * 3)
+    bwd_test(200, 1000)
+    bwd_test(912, 912, self_mode=True)
+    bwd_test(1024, 20000, T=0.07)
 print("selftest done", flush=True)
