@@ -70,6 +70,8 @@ class StepDesc(C.Structure):
                 ("keys", c_vp), ("chunk_pref", c_vp), ("counts", c_vp), ("plan", c_vp), ("anchor_meta", c_vp),
                 ("anchors_f32", c_vp), ("anchors_bf16", c_vp), ("inv_norm", c_vp), ("norm_max", c_vp),
                 ("partials", c_vp), ("rowstats", c_vp), ("dpartials", c_vp), ("dA", c_vp),
+                ("precision", c_i32), ("shadow_bf16", c_vp), ("shadow_rows", c_i64), ("contrast_norm_bound", c_f32),
+                ("row_m2", c_vp),
                 ("loss", c_vp), ("grad_embed", c_vp)]
 
 

@@ -43,6 +43,10 @@ class MemoryBank(nn.Module):
         outputs["pixel_queue_ptr"] = self.pixel_queue_ptr
         outputs["segment_queue"] = self.segment_queue
         outputs["segment_queue_ptr"] = self.segment_queue_ptr
+        if self.with_shadow:
+            if self.shadow is None:
+                self.sync_shadow()
+            outputs["bank_shadow"] = self.shadow          # engine-only: bf16 copy for the tcgen05 sweep
         return outputs
 
     def sync_shadow(self) -> torch.Tensor:
@@ -79,7 +83,10 @@ def gather_packets(packet: torch.Tensor, group=None) -> torch.Tensor:
     if world == 1:
         return packet.view(1, -1)
     out = torch.empty((world, packet.numel()), dtype=packet.dtype, device=packet.device)
-    dist.all_gather_into_tensor(out, packet.view(-1).contiguous(), group=group)
+    if packet.is_cuda:
+        dist.all_gather_into_tensor(out, packet.view(-1).contiguous(), group=group)      # NCCL over NVLink
+    else:
+        dist.all_gather(list(out.unbind(0)), packet.view(-1).contiguous(), group=group)  # gloo (CPU tests)
     return out
 
 

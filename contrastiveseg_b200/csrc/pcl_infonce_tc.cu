@@ -31,6 +31,7 @@ constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 struct TcArgs {
   const int32_t* acls; const int32_t* diag; const int32_t* plan; const int32_t* ccls;
   const float* row_m2;         // per-row stabiliser in log2 units
+  const int32_t* cls_start;    // mode 2 + sorted: first column of every label (PCL_MAX_CLASSES + 1 entries)
   int a_rows, a_pad, mode, K, R, sorted;
   int64_t n_cols;
   float k1;                    // log2(e) / T
@@ -66,6 +67,24 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 
   // ---- column-tile range of this CTA (identical in every warp) ----
   int t_lo = 0, t_hi = (int)((ncols + BN - 1) / BN);
+  if (MODE == TC_POS && a.mode == 2 && a.sorted && a.cls_start != nullptr) {
+    // positives of this row tile live in the columns of its label range (contrast labels are sorted)
+    int lo = 0x7fffffff, hi = -1;
+    for (int i = lane; i < BM; i += 32) {
+      const int r = row0 + i;
+      if (r < A) { const int c = a.acls[r]; lo = min(lo, c); hi = max(hi, c); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    lo = max(0, min(lo, PCL_MAX_CLASSES - 1));
+    hi = max(0, min(hi, PCL_MAX_CLASSES - 1));
+    t_lo = a.cls_start[lo] / BN;
+    t_hi = (a.cls_start[hi + 1] + BN - 1) / BN;
+    if (t_hi < t_lo) t_hi = t_lo;
+  }
   if (MODE == TC_POS && a.mode == 1) {
     const int last = min(A - 1, row0 + BM - 1);
     int rk_f = class_rank(a.acls[row0], a.K), rk_l = class_rank(a.acls[last], a.K);
@@ -531,6 +550,19 @@ __global__ void k_tc_prep(const float* __restrict__ anchors, __nv_bfloat16* __re
   if (lane == 0) row_m2[r] = sqrtf(ss) * cbound * k1 * 1.0001f;
 }
 
+// first column of every label for a sorted label array: start[L] = first n with ccls[n] >= L
+__global__ void k_cls_bounds_init(int32_t* __restrict__ start, int n_cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= PCL_MAX_CLASSES) start[i] = n_cols;
+}
+__global__ void k_cls_bounds(const int32_t* __restrict__ ccls, int n_cols, int32_t* __restrict__ start) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_cols) return;
+  const int cur = min(max(ccls[n], 0), PCL_MAX_CLASSES);
+  const int prev = n == 0 ? -1 : min(max(ccls[n - 1], 0), PCL_MAX_CLASSES);
+  for (int L = prev + 1; L <= cur; ++L) start[L] = n;
+}
+
 __global__ void k_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n_real, int64_t n_total) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16(i < n_real ? src[i] : 0.f);
@@ -657,6 +689,14 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
                                                      (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, cbound,
                                                      a.k1, row_m2);
   PCL_LAUNCH_CHECK();
+  if (d->mode == 2 && a.sorted) {
+    int32_t* cls_start = reinterpret_cast<int32_t*>(row_m2 + a.a_pad);       // scratch tail: PCL_MAX_CLASSES + 1 ints
+    tc::k_cls_bounds_init<<<2, 256, 0, s>>>(cls_start, (int)a.n_cols);
+    PCL_LAUNCH_CHECK();
+    tc::k_cls_bounds<<<(unsigned)ceil_div64(a.n_cols, 256), 256, 0, s>>>(d->contrast_cls, (int)a.n_cols, cls_start);
+    PCL_LAUNCH_CHECK();
+    a.cls_start = cls_start;
+  }
   // 2. tensor maps
   CUtensorMap tmA, tmB;
   st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)a.a_pad, tc::BM);

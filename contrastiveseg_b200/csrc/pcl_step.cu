@@ -18,6 +18,27 @@ static void fill_sweep(const pcl_step_desc* d, pcl_sweep_desc* w) {
   w->nan_safe = d->nan_safe;
 }
 
+static void fill_tc(const pcl_step_desc* d, pcl_tc_desc* t) {
+  memset(t, 0, sizeof(*t));
+  const int ms = d->g.max_samples;
+  t->anchors_f32 = nullptr;                              // bf16 rows were written by pcl_select_gather
+  t->anchors_bf16 = d->anchors_bf16;
+  t->anchor_cls = d->anchor_meta + 2 * (int64_t)ms;
+  t->diag_col = d->anchor_meta + 3 * (int64_t)ms;
+  t->plan = d->plan;
+  t->a_rows = ms;
+  t->D = d->g.D;
+  t->mode = d->mode;
+  t->contrast_bf16 = d->shadow_bf16;
+  t->contrast_rows_alloc = d->shadow_rows;
+  t->bank_K = d->bank_K;
+  t->bank_R = d->bank_M0 + d->bank_M1;
+  t->sorted = 1;
+  t->contrast_norm_bound = d->contrast_norm_bound;
+  t->temperature = d->temperature; t->base_temperature = d->base_temperature;
+  t->nan_safe = d->nan_safe;
+}
+
 extern "C" int pcl_step_stats(const pcl_step_desc* d, void* stream) {
   if (!d) return PCL_ERR_ARG;
   int st = pcl_class_stats(&d->g, d->labels, d->seg, d->predict, d->keys, d->chunk_pref, stream);
@@ -30,6 +51,12 @@ extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {
   int st = pcl_select_gather(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
                              d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, d->norm_max, stream);
   if (st != PCL_OK) return st;
+  if (d->precision == 1) {
+    if (!d->anchors_bf16 || !d->row_m2 || (d->mode == 1 && !d->shadow_bf16)) return PCL_ERR_ARG;
+    pcl_tc_desc t;
+    fill_tc(d, &t);
+    return pcl_infonce_tc_fwd(&t, d->row_m2, d->partials, d->rowstats, d->loss, stream);
+  }
   pcl_sweep_desc w;
   fill_sweep(d, &w);
   return pcl_infonce_fwd(&w, d->partials, d->rowstats, d->loss, stream);
@@ -37,9 +64,16 @@ extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {
 
 extern "C" int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss, void* stream) {
   if (!d) return PCL_ERR_ARG;
-  pcl_sweep_desc w;
-  fill_sweep(d, &w);
-  int st = pcl_infonce_bwd(&w, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
+  int st;
+  if (d->precision == 1) {
+    pcl_tc_desc t;
+    fill_tc(d, &t);
+    st = pcl_infonce_tc_bwd(&t, d->row_m2, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
+  } else {
+    pcl_sweep_desc w;
+    fill_sweep(d, &w);
+    st = pcl_infonce_bwd(&w, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
+  }
   if (st != PCL_OK) return st;
   return pcl_scatter_grad(&d->g, d->plan, d->anchor_meta, d->dA, d->anchors_f32, d->inv_norm, d->normalize,
                           d->grad_embed, stream);

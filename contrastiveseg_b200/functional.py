@@ -29,6 +29,7 @@ class ContrastOptions:
     perm_fn: Optional[Callable[[int], torch.Tensor]] = None   # injected permutations (parity tests)
     seed: int = 304
     precision: str = "fp32"                # "fp32" exact SIMT sweep | "bf16" tcgen05 sweep (bank / large problems)
+    contrast_norm_bound: float = 1.0       # bound of the contrast rows' L2 norm (tensor path stabiliser; 1 = normalised)
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -58,6 +59,16 @@ class ContrastWorkspace:
         ss = _abi.SweepSizes()
         _abi.check(lib.pcl_sweep_sizes(C.byref(sw), C.byref(ss)), "pcl_sweep_sizes")
         self.sweep_sizes = ss
+        n_partial, n_dpartial = ss.partial_f32, ss.dpartial_f32
+        self.tc_ok = D == 256
+        if self.tc_ok:                       # the tensor sweep uses its own split count: size for the larger of the two
+            td = _abi.TcDesc()
+            td.a_rows, td.D, td.mode = ms, D, mode
+            td.bank_K, td.bank_R = bank_K, bank_M0 + bank_M1
+            td.temperature, td.base_temperature = 1.0, 1.0
+            ts = _abi.SweepSizes()
+            _abi.check(lib.pcl_tc_sizes(C.byref(td), C.byref(ts)), "pcl_tc_sizes")
+            n_partial, n_dpartial = max(n_partial, ts.partial_f32), max(n_dpartial, ts.dpartial_f32)
         i32 = dict(dtype=torch.int32, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         self.keys = torch.empty(sizes.keys_u16, dtype=torch.int16, device=device)
@@ -69,9 +80,10 @@ class ContrastWorkspace:
         self.anchors_bf16 = torch.empty((-(-ms // 128) * 128, D), dtype=torch.bfloat16, device=device)
         self.inv_norm = torch.empty(ms, **f32)
         self.norm_max = torch.zeros(1, **f32)
-        self.partials = torch.empty(5 * ss.partial_f32, **f32)
+        self.partials = torch.empty(5 * n_partial, **f32)
         self.rowstats = torch.empty(6 * ss.rowstat_f32, **f32)
-        self.dpartials = torch.empty(ss.dpartial_f32, **f32)
+        self.dpartials = torch.empty(n_dpartial, **f32)
+        self.row_m2 = torch.empty(-(-ms // 128) * 128 + 512, **f32)
         self.dA = torch.empty((ms, D), **f32)
         self.loss = torch.zeros(1, **f32)
         self.ranks = torch.zeros(ms, **i32)
@@ -81,7 +93,7 @@ class ContrastWorkspace:
         d.g = geom
         d.mode, d.bank_K, d.bank_M0, d.bank_M1 = mode, bank_K, bank_M0, bank_M1
         for name in ("keys", "chunk_pref", "counts", "plan", "anchor_meta", "anchors_f32", "anchors_bf16", "inv_norm",
-                     "norm_max", "partials", "rowstats", "dpartials", "dA", "loss"):
+                     "norm_max", "partials", "rowstats", "dpartials", "dA", "loss", "row_m2"):
             setattr(d, name, getattr(self, name).data_ptr())
         self.desc = d
 
@@ -118,7 +130,7 @@ _step_counter = [0]
 
 class _PixelContrastFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, embed, labels, seg, predict, segq, pixq, opts: ContrastOptions):
+    def forward(ctx, embed, labels, seg, predict, segq, pixq, shadow, opts: ContrastOptions):
         lib = _abi.load()
         _require_cuda(embed, "embed")
         device = embed.device
@@ -165,6 +177,27 @@ class _PixelContrastFn(torch.autograd.Function):
         d.temperature, d.base_temperature = opts.temperature, opts.base_temperature
         d.nan_safe = int(opts.nan_safe)
         d.normalize = int(opts.normalize)
+        d.precision = 0
+        shadow_c = None
+        if opts.precision == "bf16":
+            if not ws.tc_ok:
+                raise _abi.PclError("precision='bf16' (tcgen05 sweep) needs proj_dim == 256")
+            d.precision = 1
+            d.contrast_norm_bound = float(opts.contrast_norm_bound)
+            if mode == 1:
+                if pixq_c is None or M0 != M1:
+                    raise _abi.PclError("the tensor sweep reads the bank as (segment_queue, pixel_queue) of equal size")
+                if shadow is None:           # no maintained shadow: rebuild it from the fp32 queues (one extra pass)
+                    from .bank import shadow_rows
+                    shadow = torch.empty((shadow_rows(bank_K, M0), D), dtype=torch.bfloat16, device=device)
+                    with torch.cuda.device(device):
+                        _abi.check(lib.pcl_bank_shadow_rebuild(segq_c.data_ptr(), pixq_c.data_ptr(), bank_K, M0, D,
+                                                               shadow.data_ptr(), _stream_ptr(device)),
+                                   "pcl_bank_shadow_rebuild")
+                shadow_c = shadow
+                d.shadow_bf16, d.shadow_rows = shadow_c.data_ptr(), shadow_c.shape[0]
+        elif opts.precision != "fp32":
+            raise _abi.PclError(f"unknown precision {opts.precision!r}")
         _step_counter[0] += 1
         d.seed = (int(opts.seed) * 0x9E3779B97F4A7C15 + _step_counter[0]) & 0xFFFFFFFFFFFFFFFF
         with torch.cuda.device(device):
@@ -187,7 +220,7 @@ class _PixelContrastFn(torch.autograd.Function):
             _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
         ctx.ws = ws
         ctx.embed_shape = tuple(embed_c.shape)
-        ctx.keep = (embed_c, labels_c, seg_c, pred_c, segq_c, pixq_c)     # keep inputs alive until kernels ran
+        ctx.keep = (embed_c, labels_c, seg_c, pred_c, segq_c, pixq_c, shadow_c)   # keep inputs alive until kernels ran
         if embed.requires_grad and torch.is_grad_enabled():
             ws.busy = True
         return ws.loss[0].clone()
@@ -206,17 +239,19 @@ class _PixelContrastFn(torch.autograd.Function):
             _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
         ws.busy = False
         ctx.keep = None
-        return grad, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None
 
 
 def pixel_contrast_loss(embed: torch.Tensor, labels: torch.Tensor, *, seg: Optional[torch.Tensor] = None,
                         predict: Optional[torch.Tensor] = None, segment_queue: Optional[torch.Tensor] = None,
-                        pixel_queue: Optional[torch.Tensor] = None, options: Optional[ContrastOptions] = None):
+                        pixel_queue: Optional[torch.Tensor] = None, bank_shadow: Optional[torch.Tensor] = None,
+                        options: Optional[ContrastOptions] = None):
     """Pixel-contrast loss (lib/loss/loss_contrast.py:130-147 / loss_contrast_mem.py:154-171) on the GPU engine.
 
     embed (B,D,h,w) fp32 CUDA; labels (B,Himg,Wimg) int64; either seg (B,K,h,w) logits (argmax fused) or
     predict (B,h,w) int64; optional bank queues (K,M,D).  Returns a 0-dim tensor with autograd to embed."""
-    return _PixelContrastFn.apply(embed, labels, seg, predict, segment_queue, pixel_queue, options or ContrastOptions())
+    return _PixelContrastFn.apply(embed, labels, seg, predict, segment_queue, pixel_queue, bank_shadow,
+                                  options or ContrastOptions())
 
 
 def last_workspace(embed_device: torch.device):
@@ -382,7 +417,7 @@ def infonce_tc_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contr
                               base_temperature, nan_safe, sorted_cols, norm_bound)
     ss = _abi.SweepSizes()
     _abi.check(lib.pcl_tc_sizes(C.byref(d), C.byref(ss)), "pcl_tc_sizes")
-    row_m2 = torch.empty(a_pad, dtype=torch.float32, device=dev)
+    row_m2 = torch.empty(a_pad + 512, dtype=torch.float32, device=dev)
     partials = torch.empty(5 * ss.partial_f32, dtype=torch.float32, device=dev)
     rowstats = torch.empty(6 * ss.rowstat_f32, dtype=torch.float32, device=dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -404,7 +439,7 @@ def tc_dump_logits(anchors: torch.Tensor, contrast_bf16: Optional[torch.Tensor],
     ncols = n_cols if contrast_bf16 is not None else A
     ld = -(-ncols // 256) * 256
     dump = torch.zeros((a_pad, ld), dtype=torch.float32, device=dev)
-    row_m2 = torch.empty(a_pad, dtype=torch.float32, device=dev)
+    row_m2 = torch.empty(a_pad + 512, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _abi.check(lib.pcl_tc_dump_logits(C.byref(d), row_m2.data_ptr(), dump.data_ptr(), _stream_ptr(dev)),
                    "pcl_tc_dump_logits")

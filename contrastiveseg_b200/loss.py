@@ -53,7 +53,8 @@ class PixelContrastLoss(nn.Module):
                                nan_safe=self.nan_safe, rng=self.rng, perm_fn=self.perm_fn, seed=self.seed,
                                precision=self.precision)
 
-    def forward(self, feats, labels=None, predict=None, queue=None, seg=None, normalize: bool = False):
+    def forward(self, feats, labels=None, predict=None, queue=None, seg=None, normalize: bool = False,
+                bank_shadow=None):
         """feats (B,D,h,w); labels (B,Himg,Wimg) int64; predict (B,h,w) int64 (or pass the logits as ``seg`` and
         the argmax is fused into the first kernel); queue: None, a (K,R,D) tensor (the reference's
         cat(segment_queue, pixel_queue, dim=1)) or the pair (segment_queue, pixel_queue) read in place."""
@@ -69,7 +70,7 @@ class PixelContrastLoss(nn.Module):
         elif segq is not None and opts.num_classes is None:
             opts.num_classes = segq.shape[0]
         return pixel_contrast_loss(feats, labels, seg=seg, predict=predict if seg is None else None,
-                                   segment_queue=segq, pixel_queue=pixq, options=opts)
+                                   segment_queue=segq, pixel_queue=pixq, bank_shadow=bank_shadow, options=opts)
 
 
 class _ZeroWithGraph(torch.autograd.Function):
@@ -129,7 +130,8 @@ class ContrastCELoss(nn.Module):
         elif with_embed is not True and self.skip_warmup_contrast:
             loss_contrast = _ZeroWithGraph.apply(embedding)
         else:
-            loss_contrast = self.contrast_criterion(embedding, target, seg=seg, queue=queue)
+            loss_contrast = self.contrast_criterion(embedding, target, seg=seg, queue=queue,
+                                                    bank_shadow=preds.get("bank_shadow"))
         if with_embed is True:
             return loss + self.loss_weight * loss_contrast
         return loss + 0 * loss_contrast      # keeps the projection head in the DDP graph (loss_contrast.py:189)

@@ -228,7 +228,8 @@ typedef struct {
 
 int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out);
 int pcl_to_bf16(const float* src, void* dst_bf16, int64_t n_real, int64_t n_total, void* stream);
-/* row_m2: a_rows rounded up to 128 floats of scratch (per-row stabiliser, kept for the backward). */
+/* row_m2: (a_rows rounded up to 128) + 512 floats of scratch (per-row stabiliser, kept for the backward,
+ * followed by the per-label column bounds of a sorted explicit contrast set). */
 int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
                        void* stream);
 /* Backward on the tensor cores: dA (a_rows, 256) fp32 = d loss / d anchors * (*grad_loss or 1).  row_m2 and rowstats
@@ -263,6 +264,12 @@ typedef struct {
   uint16_t* keys; int32_t* chunk_pref; int32_t* counts; int32_t* plan; int32_t* anchor_meta;
   float* anchors_f32; void* anchors_bf16; float* inv_norm; float* norm_max;
   float* partials; float* rowstats; float* dpartials; float* dA;
+  /* sweep selection: 0 = exact fp32 SIMT sweep (any D % 32 == 0, D <= 256); 1 = bf16 tcgen05 sweep (D == 256).
+   * The tensor path reads the bank through its bf16 shadow (pcl_bank_apply / pcl_bank_shadow_rebuild). */
+  int32_t precision;
+  const void* shadow_bf16; int64_t shadow_rows;
+  float contrast_norm_bound;
+  float* row_m2;                 /* (max_samples rounded up to 128) + 512 floats (tensor path only)  */
   /* outputs */
   float* loss;                   /* 1 float                                                          */
   float* grad_embed;             /* (B,D,h,w), written by pcl_step_backward                          */

@@ -1,0 +1,79 @@
+"""world_size-2 gloo tests (CPU) of the bank merge plumbing: one all_gather of the fixed-size enqueue packet,
+rank-major order, identical result on every rank; world 1 is a pass-through.  The packet application itself is
+a CUDA kernel (GPU test: tests/test_gpu_parity.py + tools/dist_bank_check.py)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from contrastiveseg_b200.bank import gather_packets
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 37
+    packet = torch.arange(n, dtype=torch.float32) + 1000.0 * rank
+    gathered = gather_packets(packet)
+    assert gathered.shape == (world, n)
+    for r in range(world):
+        assert torch.equal(gathered[r], torch.arange(n, dtype=torch.float32) + 1000.0 * r)
+    torch.save(gathered, os.path.join(out_dir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_packets_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    assert torch.equal(g0, g1)                      # every rank applies the same packets in the same order
+
+
+def test_gather_packets_without_process_group_is_passthrough():
+    p = torch.arange(5, dtype=torch.float32)
+    g = gather_packets(p)
+    assert g.shape == (1, 5) and torch.equal(g[0], p)
+
+
+def _merge_worker(rank, world, port, out_dir):
+    """Oracle-level check of the merge semantics: each rank owns different images; applying the gathered packets in
+    rank order equals one process enqueueing rank 0's images then rank 1's (the documented Q9 deviation)."""
+    from oracle import ref_port as P
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, D, M, F = 5, 16, 6, 3
+    data = make_contrast_batch(B=1, D=D, h=12, w=12, num_classes=K, img_stride=2, block=6, seed=100 + rank)
+    # the "packet" here is the raw (keys, labels) pair: gather it and replay sequentially on every rank
+    flat = torch.cat((data["embed"].reshape(-1), data["target"].reshape(-1).float()))
+    allp = gather_packets(flat)
+    bank = make_bank(K, M, D, 7)
+    bufs = [bank[k] for k in ("segment_queue", "segment_queue_ptr", "pixel_queue", "pixel_queue_ptr")]
+    ne = data["embed"].numel()
+    for r in range(world):
+        keys = allp[r, :ne].reshape(data["embed"].shape)
+        labels = allp[r, ne:].reshape(data["target"].shape).long()
+        P.dequeue_and_enqueue(keys, labels, *bufs, network_stride=2, memory_size=M, pixel_update_freq=F,
+                              perm_fn=lambda n: torch.arange(n))
+    torch.save([b.clone() for b in bufs], os.path.join(out_dir, f"b{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_ordered_merge_gives_identical_banks(tmp_path):
+    port = _free_port()
+    mp.spawn(_merge_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    b0, b1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    for x, y in zip(b0, b1):
+        assert torch.equal(x, y)
