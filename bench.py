@@ -106,7 +106,8 @@ def engine_configer(cfg, bank=False):
          "contrast": {"temperature": cfg["T"], "base_temperature": cfg["bT"], "max_samples": cfg["max_samples"],
                       "max_views": cfg["max_views"], "loss_weight": 0.1, "use_rmi": False, "rng": "device"}}
     if bank:
-        d["contrast"].update(with_memory=True, memory_size=cfg["M"], pixel_update_freq=cfg["F"])
+        # bank sweeps run on the tcgen05 path (bf16 operands through the bank shadow)
+        d["contrast"].update(with_memory=True, memory_size=cfg["M"], pixel_update_freq=cfg["F"], precision="bf16")
     return cs.Configer(d)
 
 
@@ -257,15 +258,16 @@ def run_engine(args, cfg, bank, rank, world, dev):
     crit = cs.PixelContrastLoss(cfgr)
     mbank = None
     if bank:
-        mbank = cs.MemoryBank(cfg["K"], cfg["M"], cfg["D"]).to(dev)
+        mbank = cs.MemoryBank(cfg["K"], cfg["M"], cfg["D"], with_shadow=True).to(dev)
         mbank.segment_queue.copy_(inp["segment_queue"]); mbank.pixel_queue.copy_(inp["pixel_queue"])
+        mbank.sync_shadow()
     embed = inp["embed"].clone().requires_grad_(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if cfg["B"] < 4 else None
 
     def step(e, tgt, seg):
         e.grad = None
         queue = (mbank.segment_queue, mbank.pixel_queue) if bank else None
-        loss = crit(e, tgt, seg=seg, queue=queue)
+        loss = crit(e, tgt, seg=seg, queue=queue, bank_shadow=mbank.shadow if bank else None)
         if bank:
             mbank.enqueue(e.detach(), tgt, network_stride=cfg["net_stride"], pixel_update_freq=cfg["F"])
         loss.backward()
@@ -369,8 +371,8 @@ def run_engine(args, cfg, bank, rank, world, dev):
     launches_per_step = 10 + (4 if bank else 0)
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, bank), "clocks": sampler.summary(),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if bank else "f32",
+            "data": "synthetic", "config": workload_config(cfg, bank), "clocks": sampler.summary(),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,

@@ -35,13 +35,15 @@ struct TcArgs {
   int a_rows, a_pad, mode, K, R, sorted;
   int64_t n_cols;
   float k1;                    // log2(e) / T
-  int splits;
+  int splits;                  // 2-D grid: column splits per row tile
+  int slots;                   // partial slots per row (stride of the partial arrays)
+  int persistent;              // 1: grid = CTAs, each walks a contiguous range of (row tile, column tile) pairs
 };
 
 struct SmemLayout {
   uint8_t a[NKB * A_KB_BYTES];
   uint8_t b[STAGES * B_STAGE_BYTES];
-  uint64_t full[STAGES], empty[STAGES], a_full, tmem_full[2], tmem_empty[2];
+  uint64_t full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
   float comb[3][2][BM];
 };
@@ -52,6 +54,52 @@ __device__ __forceinline__ int col_label(const TcArgs& a, int64_t n) {
 
 enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2 };   // DUMP: raw logit tiles to global (descriptor self-test)
 
+// A segment = consecutive column tiles [ct0, ct1) of one row tile, whose partial row sums go to slot `slot`.
+struct Seg { int r, ct0, ct1, slot; };
+
+// Every role (TMA / MMA / epilogue) walks the same deterministic list of segments.
+struct SegWalker {
+  long long p, p_end, P;
+  int T, G, k;
+  bool persistent, pending;
+  Seg single;
+  __device__ __forceinline__ bool next(Seg& s) {
+    if (!persistent) {
+      if (!pending) return false;
+      pending = false;
+      s = single;
+      return true;
+    }
+    if (p >= p_end) return false;
+    const int r = (int)(p / T);
+    const int ct0 = (int)(p - (long long)r * T);
+    const long long take = min((long long)(T - ct0), p_end - p);
+    // ordinal of this CTA among the CTAs that touch row tile r (CTA j owns pairs [j*P/G, (j+1)*P/G))
+    const long long rT = (long long)r * T;
+    long long kf = (rT * G) / P;
+    while (((kf + 1) * P) / G <= rT) ++kf;
+    while (kf > 0 && (kf * P) / G > rT) --kf;
+    s.r = r; s.ct0 = ct0; s.ct1 = ct0 + (int)take; s.slot = (int)(k - kf);
+    p += take;
+    return true;
+  }
+};
+
+// 2^x for x <= ~0 on the FMA/ALU pipes (Cody-Waite + degree-5 polynomial, max rel. error 2.3e-7): takes a share of
+// the exponentials off the 16/clk/SM MUFU pipe, which is co-critical with the tensor pipe in this kernel.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);            // f in [-0.5, 0.5]
+  float p = 0.0013266970636323094f;
+  p = fmaf(p, f, 0.009675459936261177f);
+  p = fmaf(p, f, 0.05550742521882057f);
+  p = fmaf(p, f, 0.24022121727466583f);
+  p = fmaf(p, f, 0.6931469440460205f);
+  p = fmaf(p, f, 1.0000001192092896f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a,
@@ -60,46 +108,62 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int A = a.plan ? min(a.plan[PCL_PLAN_A], a.a_rows) : a.a_rows;
-  const int row0 = blockIdx.x * BM;
-  if (row0 >= A) return;
-  const int split = blockIdx.y;
+  if (A <= 0) return;
   const int64_t ncols = a.mode == 0 ? (int64_t)A : a.n_cols;
+  const int T_all = (int)((ncols + BN - 1) / BN);
 
-  // ---- column-tile range of this CTA (identical in every warp) ----
-  int t_lo = 0, t_hi = (int)((ncols + BN - 1) / BN);
-  if (MODE == TC_POS && a.mode == 2 && a.sorted && a.cls_start != nullptr) {
-    // positives of this row tile live in the columns of its label range (contrast labels are sorted)
-    int lo = 0x7fffffff, hi = -1;
-    for (int i = lane; i < BM; i += 32) {
-      const int r = row0 + i;
-      if (r < A) { const int c = a.acls[r]; lo = min(lo, c); hi = max(hi, c); }
-    }
+  // ---- work list of this CTA (identical in every warp) ----
+  SegWalker w0;
+  w0.persistent = a.persistent != 0;
+  w0.pending = false;
+  w0.T = T_all; w0.G = gridDim.x; w0.k = blockIdx.x;
+  if (w0.persistent) {
+    const int R_live = (A + BM - 1) / BM;
+    w0.P = (long long)R_live * T_all;
+    w0.p = ((long long)blockIdx.x * w0.P) / gridDim.x;
+    w0.p_end = ((long long)(blockIdx.x + 1) * w0.P) / gridDim.x;
+    if (w0.p >= w0.p_end) return;
+  } else {
+    const int row0 = blockIdx.x * BM;
+    if (row0 >= A) return;
+    int t_lo = 0, t_hi = T_all;
+    if (MODE == TC_POS && a.mode == 2 && a.sorted && a.cls_start != nullptr) {
+      // positives of this row tile live in the columns of its label range (contrast labels are sorted)
+      int lo = 0x7fffffff, hi = -1;
+      for (int i = lane; i < BM; i += 32) {
+        const int r = row0 + i;
+        if (r < A) { const int c = a.acls[r]; lo = min(lo, c); hi = max(hi, c); }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      }
+      lo = max(0, min(lo, PCL_MAX_CLASSES - 1));
+      hi = max(0, min(hi, PCL_MAX_CLASSES - 1));
+      t_lo = a.cls_start[lo] / BN;
+      t_hi = (a.cls_start[hi + 1] + BN - 1) / BN;
+      if (t_hi < t_lo) t_hi = t_lo;
     }
-    lo = max(0, min(lo, PCL_MAX_CLASSES - 1));
-    hi = max(0, min(hi, PCL_MAX_CLASSES - 1));
-    t_lo = a.cls_start[lo] / BN;
-    t_hi = (a.cls_start[hi + 1] + BN - 1) / BN;
-    if (t_hi < t_lo) t_hi = t_lo;
-  }
-  if (MODE == TC_POS && a.mode == 1) {
-    const int last = min(A - 1, row0 + BM - 1);
-    int rk_f = class_rank(a.acls[row0], a.K), rk_l = class_rank(a.acls[last], a.K);
-    if (rk_l > a.K - 2) rk_l = a.K - 2;
-    if (rk_f > rk_l) { t_lo = 0; t_hi = 0; }
-    else {
-      t_lo = (int)(((int64_t)rk_f * a.R) / BN);
-      t_hi = (int)((((int64_t)(rk_l + 1) * a.R) + BN - 1) / BN);
+    if (MODE == TC_POS && a.mode == 1) {
+      const int last = min(A - 1, row0 + BM - 1);
+      int rk_f = class_rank(a.acls[row0], a.K), rk_l = class_rank(a.acls[last], a.K);
+      if (rk_l > a.K - 2) rk_l = a.K - 2;
+      if (rk_f > rk_l) { t_lo = 0; t_hi = 0; }
+      else {
+        t_lo = (int)(((int64_t)rk_f * a.R) / BN);
+        t_hi = (int)((((int64_t)(rk_l + 1) * a.R) + BN - 1) / BN);
+      }
     }
+    const int span = t_hi - t_lo;
+    const int per = (span + a.splits - 1) / a.splits;
+    const int my_lo = t_lo + blockIdx.y * per;
+    const int my_hi = min(t_hi, my_lo + per);
+    w0.single.r = blockIdx.x; w0.single.ct0 = my_lo; w0.single.ct1 = my_hi > my_lo ? my_hi : my_lo;
+    w0.single.slot = blockIdx.y;
+    w0.pending = true;
+    w0.p = w0.p_end = w0.P = 0;
   }
-  const int span = t_hi - t_lo;
-  const int per = (span + a.splits - 1) / a.splits;
-  const int my_lo = t_lo + split * per;
-  const int my_hi = min(t_hi, my_lo + per);
-  const int ntiles = my_hi > my_lo ? my_hi - my_lo : 0;
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -107,6 +171,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&sm.full[s], 1); ptx::mbar_init(&sm.empty[s], 1); }
     ptx::mbar_init(&sm.a_full, 1);
+    ptx::mbar_init(&sm.a_empty, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.tmem_full[i], 1); ptx::mbar_init(&sm.tmem_empty[i], EPI_THREADS / 32); }
     ptx::fence_barrier_init();
   }
@@ -118,46 +183,61 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0 && ntiles > 0) {
-      ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * A_KB_BYTES);
-      for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sm.a + kb * A_KB_BYTES, &tmA, &sm.a_full, kb * BK, row0);
+    if (lane == 0) {
+      SegWalker w = w0;
+      Seg sg;
       uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < ntiles; ++it) {
-        const int ct = my_lo + it;
-        for (int kb = 0; kb < NKB; ++kb) {
-          ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&sm.full[stage], B_STAGE_BYTES);
-          ptx::tma_load_2d(sm.b + stage * B_STAGE_BYTES, &tmB, &sm.full[stage], kb * BK, ct * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      int seg_idx = 0;
+      while (w.next(sg)) {
+        if (sg.ct1 <= sg.ct0) continue;
+        if (seg_idx > 0) ptx::mbar_wait(&sm.a_empty, (seg_idx - 1) & 1);     // previous segment's MMAs retired
+        ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * A_KB_BYTES);
+        for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sm.a + kb * A_KB_BYTES, &tmA, &sm.a_full, kb * BK, sg.r * BM);
+        for (int ct = sg.ct0; ct < sg.ct1; ++ct) {
+          for (int kb = 0; kb < NKB; ++kb) {
+            ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&sm.full[stage], B_STAGE_BYTES);
+            ptx::tma_load_2d(sm.b + stage * B_STAGE_BYTES, &tmB, &sm.full[stage], kb * BK, ct * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
+        ++seg_idx;
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0 && ntiles > 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
-      ptx::mbar_wait(&sm.a_full, 0);
-      ptx::tc_fence_after();
       const uint32_t a_base = ptx::smem_u32(sm.a), b_base = ptx::smem_u32(sm.b);
+      SegWalker w = w0;
+      Seg sg;
       uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < ntiles; ++it) {
-        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
+      int seg_idx = 0, it = 0;
+      while (w.next(sg)) {
+        if (sg.ct1 <= sg.ct0) continue;
+        ptx::mbar_wait(&sm.a_full, seg_idx & 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < NKB; ++kb) {
-          ptx::mbar_wait(&sm.full[stage], phase);
+        for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
+          const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+          ptx::mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < NKB; ++kb) {
+            ptx::mbar_wait(&sm.full[stage], phase);
+            ptx::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
-            const uint64_t db = ptx::make_desc_kmajor_sw128(b_base + stage * B_STAGE_BYTES + k * 32);
-            ptx::mma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
+              const uint64_t db = ptx::make_desc_kmajor_sw128(b_base + stage * B_STAGE_BYTES + k * 32);
+              ptx::mma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::mma_commit(&sm.empty[stage]);          // smem slot free once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&sm.empty[stage]);          // smem slot free once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::mma_commit(&sm.tmem_full[acc]);          // accumulator ready for the epilogue
         }
-        ptx::mma_commit(&sm.tmem_full[acc]);          // accumulator ready for the epilogue
+        ptx::mma_commit(&sm.a_empty);                   // anchor tile may be overwritten
+        ++seg_idx;
       }
     }
   } else {
@@ -165,105 +245,113 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                 // which 128 columns of the 256-column tile
     const int r_in = quarter * 32 + lane;
-    const int row = row0 + r_in;
-    const bool valid = row < A;
-    const int rcls = valid ? a.acls[row] : -1;
-    const int rdiag = valid ? (a.mode == 0 ? row : (a.diag ? a.diag[row] : -1)) : -1;
-    const float m2 = valid ? a.row_m2[row] : 0.f;
-    float neg_i = 1.f;
-    if (MODE == TC_POS) neg_i = valid ? rowstats[a.a_rows + row] : 1.f;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;       // NEG: 4 partial sums; POS: possum2, s, cnt
-    for (int it = 0; it < ntiles; ++it) {
-      const int ct = my_lo + it;
-      const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
-      const int64_t col0 = (int64_t)ct * BN + half * (BN / 2);
-      // tile class: all 128 columns valid and of one class (sorted contrast set) -> no per-element test
-      bool uniform = false;
-      int ulab = -1;
-      if (a.sorted && col0 + BN / 2 <= ncols) {
-        ulab = col_label(a, col0);
-        uniform = ulab == col_label(a, col0 + BN / 2 - 1);
-      }
-      ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * BN + half * (BN / 2);
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
-        ptx::tmem_ld_wait();
-        const int64_t cb = col0 + ch * 32;
-        if (MODE == TC_DUMP) {
-          // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * BN
-          const int64_t ld = (int64_t)((ncols + BN - 1) / BN) * BN;
+    SegWalker w = w0;
+    Seg sg;
+    int it = 0;
+    while (w.next(sg)) {
+      const int row = sg.r * BM + r_in;
+      const bool valid = row < A;
+      const int rcls = valid ? a.acls[row] : -1;
+      const int rdiag = valid ? (a.mode == 0 ? row : (a.diag ? a.diag[row] : -1)) : -1;
+      const float m2 = valid ? a.row_m2[row] : 0.f;
+      float neg_i = 1.f;
+      if (MODE == TC_POS) neg_i = valid ? rowstats[a.a_rows + row] : 1.f;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
+      for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
+        const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
+        const int64_t col0 = (int64_t)ct * BN + half * (BN / 2);
+        // tile class: all 128 columns valid and of one class (sorted contrast set) -> no per-element test
+        bool uniform = false;
+        int ulab = -1;
+        if (a.sorted && col0 + BN / 2 <= ncols) {
+          ulab = col_label(a, col0);
+          uniform = ulab == col_label(a, col0 + BN / 2 - 1);
+        }
+        ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * BN + half * (BN / 2);
+        uint32_t vbuf[2][32];
+        ptx::tmem_ld_32x32b_x32(t_row, vbuf[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) partials[(int64_t)row * ld + cb + j] = __uint_as_float(v[j]);
-        } else if (MODE == TC_NEG) {
-          if (uniform) {
-            if (valid && ulab != rcls) {
+        for (int ch = 0; ch < 4; ++ch) {
+          ptx::tmem_ld_wait();
+          if (ch < 3) ptx::tmem_ld_32x32b_x32(t_row + (ch + 1) * 32, vbuf[(ch + 1) & 1]);   // prefetch the next chunk
+          uint32_t(&v)[32] = vbuf[ch & 1];
+          const int64_t cb = col0 + ch * 32;
+          if (MODE == TC_DUMP) {
+            // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * BN
+            const int64_t ld = (int64_t)T_all * BN;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), a.k1, -m2));
-                acc1 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), a.k1, -m2));
-                acc2 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), a.k1, -m2));
-                acc3 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));
+            for (int j = 0; j < 32; ++j) partials[(int64_t)row * ld + cb + j] = __uint_as_float(v[j]);
+          } else if (MODE == TC_NEG) {
+            if (uniform) {
+              if (valid && ulab != rcls) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), a.k1, -m2));
+                  acc1 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), a.k1, -m2));
+                  acc2 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), a.k1, -m2));
+                  acc3 += exp2_poly(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));      // 1 in 4 off the MUFU pipe
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t col = cb + j;
+                if (col < ncols) {
+                  const int lab = col_label(a, col);
+                  if (valid && lab != rcls) acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+                }
               }
             }
           } else {
+            const bool all_pos = uniform && ulab == rcls && !(rdiag >= cb && rdiag < cb + 32);
+            if (uniform && ulab != rcls) {
+              // no positives of this row in the tile
+            } else if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = cb + j;
-              if (col < ncols) {
-                const int lab = col_label(a, col);
-                if (valid && lab != rcls) acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
-              }
-            }
-          }
-        } else {
-          const bool all_pos = uniform && ulab == rcls && !(rdiag >= cb && rdiag < cb + 32);
-          if (uniform && ulab != rcls) {
-            // no positives of this row in the tile
-          } else if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = cb + j;
-              bool pos = all_pos;
-              if (!all_pos) pos = col < ncols && col_label(a, col) == rcls && col != (int64_t)rdiag;
-              if (pos) {
-                const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
-                const float t = ptx::ex2_approx(x) + neg_i;
-                acc0 += x - ptx::lg2_approx(t);
-                acc1 += ptx::rcp_approx(t);
-                acc2 += 1.f;
+              for (int j = 0; j < 32; ++j) {
+                const int64_t col = cb + j;
+                bool pos = all_pos;
+                if (!all_pos) pos = col < ncols && col_label(a, col) == rcls && col != (int64_t)rdiag;
+                if (pos) {
+                  const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
+                  const float t = ptx::ex2_approx(x) + neg_i;
+                  acc0 += x - ptx::lg2_approx(t);
+                  acc1 += ptx::rcp_approx(t);
+                  acc2 += 1.f;
+                }
               }
             }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm.tmem_empty[accb]);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&sm.tmem_empty[accb]);
-    }
-    // ---- combine the two column halves, write the partials of this split ----
-    if (MODE == TC_DUMP) {
-    } else if (MODE == TC_NEG) {
-      sm.comb[0][half][r_in] = (acc0 + acc1) + (acc2 + acc3);
-    } else {
-      sm.comb[0][half][r_in] = acc0 * LN2;
-      sm.comb[1][half][r_in] = acc1;
-      sm.comb[2][half][r_in] = acc2;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-    if (half == 0 && MODE != TC_DUMP) {
-      const int64_t o = (int64_t)split * a.a_pad + row;
-      const int64_t stride = (int64_t)a.splits * a.a_pad;
-      if (MODE == TC_NEG) {
-        partials[0 * stride + o] = m2 * LN2;                               // stabiliser in natural-log units
-        partials[1 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
-      } else {
-        partials[2 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
-        partials[3 * stride + o] = sm.comb[1][0][r_in] + sm.comb[1][1][r_in];
-        partials[4 * stride + o] = sm.comb[2][0][r_in] + sm.comb[2][1][r_in];
+      // ---- combine the two column halves, write the partials of this segment ----
+      if (MODE != TC_DUMP) {
+        if (MODE == TC_NEG) {
+          sm.comb[0][half][r_in] = (acc0 + acc1) + (acc2 + acc3);
+        } else {
+          sm.comb[0][half][r_in] = acc0 * LN2;
+          sm.comb[1][half][r_in] = acc1;
+          sm.comb[2][half][r_in] = acc2;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (half == 0) {
+          const int64_t o = (int64_t)sg.slot * a.a_pad + row;
+          const int64_t stride = (int64_t)a.slots * a.a_pad;
+          if (MODE == TC_NEG) {
+            partials[0 * stride + o] = m2 * LN2;                             // stabiliser in natural-log units
+            partials[1 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+          } else {
+            partials[2 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+            partials[3 * stride + o] = sm.comb[1][0][r_in] + sm.comb[1][1][r_in];
+            partials[4 * stride + o] = sm.comb[2][0][r_in] + sm.comb[2][1][r_in];
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");       // comb reusable by the next segment
       }
     }
   }
@@ -272,6 +360,16 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// slots that no CTA writes must read as "nothing seen": m = -inf, sums = 0
+__global__ void k_fill_partials(float* __restrict__ partials, int64_t n_slot_rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slot_rows) {
+    partials[i] = -CUDART_INF_F;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) partials[k * n_slot_rows + i] = 0.f;
+  }
 }
 
 // =====================================================================================================
@@ -609,8 +707,22 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t b
 struct TcPlan {
   tc::TcArgs a;
   SweepArgs sw;         // for the shared combine / finalize kernels
-  int row_tiles;
+  int row_tiles, grid_persistent, splits_bwd;
 };
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else {
+      (void)cudaGetLastError();
+      return 148;                 // sizing on a host without a device (B200)
+    }
+  }
+  return n;
+}
 
 static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   if (!d || !d->anchor_cls || d->a_rows <= 0) return PCL_ERR_ARG;
@@ -635,17 +747,33 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
     return PCL_ERR_ARG;
   }
   a.k1 = tc::LOG2E / d->temperature;
+  const int sms = num_sms();
   const int col_tiles = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, tc::BN);
-  int splits = 148 / p->row_tiles;
+  int splits = sms / p->row_tiles;
   if (splits < 1) splits = 1;
   if (splits > col_tiles) splits = col_tiles;
   a.splits = splits;
+  // persistent NEG sweep: G CTAs walk contiguous ranges of the row_tiles x col_tiles pair list
+  const long long P = (long long)p->row_tiles * col_tiles;
+  p->grid_persistent = (int)(P < sms ? P : sms);
+  const long long U = P / p->grid_persistent;                      // pairs per CTA (floor, >= 1)
+  long long slots_neg = d->plan ? (long long)p->grid_persistent : (col_tiles / U + 2);   // live A unknown on the host
+  if (slots_neg > p->grid_persistent) slots_neg = p->grid_persistent;
+  if (slots_neg > col_tiles) slots_neg = col_tiles;
+  if (slots_neg < 1) slots_neg = 1;
+  a.slots = (int)(slots_neg > splits ? slots_neg : splits);
+  // backward sweeps 128-column tiles on a 2-D grid
+  const int col_tiles_b = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, 128);
+  int sb = sms / p->row_tiles;
+  if (sb < 1) sb = 1;
+  if (sb > col_tiles_b) sb = col_tiles_b;
+  p->splits_bwd = sb;
   SweepArgs& s = p->sw;
   s.acls = d->anchor_cls; s.diag = d->diag_col; s.plan = d->plan;
   s.a_rows = d->a_rows; s.D = tc::DDIM; s.mode = d->mode;
   s.n_cols = a.n_cols; s.tail_count = tail;
   s.inv_T = 1.f / d->temperature; s.T_over_bT = d->temperature / d->base_temperature;
-  s.nan_safe = d->nan_safe; s.row_tiles = p->row_tiles; s.splits = splits; s.a_pad = a.a_pad; s.col_tiles = col_tiles;
+  s.nan_safe = d->nan_safe; s.row_tiles = p->row_tiles; s.splits = a.slots; s.a_pad = a.a_pad; s.col_tiles = col_tiles;
   return PCL_OK;
 }
 
@@ -659,10 +787,10 @@ extern "C" int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out) {
   if (st != PCL_OK || !out) return st != PCL_OK ? st : PCL_ERR_ARG;
   out->n_real_cols = p.a.n_cols;
   out->row_tiles = p.row_tiles;
-  out->splits = p.a.splits;
-  out->partial_f32 = (int64_t)p.a.splits * p.a.a_pad;
+  out->splits = p.a.slots;
+  out->partial_f32 = (int64_t)p.a.slots * p.a.a_pad;
   out->rowstat_f32 = d->a_rows;
-  out->dpartial_f32 = (int64_t)p.a.splits * p.a.a_pad * tc::DDIM;
+  out->dpartial_f32 = (int64_t)p.splits_bwd * p.a.a_pad * tc::DDIM;
   return PCL_OK;
 }
 
@@ -711,9 +839,14 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
     PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid(p.row_tiles, a.splits);
-  tc::k_tc_fwd<tc::TC_NEG><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  const int64_t n_slot_rows = (int64_t)a.slots * a.a_pad;
+  tc::k_fill_partials<<<(unsigned)ceil_div64(n_slot_rows, 256), 256, 0, s>>>(partials, n_slot_rows);
   PCL_LAUNCH_CHECK();
+  dim3 grid(p.row_tiles, a.splits);
+  a.persistent = 1;
+  tc::k_tc_fwd<tc::TC_NEG><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  PCL_LAUNCH_CHECK();
+  a.persistent = 0;
   k_combine_neg<<<ceil_div(d->a_rows, 256), 256, 0, s>>>(p.sw, partials, rowstats);
   PCL_LAUNCH_CHECK();
   tc::k_tc_fwd<tc::TC_POS><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
@@ -765,10 +898,7 @@ extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, con
   ba.rowstats = rowstats;
   ba.rs_scale = d->temperature / d->base_temperature;
   ba.nan_safe = d->nan_safe;
-  // the backward sweeps 128-column tiles: recompute the split count for that tile width
-  const int col_tiles = (int)ceil_div64(ba.t.n_cols > 0 ? ba.t.n_cols : 1, tc::BNB);
-  int splits = ba.t.splits;
-  if (splits > col_tiles) splits = col_tiles;
+  const int splits = p.splits_bwd;       // the backward sweeps 128-column tiles on a 2-D grid
   ba.t.splits = splits;
   p.sw.splits = splits;
   CUtensorMap tmA, tmC;

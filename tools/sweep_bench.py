@@ -39,9 +39,7 @@ for A, N in points:
     K = 19
     a = torch.nn.functional.normalize(torch.randn(A, 256, generator=g), dim=1).to(dev)
     c = torch.nn.functional.normalize(torch.randn(N, 256, generator=g), dim=1).to(dev)
-    ya = torch.sort(torch.randint(0, K, (A,), generator=g)).values.to(dev)
-    ya = (ya + 1) % K            # class-rank order 1..K-1,0 like the engine's sorted anchors
-    ya = ya[torch.argsort(((ya + K - 1) % K), stable=True)]
+    ya = torch.sort(torch.randint(0, K, (A,), generator=g)).values.to(dev)     # class-sorted anchors (like the engine)
     yc = torch.sort(torch.randint(0, K, (N,), generator=g)).values.to(dev)
     c16 = Fn.to_bf16_rows(c, -(-N // 256) * 256)
     diag = torch.arange(A, device=dev) % N
