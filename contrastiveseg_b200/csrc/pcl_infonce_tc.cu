@@ -15,6 +15,7 @@
 #include "pcl_common.cuh"
 #include "pcl_sweep.cuh"
 #include "ptx_sm100.cuh"
+#include <stdlib.h>
 
 namespace pcl {
 namespace tc {
@@ -48,8 +49,8 @@ struct SmemLayout {
   float comb[3][2][BM];
 };
 
-__device__ __forceinline__ int col_label(const TcArgs& a, int64_t n) {
-  return a.ccls ? a.ccls[n] : (a.mode == 1 ? (int)(n / a.R) + 1 : a.acls[n]);
+__device__ __forceinline__ int col_label(const TcArgs& a, int n) {      // columns < 2^31
+  return a.ccls ? a.ccls[n] : (a.mode == 1 ? n / a.R + 1 : a.acls[n]);
 }
 
 enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2 };   // DUMP: raw logit tiles to global (descriptor self-test)
@@ -100,7 +101,35 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int MODE>
+
+// Boundary tiles (a class boundary or the ragged end of the contrast set inside the 32 columns): rare, so they run
+// as compact out-of-line loops over a local copy of the 32 logits instead of bloating the unrolled fast path.
+__device__ __noinline__ float neg_slow(const TcArgs& a, const uint32_t* v, int cb, int ncols, int rcls, float m2) {
+  float acc = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const int col = cb + j;
+    if (col < ncols && col_label(a, col) != rcls) acc += ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+  }
+  return acc;
+}
+
+__device__ __noinline__ void pos_slow(const TcArgs& a, const uint32_t* v, int cb, int ncols, int rcls, int rdiag,
+                                      float m2, float neg_i, float& acc0, float& acc1, float& acc2) {
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const int col = cb + j;
+    if (col < ncols && col != rdiag && col_label(a, col) == rcls) {
+      const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
+      const float t = ptx::ex2_approx(x) + neg_i;
+      acc0 += x - ptx::lg2_approx(t);
+      acc1 += ptx::rcp_approx(t);
+      acc2 += 1.f;
+    }
+  }
+}
+
+template <int MODE, bool POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a,
          float* __restrict__ partials, const float* __restrict__ rowstats) {
@@ -259,7 +288,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
       for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
         const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
-        const int64_t col0 = (int64_t)ct * BN + half * (BN / 2);
+        const int col0 = ct * BN + half * (BN / 2);
         // tile class: all 128 columns valid and of one class (sorted contrast set) -> no per-element test
         bool uniform = false;
         int ulab = -1;
@@ -277,7 +306,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           ptx::tmem_ld_wait();
           if (ch < 3) ptx::tmem_ld_32x32b_x32(t_row + (ch + 1) * 32, vbuf[(ch + 1) & 1]);   // prefetch the next chunk
           uint32_t(&v)[32] = vbuf[ch & 1];
-          const int64_t cb = col0 + ch * 32;
+          const int cb = col0 + ch * 32;
           if (MODE == TC_DUMP) {
             // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * BN
             const int64_t ld = (int64_t)T_all * BN;
@@ -291,36 +320,34 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                   acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), a.k1, -m2));
                   acc1 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), a.k1, -m2));
                   acc2 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), a.k1, -m2));
-                  acc3 += exp2_poly(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));      // 1 in 4 off the MUFU pipe
+                  if (POLY) acc3 += exp2_poly(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));   // 1 in 4 off the MUFU pipe
+                  else      acc3 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));
                 }
               }
-            } else {
+            } else if (valid) {
+              uint32_t tmp[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t col = cb + j;
-                if (col < ncols) {
-                  const int lab = col_label(a, col);
-                  if (valid && lab != rcls) acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
-                }
-              }
+              for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+              acc0 += neg_slow(a, tmp, cb, (int)ncols, rcls, m2);
             }
           } else {
-            const bool all_pos = uniform && ulab == rcls && !(rdiag >= cb && rdiag < cb + 32);
             if (uniform && ulab != rcls) {
               // no positives of this row in the tile
             } else if (valid) {
+              if (uniform && !(rdiag >= cb && rdiag < cb + 32)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t col = cb + j;
-                bool pos = all_pos;
-                if (!all_pos) pos = col < ncols && col_label(a, col) == rcls && col != (int64_t)rdiag;
-                if (pos) {
+                for (int j = 0; j < 32; ++j) {
                   const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
                   const float t = ptx::ex2_approx(x) + neg_i;
                   acc0 += x - ptx::lg2_approx(t);
                   acc1 += ptx::rcp_approx(t);
-                  acc2 += 1.f;
                 }
+                acc2 += 32.f;
+              } else {
+                uint32_t tmp[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+                pos_slow(a, tmp, cb, (int)ncols, rcls, rdiag, m2, neg_i, acc0, acc1, acc2);
               }
             }
           }
@@ -403,6 +430,43 @@ struct TcBwdArgs {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+
+// Gradient-tile elements of boundary tiles / self-contrast (needs per-column statistics): compact out-of-line loop.
+__device__ __noinline__ void bwd_slow(const TcBwdArgs& ba, const uint32_t* v, float* g, int cb, int ncols, int A,
+                                      int rcls, int rdiag, float m2, float neg_i, float cs_i, float cn_i) {
+  const TcArgs& a = ba.t;
+  const float* st = ba.rowstats;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    const int col = cb + j;
+    float gval = 0.f;
+    if (col < ncols) {
+      const int lab = col_label(a, col);
+      const float x = __uint_as_float(v[j]) * a.k1;
+      const float e = ptx::ex2_approx(x - m2);
+      if (lab == rcls) {
+        if (col != rdiag) gval = cn_i * ptx::rcp_approx(e + neg_i);     // -c (1 - e/(e+Neg))
+      } else {
+        gval = cs_i * e;
+      }
+      if (a.mode == 0) {
+        // self-contrast: the column is an anchor too, add G_ji (its statistics, same logit)
+        const float np_j = st[4 * a.a_rows + col];
+        float c_j = ba.rs_scale / ((float)A * np_j);
+        if (ba.nan_safe && !(np_j > 0.f)) c_j = 0.f;
+        const float e2 = ptx::ex2_approx(x - a.row_m2[col]);
+        const float neg_j = st[a.a_rows + col];
+        if (lab == rcls) {
+          if (col != rdiag) gval += -c_j * neg_j * ptx::rcp_approx(e2 + neg_j);
+        } else {
+          gval += c_j * st[3 * a.a_rows + col] * e2;
+        }
+      }
+    }
+    g[j] = gval;
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -522,10 +586,10 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     for (int it = 0; it < ntiles; ++it) {
       const int ct = my_lo + it;
       const uint32_t acc = it & 1, phase = (it >> 1) & 1;
-      const int64_t col0 = (int64_t)ct * BNB + half * 64;
+      const int col0 = ct * BNB + half * 64;
       bool uniform = false;
       int ulab = -1;
-      if (a.sorted && col0 + 64 <= ncols) {
+      if (a.sorted && col0 + 64 <= (int)ncols) {
         ulab = col_label(a, col0);
         uniform = ulab == col_label(a, col0 + 63);
       }
@@ -533,47 +597,30 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BNB + half * 64;
       uint32_t packed[2][16];
+      uint32_t vbuf[2][32];
+      ptx::tmem_ld_32x32b_x32(t_row, vbuf[0]);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
         ptx::tmem_ld_wait();
-        const int64_t cb = col0 + ch * 32;
+        if (ch == 0) ptx::tmem_ld_32x32b_x32(t_row + 32, vbuf[1]);         // prefetch the second chunk
+        uint32_t(&v)[32] = vbuf[ch];
+        const int cb = col0 + ch * 32;
         float gv[32];
-        if (uniform && ulab != rcls) {
+        if (!valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gv[j] = 0.f;
+        } else if (uniform && a.mode != 0 && ulab != rcls) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) gv[j] = cs_i * ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
-        } else {
+        } else if (uniform && a.mode != 0 && !(rdiag >= cb && rdiag < cb + 32)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t col = cb + j;
-            float gval = 0.f;
-            if (valid && col < ncols) {
-              const int lab = uniform ? ulab : col_label(a, col);
-              const float x = __uint_as_float(v[j]) * a.k1;
-              const float e = ptx::ex2_approx(x - m2);
-              if (lab == rcls) {
-                if (col != (int64_t)rdiag) gval = cn_i * ptx::rcp_approx(e + neg_i);     // -c (1 - e/(e+Neg))
-              } else {
-                gval = cs_i * e;
-              }
-              if (a.mode == 0) {
-                // self-contrast: the column is an anchor too, add G_ji (its statistics, same logit)
-                const int cj = (int)col;
-                const float np_j = st[4 * a.a_rows + cj];
-                float c_j = ba.rs_scale / ((float)A * np_j);
-                if (ba.nan_safe && !(np_j > 0.f)) c_j = 0.f;
-                const float e2 = ptx::ex2_approx(x - a.row_m2[cj]);
-                const float neg_j = st[a.a_rows + cj];
-                if (lab == rcls) {
-                  if (col != (int64_t)rdiag) gval += -c_j * neg_j * ptx::rcp_approx(e2 + neg_j);
-                } else {
-                  gval += c_j * st[3 * a.a_rows + cj] * e2;
-                }
-              }
-            }
-            gv[j] = gval;
-          }
+          for (int j = 0; j < 32; ++j)
+            gv[j] = cn_i * ptx::rcp_approx(ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2)) + neg_i);
+        } else {
+          uint32_t tmp[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+          bwd_slow(ba, tmp, gv, cb, (int)ncols, A, rcls, rdiag, m2, neg_i, cs_i, cn_i);
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) packed[ch][j] = pack_bf16x2(gv[2 * j], gv[2 * j + 1]);
@@ -710,6 +757,14 @@ struct TcPlan {
   int row_tiles, grid_persistent, splits_bwd;
 };
 
+// Tuning knobs for profiling runs (env PCL_TC_VARIANT, bit 0: no polynomial exp2, bit 1: 2-D grid NEG sweep,
+// bit 3: NEG sweep only).  Default 0 = the shipped configuration.
+static int tc_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PCL_TC_VARIANT"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -835,21 +890,31 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   const size_t smem = sizeof(tc::SmemLayout) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_NEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_NEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_POS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int64_t n_slot_rows = (int64_t)a.slots * a.a_pad;
   tc::k_fill_partials<<<(unsigned)ceil_div64(n_slot_rows, 256), 256, 0, s>>>(partials, n_slot_rows);
   PCL_LAUNCH_CHECK();
   dim3 grid(p.row_tiles, a.splits);
-  a.persistent = 1;
-  tc::k_tc_fwd<tc::TC_NEG><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  const int variant = tc_variant();
+  if (variant & 2) {                                   // tuning knob: 2-D grid instead of the persistent walk
+    a.persistent = 0;
+    if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    else             tc::k_tc_fwd<tc::TC_NEG, true><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  } else {
+    a.persistent = 1;
+    if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    else             tc::k_tc_fwd<tc::TC_NEG, true><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  }
   PCL_LAUNCH_CHECK();
   a.persistent = 0;
+  if (variant & 8) return PCL_OK;                      // tuning knob: time the NEG sweep alone
   k_combine_neg<<<ceil_div(d->a_rows, 256), 256, 0, s>>>(p.sw, partials, rowstats);
   PCL_LAUNCH_CHECK();
-  tc::k_tc_fwd<tc::TC_POS><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
+  tc::k_tc_fwd<tc::TC_POS, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
   PCL_LAUNCH_CHECK();
   k_finalize<<<1, 1024, 0, s>>>(p.sw, partials, rowstats, loss);
   PCL_LAUNCH_CHECK();
@@ -877,9 +942,9 @@ extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* du
   else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemLayout) + 1024;
-  PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_DUMP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.row_tiles, a.splits);
-  tc::k_tc_fwd<tc::TC_DUMP><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, dump, nullptr);
+  tc::k_tc_fwd<tc::TC_DUMP, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, dump, nullptr);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

@@ -13,6 +13,11 @@ timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; e
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
 timeout 300 python tools/sweep_bench.py > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep exit $?" >> gpurun_out/sweep.err
+if [ "${2:-}" = "variants" ]; then
+  for v in 8 9 10 11; do
+    PCL_TC_VARIANT=$v timeout 120 python tools/sweep_bench.py 16384x65536 65536x131072 1024x190000 >> gpurun_out/sweep_variants.jsonl 2>> gpurun_out/sweep.err
+  done
+fi
 if [ "${1:-}" = "ncutc" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -c 6 -o gpurun_out/tc_prof \
     python tools/sweep_bench.py 16384x65536 > gpurun_out/ncu_tc.log 2>&1
@@ -21,4 +26,4 @@ if [ "${1:-}" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 fi
-cat gpurun_out/tc_dump.log gpurun_out/tc_fwd.log gpurun_out/tc_bwd.log; tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/sweep.jsonl; tail -2 gpurun_out/sweep.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+cat gpurun_out/tc_dump.log gpurun_out/tc_fwd.log gpurun_out/tc_bwd.log; tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/sweep.jsonl; cat gpurun_out/sweep_variants.jsonl 2>/dev/null | cut -c1-200; tail -2 gpurun_out/sweep.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err

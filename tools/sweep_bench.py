@@ -15,8 +15,11 @@ dev = torch.device("cuda:0")
 peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) if os.path.exists(
     os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
 points = [(1024, 190000), (4096, 32768), (16384, 65536), (65536, 131072)]
-if len(sys.argv) > 1:
-    points = [tuple(int(x) for x in p.split("x")) for p in sys.argv[1:]]
+args = [x for x in sys.argv[1:] if "x" in x]
+if args:
+    points = [tuple(int(x) for x in p.split("x")) for p in args]
+variant = int(os.environ.get("PCL_TC_VARIANT", "0"))
+neg_only = bool(variant & 8)
 iters = 5
 
 
@@ -55,9 +58,9 @@ for A, N in points:
         Fn.infonce_tc_backward(state, st)
 
     t_f = timed(fwd)
-    t_b = timed(bwd)
+    t_b = float("nan") if neg_only else timed(bwd)
     fl = 2.0 * A * N * 256
     out = {"A": A, "N": N, "fwd_ms": t_f, "bwd_ms": t_b, "fwd_tflops": fl / t_f / 1e9, "bwd_tflops": fl / t_b / 1e9,
            "fwd_frac_of_measured_peak": fl / t_f / 1e9 / peaks["bf16_tflops"],
-           "bwd_frac_of_measured_peak": fl / t_b / 1e9 / peaks["bf16_tflops"], "loss": state_box["s"][0].item()}
+           "bwd_frac_of_measured_peak": fl / t_b / 1e9 / peaks["bf16_tflops"], "loss": state_box["s"][0].item(), "variant": variant}
     print(json.dumps(out), flush=True)
