@@ -83,7 +83,7 @@ class ContrastWorkspace:
         self.partials = torch.empty(5 * n_partial, **f32)
         self.rowstats = torch.empty(6 * ss.rowstat_f32, **f32)
         self.dpartials = torch.empty(n_dpartial, **f32)
-        self.row_m2 = torch.empty(-(-ms // 128) * 128 + 512, **f32)
+        self.row_m2 = torch.empty(-(-ms // 256) * 256 + 512, **f32)
         self.dA = torch.empty((ms, D), **f32)
         self.loss = torch.zeros(1, **f32)
         self.ranks = torch.zeros(ms, **i32)
@@ -377,8 +377,8 @@ def _tc_desc(anchors, anchor_cls, contrast_bf16, contrast_cls, n_cols, bank, dia
     dev = anchors.device
     a = anchors.detach().to(torch.float32).contiguous()
     A, D = a.shape
-    a_pad = -(-A // 128) * 128
-    a16 = torch.empty((a_pad, D), dtype=torch.bfloat16, device=dev)
+    a_pad = -(-A // 256) * 256                      # row tiles of the forward sweep
+    a16 = torch.empty((-(-A // 128) * 128, D), dtype=torch.bfloat16, device=dev)
     cls = anchor_cls.to(device=dev, dtype=torch.int32).contiguous()
     d = _abi.TcDesc()
     d.anchors_f32, d.anchors_bf16, d.anchor_cls = a.data_ptr(), a16.data_ptr(), cls.data_ptr()
@@ -437,7 +437,7 @@ def tc_dump_logits(anchors: torch.Tensor, contrast_bf16: Optional[torch.Tensor],
     d, keep, a_pad = _tc_desc(anchors, cls, contrast_bf16, ccls if contrast_bf16 is not None else None, n_cols, None,
                               None, 1.0, 1.0, False, False, 1.0)
     ncols = n_cols if contrast_bf16 is not None else A
-    ld = -(-ncols // 256) * 256
+    ld = -(-ncols // 128) * 128
     dump = torch.zeros((a_pad, ld), dtype=torch.float32, device=dev)
     row_m2 = torch.empty(a_pad + 512, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

@@ -228,7 +228,7 @@ typedef struct {
 
 int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out);
 int pcl_to_bf16(const float* src, void* dst_bf16, int64_t n_real, int64_t n_total, void* stream);
-/* row_m2: (a_rows rounded up to 128) + 512 floats of scratch (per-row stabiliser, kept for the backward,
+/* row_m2: (a_rows rounded up to 256) + 512 floats of scratch (per-row stabiliser, kept for the backward,
  * followed by the per-label column bounds of a sorted explicit contrast set). */
 int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
                        void* stream);
@@ -236,7 +236,7 @@ int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, flo
  * come from pcl_infonce_tc_fwd; dpartials: pcl_tc_sizes().dpartial_f32 floats of scratch. */
 int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
                        float* dpartials, float* dA, void* stream);
-/* Pipeline self-test: raw similarity tiles S = A.C^T into dump[(a_rows up to 128) x (n_cols up to 256)] fp32. */
+/* Pipeline self-test: raw similarity tiles S = A.C^T into dump[(a_rows up to 256) x (n_cols up to 128)] fp32. */
 int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* dump, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -269,7 +269,7 @@ typedef struct {
   int32_t precision;
   const void* shadow_bf16; int64_t shadow_rows;
   float contrast_norm_bound;
-  float* row_m2;                 /* (max_samples rounded up to 128) + 512 floats (tensor path only)  */
+  float* row_m2;                 /* (max_samples rounded up to 256) + 512 floats (tensor path only)  */
   /* outputs */
   float* loss;                   /* 1 float                                                          */
   float* grad_embed;             /* (B,D,h,w), written by pcl_step_backward                          */

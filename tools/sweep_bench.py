@@ -7,6 +7,7 @@ import sys
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import torch
+torch.set_num_threads(min(16, __import__("os").cpu_count() or 1))
 
 from contrastiveseg_b200 import functional as Fn
 from contrastiveseg_b200.synth import make_sweep_point
