@@ -20,15 +20,13 @@
 namespace pcl {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, NKB = 4, DDIM = 256;
-// forward sweep tile: 256 anchor rows (two M=128 halves sharing every contrast box) x 128 columns.  One 16 KB contrast
-// box feeds 2 x 128x128x64 MMAs -> 256 FLOP per byte pulled from L2 (a 128-row tile needs twice the L2 bandwidth and
-// saturates the ~6.3 KB/clk L2 fabric at ~65 % of the tensor peak: measured, profiles/r1_sweep_variants_v2.jsonl).
-constexpr int FM = 256, FN = 128;
-constexpr int STAGES = 5;
-constexpr int A_KB_BYTES = BM * BK * 2;          // 16 KB: one [128 x 64] box
-constexpr int A_HALF_BYTES = NKB * A_KB_BYTES;   // 64 KB: 128 rows x 256
-constexpr int B_STAGE_BYTES = FN * BK * 2;       // 16 KB
+// Forward tile = 128 rows x 256 columns (one M128 x N256 x K16 UMMA per K step).  A 256-row x 128-column variant (two
+// M128 x N128 MMAs per contrast box, half the L2 traffic) measured 18 % SLOWER: N=128 MMAs read 128 B/clk of operands
+// from shared memory and starve the TMA fill (profiles/r1_sweep_variants_v3_fm256.jsonl).
+constexpr int BM = 128, BN = 256, BK = 64, NKB = 4, DDIM = 256;
+constexpr int STAGES = 4;
+constexpr int A_KB_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;       // 32 KB
 constexpr int NUM_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int EPI_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 512;
@@ -47,10 +45,11 @@ struct TcArgs {
 };
 
 struct SmemLayout {
-  uint8_t a[2 * A_HALF_BYTES];                     // 128 KB
-  uint8_t b[STAGES * B_STAGE_BYTES];               // 80 KB
+  uint8_t a[NKB * A_KB_BYTES];
+  uint8_t b[STAGES * B_STAGE_BYTES];
   uint64_t full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  float comb[3][2][BM];
 };
 
 __device__ __forceinline__ int col_label(const TcArgs& a, int n) {      // columns < 2^31
@@ -142,8 +141,8 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int A = a.plan ? min(a.plan[PCL_PLAN_A], a.a_rows) : a.a_rows;
   if (A <= 0) return;
-  const int ncols = a.mode == 0 ? A : (int)a.n_cols;
-  const int T_all = (ncols + FN - 1) / FN;
+  const int64_t ncols = a.mode == 0 ? (int64_t)A : a.n_cols;
+  const int T_all = (int)((ncols + BN - 1) / BN);
 
   // ---- work list of this CTA (identical in every warp) ----
   SegWalker w0;
@@ -151,19 +150,19 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   w0.pending = false;
   w0.T = T_all; w0.G = gridDim.x; w0.k = blockIdx.x;
   if (w0.persistent) {
-    const int R_live = (A + FM - 1) / FM;
+    const int R_live = (A + BM - 1) / BM;
     w0.P = (long long)R_live * T_all;
     w0.p = ((long long)blockIdx.x * w0.P) / gridDim.x;
     w0.p_end = ((long long)(blockIdx.x + 1) * w0.P) / gridDim.x;
     if (w0.p >= w0.p_end) return;
   } else {
-    const int row0 = blockIdx.x * FM;
+    const int row0 = blockIdx.x * BM;
     if (row0 >= A) return;
     int t_lo = 0, t_hi = T_all;
     if (MODE == TC_POS && a.mode == 2 && a.sorted && a.cls_start != nullptr) {
       // positives of this row tile live in the columns of its label range (contrast labels are sorted)
       int lo = 0x7fffffff, hi = -1;
-      for (int i = lane; i < FM; i += 32) {
+      for (int i = lane; i < BM; i += 32) {
         const int r = row0 + i;
         if (r < A) { const int c = a.acls[r]; lo = min(lo, c); hi = max(hi, c); }
       }
@@ -174,18 +173,18 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       }
       lo = max(0, min(lo, PCL_MAX_CLASSES - 1));
       hi = max(0, min(hi, PCL_MAX_CLASSES - 1));
-      t_lo = a.cls_start[lo] / FN;
-      t_hi = (a.cls_start[hi + 1] + FN - 1) / FN;
+      t_lo = a.cls_start[lo] / BN;
+      t_hi = (a.cls_start[hi + 1] + BN - 1) / BN;
       if (t_hi < t_lo) t_hi = t_lo;
     }
     if (MODE == TC_POS && a.mode == 1) {
-      const int last = min(A - 1, row0 + FM - 1);
+      const int last = min(A - 1, row0 + BM - 1);
       int rk_f = class_rank(a.acls[row0], a.K), rk_l = class_rank(a.acls[last], a.K);
       if (rk_l > a.K - 2) rk_l = a.K - 2;
       if (rk_f > rk_l) { t_lo = 0; t_hi = 0; }
       else {
-        t_lo = (int)(((int64_t)rk_f * a.R) / FN);
-        t_hi = (int)((((int64_t)(rk_l + 1) * a.R) + FN - 1) / FN);
+        t_lo = (int)(((int64_t)rk_f * a.R) / BN);
+        t_hi = (int)((((int64_t)(rk_l + 1) * a.R) + BN - 1) / BN);
       }
     }
     const int span = t_hi - t_lo;
@@ -224,15 +223,13 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       while (w.next(sg)) {
         if (sg.ct1 <= sg.ct0) continue;
         if (seg_idx > 0) ptx::mbar_wait(&sm.a_empty, (seg_idx - 1) & 1);     // previous segment's MMAs retired
-        ptx::mbar_arrive_expect_tx(&sm.a_full, 2 * A_HALF_BYTES);
-        for (int h = 0; h < 2; ++h)
-          for (int kb = 0; kb < NKB; ++kb)
-            ptx::tma_load_2d(sm.a + h * A_HALF_BYTES + kb * A_KB_BYTES, &tmA, &sm.a_full, kb * BK, sg.r * FM + h * BM);
+        ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * A_KB_BYTES);
+        for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sm.a + kb * A_KB_BYTES, &tmA, &sm.a_full, kb * BK, sg.r * BM);
         for (int ct = sg.ct0; ct < sg.ct1; ++ct) {
           for (int kb = 0; kb < NKB; ++kb) {
             ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&sm.full[stage], B_STAGE_BYTES);
-            ptx::tma_load_2d(sm.b + stage * B_STAGE_BYTES, &tmB, &sm.full[stage], kb * BK, ct * FN);
+            ptx::tma_load_2d(sm.b + stage * B_STAGE_BYTES, &tmB, &sm.full[stage], kb * BK, ct * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -242,7 +239,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, FN, 0, 0);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
       const uint32_t a_base = ptx::smem_u32(sm.a), b_base = ptx::smem_u32(sm.b);
       SegWalker w = w0;
       Seg sg;
@@ -256,23 +253,20 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
           ptx::mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
           ptx::tc_fence_after();
-          // TMEM: [accumulator stage][row half][128 columns]
-          const uint32_t d0 = tmem_base + acc * (2 * FN), d1 = d0 + FN;
+          const uint32_t d_tmem = tmem_base + acc * BN;
           for (int kb = 0; kb < NKB; ++kb) {
             ptx::mbar_wait(&sm.full[stage], phase);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
               const uint64_t db = ptx::make_desc_kmajor_sw128(b_base + stage * B_STAGE_BYTES + k * 32);
-              const uint64_t da0 = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
-              const uint64_t da1 = ptx::make_desc_kmajor_sw128(a_base + A_HALF_BYTES + kb * A_KB_BYTES + k * 32);
-              ptx::mma_f16_ss(d0, da0, db, idesc, (kb | k) != 0 ? 1u : 0u);
-              ptx::mma_f16_ss(d1, da1, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             ptx::mma_commit(&sm.empty[stage]);          // smem slot free once these MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&sm.tmem_full[acc]);          // both accumulator halves ready for the epilogue
+          ptx::mma_commit(&sm.tmem_full[acc]);          // accumulator ready for the epilogue
         }
         ptx::mma_commit(&sm.a_empty);                   // anchor tile may be overwritten
         ++seg_idx;
@@ -281,13 +275,13 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   } else {
     // =========================== epilogue warps ===========================
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
-    const int mhalf = (warp - 2) >> 2;                // which 128 rows of the 256-row tile
-    const int r_in = mhalf * BM + quarter * 32 + lane;
+    const int half = (warp - 2) >> 2;                 // which 128 columns of the 256-column tile
+    const int r_in = quarter * 32 + lane;
     SegWalker w = w0;
     Seg sg;
     int it = 0;
     while (w.next(sg)) {
-      const int row = sg.r * FM + r_in;
+      const int row = sg.r * BM + r_in;
       const bool valid = row < A;
       const int rcls = valid ? a.acls[row] : -1;
       const int rdiag = valid ? (a.mode == 0 ? row : (a.diag ? a.diag[row] : -1)) : -1;
@@ -297,17 +291,17 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
       for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
         const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
-        const int col0 = ct * FN;
+        const int col0 = ct * BN + half * (BN / 2);
         // tile class: all 128 columns valid and of one class (sorted contrast set) -> no per-element test
         bool uniform = false;
         int ulab = -1;
-        if (a.sorted && col0 + FN <= ncols) {
+        if (a.sorted && col0 + BN / 2 <= ncols) {
           ulab = col_label(a, col0);
-          uniform = ulab == col_label(a, col0 + FN - 1);
+          uniform = ulab == col_label(a, col0 + BN / 2 - 1);
         }
         ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * (2 * FN) + mhalf * FN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * BN + half * (BN / 2);
         uint32_t vbuf[2][32];
         ptx::tmem_ld_32x32b_x32(t_row, vbuf[0]);
 #pragma unroll
@@ -317,8 +311,8 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           uint32_t(&v)[32] = vbuf[ch & 1];
           const int cb = col0 + ch * 32;
           if (MODE == TC_DUMP) {
-            // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * FN
-            const int64_t ld = (int64_t)T_all * FN;
+            // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * BN
+            const int64_t ld = (int64_t)T_all * BN;
 #pragma unroll
             for (int j = 0; j < 32; ++j) partials[(int64_t)row * ld + cb + j] = __uint_as_float(v[j]);
           } else if (MODE == TC_NEG) {
@@ -337,7 +331,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
               uint32_t tmp[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) tmp[j] = v[j];
-              acc0 += neg_slow(a, tmp, cb, ncols, rcls, m2);
+              acc0 += neg_slow(a, tmp, cb, (int)ncols, rcls, m2);
             }
           } else {
             if (uniform && ulab != rcls) {
@@ -356,7 +350,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                 uint32_t tmp[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) tmp[j] = v[j];
-                pos_slow(a, tmp, cb, ncols, rcls, rdiag, m2, neg_i, acc0, acc1, acc2);
+                pos_slow(a, tmp, cb, (int)ncols, rcls, rdiag, m2, neg_i, acc0, acc1, acc2);
               }
             }
           }
@@ -365,18 +359,29 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&sm.tmem_empty[accb]);
       }
-      // ---- partials of this segment: every thread owns one full row of the tile ----
+      // ---- combine the two column halves, write the partials of this segment ----
       if (MODE != TC_DUMP) {
-        const int64_t o = (int64_t)sg.slot * a.a_pad + row;
-        const int64_t stride = (int64_t)a.slots * a.a_pad;
         if (MODE == TC_NEG) {
-          partials[0 * stride + o] = m2 * LN2;                               // stabiliser in natural-log units
-          partials[1 * stride + o] = (acc0 + acc1) + (acc2 + acc3);
+          sm.comb[0][half][r_in] = (acc0 + acc1) + (acc2 + acc3);
         } else {
-          partials[2 * stride + o] = acc0 * LN2;
-          partials[3 * stride + o] = acc1;
-          partials[4 * stride + o] = acc2;
+          sm.comb[0][half][r_in] = acc0 * LN2;
+          sm.comb[1][half][r_in] = acc1;
+          sm.comb[2][half][r_in] = acc2;
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (half == 0) {
+          const int64_t o = (int64_t)sg.slot * a.a_pad + row;
+          const int64_t stride = (int64_t)a.slots * a.a_pad;
+          if (MODE == TC_NEG) {
+            partials[0 * stride + o] = m2 * LN2;                             // stabiliser in natural-log units
+            partials[1 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+          } else {
+            partials[2 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+            partials[3 * stride + o] = sm.comb[1][0][r_in] + sm.comb[1][1][r_in];
+            partials[4 * stride + o] = sm.comb[2][0][r_in] + sm.comb[2][1][r_in];
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");       // comb reusable by the next segment
       }
     }
   }
@@ -675,20 +680,18 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 
 // anchors fp32 -> bf16 rows (optional) and the per-row stabiliser m2 = |bf16(a)| * cbound * log2(e)/T
 __global__ void k_tc_prep(const float* __restrict__ anchors, __nv_bfloat16* __restrict__ out_bf16,
-                          const __nv_bfloat16* __restrict__ in_bf16, int a_rows, int a_alloc, int a_pad, float cbound,
-                          float k1, float* __restrict__ row_m2) {
+                          const __nv_bfloat16* __restrict__ in_bf16, int a_rows, int a_pad, float cbound, float k1,
+                          float* __restrict__ row_m2) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= a_pad) return;
   float ss = 0.f;
   for (int d = lane; d < DDIM; d += 32) {
-    __nv_bfloat16 h = __float2bfloat16(0.f);
+    __nv_bfloat16 h;
     if (out_bf16) {
-      if (r < a_alloc) {
-        h = __float2bfloat16(r < a_rows ? anchors[(int64_t)r * DDIM + d] : 0.f);
-        out_bf16[(int64_t)r * DDIM + d] = h;
-      }
-    } else if (r < a_alloc) {
+      h = __float2bfloat16(r < a_rows ? anchors[(int64_t)r * DDIM + d] : 0.f);
+      out_bf16[(int64_t)r * DDIM + d] = h;
+    } else {
       h = in_bf16[(int64_t)r * DDIM + d];
     }
     const float f = __bfloat162float(h);
@@ -757,7 +760,7 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t b
 struct TcPlan {
   tc::TcArgs a;
   SweepArgs sw;         // for the shared combine / finalize kernels
-  int row_tiles, row_tiles_b, a_alloc, grid_persistent, splits_bwd;
+  int row_tiles, grid_persistent, splits_bwd;
 };
 
 // Tuning knobs for profiling runs (env PCL_TC_VARIANT, bit 0: no polynomial exp2, bit 1: 2-D grid NEG sweep,
@@ -790,10 +793,8 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   tc::TcArgs& a = p->a;
   a.acls = d->anchor_cls; a.diag = d->diag_col; a.plan = d->plan; a.ccls = nullptr;
   a.a_rows = d->a_rows; a.mode = d->mode;
-  p->row_tiles = ceil_div(d->a_rows, tc::FM);          // forward row tiles (256 rows)
-  p->row_tiles_b = ceil_div(d->a_rows, tc::BM);        // backward row tiles (128 rows)
-  a.a_pad = p->row_tiles * tc::FM;
-  p->a_alloc = ceil_div(d->a_rows, 128) * 128;         // rows of the bf16 anchor buffer (TMA reads beyond it as zero)
+  p->row_tiles = ceil_div(d->a_rows, tc::BM);
+  a.a_pad = p->row_tiles * tc::BM;
   int tail = 0;
   if (d->mode == 0) {
     a.n_cols = d->a_rows; a.sorted = 0; a.K = 0; a.R = 1;
@@ -808,7 +809,7 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   }
   a.k1 = tc::LOG2E / d->temperature;
   const int sms = num_sms();
-  const int col_tiles = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, tc::FN);
+  const int col_tiles = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, tc::BN);
   int splits = sms / p->row_tiles;
   if (splits < 1) splits = 1;
   if (splits > col_tiles) splits = col_tiles;
@@ -824,7 +825,7 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   a.slots = (int)(slots_neg > splits ? slots_neg : splits);
   // backward sweeps 128-column tiles on a 2-D grid
   const int col_tiles_b = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, 128);
-  int sb = sms / p->row_tiles_b;
+  int sb = sms / p->row_tiles;
   if (sb < 1) sb = 1;
   if (sb > col_tiles_b) sb = col_tiles_b;
   p->splits_bwd = sb;
@@ -874,8 +875,8 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   // 1. bf16 anchors (if fp32 given) + row stabilisers
   const float cbound = d->contrast_norm_bound > 0.f ? d->contrast_norm_bound : 1.0f;
   tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
-                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, p.a_alloc, a.a_pad,
-                                                     cbound, a.k1, row_m2);
+                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, cbound,
+                                                     a.k1, row_m2);
   PCL_LAUNCH_CHECK();
   if (d->mode == 2 && a.sorted) {
     int32_t* cls_start = reinterpret_cast<int32_t*>(row_m2 + a.a_pad);       // scratch tail: PCL_MAX_CLASSES + 1 ints
@@ -887,10 +888,10 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   }
   // 2. tensor maps
   CUtensorMap tmA, tmB;
-  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)p.a_alloc, tc::BM);
+  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)a.a_pad, tc::BM);
   if (st != PCL_OK) return st;
-  if (d->mode == 0) st = make_tmap(&tmB, d->anchors_bf16, (uint64_t)p.a_alloc, tc::FN);
-  else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::FN);
+  if (d->mode == 0) st = make_tmap(&tmB, d->anchors_bf16, (uint64_t)a.a_pad, tc::BN);
+  else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemLayout) + 1024;
   static bool attr_done = false;
@@ -937,14 +938,14 @@ extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* du
   tc::TcArgs& a = p.a;
   a.row_m2 = row_m2;
   tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
-                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, p.a_alloc, a.a_pad, 1.f,
-                                                     a.k1, row_m2);
+                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, 1.f, a.k1,
+                                                     row_m2);
   PCL_LAUNCH_CHECK();
   CUtensorMap tmA, tmB;
-  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)p.a_alloc, tc::BM);
+  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)a.a_pad, tc::BM);
   if (st != PCL_OK) return st;
-  if (d->mode == 0) st = make_tmap(&tmB, d->anchors_bf16, (uint64_t)p.a_alloc, tc::FN);
-  else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::FN);
+  if (d->mode == 0) st = make_tmap(&tmB, d->anchors_bf16, (uint64_t)a.a_pad, tc::BN);
+  else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemLayout) + 1024;
   PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_DUMP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -972,9 +973,9 @@ extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, con
   ba.t.splits = splits;
   p.sw.splits = splits;
   CUtensorMap tmA, tmC;
-  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)p.a_alloc, tc::BM);
+  st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)ba.t.a_pad, tc::BM);
   if (st != PCL_OK) return st;
-  if (d->mode == 0) st = make_tmap(&tmC, d->anchors_bf16, (uint64_t)p.a_alloc, tc::BNB);
+  if (d->mode == 0) st = make_tmap(&tmC, d->anchors_bf16, (uint64_t)ba.t.a_pad, tc::BNB);
   else st = make_tmap(&tmC, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : ba.t.n_cols), tc::BNB);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemBwd) + 1024;
@@ -983,7 +984,7 @@ extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, con
     PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid(p.row_tiles_b, splits);
+  dim3 grid(p.row_tiles, splits);
   tc::k_tc_bwd<<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmC, ba, dpartials);
   PCL_LAUNCH_CHECK();
   const int64_t total = (int64_t)d->a_rows * tc::DDIM;

@@ -437,7 +437,7 @@ def tc_dump_logits(anchors: torch.Tensor, contrast_bf16: Optional[torch.Tensor],
     d, keep, a_pad = _tc_desc(anchors, cls, contrast_bf16, ccls if contrast_bf16 is not None else None, n_cols, None,
                               None, 1.0, 1.0, False, False, 1.0)
     ncols = n_cols if contrast_bf16 is not None else A
-    ld = -(-ncols // 128) * 128
+    ld = -(-ncols // 256) * 256
     dump = torch.zeros((a_pad, ld), dtype=torch.float32, device=dev)
     row_m2 = torch.empty(a_pad + 512, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

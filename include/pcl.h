@@ -236,7 +236,7 @@ int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, flo
  * come from pcl_infonce_tc_fwd; dpartials: pcl_tc_sizes().dpartial_f32 floats of scratch. */
 int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
                        float* dpartials, float* dA, void* stream);
-/* Pipeline self-test: raw similarity tiles S = A.C^T into dump[(a_rows up to 256) x (n_cols up to 128)] fp32. */
+/* Pipeline self-test: raw similarity tiles S = A.C^T into dump[(a_rows up to 256) x (n_cols up to 256)] fp32. */
 int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* dump, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

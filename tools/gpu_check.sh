@@ -19,8 +19,8 @@ if [ "${2:-}" = "variants" ]; then
   done
 fi
 if [ "${1:-}" = "ncutc" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -c 6 -o gpurun_out/tc_prof \
-    python tools/sweep_bench.py 16384x65536 > gpurun_out/ncu_tc.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_ -c 3 -o gpurun_out/tc_prof \
+    python tools/sweep_bench.py 65536x131072 > gpurun_out/ncu_tc.log 2>&1
 fi
 if [ "${1:-}" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
