@@ -105,33 +105,6 @@ __device__ __forceinline__ float exp2_poly(float x) {
 }
 
 
-// Boundary tiles (a class boundary or the ragged end of the contrast set inside the 32 columns): rare, so they run
-// as compact out-of-line loops over a local copy of the 32 logits instead of bloating the unrolled fast path.
-__device__ __noinline__ float neg_slow(const TcArgs& a, const uint32_t* v, int cb, int ncols, int rcls, float m2) {
-  float acc = 0.f;
-#pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const int col = cb + j;
-    if (col < ncols && col_label(a, col) != rcls) acc += ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
-  }
-  return acc;
-}
-
-__device__ __noinline__ void pos_slow(const TcArgs& a, const uint32_t* v, int cb, int ncols, int rcls, int rdiag,
-                                      float m2, float neg_i, float& acc0, float& acc1, float& acc2) {
-#pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const int col = cb + j;
-    if (col < ncols && col != rdiag && col_label(a, col) == rcls) {
-      const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
-      const float t = ptx::ex2_approx(x) + neg_i;
-      acc0 += x - ptx::lg2_approx(t);
-      acc1 += ptx::rcp_approx(t);
-      acc2 += 1.f;
-    }
-  }
-}
-
 template <int MODE, bool POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a,
@@ -292,12 +265,20 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
         const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
         const int col0 = ct * BN + half * (BN / 2);
-        // tile class: all 128 columns valid and of one class (sorted contrast set) -> no per-element test
-        bool uniform = false;
-        int ulab = -1;
-        if (a.sorted && col0 + BN / 2 <= ncols) {
-          ulab = col_label(a, col0);
-          uniform = ulab == col_label(a, col0 + BN / 2 - 1);
+        // Per 32-column chunk: if the chunk is complete and of one class (sorted contrast set) every row treats it as
+        // all-negative or all-positive without a per-element test.  Mixed chunks (a class boundary, the ragged end,
+        // self-contrast) fetch one label per lane and broadcast it with warp shuffles — no dependent loads.
+        int clab[4];
+        bool cuni[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int cb = col0 + ch * 32;
+          cuni[ch] = false;
+          clab[ch] = -2;
+          if (a.sorted && cb + 32 <= ncols) {
+            clab[ch] = col_label(a, cb);
+            cuni[ch] = clab[ch] == col_label(a, cb + 31);
+          }
         }
         ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
         ptx::tc_fence_after();
@@ -310,6 +291,8 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           if (ch < 3) ptx::tmem_ld_32x32b_x32(t_row + (ch + 1) * 32, vbuf[(ch + 1) & 1]);   // prefetch the next chunk
           uint32_t(&v)[32] = vbuf[ch & 1];
           const int cb = col0 + ch * 32;
+          const bool uniform = cuni[ch];
+          const int ulab = clab[ch];
           if (MODE == TC_DUMP) {
             // partials doubles as the dump buffer: [a_pad][ld], ld = column tiles * BN
             const int64_t ld = (int64_t)T_all * BN;
@@ -327,30 +310,41 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                   else      acc3 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), a.k1, -m2));
                 }
               }
-            } else if (valid) {
-              uint32_t tmp[32];
+            } else {
+              const int mylab = (cb + lane < ncols) ? col_label(a, cb + lane) : -2;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) tmp[j] = v[j];
-              acc0 += neg_slow(a, tmp, cb, (int)ncols, rcls, m2);
+              for (int j = 0; j < 32; ++j) {
+                const int lj = __shfl_sync(0xffffffffu, mylab, j);
+                const float e = ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+                acc0 += (valid && lj != -2 && lj != rcls) ? e : 0.f;
+              }
             }
           } else {
-            if (uniform && ulab != rcls) {
-              // no positives of this row in the tile
-            } else if (valid) {
-              if (uniform && !(rdiag >= cb && rdiag < cb + 32)) {
+            if (uniform) {
+              if (valid && ulab == rcls) {
+                const bool has_diag = rdiag >= cb && rdiag < cb + 32;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
                   const float t = ptx::ex2_approx(x) + neg_i;
+                  const float keep = (has_diag && cb + j == rdiag) ? 0.f : 1.f;
+                  acc0 += keep * (x - ptx::lg2_approx(t));
+                  acc1 += keep * ptx::rcp_approx(t);
+                  acc2 += keep;
+                }
+              }
+            } else {
+              const int mylab = (cb + lane < ncols) ? col_label(a, cb + lane) : -2;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int lj = __shfl_sync(0xffffffffu, mylab, j);
+                if (valid && lj == rcls && cb + j != rdiag) {
+                  const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
+                  const float t = ptx::ex2_approx(x) + neg_i;
                   acc0 += x - ptx::lg2_approx(t);
                   acc1 += ptx::rcp_approx(t);
+                  acc2 += 1.f;
                 }
-                acc2 += 32.f;
-              } else {
-                uint32_t tmp[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) tmp[j] = v[j];
-                pos_slow(a, tmp, cb, (int)ncols, rcls, rdiag, m2, neg_i, acc0, acc1, acc2);
               }
             }
           }
@@ -435,42 +429,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-
-// Gradient-tile elements of boundary tiles / self-contrast (needs per-column statistics): compact out-of-line loop.
-__device__ __noinline__ void bwd_slow(const TcBwdArgs& ba, const uint32_t* v, float* g, int cb, int ncols, int A,
-                                      int rcls, int rdiag, float m2, float neg_i, float cs_i, float cn_i) {
-  const TcArgs& a = ba.t;
-  const float* st = ba.rowstats;
-#pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    const int col = cb + j;
-    float gval = 0.f;
-    if (col < ncols) {
-      const int lab = col_label(a, col);
-      const float x = __uint_as_float(v[j]) * a.k1;
-      const float e = ptx::ex2_approx(x - m2);
-      if (lab == rcls) {
-        if (col != rdiag) gval = cn_i * ptx::rcp_approx(e + neg_i);     // -c (1 - e/(e+Neg))
-      } else {
-        gval = cs_i * e;
-      }
-      if (a.mode == 0) {
-        // self-contrast: the column is an anchor too, add G_ji (its statistics, same logit)
-        const float np_j = st[4 * a.a_rows + col];
-        float c_j = ba.rs_scale / ((float)A * np_j);
-        if (ba.nan_safe && !(np_j > 0.f)) c_j = 0.f;
-        const float e2 = ptx::ex2_approx(x - a.row_m2[col]);
-        const float neg_j = st[a.a_rows + col];
-        if (lab == rcls) {
-          if (col != rdiag) gval += -c_j * neg_j * ptx::rcp_approx(e2 + neg_j);
-        } else {
-          gval += c_j * st[3 * a.a_rows + col] * e2;
-        }
-      }
-    }
-    g[j] = gval;
-  }
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, TcBwdArgs ba,
@@ -590,11 +548,17 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int ct = my_lo + it;
       const uint32_t acc = it & 1, phase = (it >> 1) & 1;
       const int col0 = ct * BNB + half * 64;
-      bool uniform = false;
-      int ulab = -1;
-      if (a.sorted && col0 + 64 <= (int)ncols) {
-        ulab = col_label(a, col0);
-        uniform = ulab == col_label(a, col0 + 63);
+      int clab[2];
+      bool cuni[2];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int cb = col0 + ch * 32;
+        cuni[ch] = false;
+        clab[ch] = -2;
+        if (a.sorted && a.mode != 0 && cb + 32 <= (int)ncols) {
+          clab[ch] = col_label(a, cb);
+          cuni[ch] = clab[ch] == col_label(a, cb + 31);
+        }
       }
       ptx::mbar_wait(&sm.s_full[acc], phase);
       ptx::tc_fence_after();
@@ -609,24 +573,61 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         uint32_t(&v)[32] = vbuf[ch];
         const int cb = col0 + ch * 32;
         float gv[32];
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) gv[j] = 0.f;
-        } else if (uniform && a.mode != 0 && ulab != rcls) {
+        if (cuni[ch] && clab[ch] != rcls) {
+          // all-negative chunk: G = c S e   (cs_i == 0 for rows beyond A)
 #pragma unroll
           for (int j = 0; j < 32; ++j) gv[j] = cs_i * ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
-        } else if (uniform && a.mode != 0 && !(rdiag >= cb && rdiag < cb + 32)) {
+        } else if (cuni[ch]) {
+          // all-positive chunk: G = -c Neg / (e + Neg), zero on the masked (i,i) column
+          const bool has_diag = rdiag >= cb && rdiag < cb + 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            gv[j] = cn_i * ptx::rcp_approx(ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2)) + neg_i);
+          for (int j = 0; j < 32; ++j) {
+            const float gpos = cn_i * ptx::rcp_approx(ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2)) + neg_i);
+            gv[j] = (has_diag && cb + j == rdiag) ? 0.f : gpos;
+          }
+        } else if (a.mode != 0) {
+          // mixed chunk: one label per lane, broadcast with shuffles
+          const int mylab = (cb + lane < (int)ncols) ? col_label(a, cb + lane) : -2;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int lj = __shfl_sync(0xffffffffu, mylab, j);
+            const float e = ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+            const float gneg = cs_i * e;
+            const float gpos = (cb + j == rdiag) ? 0.f : cn_i * ptx::rcp_approx(e + neg_i);
+            gv[j] = (!valid || lj == -2) ? 0.f : (lj == rcls ? gpos : gneg);
+          }
         } else {
-          uint32_t tmp[32];
-          float gtmp[32];                     // local-memory staging keeps gv itself in registers on the fast paths
+          // self-contrast: every column is an anchor too -> H = G + G^T needs the column's statistics; lane L holds
+          // those of column cb + L and they are broadcast per element
+          const int cj = cb + lane;
+          const bool cok = cj < (int)ncols;
+          const int mylab = cok ? a.acls[cj] : -2;
+          float my_m2 = 0.f, my_neg = 1.f, my_cs = 0.f, my_cn = 0.f;
+          if (cok) {
+            const float np_j = st[4 * a.a_rows + cj];
+            float c_j = ba.rs_scale / ((float)A * np_j);
+            if (ba.nan_safe && !(np_j > 0.f)) c_j = 0.f;
+            my_m2 = a.row_m2[cj];
+            my_neg = st[a.a_rows + cj];
+            my_cs = c_j * st[3 * a.a_rows + cj];
+            my_cn = -c_j * my_neg;
+          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tmp[j] = v[j];
-          bwd_slow(ba, tmp, gtmp, cb, (int)ncols, A, rcls, rdiag, m2, neg_i, cs_i, cn_i);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) gv[j] = gtmp[j];
+          for (int j = 0; j < 32; ++j) {
+            const int lj = __shfl_sync(0xffffffffu, mylab, j);
+            const float m2j = __shfl_sync(0xffffffffu, my_m2, j);
+            const float negj = __shfl_sync(0xffffffffu, my_neg, j);
+            const float csj = __shfl_sync(0xffffffffu, my_cs, j);
+            const float cnj = __shfl_sync(0xffffffffu, my_cn, j);
+            const float x = __uint_as_float(v[j]) * a.k1;
+            const float e = ptx::ex2_approx(x - m2);
+            const float e2 = ptx::ex2_approx(x - m2j);
+            const bool same = lj == rcls;
+            const bool diag = (cb + j == rdiag);
+            const float g_ij = same ? (diag ? 0.f : cn_i * ptx::rcp_approx(e + neg_i)) : cs_i * e;
+            const float g_ji = same ? (diag ? 0.f : cnj * ptx::rcp_approx(e2 + negj)) : csj * e2;
+            gv[j] = (!valid || lj == -2) ? 0.f : (g_ij + g_ji);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) packed[ch][j] = pack_bf16x2(gv[2 * j], gv[2 * j + 1]);

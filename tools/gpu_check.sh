@@ -14,7 +14,7 @@ timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "s
 timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
 timeout 300 python tools/sweep_bench.py > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep exit $?" >> gpurun_out/sweep.err
 if [ "${2:-}" = "variants" ]; then
-  for v in 8 9 10 11; do
+  for v in 8 9; do
     PCL_TC_VARIANT=$v timeout 120 python tools/sweep_bench.py 16384x65536 65536x131072 1024x190000 >> gpurun_out/sweep_variants.jsonl 2>> gpurun_out/sweep.err
   done
 fi
