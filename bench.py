@@ -99,15 +99,16 @@ def make_inputs(cfg, seed, device=None, bank=False):
     return out
 
 
-def engine_configer(cfg, bank=False):
+def engine_configer(cfg, bank=False, precision="bf16"):
     import contrastiveseg_b200 as cs
     d = {"data": {"num_classes": cfg["K"]}, "network": {"stride": cfg.get("net_stride", 4)},
          "loss": {"params": {"ce_ignore_index": -1, "ce_reduction": "elementwise_mean"}},
          "contrast": {"temperature": cfg["T"], "base_temperature": cfg["bT"], "max_samples": cfg["max_samples"],
-                      "max_views": cfg["max_views"], "loss_weight": 0.1, "use_rmi": False, "rng": "device"}}
+                      "max_views": cfg["max_views"], "loss_weight": 0.1, "use_rmi": False, "rng": "device",
+                      "precision": precision}}
     if bank:
         # bank sweeps run on the tcgen05 path (bf16 operands through the bank shadow)
-        d["contrast"].update(with_memory=True, memory_size=cfg["M"], pixel_update_freq=cfg["F"], precision="bf16")
+        d["contrast"].update(with_memory=True, memory_size=cfg["M"], pixel_update_freq=cfg["F"])
     return cs.Configer(d)
 
 
@@ -195,7 +196,7 @@ def workload_config(cfg, bank, B=None):
 # ---------------------------------------------------------------------------------------------------
 # engine arm
 # ---------------------------------------------------------------------------------------------------
-def stage_timings(cfg, inp, dev, iters=20):
+def stage_timings(cfg, inp, dev, precision, iters=20):
     """CUDA-event time of every C-ABI stage on the launching stream (dominant-kernel roofline)."""
     import ctypes as C
     from contrastiveseg_b200 import _abi, functional as Fn
@@ -216,15 +217,25 @@ def stage_timings(cfg, inp, dev, iters=20):
     sw.diag_col, sw.plan = ws.anchor_meta.data_ptr() + 12 * ms_, ws.plan.data_ptr()
     sw.a_rows, sw.D, sw.mode = ms_, cfg["D"], 0
     sw.temperature, sw.base_temperature = cfg["T"], cfg["bT"]
+    td = _abi.TcDesc()
+    td.anchors_bf16, td.anchor_cls = ws.anchors_bf16.data_ptr(), sw.anchor_cls
+    td.diag_col, td.plan, td.a_rows, td.D, td.mode = sw.diag_col, sw.plan, ms_, cfg["D"], 0
+    td.contrast_norm_bound, td.temperature, td.base_temperature = 1.0, cfg["T"], cfg["bT"]
     g = C.byref(geom)
+    if precision == "bf16":
+        fwd = lambda: lib.pcl_infonce_tc_fwd(C.byref(td), d.row_m2, d.partials, d.rowstats, d.loss, stream)
+        bwd = lambda: lib.pcl_infonce_tc_bwd(C.byref(td), d.row_m2, d.rowstats, None, d.dpartials, d.dA, stream)
+    else:
+        fwd = lambda: lib.pcl_infonce_fwd(C.byref(sw), d.partials, d.rowstats, d.loss, stream)
+        bwd = lambda: lib.pcl_infonce_bwd(C.byref(sw), d.rowstats, None, d.dpartials, d.dA, stream)
     stages = {
-        "class_stats": lambda: lib.pcl_class_stats(g, d.labels, d.seg, None, d.keys, d.chunk_pref, stream),
-        "plan_anchors": lambda: lib.pcl_plan_anchors(g, d.chunk_pref, d.counts, d.plan, stream),
+        "class_stats": lambda: lib.pcl_class_stats(g, d.labels, d.seg, None, d.keys, d.chunk_pref, d.counts, stream),
+        "plan_anchors": lambda: lib.pcl_plan_anchors(g, d.counts, d.plan, stream),
         "select_gather": lambda: lib.pcl_select_gather(g, d.embed, d.keys, d.chunk_pref, d.plan, None, 12345, 0,
                                                        d.anchor_meta, d.anchors_f32, d.anchors_bf16, d.inv_norm,
                                                        d.norm_max, stream),
-        "infonce_fwd": lambda: lib.pcl_infonce_fwd(C.byref(sw), d.partials, d.rowstats, d.loss, stream),
-        "infonce_bwd": lambda: lib.pcl_infonce_bwd(C.byref(sw), d.rowstats, None, d.dpartials, d.dA, stream),
+        "infonce_fwd": fwd,
+        "infonce_bwd": bwd,
         "scatter_grad": lambda: lib.pcl_scatter_grad(g, d.plan, d.anchor_meta, d.dA, d.anchors_f32, d.inv_norm, 0,
                                                      d.grad_embed, stream),
     }
@@ -247,6 +258,50 @@ def stage_timings(cfg, inp, dev, iters=20):
     return out, A
 
 
+def tensor_sweep_roofline(dev, peaks, A=16384, N=65536, iters=5):
+    """The dense contraction alone (similarity + negative-sum sweep on tcgen05) at one S4 point (BASELINE configs[4]):
+    algorithmic FLOPs 2*A*N*D over the CUDA-event time, vs the measured bf16 peak."""
+    from contrastiveseg_b200 import functional as Fn
+    g = torch.Generator().manual_seed(7)
+    a = torch.nn.functional.normalize(torch.randn(A, 256, generator=g), dim=1).to(dev)
+    c = torch.nn.functional.normalize(torch.randn(N, 256, generator=g), dim=1).to(dev)
+    ya = torch.sort(torch.randint(0, 19, (A,), generator=g)).values.to(dev)
+    yc = torch.sort(torch.randint(0, 19, (N,), generator=g)).values.to(dev)
+    c16 = Fn.to_bf16_rows(c, -(-N // 256) * 256)
+    diag = torch.arange(A, device=dev) % N
+    out = {}
+    for name, neg_only in (("neg_sweep", True), ("forward", False)):
+        run = lambda: Fn.infonce_tc_forward(a, ya, contrast_bf16=c16, contrast_cls=yc, n_cols=N, diag_col=diag,
+                                            temperature=0.07, base_temperature=0.07, neg_only=neg_only)
+        for _ in range(3):
+            res = run()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); res = run(); e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        out[name] = ts[len(ts) // 2]
+    state = res
+    loss, st, stt = state
+    tb = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); Fn.infonce_tc_backward(stt, st); e1.record()
+        torch.cuda.synchronize(dev)
+        tb.append(e0.elapsed_time(e1))
+    tb.sort()
+    out["backward"] = tb[len(tb) // 2]
+    fl = 2.0 * A * N * 256
+    ach = fl / (out["neg_sweep"] * 1e-3) / 1e12
+    return {"kernel": "k_tc_fwd<NEG> (anchor x bank similarity + negative-sum sweep, tcgen05)", "bound": "tensor",
+            "workload": f"S4 sweep point A={A} x N={N}, D=256, bf16 operands", "achieved": ach,
+            "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+            "peak_source": peaks["source"], "traffic": None, "ms": out,
+            "forward_tflops": fl / (out["forward"] * 1e-3) / 1e12, "backward_tflops": fl / (out["backward"] * 1e-3) / 1e12}
+
+
 def run_engine(args, cfg, bank, rank, world, dev):
     import contrastiveseg_b200 as cs
     from contrastiveseg_b200 import _abi
@@ -254,7 +309,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
     peaks = load_peaks()
     inp_h = make_inputs(cfg, 304 + rank, None, bank)
     inp = {k: v.to(dev) for k, v in inp_h.items()}
-    cfgr = engine_configer(cfg, bank)
+    cfgr = engine_configer(cfg, bank, args.precision)
     crit = cs.PixelContrastLoss(cfgr)
     mbank = None
     if bank:
@@ -333,7 +388,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
     roof = None
     stages = {}
     if not bank:
-        stages, A = stage_timings(cfg, inp, dev)
+        stages, A = stage_timings(cfg, inp, dev, args.precision)
         dom = max(stages, key=stages.get)
         BDHW4 = cfg["B"] * cfg["D"] * cfg["h"] * cfg["w"] * 4
         alg_bytes = {
@@ -351,7 +406,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             ach = flops / (stages[dom] * 1e-3) / 1e12
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "note": "exact fp32 SIMT sweep at A=N<=1024 (latency-bound regime, SURVEY §8d); tensor path is for bank/sweep sizes"}
+                    "note": "A=N<=1024 is the launch/latency-bound regime of the sweep (SURVEY §8d); tensor_roofline reports the S4 point"}
     # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -368,15 +423,16 @@ def run_engine(args, cfg, bank, rank, world, dev):
         cpu = {"value": Bc * n_cpu / cdt, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"{n_cpu} steps at batch {Bc} (of {cfg['B']}) after 1 warm-up, fp32 torch CPU on {threads} of "
                          f"{os.cpu_count()} host threads (fastest setting), {cdt / n_cpu * 1e3:.0f} ms/step"}
-    launches_per_step = 10 + (4 if bank else 0)
+    tens = tensor_sweep_roofline(dev, peaks) if (world == 1 and cfg["D"] == 256) else None
+    launches_per_step = (12 if args.precision == "bf16" else 10) + (4 if bank else 0)
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if bank else "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic", "config": workload_config(cfg, bank), "clocks": sampler.summary(),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "impl": "engine"}
+            "stage_ms": stages, "tensor_roofline": tens, "precision": args.precision, "impl": "engine"}
 
 
 def main():
@@ -387,6 +443,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="s1", choices=["s1", "s2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="InfoNCE sweeps: bf16 operands on tcgen05 tensor cores (default) or the exact fp32 SIMT sweep")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

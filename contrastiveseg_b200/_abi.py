@@ -57,7 +57,7 @@ class TcDesc(C.Structure):
                 ("a_rows", c_i32), ("D", c_i32), ("mode", c_i32),
                 ("contrast_bf16", c_vp), ("contrast_cls", c_vp), ("n_cols", c_i64), ("contrast_rows_alloc", c_i64),
                 ("bank_K", c_i32), ("bank_R", c_i32), ("sorted", c_i32), ("contrast_norm_bound", c_f32),
-                ("temperature", c_f32), ("base_temperature", c_f32), ("nan_safe", c_i32)]
+                ("temperature", c_f32), ("base_temperature", c_f32), ("nan_safe", c_i32), ("neg_only", c_i32)]
 
 
 class StepDesc(C.Structure):
@@ -82,8 +82,8 @@ SIGNATURES = {
     "pcl_last_cuda_error": (C.c_char_p, []),
     "pcl_device_count": (c_i32, []),
     "pcl_select_sizes": (c_i32, [C.POINTER(Geom), C.POINTER(SelectSizes)]),
-    "pcl_class_stats": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "pcl_plan_anchors": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp]),
+    "pcl_class_stats": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_plan_anchors": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp]),
     "pcl_select_gather": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp, c_vp, c_u64, c_i32, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_vp]),
     "pcl_sweep_sizes": (c_i32, [C.POINTER(SweepDesc), C.POINTER(SweepSizes)]),

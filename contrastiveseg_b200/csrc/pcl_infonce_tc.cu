@@ -764,8 +764,9 @@ struct TcPlan {
   int row_tiles, grid_persistent, splits_bwd;
 };
 
-// Tuning knobs for profiling runs (env PCL_TC_VARIANT, bit 0: no polynomial exp2, bit 1: 2-D grid NEG sweep,
-// bit 3: NEG sweep only).  Default 0 = the shipped configuration.
+// Tuning knobs for profiling runs (env PCL_TC_VARIANT, bit 0: polynomial exp2 for 1 in 4 logits, bit 1: 2-D grid
+// NEG sweep, bit 3: NEG sweep only).  Default 0 = the shipped configuration (all-MUFU exp2, persistent walk):
+// measured 1310 vs 1196 TFLOP/s with the polynomial share at 65536 x 131072 (profiles/r1_sweep_variants_v4.jsonl).
 static int tc_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("PCL_TC_VARIANT"); v = e ? atoi(e) : 0; }
@@ -909,16 +910,16 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   const int variant = tc_variant();
   if (variant & 2) {                                   // tuning knob: 2-D grid instead of the persistent walk
     a.persistent = 0;
-    if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
-    else             tc::k_tc_fwd<tc::TC_NEG, true><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, true><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    else             tc::k_tc_fwd<tc::TC_NEG, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
   } else {
     a.persistent = 1;
-    if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
-    else             tc::k_tc_fwd<tc::TC_NEG, true><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, true><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    else             tc::k_tc_fwd<tc::TC_NEG, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
   }
   PCL_LAUNCH_CHECK();
   a.persistent = 0;
-  if (variant & 8) return PCL_OK;                      // tuning knob: time the NEG sweep alone
+  if ((variant & 8) || d->neg_only) return PCL_OK;     // similarity + negative-sum sweep only (roofline measurement)
   k_combine_neg<<<ceil_div(d->a_rows, 256), 256, 0, s>>>(p.sw, partials, rowstats);
   PCL_LAUNCH_CHECK();
   tc::k_tc_fwd<tc::TC_POS, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);

@@ -9,54 +9,58 @@
 //             of the pixel's D channels from NCHW, optional L2-normalise, fp32 + bf16 rows
 //   k_scatter dense-gradient writer (after a memset): one warp per anchor row
 #include "pcl_common.cuh"
+#include <math_constants.h>
 
 namespace pcl {
 
 // ------------------------------------------------------------------------------------------------
 // k_keys
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PCL_CHUNK)
 k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __restrict__ labels,
        const float* __restrict__ seg, const int64_t* __restrict__ predict, uint16_t* __restrict__ keys,
-       int32_t* __restrict__ chunk_hist) {
+       int32_t* __restrict__ chunk_hist, int32_t* __restrict__ counts) {
   extern __shared__ int s_hist[];                 // 2K+1 bins
   const int K = g.K, NK = 2 * K;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int HW = g.h * g.w;
   for (int i = threadIdx.x; i <= NK; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  const int64_t* lab_b = labels + (int64_t)b * g.Himg * g.Wimg;
+  const int p = chunk * PCL_CHUNK + threadIdx.x;   // one pixel per thread: coalesced plane reads, K loads in flight
+  if (p < HW) {
+    const int py = p / g.w, px = p - py * g.w;
+    const int sy = nearest_src(py, scale_h, g.Himg), sx = nearest_src(px, scale_w, g.Wimg);
+    const int64_t lab = labels[(int64_t)b * g.Himg * g.Wimg + (int64_t)sy * g.Wimg + sx];
+    int key = NK;
+    if (lab >= 0 && lab < K && lab != (int64_t)g.ignore_label) {
+      int pred;
+      if (seg != nullptr) {
+        const float* sp = seg + (int64_t)b * K * HW + p;
+        float best = -CUDART_INF_F;
+        pred = 0;
+        for (int c0 = 0; c0 < K; c0 += 8) {
+          float v[8];
 #pragma unroll
-  for (int j = 0; j < PCL_CHUNK / 256; ++j) {
-    int p = chunk * PCL_CHUNK + j * 256 + threadIdx.x;
-    if (p < HW) {
-      int py = p / g.w, px = p - py * g.w;
-      int sy = nearest_src(py, scale_h, g.Himg), sx = nearest_src(px, scale_w, g.Wimg);
-      int64_t lab = lab_b[(int64_t)sy * g.Wimg + sx];
-      int key = NK;
-      if (lab >= 0 && lab < K && lab != (int64_t)g.ignore_label) {
-        int pred;
-        if (seg != nullptr) {
-          const float* sp = seg + (int64_t)b * K * HW + p;
-          float best = sp[0];
-          pred = 0;
-          for (int c = 1; c < K; ++c) {
-            float v = sp[(int64_t)c * HW];
-            if (v > best) { best = v; pred = c; }
-          }
-        } else {
-          int64_t pv = predict[(int64_t)b * HW + p];
-          pred = (pv >= 0 && pv < K) ? (int)pv : -1;
+          for (int u = 0; u < 8; ++u) v[u] = (c0 + u < K) ? __ldg(sp + (int64_t)(c0 + u) * HW) : -CUDART_INF_F;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (v[u] > best) { best = v[u]; pred = c0 + u; }       // first maximum wins, like torch.max
         }
-        key = 2 * (int)lab + (pred == (int)lab ? 1 : 0);
+      } else {
+        const int64_t pv = predict[(int64_t)b * HW + p];
+        pred = (pv >= 0 && pv < K) ? (int)pv : -1;
       }
-      keys[(int64_t)b * HW + p] = (uint16_t)key;
-      atomicAdd(&s_hist[key], 1);
+      key = 2 * (int)lab + (pred == (int)lab ? 1 : 0);
     }
+    keys[(int64_t)b * HW + p] = (uint16_t)key;
+    atomicAdd(&s_hist[key], 1);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NK; i += blockDim.x)
-    chunk_hist[((int64_t)b * NK + i) * nchunk + chunk] = s_hist[i];
+  for (int i = threadIdx.x; i < NK; i += blockDim.x) {
+    const int v = s_hist[i];
+    chunk_hist[((int64_t)b * NK + i) * nchunk + chunk] = v;
+    if (v) atomicAdd(&counts[b * NK + i], v);     // integer totals: order-independent
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -67,22 +71,17 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
 constexpr int PLAN_THREADS = 256;
 
 __global__ void __launch_bounds__(PLAN_THREADS)
-k_plan(pcl_geom g, int nchunk, int32_t* __restrict__ chunk_pref, int32_t* __restrict__ counts,
-       int32_t* __restrict__ plan) {
+k_plan(pcl_geom g, int nchunk, const int32_t* __restrict__ counts, int32_t* __restrict__ plan) {
   __shared__ int s_scan[PLAN_THREADS];
   __shared__ int s_cls_cnt[PCL_MAX_CLASSES];
   __shared__ int s_cls_start[PCL_MAX_CLASSES];
-  __shared__ int s_TC, s_V;
+  __shared__ int s_TC, s_V, s_err;
   const int K = g.K, NK = 2 * K, B = g.B;
   const int tid = threadIdx.x;
+  if (tid == 0) s_err = 0;
 
-  // 1. per (image,key): exclusive prefix over chunks, total into counts
-  for (int row = tid; row < B * NK; row += PLAN_THREADS) {
-    int32_t* p = chunk_pref + (int64_t)row * nchunk;
-    int run = 0;
-    for (int c = 0; c < nchunk; ++c) { int v = p[c]; p[c] = run; run += v; }
-    counts[row] = run;
-  }
+  // 1. per-image key totals were accumulated by k_keys (integer atomics); chunk_pref keeps the raw per-chunk
+  //    histograms — k_select scans the 32-entry row it needs with warp shuffles
   for (int c = tid; c < K; c += PLAN_THREADS) s_cls_cnt[c] = 0;
   __syncthreads();
 
@@ -125,7 +124,7 @@ k_plan(pcl_geom g, int nchunk, int32_t* __restrict__ chunk_pref, int32_t* __rest
       ++t;
     }
   }
-  if (split_err) atomicOr(&plan[PCL_PLAN_FLAGS], PCL_FLAG_SPLIT_ERROR);
+  if (split_err) atomicOr(&s_err, 1);
   __syncthreads();
   if (tid == 0) {
     // class-sorted start rows, rank order 1,2,...,K-1,0
@@ -138,11 +137,12 @@ k_plan(pcl_geom g, int nchunk, int32_t* __restrict__ chunk_pref, int32_t* __rest
     plan[PCL_PLAN_TC] = TC;
     plan[PCL_PLAN_V] = V;
     plan[PCL_PLAN_A] = TC * V;
-    int f = 0;
+    int f = s_err ? PCL_FLAG_SPLIT_ERROR : 0;
     if (TC == 0) f |= PCL_FLAG_NO_CLASS;
     if (TC > 0 && V == 0) f |= PCL_FLAG_ZERO_VIEWS;
-    atomicOr(&plan[PCL_PLAN_FLAGS], f);
+    plan[PCL_PLAN_FLAGS] = f;
     plan[PCL_PLAN_NPAIR_MAX] = E;
+    for (int i = PCL_PLAN_NPAIR_MAX + 1; i < PCL_PLAN_HEADER; ++i) plan[i] = 0;
   }
   __syncthreads();
   // 3. sorted base per pair: V * (class start + number of earlier images that kept the class)
@@ -170,11 +170,26 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int TC = plan[PCL_PLAN_TC], V = plan[PCL_PLAN_V];
-  if (V <= 0 || i >= TC * V) return;
+  const int D = g.D, ms = g.max_samples;
+  if (i >= ms) {
+    // padding rows of the bf16 copy (rounded up to 128 rows for the 128-row TMA boxes)
+    if (anchors_bf16 != nullptr && i < ((ms + 127) / 128) * 128)
+      for (int d = lane; d < D; d += 32) anchors_bf16[(int64_t)i * D + d] = __float2bfloat16(0.f);
+    return;
+  }
+  if (V <= 0 || i >= TC * V) {
+    // dead row (the class-sorted rows [0, A) are dense): zero it so padded tiles read zeros
+    for (int d = lane; d < D; d += 32) {
+      anchors[(int64_t)i * D + d] = 0.f;
+      if (anchors_bf16 != nullptr) anchors_bf16[(int64_t)i * D + d] = __float2bfloat16(0.f);
+    }
+    if (lane == 0) { meta[i] = -1; meta[ms + i] = -1; meta[2 * ms + i] = -1; meta[3 * ms + i] = -1; inv_norm[i] = 0.f; }
+    return;
+  }
   const int t = i / V, v = i - t * V;
   const int32_t* q = plan + PCL_PLAN_HEADER + (int64_t)t * 8;
   const int b = q[0], c = q[1], nh = q[2], ne = q[3], kh = q[4], base = q[6];
-  const int K = g.K, NK = 2 * K, HW = g.h * g.w, D = g.D;
+  const int K = g.K, NK = 2 * K, HW = g.h * g.w;
   const bool easy = v >= kh;
   const int j = easy ? v - kh : v;
   const int n = easy ? ne : nh;
@@ -185,21 +200,28 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
   if (rank < 0) rank = 0;
   if (rank >= n) rank = n - 1;               // defensive: malformed injected table
 
-  // chunk that holds the rank-th pixel of this key
-  const int32_t* pref = chunk_pref + ((int64_t)b * NK + key) * nchunk;
-  int chunk = -1;
-  for (int c0 = 0; c0 < nchunk; c0 += 32) {
-    int ch = c0 + lane;
-    bool ok = false;
-    if (ch < nchunk) {
-      int lo = pref[ch];
-      ok = lo <= rank && (ch + 1 == nchunk || pref[ch + 1] > rank);
+  // chunk that holds the rank-th pixel of this key: warp scan of the per-chunk histogram row
+  const int32_t* hist = chunk_pref + ((int64_t)b * NK + key) * nchunk;
+  int chunk = -1, local = 0, run = 0;
+  for (int c0 = 0; c0 < nchunk && chunk < 0; c0 += 32) {
+    const int ch = c0 + lane;
+    const int cnt = ch < nchunk ? hist[ch] : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
     }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (m) { chunk = c0 + __ffs(m) - 1; break; }
+    const int lo = run + incl - cnt;
+    const unsigned m = __ballot_sync(0xffffffffu, cnt > 0 && rank >= lo && rank < lo + cnt);
+    if (m) {
+      const int src = __ffs(m) - 1;
+      chunk = c0 + src;
+      local = rank - __shfl_sync(0xffffffffu, lo, src);
+    }
+    run += __shfl_sync(0xffffffffu, incl, 31);
   }
   if (chunk < 0) return;                       // cannot happen for a consistent table
-  const int local = rank - pref[chunk];
 
   // ordered scan of the chunk: lane L owns pixels [32L, 32L+32)
   const int p0 = chunk * PCL_CHUNK + lane * 32;
@@ -250,7 +272,6 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
     if (anchors_bf16 != nullptr) anchors_bf16[(int64_t)s * D + d] = __float2bfloat16(y);
   }
   if (lane == 0) {
-    const int ms = g.max_samples;
     meta[s] = pix;
     meta[ms + s] = b;
     meta[2 * ms + s] = c;
@@ -321,30 +342,29 @@ extern "C" int pcl_select_sizes(const pcl_geom* g, pcl_select_sizes_t* out) {
 }
 
 extern "C" int pcl_class_stats(const pcl_geom* g, const int64_t* labels, const float* seg, const int64_t* predict,
-                               uint16_t* keys, int32_t* chunk_pref, void* stream) {
+                               uint16_t* keys, int32_t* chunk_pref, int32_t* counts, void* stream) {
   int st = check_geom(g);
   if (st != PCL_OK) return st;
-  PCL_REQUIRE(labels && keys && chunk_pref && (seg || predict));
+  PCL_REQUIRE(labels && keys && chunk_pref && counts && (seg || predict));
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t HW = (int64_t)g->h * g->w;
   const int nchunk = (int)ceil_div64(HW, PCL_CHUNK);
   const float scale_h = (float)g->Himg / (float)g->h, scale_w = (float)g->Wimg / (float)g->w;
+  PCL_CUDA(cudaMemsetAsync(counts, 0, (size_t)g->B * 2 * g->K * sizeof(int32_t), s));
   dim3 grid(nchunk, g->B);
   size_t smem = (2 * g->K + 1) * sizeof(int);
-  k_keys<<<grid, 256, smem, s>>>(*g, nchunk, scale_h, scale_w, labels, seg, predict, keys, chunk_pref);
+  k_keys<<<grid, PCL_CHUNK, smem, s>>>(*g, nchunk, scale_h, scale_w, labels, seg, predict, keys, chunk_pref, counts);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
 
-extern "C" int pcl_plan_anchors(const pcl_geom* g, int32_t* chunk_pref, int32_t* counts, int32_t* plan,
-                                void* stream) {
+extern "C" int pcl_plan_anchors(const pcl_geom* g, const int32_t* counts, int32_t* plan, void* stream) {
   int st = check_geom(g);
   if (st != PCL_OK) return st;
-  PCL_REQUIRE(chunk_pref && counts && plan);
+  PCL_REQUIRE(counts && plan);
   cudaStream_t s = (cudaStream_t)stream;
   const int nchunk = (int)ceil_div64((int64_t)g->h * g->w, PCL_CHUNK);
-  PCL_CUDA(cudaMemsetAsync(plan, 0, PCL_PLAN_HEADER * sizeof(int32_t), s));
-  k_plan<<<1, PLAN_THREADS, 0, s>>>(*g, nchunk, chunk_pref, counts, plan);
+  k_plan<<<1, PLAN_THREADS, 0, s>>>(*g, nchunk, counts, plan);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
@@ -359,18 +379,14 @@ extern "C" int pcl_select_gather(const pcl_geom* g, const float* embed, const ui
   cudaStream_t s = (cudaStream_t)stream;
   const int ms = g->max_samples;
   const int nchunk = (int)ceil_div64((int64_t)g->h * g->w, PCL_CHUNK);
-  PCL_CUDA(cudaMemsetAsync(anchor_meta, 0xFF, 4 * (size_t)ms * sizeof(int32_t), s));
-  PCL_CUDA(cudaMemsetAsync(anchors_f32, 0, (size_t)ms * g->D * sizeof(float), s));
-  if (anchors_bf16) {
-    size_t rows = (size_t)ceil_div(ms, 128) * 128;
-    PCL_CUDA(cudaMemsetAsync(anchors_bf16, 0, rows * g->D * sizeof(__nv_bfloat16), s));
-  }
-  PCL_CUDA(cudaMemsetAsync(inv_norm, 0, (size_t)ms * sizeof(float), s));
   PCL_CUDA(cudaMemsetAsync(norm_max, 0, sizeof(float), s));
   const int warps = 8;
-  k_select<<<ceil_div(ms, warps), warps * 32, 0, s>>>(*g, nchunk, embed, keys, chunk_pref, plan, ranks, seed,
-                                                     normalize, anchor_meta, anchors_f32,
-                                                     (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max);
+  // rows in [A, max_samples) are zero-filled by the kernel itself (no separate memsets); the bf16 copy is padded to
+  // a multiple of 128 rows: cover those too
+  const int rows = anchors_bf16 ? ceil_div(ms, 128) * 128 : ms;
+  k_select<<<ceil_div(rows, warps), warps * 32, 0, s>>>(*g, nchunk, embed, keys, chunk_pref, plan, ranks, seed,
+                                                       normalize, anchor_meta, anchors_f32,
+                                                       (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

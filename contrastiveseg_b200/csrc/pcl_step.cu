@@ -41,9 +41,9 @@ static void fill_tc(const pcl_step_desc* d, pcl_tc_desc* t) {
 
 extern "C" int pcl_step_stats(const pcl_step_desc* d, void* stream) {
   if (!d) return PCL_ERR_ARG;
-  int st = pcl_class_stats(&d->g, d->labels, d->seg, d->predict, d->keys, d->chunk_pref, stream);
+  int st = pcl_class_stats(&d->g, d->labels, d->seg, d->predict, d->keys, d->chunk_pref, d->counts, stream);
   if (st != PCL_OK) return st;
-  return pcl_plan_anchors(&d->g, d->chunk_pref, d->counts, d->plan, stream);
+  return pcl_plan_anchors(&d->g, d->counts, d->plan, stream);
 }
 
 extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {

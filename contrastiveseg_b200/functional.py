@@ -408,13 +408,15 @@ def _tc_desc(anchors, anchor_cls, contrast_bf16, contrast_cls, n_cols, bank, dia
 def infonce_tc_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast_bf16: Optional[torch.Tensor] = None,
                        contrast_cls: Optional[torch.Tensor] = None, n_cols: int = 0, bank=None,
                        diag_col: Optional[torch.Tensor] = None, temperature: float = 0.1, base_temperature: float = 0.07,
-                       nan_safe: bool = False, sorted_cols: bool = True, norm_bound: float = 1.0):
-    """bf16 tcgen05 sweep.  Returns (loss (1,), rowstats (6, A), state)."""
+                       nan_safe: bool = False, sorted_cols: bool = True, norm_bound: float = 1.0, neg_only: bool = False):
+    """bf16 tcgen05 sweep.  Returns (loss (1,), rowstats (6, A), state).  neg_only=True runs just the similarity +
+    negative-sum sweep (roofline measurement of the dense contraction)."""
     lib = _abi.load()
     _require_cuda(anchors, "anchors")
     dev = anchors.device
     d, keep, a_pad = _tc_desc(anchors, anchor_cls, contrast_bf16, contrast_cls, n_cols, bank, diag_col, temperature,
                               base_temperature, nan_safe, sorted_cols, norm_bound)
+    d.neg_only = int(neg_only)
     ss = _abi.SweepSizes()
     _abi.check(lib.pcl_tc_sizes(C.byref(d), C.byref(ss)), "pcl_tc_sizes")
     row_m2 = torch.empty(a_pad + 512, dtype=torch.float32, device=dev)

@@ -62,7 +62,7 @@ typedef struct {
 /* Element counts of the selection scratch buffers for a geometry. */
 typedef struct {
   int64_t keys_u16;            /* B*h*w             uint16 pixel keys (2*label + easy, 2K = ignored) */
-  int64_t chunk_pref_i32;      /* B*2K*nchunk       exclusive per-chunk prefix of key counts        */
+  int64_t chunk_pref_i32;      /* B*2K*nchunk       per-chunk histogram of the pixel keys           */
   int64_t counts_i32;          /* B*2K              per-image key totals                            */
   int64_t plan_i32;            /* header + 8 words per (image,class) pair                           */
   int64_t anchor_meta_i32;     /* 4*max_samples     pixel, image, class, reference row              */
@@ -81,12 +81,12 @@ int pcl_select_sizes(const pcl_geom* g, pcl_select_sizes_t* out);
  *   predict  (B,h,w) int64 or NULL       — used when seg is NULL
  * ----------------------------------------------------------------------------------------------*/
 int pcl_class_stats(const pcl_geom* g, const int64_t* labels, const float* seg, const int64_t* predict,
-                    uint16_t* keys, int32_t* chunk_pref, void* stream);
+                    uint16_t* keys, int32_t* chunk_pref, int32_t* counts, void* stream);
 
 /* a4: class filter (count > max_views), TC, V = min(max_samples / TC, max_views), hard/easy split
  * rule and the class-sorted anchor row layout.  Replaces lib/loss/loss_contrast.py:37-48,63-77.
- * chunk_pref is turned into exclusive prefixes in place; counts and plan are written. */
-int pcl_plan_anchors(const pcl_geom* g, int32_t* chunk_pref, int32_t* counts, int32_t* plan, void* stream);
+ * Reads the per-image key totals `counts` written by pcl_class_stats; writes the plan. */
+int pcl_plan_anchors(const pcl_geom* g, const int32_t* counts, int32_t* plan, void* stream);
 
 /* a4 (second half) + gather: choose the pixels of every anchor row and gather their embeddings.
  * Replaces lib/loss/loss_contrast.py:79-86 (randperm, index, X_[ptr] = X[ii, indices]) and the
@@ -224,6 +224,8 @@ typedef struct {
   float contrast_norm_bound;
   float temperature, base_temperature;
   int32_t nan_safe;
+  int32_t neg_only;              /* 1: stop after the similarity + negative-sum sweep (the dense contraction alone,
+                                    used to report its roofline fraction); loss / rowstats are then not final */
 } pcl_tc_desc;
 
 int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out);
