@@ -426,3 +426,76 @@ def test_bank_shadow_tracks_enqueue_and_tensor_path_uses_it():
     l16 = c16(data["embed"].to(DEV), data["target"].to(DEV), seg=data["seg"].to(DEV),
               queue=(bank.segment_queue, bank.pixel_queue), bank_shadow=bank.shadow)
     assert rel_err(l16.item(), l32.item()) < 1e-4
+
+
+def test_torch_cpu_rng_mode_draws_the_reference_stream():
+    """rng='torch_cpu': same torch CPU seed -> the engine samples exactly what the reference code path samples."""
+    g = load_golden("nomem_small")
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    embed = torch.from_numpy(g["embed"])
+    target, predict = torch.from_numpy(g["target"]), torch.from_numpy(g["predict"])
+    torch.manual_seed(1234)
+    e1 = embed.clone().double().requires_grad_(True)
+    ref = P.pixel_contrast_loss(e1, target, predict, temperature=T, base_temperature=bT, max_samples=int(ms),
+                                max_views=int(mv))                       # draws torch.randperm like the reference
+    crit = cs.PixelContrastLoss(_cfg(T, bT, ms, mv, K, {"rng": "torch_cpu"}))
+    torch.manual_seed(1234)
+    loss = crit(embed.to(DEV), target.to(DEV), predict.to(DEV))
+    assert rel_err(loss.item(), ref.item()) < 2e-6
+
+
+def test_trainer_hook_end_to_end_with_bank():
+    """C1-style plumbing: a small stand-in network ({'seg','embed','key','lb_key'} contract of hrnet.py:183-188),
+    the drop-in loss + bank through ContrastTrainerHook, SGD steps; first-step loss equals the oracle port."""
+    import torch.nn as nn
+    torch.manual_seed(0)
+    K, D = 5, 32
+
+    class TinyNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = nn.Sequential(nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.ReLU(),
+                                      nn.Conv2d(16, 24, 3, stride=2, padding=1), nn.ReLU())
+            self.cls = nn.Conv2d(24, K, 1)
+            self.proj = cs.ProjectionHead(24, D, proj="convmlp", bn_type="torchbn")
+
+        def forward(self, x, targets):
+            f = self.body(x)
+            emb = self.proj(f)
+            return {"seg": self.cls(f), "embed": emb, "key": emb.detach(), "lb_key": targets}
+
+    cfg = cs.Configer({"data": {"num_classes": K}, "network": {"stride": 4},
+                       "loss": {"loss_type": "mem_contrast_ce_loss", "params": {"ce_ignore_index": -1}},
+                       "contrast": {"temperature": 0.07, "base_temperature": 0.07, "max_samples": 64, "max_views": 4,
+                                    "loss_weight": 0.1, "use_rmi": False, "use_lovasz": False, "warmup_iters": 1,
+                                    "with_memory": True, "memory_size": 16, "pixel_update_freq": 3}})
+    net = TinyNet().to(DEV)
+    bank = cs.MemoryBank(K, 16, D).to(DEV)
+    hook = cs.ContrastTrainerHook(cfg, bank)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01)
+    x = torch.randn(2, 3, 64, 64, device=DEV)
+    from contrastiveseg_b200.synth import block_label_map
+    tgt = block_label_map(2, 64, 64, 16, K, torch.Generator().manual_seed(3)).to(DEV)
+    ptr0 = bank.pixel_queue_ptr.clone()
+    losses = []
+    for it in range(3):
+        out = net(x, tgt)
+        if it == 1:          # compare the loss value of one post-warm-up step with the oracle on the same samples
+            rec = P.PermRecorder(torch.Generator().manual_seed(9))
+            hook.pixel_loss.contrast_criterion.perm_fn = rec
+            sq, pq = bank.segment_queue.clone().cpu(), bank.pixel_queue.clone().cpu()
+        loss = hook.loss_step(out, tgt, iters=it)
+        if it == 1:
+            hook.pixel_loss.contrast_criterion.perm_fn = None
+            ref = P.contrast_ce_loss({"seg": out["seg"].detach().cpu(), "embed": out["embed"].detach().cpu(),
+                                      "segment_queue": sq, "pixel_queue": pq}, tgt.cpu(), with_embed=True,
+                                     loss_weight=0.1, temperature=0.07, base_temperature=0.07, max_samples=64, max_views=4,
+                                     with_memory=True, perm_fn=P.PermReplay(rec.draws))
+            assert rel_err(loss.item(), ref.item()) < 1e-5
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses))
+    assert not torch.equal(bank.pixel_queue_ptr, ptr0)            # the bank advanced
+    assert net.proj.proj[0].weight.grad is not None and net.proj.proj[0].weight.grad.abs().sum().item() > 0
