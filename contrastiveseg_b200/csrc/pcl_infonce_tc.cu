@@ -150,6 +150,17 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       t_hi = (a.cls_start[hi + 1] + BN - 1) / BN;
       if (t_hi < t_lo) t_hi = t_lo;
     }
+    if (MODE == TC_POS && a.mode == 0 && a.sorted) {
+      // self-contrast with class-grouped anchors: the positives of this row tile are the rows of its classes, one
+      // contiguous run [lo, hi) around the tile
+      const int last = min(A - 1, row0 + BM - 1);
+      const int c_first = a.acls[row0], c_last = a.acls[last];
+      int lo = row0, hi = last + 1;
+      while (lo > 0 && a.acls[lo - 1] == c_first) --lo;
+      while (hi < A && a.acls[hi] == c_last) ++hi;
+      t_lo = lo / BN;
+      t_hi = (hi + BN - 1) / BN;
+    }
     if (MODE == TC_POS && a.mode == 1) {
       const int last = min(A - 1, row0 + BM - 1);
       int rk_f = class_rank(a.acls[row0], a.K), rk_l = class_rank(a.acls[last], a.K);
@@ -262,22 +273,37 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       float neg_i = 1.f;
       if (MODE == TC_POS) neg_i = valid ? rowstats[a.a_rows + row] : 1.f;
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
+      int nlab_lo[4], nlab_hi[4];                              // first / last label of the 4 chunks of the next tile
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const int cb = sg.ct0 * BN + half * (BN / 2) + ch * 32;
+        const bool in = sg.ct0 < sg.ct1 && a.sorted && cb + 32 <= ncols;
+        nlab_lo[ch] = in ? col_label(a, cb) : -2;
+        nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
+      }
       for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
         const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
         const int col0 = ct * BN + half * (BN / 2);
         // Per 32-column chunk: if the chunk is complete and of one class (sorted contrast set) every row treats it as
         // all-negative or all-positive without a per-element test.  Mixed chunks (a class boundary, the ragged end,
         // self-contrast) fetch one label per lane and broadcast it with warp shuffles — no dependent loads.
+        // (labels were fetched one tile ahead: the loads are in flight while the previous tile is processed)
         int clab[4];
         bool cuni[4];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int cb = col0 + ch * 32;
-          cuni[ch] = false;
-          clab[ch] = -2;
-          if (a.sorted && cb + 32 <= ncols) {
-            clab[ch] = col_label(a, cb);
-            cuni[ch] = clab[ch] == col_label(a, cb + 31);
+          clab[ch] = nlab_lo[ch];
+          cuni[ch] = a.sorted && cb + 32 <= ncols && nlab_lo[ch] == nlab_hi[ch];
+        }
+        if (ct + 1 < sg.ct1) {
+          const int ncol0 = (ct + 1) * BN + half * (BN / 2);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int cb = ncol0 + ch * 32;
+            const bool in = a.sorted && cb + 32 <= ncols;
+            nlab_lo[ch] = in ? col_label(a, cb) : -2;
+            nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
           }
         }
         ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
@@ -486,9 +512,8 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const uint32_t a_base = ptx::smem_u32(sm.a), c_base = ptx::smem_u32(sm.c), g_base = ptx::smem_u32(sm.g);
       ptx::mbar_wait(&sm.a_full, 0);
       ptx::tc_fence_after();
-      auto mma2 = [&](int t) {
+      auto mma2 = [&](int t) {                    // caller has observed g_full of tile t
         const int stage = t & 1;
-        ptx::mbar_wait(&sm.g_full, t & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BNB / 16; ++k) {
@@ -501,26 +526,44 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         ptx::mma_commit(&sm.g_empty);
         ptx::mma_commit(&sm.c_empty[stage]);
       };
-      for (int it = 0; it < ntiles; ++it) {
-        const int stage = it & 1, phase = (it >> 1) & 1;
-        const uint32_t acc = it & 1;
-        ptx::mbar_wait(&sm.s_empty[acc], phase ^ 1);
-        ptx::mbar_wait(&sm.c_full[stage], phase);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BNB;
+      // Readiness-driven issue order: MMA1(n1) (needs a free S buffer and the contrast tile) and MMA2(n2) (needs the
+      // gradient tile G(n2) from the epilogue) are issued as soon as their inputs are ready, so a slow epilogue of
+      // tile n2 never delays the similarity MMA of the tiles behind it.
+      int n1 = 0, n2 = 0;
+      uint32_t idle = 0;
+      while (n2 < ntiles) {
+        bool progressed = false;
+        if (n1 < ntiles) {
+          const int stage = n1 & 1, phase = (n1 >> 1) & 1;
+          const uint32_t acc = n1 & 1;
+          if (ptx::mbar_try_wait(&sm.s_empty[acc], phase ^ 1) && ptx::mbar_try_wait(&sm.c_full[stage], phase)) {
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BNB;
 #pragma unroll
-        for (int kb = 0; kb < NKB; ++kb) {
+            for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
-            const uint64_t dc = ptx::make_desc_kmajor_sw128(c_base + stage * C_STAGE_BYTES + kb * C_KB_BYTES + k * 32);
-            ptx::mma_f16_ss(d_tmem, da, dc, idesc1, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * A_KB_BYTES + k * 32);
+                const uint64_t dc = ptx::make_desc_kmajor_sw128(c_base + stage * C_STAGE_BYTES + kb * C_KB_BYTES + k * 32);
+                ptx::mma_f16_ss(d_tmem, da, dc, idesc1, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::mma_commit(&sm.s_full[acc]);
+            ++n1;
+            progressed = true;
           }
         }
-        ptx::mma_commit(&sm.s_full[acc]);
-        if (it > 0) mma2(it - 1);                 // deferred one tile: epilogue(it-1) overlaps MMA1(it)
+        if (n2 < n1 && ptx::mbar_try_wait(&sm.g_full, n2 & 1)) {
+          mma2(n2);
+          ++n2;
+          progressed = true;
+        }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 26)) {
+          printf("pcl: k_tc_bwd MMA issuer stuck block (%d,%d) n1=%d n2=%d of %d\n", blockIdx.x, blockIdx.y, n1, n2, ntiles);
+          __trap();
+        }
       }
-      mma2(ntiles - 1);
       ptx::mma_commit(&sm.da_full);
     }
   } else {
@@ -544,6 +587,14 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const float cs_i = c_i * s_i;
     const float cn_i = -c_i * neg_i;
     uint8_t* g_row = sm.g + r_in * 128;           // + kblock * 16 KB + swizzled 16-byte chunk
+    int nlab_lo[2], nlab_hi[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int cb = my_lo * BNB + half * 64 + ch * 32;
+      const bool in = ntiles > 0 && a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
+      nlab_lo[ch] = in ? col_label(a, cb) : -2;
+      nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
+    }
     for (int it = 0; it < ntiles; ++it) {
       const int ct = my_lo + it;
       const uint32_t acc = it & 1, phase = (it >> 1) & 1;
@@ -553,11 +604,16 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         const int cb = col0 + ch * 32;
-        cuni[ch] = false;
-        clab[ch] = -2;
-        if (a.sorted && a.mode != 0 && cb + 32 <= (int)ncols) {
-          clab[ch] = col_label(a, cb);
-          cuni[ch] = clab[ch] == col_label(a, cb + 31);
+        clab[ch] = nlab_lo[ch];
+        cuni[ch] = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols && nlab_lo[ch] == nlab_hi[ch];
+      }
+      if (it + 1 < ntiles) {                       // labels of the next tile: loads fly while this tile is processed
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int cb = (ct + 1) * BNB + half * 64 + ch * 32;
+          const bool in = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
+          nlab_lo[ch] = in ? col_label(a, cb) : -2;
+          nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
         }
       }
       ptx::mbar_wait(&sm.s_full[acc], phase);
@@ -799,7 +855,9 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   a.a_pad = p->row_tiles * tc::BM;
   int tail = 0;
   if (d->mode == 0) {
-    a.n_cols = d->a_rows; a.sorted = 0; a.K = 0; a.R = 1;
+    // self-contrast: the columns are the anchors, which the engine keeps grouped by class (any grouping order makes
+    // "first label == last label" a valid uniformity test for a 32-column chunk)
+    a.n_cols = d->a_rows; a.sorted = d->sorted ? 1 : 0; a.K = 0; a.R = 1;
   } else if (d->mode == 1) {
     if (d->bank_K < 1 || d->bank_R < 1) return PCL_ERR_ARG;
     a.K = d->bank_K; a.R = d->bank_R; a.n_cols = (int64_t)(d->bank_K - 1) * d->bank_R; a.sorted = 1; tail = d->bank_R;
