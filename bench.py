@@ -38,6 +38,15 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from a .ncu-rep); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("dram_bytes")
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -389,7 +398,9 @@ def run_engine(args, cfg, bank, rank, world, dev):
     stages = {}
     if not bank:
         stages, A = stage_timings(cfg, inp, dev, args.precision)
-        dom = max(stages, key=stages.get)
+        # roofline of the one single-pass bandwidth-bound kernel of the step, the dense-gradient writer (the other
+        # stages are chains of short latency-bound launches at A <= 1024; stage_ms lists them all)
+        dom = "scatter_grad"
         BDHW4 = cfg["B"] * cfg["D"] * cfg["h"] * cfg["w"] * 4
         alg_bytes = {
             "scatter_grad": BDHW4 + 2 * A * cfg["D"] * 4,
@@ -399,8 +410,9 @@ def run_engine(args, cfg, bank, rank, world, dev):
         if dom in alg_bytes:
             ach = alg_bytes[dom] / (stages[dom] * 1e-3) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                    "algorithmic_bytes": alg_bytes[dom]}
+                    "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("k_zero_scatter"),
+                    "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes[dom],
+                    "kernel_name": "k_zero_scatter" if dom == "scatter_grad" else dom}
         else:
             flops = 2.0 * A * A * cfg["D"] * (2 if dom == "infonce_fwd" else 2)
             ach = flops / (stages[dom] * 1e-3) / 1e12

@@ -311,6 +311,32 @@ k_scatter(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_zero_scatter: the dense gradient in ONE pass — each CTA owns one (image, channel) plane of h*w floats, zero-fills
+// it with 16-byte stores and then drops in the gradient entries of the anchors sampled from that image.
+// HBM-bound: writes B*D*h*w*4 bytes once (the floor of the backward: autograd needs the dense tensor).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_zero_scatter(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restrict__ meta,
+               const float* __restrict__ dA, float* __restrict__ grad) {
+  const int plane = blockIdx.x;
+  const int D = g.D, ms = g.max_samples;
+  const int b = plane / D, d = plane - b * D;
+  const int64_t HW = (int64_t)g.h * g.w;
+  float* dst = grad + (int64_t)plane * HW;
+  if ((HW & 3) == 0) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = threadIdx.x; i < HW / 4; i += blockDim.x) d4[i] = z;
+  } else {
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) dst[i] = 0.f;
+  }
+  __syncthreads();
+  const int A = min(plan[PCL_PLAN_A], ms);
+  for (int s = threadIdx.x; s < A; s += blockDim.x)
+    if (meta[ms + s] == b) dst[meta[s]] = dA[(int64_t)s * D + d];
+}
+
 }  // namespace pcl
 
 using namespace pcl;
@@ -399,6 +425,11 @@ extern "C" int pcl_scatter_grad(const pcl_geom* g, const int32_t* plan, const in
   PCL_REQUIRE(plan && anchor_meta && dA && grad_embed);
   if (normalize) PCL_REQUIRE(anchors_f32 && inv_norm);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!normalize) {
+    k_zero_scatter<<<(unsigned)(g->B * g->D), 256, 0, s>>>(*g, plan, anchor_meta, dA, grad_embed);
+    PCL_LAUNCH_CHECK();
+    return PCL_OK;
+  }
   size_t bytes = (size_t)g->B * g->D * g->h * g->w * sizeof(float);
   PCL_CUDA(cudaMemsetAsync(grad_embed, 0, bytes, s));
   const int warps = 8;

@@ -499,3 +499,28 @@ def test_trainer_hook_end_to_end_with_bank():
     assert all(np.isfinite(losses))
     assert not torch.equal(bank.pixel_queue_ptr, ptr0)            # the bank advanced
     assert net.proj.proj[0].weight.grad is not None and net.proj.proj[0].weight.grad.abs().sum().item() > 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_coco_stuff_shape_171_classes_with_bank(precision):
+    """BASELINE configs[3] geometry (520x520 -> 66x66 embedding, 171 classes, non-divisible nearest interpolation,
+    bank) at a reduced memory size; both sweeps against the float64 oracle on replayed permutations."""
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    K, D, M = 171, 256, 24
+    data = make_contrast_batch(B=2, D=D, h=66, w=66, num_classes=K, img_stride=8, block=40, seed=171, himg=520, wimg=520)
+    bank = make_bank(K, M, D, 172)
+    rec = P.PermRecorder(torch.Generator().manual_seed(4))
+    e64 = data["embed"].double().requires_grad_(True)
+    queue = torch.cat((bank["segment_queue"], bank["pixel_queue"]), 1)
+    ref = P.pixel_contrast_loss(e64, data["target"], data["seg"].argmax(1), temperature=0.07, base_temperature=0.07,
+                                max_samples=1024, max_views=10, queue=queue.double(), perm_fn=rec)
+    ref.backward()
+    crit = cs.PixelContrastLoss(_cfg(0.07, 0.07, 1024, 10, K, {"precision": precision}))
+    crit.perm_fn = P.PermReplay(rec.draws)
+    embed = data["embed"].to(DEV).requires_grad_(True)
+    loss = crit(embed, data["target"].to(DEV), seg=data["seg"].to(DEV),
+                queue=(bank["segment_queue"].to(DEV), bank["pixel_queue"].to(DEV)))
+    loss.backward()
+    tol_l, tol_g = (2e-6, 1e-5) if precision == "fp32" else (1e-4, 4e-3)
+    assert rel_err(loss.item(), ref.item()) < tol_l
+    assert (embed.grad.cpu().double() - e64.grad).abs().max().item() <= tol_g * e64.grad.abs().max().item()
