@@ -348,8 +348,8 @@ def run_engine(args, cfg, bank, rank, world, dev):
     barrier()
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    per_step = []
     barrier()
+    t_wall0 = time.perf_counter()
     ev[0].record()
     for _ in range(args.steps):
         if flush is not None:
@@ -357,6 +357,14 @@ def run_engine(args, cfg, bank, rank, world, dev):
         step(embed, inp["target"], inp["seg"])
     ev[1].record()
     barrier()
+    # nvidia-smi samples every 100 ms; a short timed region (K steps of ~0.2 ms) would see no sample, so the SAME
+    # step loop keeps running (untimed) until the sampler has covered >= 0.6 s under load
+    clock_window = "timed region"
+    while time.perf_counter() - t_wall0 < 0.6:
+        clock_window = "timed region + untimed continuation of the same step loop to 0.6 s"
+        for _ in range(50):
+            step(embed, inp["target"], inp["seg"])
+        torch.cuda.synchronize(dev)
     sampler.stop()
     t_ms = ev[0].elapsed_time(ev[1])
     tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
@@ -440,7 +448,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
-            "data": "synthetic", "config": workload_config(cfg, bank), "clocks": sampler.summary(),
+            "data": "synthetic", "config": workload_config(cfg, bank), "clocks": dict(sampler.summary(), window=clock_window),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,

@@ -156,8 +156,20 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int last = min(A - 1, row0 + BM - 1);
       const int c_first = a.acls[row0], c_last = a.acls[last];
       int lo = row0, hi = last + 1;
-      while (lo > 0 && a.acls[lo - 1] == c_first) --lo;
-      while (hi < A && a.acls[hi] == c_last) ++hi;
+      for (;;) {                                   // warp-parallel run search: 32 rows per probe, no dependent loads
+        const int idx = lo - 1 - lane;
+        const unsigned m = __ballot_sync(0xffffffffu, idx >= 0 && a.acls[idx] == c_first);
+        const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;
+        lo -= run;
+        if (run < 32) break;
+      }
+      for (;;) {
+        const int idx = hi + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, idx < A && a.acls[idx] == c_last);
+        const int run = (m == 0xffffffffu) ? 32 : __ffs(~m) - 1;
+        hi += run;
+        if (run < 32) break;
+      }
       t_lo = lo / BN;
       t_hi = (hi + BN - 1) / BN;
     }
