@@ -356,6 +356,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             flush.zero_()
         step(embed, inp["target"], inp["seg"])
     ev[1].record()
+    t_enqueue = time.perf_counter() - t_wall0        # host time to enqueue the K steps (no sync inside)
     barrier()
     # nvidia-smi samples every 100 ms; a short timed region (K steps of ~0.2 ms) would see no sample, so the SAME
     # step loop keeps running (untimed) until the sampler has covered >= 0.6 s under load
@@ -452,7 +453,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "tensor_roofline": tens, "precision": args.precision, "impl": "engine"}
+            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "precision": args.precision, "impl": "engine"}
 
 
 def main():

@@ -64,6 +64,10 @@ class ContrastWorkspace:
         if self.tc_ok:                       # the tensor sweep uses its own split count: size for the larger of the two
             td = _abi.TcDesc()
             td.a_rows, td.D, td.mode = ms, D, mode
+            # the step passes the device-side plan (live anchor count unknown on the host): the partial-slot count
+            # depends on that, so size with a non-null plan exactly like the runtime descriptor
+            self.plan = torch.zeros(sizes.plan_i32, dtype=torch.int32, device=device)
+            td.plan = self.plan.data_ptr()
             td.bank_K, td.bank_R = bank_K, bank_M0 + bank_M1
             td.temperature, td.base_temperature = 1.0, 1.0
             ts = _abi.SweepSizes()
@@ -74,7 +78,8 @@ class ContrastWorkspace:
         self.keys = torch.empty(sizes.keys_u16, dtype=torch.int16, device=device)
         self.chunk_pref = torch.empty(sizes.chunk_pref_i32, **i32)
         self.counts = torch.empty(sizes.counts_i32, **i32)
-        self.plan = torch.zeros(sizes.plan_i32, **i32)
+        if not hasattr(self, "plan"):
+            self.plan = torch.zeros(sizes.plan_i32, **i32)
         self.anchor_meta = torch.empty(sizes.anchor_meta_i32, **i32)
         self.anchors_f32 = torch.empty((ms, D), **f32)
         self.anchors_bf16 = torch.empty((-(-ms // 128) * 128, D), dtype=torch.bfloat16, device=device)

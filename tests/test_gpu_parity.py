@@ -524,3 +524,31 @@ def test_coco_stuff_shape_171_classes_with_bank(precision):
     tol_l, tol_g = (2e-6, 1e-5) if precision == "fp32" else (1e-4, 4e-3)
     assert rel_err(loss.item(), ref.item()) < tol_l
     assert (embed.grad.cpu().double() - e64.grad).abs().max().item() <= tol_g * e64.grad.abs().max().item()
+
+
+def test_bank_tensor_path_workspace_sizes_cover_runtime_slots():
+    """Regression: the step's partial buffers must be sized for the persistent sweep's slot count with a device-side
+    plan (148 slots), not the host-known case (a buffer overrun here corrupted neighbouring allocations)."""
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    K, D, M = 19, 256, 2000
+    data = make_contrast_batch(B=1, D=D, h=64, w=64, num_classes=K, img_stride=4, block=16, seed=3)
+    bank = make_bank(K, M, D, 4)
+    crit = cs.PixelContrastLoss(_cfg(0.07, 0.07, 1024, 100, K, {"precision": "bf16"}))
+    embed = data["embed"].to(DEV).requires_grad_(True)
+    guard = torch.zeros(1 << 20, device=DEV)                  # neighbour allocation that must stay untouched
+    for _ in range(3):
+        loss = crit(embed, data["target"].to(DEV), seg=data["seg"].to(DEV),
+                    queue=(bank["segment_queue"].to(DEV), bank["pixel_queue"].to(DEV)))
+        loss.backward()
+    torch.cuda.synchronize()
+    ws = Fn.last_workspace(embed.device)
+    import ctypes as C
+    from contrastiveseg_b200 import _abi
+    td = _abi.TcDesc()
+    td.a_rows, td.D, td.mode, td.bank_K, td.bank_R = 1024, D, 1, K, 2 * M
+    td.plan = ws.plan.data_ptr()
+    td.temperature = td.base_temperature = 1.0
+    ss = _abi.SweepSizes()
+    _abi.check(_abi.load().pcl_tc_sizes(C.byref(td), C.byref(ss)))
+    assert ws.partials.numel() >= 5 * ss.partial_f32 and ws.dpartials.numel() >= ss.dpartial_f32
+    assert guard.abs().max().item() == 0 and torch.isfinite(loss).item()
