@@ -36,6 +36,24 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """torch.cuda.device(...) only when the tensor's device is not already current (saves ~10 us per call)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device: torch.device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise _abi.PclError(f"{name} must be a CUDA tensor: the engine has no CPU path")
@@ -141,14 +159,18 @@ class _PixelContrastFn(torch.autograd.Function):
         device = embed.device
         if embed.dtype != torch.float32:
             raise _abi.PclError("embed must be float32 (the reference trainer runs without AMP)")
-        embed_c = embed.contiguous()
-        labels_c = labels.to(device=device, dtype=torch.int64).contiguous()
+        embed_c = embed if embed.is_contiguous() else embed.contiguous()
+        labels_c = labels
+        if labels.device != device or labels.dtype != torch.int64 or not labels.is_contiguous():
+            labels_c = labels.to(device=device, dtype=torch.int64).contiguous()
         B, D, h, w = embed_c.shape
         if labels_c.dim() != 3 or labels_c.shape[0] != B:
             raise _abi.PclError("labels must be (B, Himg, Wimg)")
         seg_c = pred_c = None
         if seg is not None:
-            seg_c = seg.detach().to(torch.float32).contiguous()
+            seg_c = seg.detach()
+            if seg_c.dtype != torch.float32 or not seg_c.is_contiguous():
+                seg_c = seg_c.to(torch.float32).contiguous()
             if seg_c.shape[0] != B or tuple(seg_c.shape[2:]) != (h, w):
                 raise _abi.PclError("seg must be (B, K, h, w) at the embedding resolution")
         elif predict is not None:
@@ -159,21 +181,34 @@ class _PixelContrastFn(torch.autograd.Function):
         segq_c = pixq_c = None
         if segq is not None:
             mode = 1
-            segq_c = segq.detach().to(torch.float32).contiguous()
+            segq_c = segq.detach()
+            if segq_c.dtype != torch.float32 or not segq_c.is_contiguous():
+                segq_c = segq_c.to(torch.float32).contiguous()
             bank_K, M0 = segq_c.shape[0], segq_c.shape[1]
             if pixq is not None:
-                pixq_c = pixq.detach().to(torch.float32).contiguous()
+                pixq_c = pixq.detach()
+                if pixq_c.dtype != torch.float32 or not pixq_c.is_contiguous():
+                    pixq_c = pixq_c.to(torch.float32).contiguous()
                 M1 = pixq_c.shape[1]
             if segq_c.shape[2] != D:
                 raise _abi.PclError("bank feature dim differs from the embedding dim")
         K = opts.num_classes or (seg_c.shape[1] if seg_c is not None else (bank_K if mode == 1 else _abi.MAX_CLASSES))
         if seg_c is not None and seg_c.shape[1] != K:
             raise _abi.PclError("num_classes differs from the number of seg planes")
-        geom = _abi.Geom(B, D, h, w, labels_c.shape[1], labels_c.shape[2], K, opts.max_samples, opts.max_views,
-                         opts.ignore_label)
         key = (B, D, h, w, labels_c.shape[1], labels_c.shape[2], K, opts.max_samples, opts.max_views,
                opts.ignore_label, mode, bank_K, M0, M1)
-        ws = _get_workspace(device, key, geom, mode, bank_K, M0, M1)
+        lst = _WS_CACHE.get((device.index, key))
+        ws = None
+        if lst:
+            for cand in lst:
+                if not cand.busy:
+                    ws = cand
+                    _LAST_WS[device.index] = ws
+                    break
+        if ws is None:
+            geom = _abi.Geom(B, D, h, w, labels_c.shape[1], labels_c.shape[2], K, opts.max_samples, opts.max_views,
+                             opts.ignore_label)
+            ws = _get_workspace(device, key, geom, mode, bank_K, M0, M1)
         d = ws.desc
         d.embed, d.labels = embed_c.data_ptr(), labels_c.data_ptr()
         d.seg = _abi.ptr(seg_c)
@@ -205,7 +240,9 @@ class _PixelContrastFn(torch.autograd.Function):
             raise _abi.PclError(f"unknown precision {opts.precision!r}")
         _step_counter[0] += 1
         d.seed = (int(opts.seed) * 0x9E3779B97F4A7C15 + _step_counter[0]) & 0xFFFFFFFFFFFFFFFF
-        with torch.cuda.device(device):
+        out = torch.empty((), dtype=torch.float32, device=device)     # the loss is written here directly
+        d.loss = out.data_ptr()
+        with _on_device(device):
             stream = _stream_ptr(device)
             _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
             if opts.perm_fn is not None or opts.rng == "torch_cpu":
@@ -228,7 +265,7 @@ class _PixelContrastFn(torch.autograd.Function):
         ctx.keep = (embed_c, labels_c, seg_c, pred_c, segq_c, pixq_c, shadow_c)   # keep inputs alive until kernels ran
         if embed.requires_grad and torch.is_grad_enabled():
             ws.busy = True
-        return ws.loss[0].clone()
+        return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -237,10 +274,12 @@ class _PixelContrastFn(torch.autograd.Function):
         ws = ctx.ws
         device = ws.device
         grad = torch.empty(ctx.embed_shape, dtype=torch.float32, device=device)
-        go = grad_out.detach().to(device=device, dtype=torch.float32).contiguous().view(1)
+        go = grad_out
+        if go.device != device or go.dtype != torch.float32 or not go.is_contiguous():
+            go = go.detach().to(device=device, dtype=torch.float32).contiguous()
         d = ws.desc
         d.grad_embed = grad.data_ptr()
-        with torch.cuda.device(device):
+        with _on_device(device):
             _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
         ws.busy = False
         ctx.keep = None
