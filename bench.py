@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -344,9 +344,12 @@ def run_engine(args, cfg, bank, rank, world, dev):
 
     for _ in range(max(args.warmup, 3)):
         step(embed, inp["target"], inp["seg"])
+    # one nvidia-smi poller for the whole job (rank 0, its own GPU): every poll takes driver locks that stall kernel
+    # launches of ALL ranks, so N pollers would perturb a host-launch-bound step
     sampler = ClockSampler(dev.index)
     barrier()
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -358,11 +361,11 @@ def run_engine(args, cfg, bank, rank, world, dev):
     ev[1].record()
     t_enqueue = time.perf_counter() - t_wall0        # host time to enqueue the K steps (no sync inside)
     barrier()
-    # nvidia-smi samples every 100 ms; a short timed region (K steps of ~0.2 ms) would see no sample, so the SAME
-    # step loop keeps running (untimed) until the sampler has covered >= 0.6 s under load
+    # nvidia-smi samples every 200 ms; a short timed region (K steps of ~0.2 ms) would see no sample, so the SAME
+    # step loop keeps running (untimed) until the sampler has covered >= 0.9 s under load
     clock_window = "timed region"
-    while time.perf_counter() - t_wall0 < 0.6:
-        clock_window = "timed region + untimed continuation of the same step loop to 0.6 s"
+    while time.perf_counter() - t_wall0 < 0.9:
+        clock_window = "timed region + untimed continuation of the same step loop to 0.9 s"
         for _ in range(50):
             step(embed, inp["target"], inp["seg"])
         torch.cuda.synchronize(dev)

@@ -750,7 +750,16 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 // anchors fp32 -> bf16 rows (optional) and the per-row stabiliser m2 = |bf16(a)| * cbound * log2(e)/T
 __global__ void k_tc_prep(const float* __restrict__ anchors, __nv_bfloat16* __restrict__ out_bf16,
                           const __nv_bfloat16* __restrict__ in_bf16, int a_rows, int a_pad, float cbound, float k1,
-                          float* __restrict__ row_m2) {
+                          float* __restrict__ row_m2, float* __restrict__ partials, int64_t n_slot_rows) {
+  // (a) partial slots that no CTA will write must read as "nothing seen": m = -inf, sums = 0
+  if (partials != nullptr) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_slot_rows; i += (int64_t)gridDim.x * blockDim.x) {
+      partials[i] = -CUDART_INF_F;
+#pragma unroll
+      for (int k = 1; k < 5; ++k) partials[k * n_slot_rows + i] = 0.f;
+    }
+  }
+  // (b) bf16 anchor rows (optional) and the per-row stabiliser
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= a_pad) return;
@@ -946,9 +955,10 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   a.row_m2 = row_m2;
   // 1. bf16 anchors (if fp32 given) + row stabilisers
   const float cbound = d->contrast_norm_bound > 0.f ? d->contrast_norm_bound : 1.0f;
+  const int64_t n_slot_rows = (int64_t)a.slots * a.a_pad;
   tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
                                                      (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, cbound,
-                                                     a.k1, row_m2);
+                                                     a.k1, row_m2, partials, n_slot_rows);
   PCL_LAUNCH_CHECK();
   if (d->mode == 2 && a.sorted) {
     int32_t* cls_start = reinterpret_cast<int32_t*>(row_m2 + a.a_pad);       // scratch tail: PCL_MAX_CLASSES + 1 ints
@@ -973,9 +983,6 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
     PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_POS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int64_t n_slot_rows = (int64_t)a.slots * a.a_pad;
-  tc::k_fill_partials<<<(unsigned)ceil_div64(n_slot_rows, 256), 256, 0, s>>>(partials, n_slot_rows);
-  PCL_LAUNCH_CHECK();
   dim3 grid(p.row_tiles, a.splits);
   const int variant = tc_variant();
   if (variant & 2) {                                   // tuning knob: 2-D grid instead of the persistent walk
@@ -1011,7 +1018,7 @@ extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* du
   a.row_m2 = row_m2;
   tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
                                                      (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, 1.f, a.k1,
-                                                     row_m2);
+                                                     row_m2, nullptr, 0);
   PCL_LAUNCH_CHECK();
   CUtensorMap tmA, tmB;
   st = make_tmap(&tmA, d->anchors_bf16, (uint64_t)a.a_pad, tc::BM);

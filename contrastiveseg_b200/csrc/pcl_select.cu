@@ -277,7 +277,7 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
     meta[2 * ms + s] = c;
     meta[3 * ms + s] = v * TC + t;
     inv_norm[s] = inv;
-    atomicMax(reinterpret_cast<int*>(norm_max), __float_as_int(nrm * inv));
+    if (norm_max != nullptr) atomicMax(reinterpret_cast<int*>(norm_max), __float_as_int(nrm * inv));
   }
 }
 
@@ -401,11 +401,11 @@ extern "C" int pcl_select_gather(const pcl_geom* g, const float* embed, const ui
                                  void* anchors_bf16, float* inv_norm, float* norm_max, void* stream) {
   int st = check_geom(g);
   if (st != PCL_OK) return st;
-  PCL_REQUIRE(embed && keys && chunk_pref && plan && anchor_meta && anchors_f32 && inv_norm && norm_max);
+  PCL_REQUIRE(embed && keys && chunk_pref && plan && anchor_meta && anchors_f32 && inv_norm);
   cudaStream_t s = (cudaStream_t)stream;
   const int ms = g->max_samples;
   const int nchunk = (int)ceil_div64((int64_t)g->h * g->w, PCL_CHUNK);
-  PCL_CUDA(cudaMemsetAsync(norm_max, 0, sizeof(float), s));
+  if (norm_max) PCL_CUDA(cudaMemsetAsync(norm_max, 0, sizeof(float), s));     // optional output
   const int warps = 8;
   // rows in [A, max_samples) are zero-filled by the kernel itself (no separate memsets); the bf16 copy is padded to
   // a multiple of 128 rows: cover those too

@@ -116,7 +116,7 @@ class ContrastWorkspace:
         d.g = geom
         d.mode, d.bank_K, d.bank_M0, d.bank_M1 = mode, bank_K, bank_M0, bank_M1
         for name in ("keys", "chunk_pref", "counts", "plan", "anchor_meta", "anchors_f32", "anchors_bf16", "inv_norm",
-                     "norm_max", "partials", "rowstats", "dpartials", "dA", "loss", "row_m2"):
+                     "partials", "rowstats", "dpartials", "dA", "loss", "row_m2"):      # norm_max: optional, unused
             setattr(d, name, getattr(self, name).data_ptr())
         self.desc = d
 

@@ -100,7 +100,7 @@ int pcl_plan_anchors(const pcl_geom* g, const int32_t* counts, int32_t* plan, vo
  *   anchor_meta (4,max_samples) int32: pixel, image, class, reference row r = v*TC + t
  *   anchors_f32 (max_samples,D), anchors_bf16 (max_samples rounded up to 128, D) or NULL,
  *   inv_norm (max_samples) fp32 (1/||x|| of the raw column; 1 when normalize == 0),
- *   norm_max  1 float, max over anchors of ||a|| (stabiliser bound for the tensor path). */
+ *   norm_max  optional (may be NULL): 1 float, max over anchors of ||a||. */
 int pcl_select_gather(const pcl_geom* g, const float* embed, const uint16_t* keys, const int32_t* chunk_pref,
                       const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize,
                       int32_t* anchor_meta, float* anchors_f32, void* anchors_bf16, float* inv_norm,
