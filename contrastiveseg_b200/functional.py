@@ -504,3 +504,58 @@ def infonce_tc_backward(state, rowstats: torch.Tensor, grad_loss: Optional[torch
                                           _abi.ptr(grad_loss), dpart.data_ptr(), dA.data_ptr(), _stream_ptr(dev)),
                    "pcl_infonce_tc_bwd")
     return dA
+
+
+# ------------------------------------------------------------------------------------------------
+# §8f row 1: fused bilinear up-sampling (align_corners=True) + weighted cross-entropy with ignore_index
+# (lib/loss/loss_contrast.py:180-181 + lib/loss/loss_helper.py:169-212)
+# ------------------------------------------------------------------------------------------------
+class _SegCeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seg, target, weight, ignore_index):
+        lib = _abi.load()
+        _require_cuda(seg, "seg")
+        dev = seg.device
+        seg_c = seg if (seg.dtype == torch.float32 and seg.is_contiguous()) else seg.to(torch.float32).contiguous()
+        tgt = target
+        if tgt.device != dev or tgt.dtype != torch.int64 or not tgt.is_contiguous():
+            tgt = tgt.to(device=dev, dtype=torch.int64).contiguous()
+        B, K, h, w = seg_c.shape
+        H, W = tgt.shape[1], tgt.shape[2]
+        wt = None
+        if weight is not None:
+            wt = weight.to(device=dev, dtype=torch.float32).contiguous()
+        scratch = torch.empty(lib.pcl_seg_ce_scratch_floats(B, H, W), dtype=torch.float32, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            _abi.check(lib.pcl_seg_ce_fwd(seg_c.data_ptr(), tgt.data_ptr(), _abi.ptr(wt), B, K, h, w, H, W, int(ignore_index),
+                                          scratch.data_ptr(), out.data_ptr(), _stream_ptr(dev)), "pcl_seg_ce_fwd")
+        ctx.keep = (seg_c, tgt, wt, scratch)
+        ctx.dims = (B, K, h, w, H, W, int(ignore_index))
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        lib = _abi.load()
+        seg_c, tgt, wt, scratch = ctx.keep
+        B, K, h, w, H, W, ign = ctx.dims
+        dev = seg_c.device
+        go = grad_out
+        if go.device != dev or go.dtype != torch.float32 or not go.is_contiguous():
+            go = go.detach().to(device=dev, dtype=torch.float32).contiguous()
+        dseg = torch.empty_like(seg_c)
+        with _on_device(dev):
+            _abi.check(lib.pcl_seg_ce_bwd(seg_c.data_ptr(), tgt.data_ptr(), _abi.ptr(wt), B, K, h, w, H, W, ign,
+                                          scratch.data_ptr(), go.data_ptr(), dseg.data_ptr(), _stream_ptr(dev)),
+                       "pcl_seg_ce_bwd")
+        ctx.keep = None
+        return dseg, None, None, None
+
+
+def upsample_cross_entropy(seg: torch.Tensor, target: torch.Tensor, weight: Optional[torch.Tensor] = None,
+                           ignore_index: int = -1) -> torch.Tensor:
+    """mean CE of bilinearly (align_corners=True) up-sampled logits against a full-resolution label map, fused:
+    == F.cross_entropy(F.interpolate(seg, target.shape[1:], mode='bilinear', align_corners=True), target,
+                       weight, ignore_index=ignore_index)  without the (B,K,Himg,Wimg) intermediate."""
+    return _SegCeFn.apply(seg, target, weight, ignore_index)

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .functional import ContrastOptions, pixel_contrast_loss
+from .functional import ContrastOptions, pixel_contrast_loss, upsample_cross_entropy
 from .loss_helper import FSAuxCELoss, FSCELoss
 
 
@@ -107,12 +107,25 @@ class ContrastCELoss(nn.Module):
         self.seg_criterion = seg_criterion
         self.contrast_criterion = PixelContrastLoss(configer)
         self.skip_warmup_contrast = bool(_opt(configer, "skip_warmup_contrast", False))
+        # §8f row 1: bilinear up-sampling + CE fused in one kernel pair (no (B,K,Himg,Wimg) intermediate); applies when
+        # the seg criterion is the plain mean-reduced CE of the reference configs
+        self.fused_seg_ce = bool(_opt(configer, "fused_seg_ce", True))
+
+    def _fused_ce(self, seg, target, ce_module):
+        ce = ce_module.ce_loss
+        return upsample_cross_entropy(seg, target, ce.weight, ce.ignore_index)
+
+    def _can_fuse(self, ce_module, seg):
+        return (self.fused_seg_ce and isinstance(ce_module, FSCELoss) and seg.is_cuda and
+                ce_module.ce_loss.reduction == "mean" and getattr(ce_module.ce_loss, "label_smoothing", 0.0) == 0.0)
 
     @staticmethod
     def _default_seg_criterion(configer):
         return FSCELoss(configer)
 
     def _seg_loss(self, preds, target):
+        if self._can_fuse(self.seg_criterion, preds["seg"]):
+            return self._fused_ce(preds["seg"], target, self.seg_criterion)
         h, w = target.size(1), target.size(2)
         pred = F.interpolate(input=preds["seg"], size=(h, w), mode="bilinear", align_corners=True)
         return self.seg_criterion(pred, target)
@@ -146,6 +159,11 @@ class ContrastAuxCELoss(ContrastCELoss):
 
     def _seg_loss(self, preds, target):
         assert "seg_aux" in preds
+        crit = self.seg_criterion
+        if isinstance(crit, FSAuxCELoss) and self._can_fuse(crit.ce_loss, preds["seg"]):
+            lw = crit.configer.get("network", "loss_weights")
+            return (lw["seg_loss"] * self._fused_ce(preds["seg"], target, crit.ce_loss) +
+                    lw["aux_loss"] * self._fused_ce(preds["seg_aux"], target, crit.ce_loss))
         h, w = target.size(1), target.size(2)
         pred = F.interpolate(input=preds["seg"], size=(h, w), mode="bilinear", align_corners=True)
         pred_aux = F.interpolate(input=preds["seg_aux"], size=(h, w), mode="bilinear", align_corners=True)

@@ -168,6 +168,20 @@ int pcl_l2norm_fwd(const float* x, float* y, int32_t B, int32_t D, int64_t HW, v
 int pcl_l2norm_bwd(const float* x, const float* gy, float* gx, int32_t B, int32_t D, int64_t HW, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * §8f row 1 (next row): the segmentation CE of ContrastCELoss.forward, fused.  Replaces
+ * lib/loss/loss_contrast.py:180-181 (F.interpolate(seg, (Himg,Wimg), bilinear, align_corners=True)) +
+ * lib/loss/loss_helper.py:169-212 (nn.CrossEntropyLoss(weight, ignore_index, reduction mean)) and their autograd
+ * backward; the (B,K,Himg,Wimg) up-sampled logits are never materialised.
+ *   seg (B,K,h,w) fp32, target (B,Himg,Wimg) int64, class_weight (K) fp32 or NULL, scratch: pcl_seg_ce_scratch_floats.
+ * ----------------------------------------------------------------------------------------------*/
+int64_t pcl_seg_ce_scratch_floats(int32_t B, int32_t Himg, int32_t Wimg);
+int pcl_seg_ce_fwd(const float* seg, const int64_t* target, const float* class_weight, int32_t B, int32_t K, int32_t h,
+                   int32_t w, int32_t Himg, int32_t Wimg, int32_t ignore_index, float* scratch, float* loss, void* stream);
+int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const float* class_weight, int32_t B, int32_t K, int32_t h,
+                   int32_t w, int32_t Himg, int32_t Wimg, int32_t ignore_index, const float* scratch,
+                   const float* grad_loss, float* dseg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * a7 + a8: memory bank.  Replaces segmentor/trainer_contrastive.py:102-138 (_dequeue_and_enqueue).
  * Step 1 (parallel): build this rank's enqueue packet.  Step 2 (ordered): apply the packets of all
  * ranks in rank order — world 1 reproduces the reference exactly, world > 1 is the allgather merge

@@ -552,3 +552,48 @@ def test_bank_tensor_path_workspace_sizes_cover_runtime_slots():
     _abi.check(_abi.load().pcl_tc_sizes(C.byref(td), C.byref(ss)))
     assert ws.partials.numel() >= 5 * ss.partial_f32 and ws.dpartials.numel() >= ss.dpartial_f32
     assert guard.abs().max().item() == 0 and torch.isfinite(loss).item()
+
+
+# ---------------------------------------------------------------------------------------------------
+# §8f row 1: fused bilinear(align_corners) up-sampling + weighted CE with ignore_index.  Tolerance: loss 1e-6 rel,
+# gradient 1e-5 * max|g| against the float64 torch ops of the reference (oracle.ref_port.seg_cross_entropy).
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,K,h,w,H,W,weighted", [(2, 5, 16, 20, 32, 40, False), (1, 19, 13, 10, 50, 37, True),
+                                                  (2, 7, 8, 8, 8, 8, False), (1, 3, 5, 7, 1, 9, True)])
+def test_fused_upsample_cross_entropy(B, K, h, w, H, W, weighted):
+    g = torch.Generator().manual_seed(B * 100 + K)
+    seg = torch.randn(B, K, h, w, generator=g) * 2.0
+    target = torch.randint(-1, K, (B, H, W), generator=g)
+    weight = (torch.rand(K, generator=g) + 0.5) if weighted else None
+    s1 = seg.clone().to(DEV).requires_grad_(True)
+    loss = cs.upsample_cross_entropy(s1, target.to(DEV), weight.to(DEV) if weighted else None, -1)
+    gout = torch.tensor(0.7, device=DEV)
+    loss.backward(gout)
+    s2 = seg.clone().double().requires_grad_(True)
+    ref = P.seg_cross_entropy(s2, target, -1, weight.double() if weighted else None)
+    ref.backward(torch.tensor(0.7, dtype=torch.float64))
+    assert rel_err(loss.item(), ref.item()) < 2e-6
+    assert (s1.grad.cpu().double() - s2.grad).abs().max().item() <= 1e-5 * s2.grad.abs().max().item() + 1e-12
+
+
+def test_fused_seg_ce_full_size_and_wrapper_toggle():
+    """Cityscapes shape (B=8, 19 x 128 x 256 -> 512 x 1024): fused vs the PyTorch ops on the GPU, and the wrapper
+    gives the same loss with fused_seg_ce on / off."""
+    from contrastiveseg_b200.synth import make_contrast_batch
+    data = make_contrast_batch(B=8, D=32, h=128, w=256, num_classes=19, img_stride=4, block=32, seed=304)
+    seg, tgt = data["seg"].to(DEV), data["target"].to(DEV)
+    s1 = seg.clone().requires_grad_(True)
+    l1 = cs.upsample_cross_entropy(s1, tgt, None, -1)
+    l1.backward()
+    s2 = seg.clone().requires_grad_(True)
+    l2 = F.cross_entropy(F.interpolate(s2, size=tgt.shape[1:], mode="bilinear", align_corners=True), tgt, ignore_index=-1)
+    l2.backward()
+    assert rel_err(l1.item(), l2.item()) < 5e-6
+    assert (s1.grad - s2.grad).abs().max().item() <= 2e-5 * s2.grad.abs().max().item()
+    losses = []
+    for fused in (True, False):
+        rec_seed = torch.Generator().manual_seed(1)
+        crit = cs.ContrastCELoss(_cfg(0.1, 0.07, 256, 20, 19, {"fused_seg_ce": fused})).to(DEV)
+        crit.contrast_criterion.perm_fn = P.PermRecorder(rec_seed)
+        losses.append(crit({"seg": seg, "embed": data["embed"].to(DEV)}, tgt, with_embed=True).item())
+    assert rel_err(losses[0], losses[1]) < 5e-6
