@@ -448,6 +448,30 @@ def run_engine(args, cfg, bank, rank, world, dev):
                "sample": f"{n_cpu} steps at batch {Bc} (of {cfg['B']}) after 1 warm-up, fp32 torch CPU on {threads} of "
                          f"{os.cpu_count()} host threads (fastest setting), {cdt / n_cpu * 1e3:.0f} ms/step"}
     tens = tensor_sweep_roofline(dev, peaks) if (world == 1 and cfg["D"] == 256) else None
+    # whole ContrastCELoss.forward + backward (seg CE + contrast): the reference's "Loss Time" scope, with the fused
+    # up-sample + CE kernels (§8f row 1) and with the PyTorch seg-CE ops
+    wrapper = None
+    if world == 1 and not bank:
+        wrapper = {}
+        for name, fused in (("fused_seg_ce_ms", True), ("torch_seg_ce_ms", False)):
+            cw = engine_configer(cfg, bank, args.precision)
+            cw.add(["contrast", "fused_seg_ce"], fused)
+            mod = cs.ContrastCELoss(cw).to(dev)
+            seg_l = inp["seg"].clone().requires_grad_(True)
+
+            def wstep():
+                embed.grad = None; seg_l.grad = None
+                mod({"seg": seg_l, "embed": embed}, inp["target"], with_embed=True).backward()
+            for _ in range(5):
+                wstep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(30):
+                wstep()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            wrapper[name] = e0.elapsed_time(e1) / 30
     launches_per_step = (12 if args.precision == "bf16" else 10) + (4 if bank else 0)
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
@@ -456,7 +480,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "precision": args.precision, "impl": "engine"}
+            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "precision": args.precision, "impl": "engine"}
 
 
 def main():
