@@ -100,7 +100,105 @@ k_segce_finalize(const float* __restrict__ part_nll, const float* __restrict__ p
   }
 }
 
-// first / last output index whose bilinear footprint touches source index s:  |r*o - s| < 1
+// Backward, tile formulation: one CTA = a 32 x 32 tile of label pixels of one image.
+//   A  thread per label pixel: G[c] = coef * w_t * (softmax_c - [c == t]) for all K classes -> shared memory
+//   B  separable transpose of the bilinear map, x direction:  Hx[c][row][xs] = sum_x wx(x, xs) * G[c][row][x]
+//   C  y direction + flush: dseg[c][ys][xs] += sum_row wy(row, ys) * Hx[c][row][xs]   (global atomics only on the
+//      <= 10 x 10 source cells of the tile; a cell is shared by at most 4 tiles)
+// Each (pixel, class) softmax is evaluated once (the per-logit gather needs 16x as many).
+constexpr int BT = 32;                 // tile edge (label pixels)
+constexpr int SRC_MAX = 34;            // source cells per tile edge (scale >= 1: up to 32 + 2)
+
+__global__ void __launch_bounds__(BT * BT)
+k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __restrict__ fin,
+                 const float* __restrict__ grad_out, float* __restrict__ dseg, int kc) {
+  extern __shared__ float sm[];
+  float* G = sm;                                   // [kc][BT][BT]
+  float* Hx = G + (size_t)kc * BT * BT;            // [kc][BT][SRC_MAX]
+  __shared__ int s_y0[BT], s_y1[BT], s_x0[BT], s_x1[BT];
+  __shared__ float s_ly[BT], s_lx[BT];
+  const int tx = threadIdx.x & (BT - 1), ty = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BT;
+  const int x = X0 + tx, y = Y0 + ty;
+  const int64_t hw = (int64_t)a.h * a.w, HWo = (int64_t)a.H * a.W;
+  if (threadIdx.x < BT) {
+    int i0, i1; float l;
+    src_coord(min(Y0 + (int)threadIdx.x, a.H - 1), a.ry, a.h, i0, i1, l);
+    s_y0[threadIdx.x] = i0; s_y1[threadIdx.x] = i1; s_ly[threadIdx.x] = l;
+    src_coord(min(X0 + (int)threadIdx.x, a.W - 1), a.rx, a.w, i0, i1, l);
+    s_x0[threadIdx.x] = i0; s_x1[threadIdx.x] = i1; s_lx[threadIdx.x] = l;
+  }
+  __syncthreads();
+  const int ys_base = s_y0[0], xs_base = s_x0[0];
+  const int ny = min(Y0 + BT, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;          // valid rows / cols of the tile
+  const int ys_n = s_y1[ny - 1] - ys_base + 1, xs_n = s_x1[nx - 1] - xs_base + 1;
+  const bool inside = x < a.W && y < a.H;
+  const float scale = (grad_out ? grad_out[0] : 1.f) / fin[1];
+  int64_t t = -1;
+  float lse_p = 0.f, coef = 0.f;
+  if (inside) {
+    t = a.target[(int64_t)b * HWo + (int64_t)y * a.W + x];
+    if (t != (int64_t)a.ignore_index && t >= 0 && t < a.K) {
+      coef = scale * (a.weight ? a.weight[t] : 1.f);
+      lse_p = lse[(int64_t)b * HWo + (int64_t)y * a.W + x];
+    } else {
+      t = -1;
+    }
+  }
+  const int y0 = s_y0[ty], y1 = s_y1[ty], x0 = s_x0[tx], x1 = s_x1[tx];
+  const float ly = s_ly[ty], lx = s_lx[tx];
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const int64_t o00 = (int64_t)y0 * a.w + x0, o01 = (int64_t)y0 * a.w + x1, o10 = (int64_t)y1 * a.w + x0,
+                o11 = (int64_t)y1 * a.w + x1;
+  for (int c0 = 0; c0 < a.K; c0 += kc) {
+    const int cn = min(kc, a.K - c0);
+    // ---- A: gradient w.r.t. the (virtual) up-sampled logits ----
+    for (int cc = 0; cc < cn; ++cc) {
+      float g = 0.f;
+      if (t >= 0) {
+        const float* p = a.seg + ((int64_t)b * a.K + c0 + cc) * hw;
+        const float v = w00 * p[o00] + w01 * p[o01] + w10 * p[o10] + w11 * p[o11];
+        g = coef * (expf(v - lse_p) - ((c0 + cc) == (int)t ? 1.f : 0.f));
+      }
+      G[((size_t)cc * BT + ty) * BT + tx] = g;
+    }
+    __syncthreads();
+    // ---- B: x direction ----
+    for (int i = threadIdx.x; i < cn * BT * xs_n; i += BT * BT) {
+      const int xs = i % xs_n, row = (i / xs_n) % BT, cc = i / (xs_n * BT);
+      const int xg = xs_base + xs;
+      const float* gr = G + ((size_t)cc * BT + row) * BT;
+      float acc = 0.f;
+      for (int k = 0; k < nx; ++k) {
+        float wgt = 0.f;
+        if (s_x0[k] == xg) wgt += 1.f - s_lx[k];
+        if (s_x1[k] == xg) wgt += s_lx[k];
+        acc += wgt * gr[k];
+      }
+      Hx[((size_t)cc * BT + row) * SRC_MAX + xs] = acc;
+    }
+    __syncthreads();
+    // ---- C: y direction, flush ----
+    for (int i = threadIdx.x; i < cn * ys_n * xs_n; i += BT * BT) {
+      const int xs = i % xs_n, ysl = (i / xs_n) % ys_n, cc = i / (xs_n * ys_n);
+      const int yg = ys_base + ysl;
+      float acc = 0.f;
+      for (int k = 0; k < ny; ++k) {
+        float wgt = 0.f;
+        if (s_y0[k] == yg) wgt += 1.f - s_ly[k];
+        if (s_y1[k] == yg) wgt += s_ly[k];
+        acc += wgt * Hx[((size_t)cc * BT + k) * SRC_MAX + xs];
+      }
+      if (acc != 0.f) atomicAdd(&dseg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)yg * a.w + xs_base + xs], acc);
+    }
+    __syncthreads();
+  }
+}
+
+// General backward (any scale, e.g. label grid smaller than the logits): one thread per logit gathers over the label
+// pixels in its bilinear footprint.  Deterministic, but evaluates every (pixel, class) softmax up to 16 times; the tile
+// kernel above is used whenever the label grid is at least as large as the logit grid (the reference's case).
 __device__ __forceinline__ void footprint(int s, float r, int out_size, int& lo, int& hi) {
   if (r <= 0.f) { lo = 0; hi = out_size - 1; return; }
   lo = (int)floorf(((float)s - 1.f) / r) - 1;
@@ -110,8 +208,8 @@ __device__ __forceinline__ void footprint(int s, float r, int out_size, int& lo,
 }
 
 __global__ void __launch_bounds__(CE_THREADS)
-k_segce_bwd(SegCeArgs a, const float* __restrict__ lse, const float* __restrict__ fin, const float* __restrict__ grad_out,
-            float* __restrict__ dseg) {
+k_segce_bwd_gather(SegCeArgs a, const float* __restrict__ lse, const float* __restrict__ fin,
+                   const float* __restrict__ grad_out, float* __restrict__ dseg) {
   const int64_t hw = (int64_t)a.h * a.w;
   const int64_t e = (int64_t)blockIdx.x * CE_THREADS + threadIdx.x;
   const int bc = blockIdx.y;
@@ -130,7 +228,7 @@ k_segce_bwd(SegCeArgs a, const float* __restrict__ lse, const float* __restrict_
     src_coord(y, a.ry, a.h, y0, y1, ly);
     float wy = 0.f;
     if (y0 == ys) wy += 1.f - ly;
-    if (y1 == ys) wy += ly;                       // y0 == y1 at the last row: both terms apply (weights sum to 1)
+    if (y1 == ys) wy += ly;
     if (wy == 0.f) continue;
     for (int x = xlo; x <= xhi; ++x) {
       int x0, x1; float lx;
@@ -206,7 +304,22 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
   const float* lse = scratch;
   const float* fin = scratch + (int64_t)B * HWo + 2 * blocks;
   const int64_t hw = (int64_t)h * w;
-  k_segce_bwd<<<dim3((unsigned)ceil_div64(hw, CE_THREADS), B * K), CE_THREADS, 0, s>>>(a, lse, fin, grad_loss, dseg);
+  if (H < h || W < w) {                                     // down-sampling: general gather kernel
+    k_segce_bwd_gather<<<dim3((unsigned)ceil_div64(hw, CE_THREADS), B * K), CE_THREADS, 0, s>>>(a, lse, fin, grad_loss, dseg);
+    PCL_LAUNCH_CHECK();
+    return PCL_OK;
+  }
+  PCL_CUDA(cudaMemsetAsync(dseg, 0, (size_t)B * K * hw * sizeof(float), s));
+  // classes per pass so that G (kc*32*32) + Hx (kc*32*34) floats fit 2 CTAs per SM
+  int kc = K < 12 ? K : 12;
+  const size_t smem = (size_t)kc * (BT * BT + BT * SRC_MAX) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    PCL_CUDA(cudaFuncSetAttribute(k_segce_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * (BT * BT + BT * SRC_MAX) * 4));
+    attr_done = true;
+  }
+  k_segce_bwd_tile<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, fin, grad_loss,
+                                                                                                     dseg, kc);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

@@ -12,6 +12,7 @@ timeout 300 python tools/tc_selftest.py bwd > gpurun_out/tc_bwd.log 2>&1; echo "
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
+timeout 120 python tools/segce_bench.py > gpurun_out/segce.log 2>&1
 timeout 300 python tools/sweep_bench.py > gpurun_out/sweep.jsonl 2> gpurun_out/sweep.err; echo "sweep exit $?" >> gpurun_out/sweep.err
 if [ "${2:-}" = "variants" ]; then
   for v in 8 9; do
@@ -26,4 +27,4 @@ if [ "${1:-}" = "ncu" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 fi
-cat gpurun_out/tc_dump.log gpurun_out/tc_fwd.log gpurun_out/tc_bwd.log; tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/sweep.jsonl; cat gpurun_out/sweep_variants.jsonl 2>/dev/null | cut -c1-200; tail -2 gpurun_out/sweep.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+cat gpurun_out/tc_dump.log gpurun_out/tc_fwd.log gpurun_out/tc_bwd.log; tail -15 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/segce.log; cat gpurun_out/sweep.jsonl; cat gpurun_out/sweep_variants.jsonl 2>/dev/null | cut -c1-200; tail -2 gpurun_out/sweep.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
