@@ -29,57 +29,83 @@ __device__ __forceinline__ void src_coord(int o, float r, int in_size, int& i0, 
 }
 
 constexpr int CE_THREADS = 256;
+constexpr int BT = 32;                 // tile edge (label pixels): one CTA = 32 x 32 label pixels of one image
+constexpr int KC_FWD = 8;              // classes staged per pass in the forward
 
-__global__ void __launch_bounds__(CE_THREADS)
-k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_nll, float* __restrict__ part_w) {
-  __shared__ float s_n[CE_THREADS], s_w[CE_THREADS];
-  const int64_t HWo = (int64_t)a.H * a.W;
-  const int64_t pix = (int64_t)blockIdx.x * CE_THREADS + threadIdx.x;
-  const int b = blockIdx.y;
+// Source patch geometry of a tile (identical for every thread of the CTA).
+struct TileGeo {
+  int ys_base, xs_base, ys_n, xs_n, ny, nx;
+};
+
+// Forward, tile formulation: the <= (32*ry+2) x (32*rx+2) source logits of the tile are staged in shared memory per class
+// chunk; every thread (one label pixel) runs an online log-sum-exp over the classes from shared memory.
+__global__ void __launch_bounds__(BT * BT)
+k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_nll, float* __restrict__ part_w, int pitch) {
+  extern __shared__ float sm[];                    // [KC_FWD][pitch] source patch
+  __shared__ float s_n[BT * BT / 32], s_w[BT * BT / 32];
+  __shared__ int s_y0[BT], s_y1[BT], s_x0[BT], s_x1[BT];
+  __shared__ float s_ly[BT], s_lx[BT];
+  const int tx = threadIdx.x & (BT - 1), ty = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BT;
+  const int x = X0 + tx, y = Y0 + ty;
+  const int64_t hw = (int64_t)a.h * a.w, HWo = (int64_t)a.H * a.W;
+  if (threadIdx.x < BT) {
+    int i0, i1; float l;
+    src_coord(min(Y0 + (int)threadIdx.x, a.H - 1), a.ry, a.h, i0, i1, l);
+    s_y0[threadIdx.x] = i0; s_y1[threadIdx.x] = i1; s_ly[threadIdx.x] = l;
+    src_coord(min(X0 + (int)threadIdx.x, a.W - 1), a.rx, a.w, i0, i1, l);
+    s_x0[threadIdx.x] = i0; s_x1[threadIdx.x] = i1; s_lx[threadIdx.x] = l;
+  }
+  __syncthreads();
+  const int ys_base = s_y0[0], xs_base = s_x0[0];
+  const int ny = min(Y0 + BT, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;
+  const int ys_n = s_y1[ny - 1] - ys_base + 1, xs_n = s_x1[nx - 1] - xs_base + 1;
+  const bool inside = x < a.W && y < a.H;
+  const int ly0 = s_y0[ty] - ys_base, ly1 = s_y1[ty] - ys_base, lx0 = s_x0[tx] - xs_base, lx1 = s_x1[tx] - xs_base;
+  const float ly = s_ly[ty], lx = s_lx[tx];
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const int i00 = ly0 * xs_n + lx0, i01 = ly0 * xs_n + lx1, i10 = ly1 * xs_n + lx0, i11 = ly1 * xs_n + lx1;
+  int64_t t = -1;
+  if (inside) t = a.target[(int64_t)b * HWo + (int64_t)y * a.W + x];
+  float m = -CUDART_INF_F, se = 0.f, vt = 0.f;
+  for (int c0 = 0; c0 < a.K; c0 += KC_FWD) {
+    const int cn = min(KC_FWD, a.K - c0);
+    const int patch = ys_n * xs_n;
+    for (int i = threadIdx.x; i < cn * patch; i += BT * BT) {
+      const int cc = i / patch, r = i - cc * patch;
+      const int yy = r / xs_n, xx = r - yy * xs_n;
+      sm[cc * pitch + r] = a.seg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)(ys_base + yy) * a.w + xs_base + xx];
+    }
+    __syncthreads();
+    for (int cc = 0; cc < cn; ++cc) {
+      const float* p = sm + cc * pitch;
+      const float v = w00 * p[i00] + w01 * p[i01] + w10 * p[i10] + w11 * p[i11];
+      if (v > m) { se = se * expf(m - v) + 1.f; m = v; }       // online log-sum-exp
+      else       { se += expf(v - m); }
+      if (c0 + cc == (int)t) vt = v;
+    }
+    __syncthreads();
+  }
   float nll = 0.f, wt = 0.f;
-  if (pix < HWo) {
-    const int y = (int)(pix / a.W), x = (int)(pix - (int64_t)y * a.W);
-    int y0, y1, x0, x1; float ly, lx;
-    src_coord(y, a.ry, a.h, y0, y1, ly);
-    src_coord(x, a.rx, a.w, x0, x1, lx);
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    const int64_t hw = (int64_t)a.h * a.w;
-    const float* sb = a.seg + (int64_t)b * a.K * hw;
-    const int64_t o00 = (int64_t)y0 * a.w + x0, o01 = (int64_t)y0 * a.w + x1, o10 = (int64_t)y1 * a.w + x0,
-                  o11 = (int64_t)y1 * a.w + x1;
-    float m = -CUDART_INF_F;
-    for (int c = 0; c < a.K; ++c) {
-      const float* p = sb + (int64_t)c * hw;
-      const float v = w00 * p[o00] + w01 * p[o01] + w10 * p[o10] + w11 * p[o11];
-      m = fmaxf(m, v);
-    }
-    float se = 0.f;
-    const int64_t t = a.target[(int64_t)b * HWo + pix];
-    float vt = 0.f;
-    for (int c = 0; c < a.K; ++c) {
-      const float* p = sb + (int64_t)c * hw;
-      const float v = w00 * p[o00] + w01 * p[o01] + w10 * p[o10] + w11 * p[o11];
-      se += expf(v - m);
-      if (c == (int)t) vt = v;
-    }
+  if (inside) {
     const float lse = m + logf(se);
-    lse_out[(int64_t)b * HWo + pix] = lse;
+    lse_out[(int64_t)b * HWo + (int64_t)y * a.W + x] = lse;
     if (t != (int64_t)a.ignore_index && t >= 0 && t < a.K) {
       const float wc = a.weight ? a.weight[t] : 1.f;
       nll = wc * (lse - vt);
       wt = wc;
     }
   }
-  s_n[threadIdx.x] = nll; s_w[threadIdx.x] = wt;
+  nll = warp_sum(nll); wt = warp_sum(wt);
+  if ((threadIdx.x & 31) == 0) { s_n[threadIdx.x >> 5] = nll; s_w[threadIdx.x >> 5] = wt; }
   __syncthreads();
-  for (int o = CE_THREADS / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { s_n[threadIdx.x] += s_n[threadIdx.x + o]; s_w[threadIdx.x] += s_w[threadIdx.x + o]; }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
-    part_nll[blk] = s_n[0];
-    part_w[blk] = s_w[0];
+    float an = 0.f, aw = 0.f;
+    for (int i = 0; i < BT * BT / 32; ++i) { an += s_n[i]; aw += s_w[i]; }      // fixed order
+    const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    part_nll[blk] = an;
+    part_w[blk] = aw;
   }
 }
 
@@ -100,21 +126,22 @@ k_segce_finalize(const float* __restrict__ part_nll, const float* __restrict__ p
   }
 }
 
-// Backward, tile formulation: one CTA = a 32 x 32 tile of label pixels of one image.
-//   A  thread per label pixel: G[c] = coef * w_t * (softmax_c - [c == t]) for all K classes -> shared memory
+// Backward, tile formulation: one CTA = a 32 x 32 tile of label pixels of one image, classes in chunks of kc.
+//   A  thread per label pixel: G[c] = coef * w_t * (softmax_c - [c == t]) from the staged source patch -> shared memory
 //   B  separable transpose of the bilinear map, x direction:  Hx[c][row][xs] = sum_x wx(x, xs) * G[c][row][x]
 //   C  y direction + flush: dseg[c][ys][xs] += sum_row wy(row, ys) * Hx[c][row][xs]   (global atomics only on the
-//      <= 10 x 10 source cells of the tile; a cell is shared by at most 4 tiles)
-// Each (pixel, class) softmax is evaluated once (the per-logit gather needs 16x as many).
-constexpr int BT = 32;                 // tile edge (label pixels)
+//      source cells of the tile; a cell is shared by at most 4 tiles)
+// Each (pixel, class) softmax is evaluated once (the per-logit gather below needs 16x as many); B and C only visit the
+// label columns / rows inside the footprint of their source cell.
 constexpr int SRC_MAX = 34;            // source cells per tile edge (scale >= 1: up to 32 + 2)
 
 __global__ void __launch_bounds__(BT * BT)
 k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __restrict__ fin,
-                 const float* __restrict__ grad_out, float* __restrict__ dseg, int kc) {
+                 const float* __restrict__ grad_out, float* __restrict__ dseg, int kc, int pitch) {
   extern __shared__ float sm[];
   float* G = sm;                                   // [kc][BT][BT]
   float* Hx = G + (size_t)kc * BT * BT;            // [kc][BT][SRC_MAX]
+  float* S = Hx + (size_t)kc * BT * SRC_MAX;       // [kc][pitch] source patch
   __shared__ int s_y0[BT], s_y1[BT], s_x0[BT], s_x1[BT];
   __shared__ float s_ly[BT], s_lx[BT];
   const int tx = threadIdx.x & (BT - 1), ty = threadIdx.x >> 5;
@@ -133,6 +160,7 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
   const int ys_base = s_y0[0], xs_base = s_x0[0];
   const int ny = min(Y0 + BT, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;          // valid rows / cols of the tile
   const int ys_n = s_y1[ny - 1] - ys_base + 1, xs_n = s_x1[nx - 1] - xs_base + 1;
+  const int patch = ys_n * xs_n;
   const bool inside = x < a.W && y < a.H;
   const float scale = (grad_out ? grad_out[0] : 1.f) / fin[1];
   int64_t t = -1;
@@ -146,31 +174,42 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
       t = -1;
     }
   }
-  const int y0 = s_y0[ty], y1 = s_y1[ty], x0 = s_x0[tx], x1 = s_x1[tx];
+  const int ly0 = s_y0[ty] - ys_base, ly1 = s_y1[ty] - ys_base, lx0 = s_x0[tx] - xs_base, lx1 = s_x1[tx] - xs_base;
   const float ly = s_ly[ty], lx = s_lx[tx];
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const int64_t o00 = (int64_t)y0 * a.w + x0, o01 = (int64_t)y0 * a.w + x1, o10 = (int64_t)y1 * a.w + x0,
-                o11 = (int64_t)y1 * a.w + x1;
+  const int i00 = ly0 * xs_n + lx0, i01 = ly0 * xs_n + lx1, i10 = ly1 * xs_n + lx0, i11 = ly1 * xs_n + lx1;
+  const float inv_rx = a.rx > 0.f ? 1.f / a.rx : 0.f, inv_ry = a.ry > 0.f ? 1.f / a.ry : 0.f;
   for (int c0 = 0; c0 < a.K; c0 += kc) {
     const int cn = min(kc, a.K - c0);
+    for (int i = threadIdx.x; i < cn * patch; i += BT * BT) {
+      const int cc = i / patch, r = i - cc * patch;
+      const int yy = r / xs_n, xx = r - yy * xs_n;
+      S[cc * pitch + r] = a.seg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)(ys_base + yy) * a.w + xs_base + xx];
+    }
+    __syncthreads();
     // ---- A: gradient w.r.t. the (virtual) up-sampled logits ----
     for (int cc = 0; cc < cn; ++cc) {
       float g = 0.f;
       if (t >= 0) {
-        const float* p = a.seg + ((int64_t)b * a.K + c0 + cc) * hw;
-        const float v = w00 * p[o00] + w01 * p[o01] + w10 * p[o10] + w11 * p[o11];
+        const float* p = S + cc * pitch;
+        const float v = w00 * p[i00] + w01 * p[i01] + w10 * p[i10] + w11 * p[i11];
         g = coef * (expf(v - lse_p) - ((c0 + cc) == (int)t ? 1.f : 0.f));
       }
       G[((size_t)cc * BT + ty) * BT + tx] = g;
     }
     __syncthreads();
-    // ---- B: x direction ----
+    // ---- B: x direction (only the label columns whose footprint touches source column xg) ----
     for (int i = threadIdx.x; i < cn * BT * xs_n; i += BT * BT) {
       const int xs = i % xs_n, row = (i / xs_n) % BT, cc = i / (xs_n * BT);
       const int xg = xs_base + xs;
+      int klo = 0, khi = nx - 1;
+      if (a.rx > 0.f) {
+        klo = max(0, (int)floorf(((float)xg - 1.f) * inv_rx) - 1 - X0);
+        khi = min(nx - 1, (int)ceilf(((float)xg + 1.f) * inv_rx) + 1 - X0);
+      }
       const float* gr = G + ((size_t)cc * BT + row) * BT;
       float acc = 0.f;
-      for (int k = 0; k < nx; ++k) {
+      for (int k = klo; k <= khi; ++k) {
         float wgt = 0.f;
         if (s_x0[k] == xg) wgt += 1.f - s_lx[k];
         if (s_x1[k] == xg) wgt += s_lx[k];
@@ -183,8 +222,13 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
     for (int i = threadIdx.x; i < cn * ys_n * xs_n; i += BT * BT) {
       const int xs = i % xs_n, ysl = (i / xs_n) % ys_n, cc = i / (xs_n * ys_n);
       const int yg = ys_base + ysl;
+      int klo = 0, khi = ny - 1;
+      if (a.ry > 0.f) {
+        klo = max(0, (int)floorf(((float)yg - 1.f) * inv_ry) - 1 - Y0);
+        khi = min(ny - 1, (int)ceilf(((float)yg + 1.f) * inv_ry) + 1 - Y0);
+      }
       float acc = 0.f;
-      for (int k = 0; k < ny; ++k) {
+      for (int k = klo; k <= khi; ++k) {
         float wgt = 0.f;
         if (s_y0[k] == yg) wgt += 1.f - s_ly[k];
         if (s_y1[k] == yg) wgt += s_ly[k];
@@ -264,8 +308,14 @@ static int make_ce(const float* seg, const int64_t* target, const float* weight,
   return PCL_OK;
 }
 
+static int patch_pitch(const SegCeArgs& a) {
+  // upper bound of the source cells a 32 x 32 label tile touches (ys_n * xs_n), + 1 to de-phase the class planes
+  const int py = (int)(31.f * a.ry) + 3, px = (int)(31.f * a.rx) + 3;
+  return (py < a.h + 1 ? py : a.h + 1) * (px < a.w + 1 ? px : a.w + 1) + 1;
+}
+
 extern "C" int64_t pcl_seg_ce_scratch_floats(int32_t B, int32_t H, int32_t W) {
-  const int64_t blocks = ceil_div64((int64_t)H * W, CE_THREADS) * B;
+  const int64_t blocks = (int64_t)ceil_div(H, 32) * ceil_div(W, 32) * B;
   return (int64_t)B * H * W + 2 * blocks + 2;            // lse | partial nll | partial weight | (loss, weight sum)
 }
 
@@ -278,12 +328,16 @@ extern "C" int pcl_seg_ce_fwd(const float* seg, const int64_t* target, const flo
   PCL_REQUIRE(scratch && loss);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t HWo = (int64_t)H * W;
-  const int64_t bx = ceil_div64(HWo, CE_THREADS), blocks = bx * B;
+  const int64_t blocks = (int64_t)ceil_div(H, BT) * ceil_div(W, BT) * B;
   float* lse = scratch;
   float* pn = scratch + (int64_t)B * HWo;
   float* pw = pn + blocks;
   float* fin = pw + blocks;
-  k_segce_fwd<<<dim3((unsigned)bx, B), CE_THREADS, 0, s>>>(a, lse, pn, pw);
+  const int pitch = patch_pitch(a);
+  const size_t smem = (size_t)KC_FWD * pitch * sizeof(float);
+  if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
+  PCL_CUDA(cudaFuncSetAttribute(k_segce_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_segce_fwd<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, pn, pw, pitch);
   PCL_LAUNCH_CHECK();
   k_segce_finalize<<<1, 1024, 0, s>>>(pn, pw, blocks, fin);
   PCL_LAUNCH_CHECK();
@@ -300,7 +354,7 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
   PCL_REQUIRE(scratch && dseg);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t HWo = (int64_t)H * W;
-  const int64_t blocks = ceil_div64(HWo, CE_THREADS) * B;
+  const int64_t blocks = (int64_t)ceil_div(H, BT) * ceil_div(W, BT) * B;
   const float* lse = scratch;
   const float* fin = scratch + (int64_t)B * HWo + 2 * blocks;
   const int64_t hw = (int64_t)h * w;
@@ -310,16 +364,15 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
     return PCL_OK;
   }
   PCL_CUDA(cudaMemsetAsync(dseg, 0, (size_t)B * K * hw * sizeof(float), s));
-  // classes per pass so that G (kc*32*32) + Hx (kc*32*34) floats fit 2 CTAs per SM
-  int kc = K < 12 ? K : 12;
-  const size_t smem = (size_t)kc * (BT * BT + BT * SRC_MAX) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    PCL_CUDA(cudaFuncSetAttribute(k_segce_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * (BT * BT + BT * SRC_MAX) * 4));
-    attr_done = true;
-  }
+  // classes per pass: G (kc*32*32) + Hx (kc*32*34) + source patch (kc*pitch) floats, two CTAs per SM when possible
+  const int pitch = patch_pitch(a);
+  int kc = K < 10 ? K : 10;
+  while (kc > 1 && (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float) > 110 * 1024) --kc;
+  const size_t smem = (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float);
+  if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
+  PCL_CUDA(cudaFuncSetAttribute(k_segce_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_segce_bwd_tile<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, fin, grad_loss,
-                                                                                                     dseg, kc);
+                                                                                                     dseg, kc, pitch);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
