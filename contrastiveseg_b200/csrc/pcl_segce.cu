@@ -81,15 +81,15 @@ k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_n
     for (int cc = 0; cc < cn; ++cc) {
       const float* p = sm + cc * pitch;
       const float v = w00 * p[i00] + w01 * p[i01] + w10 * p[i10] + w11 * p[i11];
-      if (v > m) { se = se * expf(m - v) + 1.f; m = v; }       // online log-sum-exp
-      else       { se += expf(v - m); }
+      if (v > m) { se = se * __expf(m - v) + 1.f; m = v; }     // online log-sum-exp
+      else       { se += __expf(v - m); }
       if (c0 + cc == (int)t) vt = v;
     }
     __syncthreads();
   }
   float nll = 0.f, wt = 0.f;
   if (inside) {
-    const float lse = m + logf(se);
+    const float lse = m + __logf(se);
     lse_out[(int64_t)b * HWo + (int64_t)y * a.W + x] = lse;
     if (t != (int64_t)a.ignore_index && t >= 0 && t < a.K) {
       const float wc = a.weight ? a.weight[t] : 1.f;
@@ -193,7 +193,7 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
       if (t >= 0) {
         const float* p = S + cc * pitch;
         const float v = w00 * p[i00] + w01 * p[i01] + w10 * p[i10] + w11 * p[i11];
-        g = coef * (expf(v - lse_p) - ((c0 + cc) == (int)t ? 1.f : 0.f));
+        g = coef * (__expf(v - lse_p) - ((c0 + cc) == (int)t ? 1.f : 0.f));
       }
       G[((size_t)cc * BT + ty) * BT + tx] = g;
     }
