@@ -30,7 +30,7 @@ __device__ __forceinline__ void src_coord(int o, float r, int in_size, int& i0, 
 
 constexpr int CE_THREADS = 256;
 constexpr int BT = 32;                 // tile edge (label pixels): one CTA = 32 x 32 label pixels of one image
-constexpr int KC_FWD = 8;              // classes staged per pass in the forward
+constexpr int KC_FWD_MAX = 32;         // classes staged per pass in the forward (one pass for K <= 32: one exposed load latency)
 
 // Source patch geometry of a tile (identical for every thread of the CTA).
 struct TileGeo {
@@ -40,8 +40,9 @@ struct TileGeo {
 // Forward, tile formulation: the <= (32*ry+2) x (32*rx+2) source logits of the tile are staged in shared memory per class
 // chunk; every thread (one label pixel) runs an online log-sum-exp over the classes from shared memory.
 __global__ void __launch_bounds__(BT * BT)
-k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_nll, float* __restrict__ part_w, int pitch) {
-  extern __shared__ float sm[];                    // [KC_FWD][pitch] source patch
+k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_nll, float* __restrict__ part_w, int pitch,
+            int kc) {
+  extern __shared__ float sm[];                    // [kc][pitch] source patch
   __shared__ float s_n[BT * BT / 32], s_w[BT * BT / 32];
   __shared__ int s_y0[BT], s_y1[BT], s_x0[BT], s_x1[BT];
   __shared__ float s_ly[BT], s_lx[BT];
@@ -69,8 +70,8 @@ k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_n
   int64_t t = -1;
   if (inside) t = a.target[(int64_t)b * HWo + (int64_t)y * a.W + x];
   float m = -CUDART_INF_F, se = 0.f, vt = 0.f;
-  for (int c0 = 0; c0 < a.K; c0 += KC_FWD) {
-    const int cn = min(KC_FWD, a.K - c0);
+  for (int c0 = 0; c0 < a.K; c0 += kc) {
+    const int cn = min(kc, a.K - c0);
     const int patch = ys_n * xs_n;
     for (int i = threadIdx.x; i < cn * patch; i += BT * BT) {
       const int cc = i / patch, r = i - cc * patch;
@@ -334,10 +335,12 @@ extern "C" int pcl_seg_ce_fwd(const float* seg, const int64_t* target, const flo
   float* pw = pn + blocks;
   float* fin = pw + blocks;
   const int pitch = patch_pitch(a);
-  const size_t smem = (size_t)KC_FWD * pitch * sizeof(float);
+  int kc = K < KC_FWD_MAX ? K : KC_FWD_MAX;
+  while (kc > 1 && (size_t)kc * pitch * sizeof(float) > 96 * 1024) --kc;
+  const size_t smem = (size_t)kc * pitch * sizeof(float);
   if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
   PCL_CUDA(cudaFuncSetAttribute(k_segce_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_segce_fwd<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, pn, pw, pitch);
+  k_segce_fwd<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, pn, pw, pitch, kc);
   PCL_LAUNCH_CHECK();
   k_segce_finalize<<<1, 1024, 0, s>>>(pn, pw, blocks, fin);
   PCL_LAUNCH_CHECK();
@@ -366,8 +369,8 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
   PCL_CUDA(cudaMemsetAsync(dseg, 0, (size_t)B * K * hw * sizeof(float), s));
   // classes per pass: G (kc*32*32) + Hx (kc*32*34) + source patch (kc*pitch) floats, two CTAs per SM when possible
   const int pitch = patch_pitch(a);
-  int kc = K < 10 ? K : 10;
-  while (kc > 1 && (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float) > 110 * 1024) --kc;
+  int kc = K < 24 ? K : 24;                  // one pass for K <= 24 (fewer bulk-synchronous phases per CTA)
+  while (kc > 1 && (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float) > 200 * 1024) --kc;
   const size_t smem = (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float);
   if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
   PCL_CUDA(cudaFuncSetAttribute(k_segce_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
