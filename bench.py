@@ -472,7 +472,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             e1.record()
             torch.cuda.synchronize(dev)
             wrapper[name] = e0.elapsed_time(e1) / 30
-    launches_per_step = (12 if args.precision == "bf16" else 10) + (4 if bank else 0)
+    launches_per_step = (8 if args.precision == "bf16" else 10) + (4 if bank else 0)   # our kernels per step (memsets not counted)
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",

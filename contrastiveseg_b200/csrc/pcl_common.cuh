@@ -29,6 +29,19 @@ void set_cuda_error(cudaError_t e, const char* file, int line);
     if (!(cond)) return PCL_ERR_ARG;      \
   } while (0)
 
+// internal (not part of the C ABI): fused variants used by pcl_step_forward / pcl_step_backward
+int select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t* keys, const int32_t* chunk_pref,
+                     const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize, int32_t* anchor_meta,
+                     float* anchors_f32, void* anchors_bf16, float* inv_norm, float* norm_max, float* row_m2,
+                     float m2_scale, float* partials, int64_t n_slot_rows, void* stream);
+int tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
+              bool skip_prep);
+int tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale);
+int tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss, float* dpartials,
+              float* dA, void* stream, int* splits_out, int* a_pad_out);
+int zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
+                        int splits, int a_pad, float inv_T, const float* grad_loss, float* grad_embed, void* stream);
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

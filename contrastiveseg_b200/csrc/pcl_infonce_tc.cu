@@ -41,6 +41,7 @@ struct TcArgs {
   float k1;                    // log2(e) / T
   int splits;                  // 2-D grid: column splits per row tile
   int slots;                   // partial slots per row (stride of the partial arrays)
+  int tail_count;              // analytic all-zero columns of label 0 (bank mode: R)
   int persistent;              // 1: grid = CTAs, each walks a contiguous range of (row tile, column tile) pairs
 };
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
 template <int MODE, bool POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a,
-         float* __restrict__ partials, const float* __restrict__ rowstats) {
+         float* __restrict__ partials, float* __restrict__ rowstats_out) {
   extern __shared__ uint8_t smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,7 +284,21 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const int rdiag = valid ? (a.mode == 0 ? row : (a.diag ? a.diag[row] : -1)) : -1;
       const float m2 = valid ? a.row_m2[row] : 0.f;
       float neg_i = 1.f;
-      if (MODE == TC_POS) neg_i = valid ? rowstats[a.a_rows + row] : 1.f;
+      if (MODE == TC_POS) {
+        // Sum over negatives = fixed-order sum of the NEG sweep's partial slots (unwritten slots hold 0) + the analytic
+        // zero tail of the flattened bank (Q3).  The CTA of split 0 publishes (m, Neg) for the backward.
+        if (valid) {
+          const int64_t stride = (int64_t)a.slots * a.a_pad;
+          float n = 0.f;
+          for (int pslot = 0; pslot < a.slots; ++pslot) n += partials[stride + (int64_t)pslot * a.a_pad + row];
+          if (a.tail_count > 0 && rcls != 0) n += (float)a.tail_count * ptx::ex2_approx(-m2);
+          neg_i = n;
+          if (sg.slot == 0 && rowstats_out != nullptr) {
+            rowstats_out[row] = m2 * LN2;
+            rowstats_out[a.a_rows + row] = n;
+          }
+        }
+      }
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
       int nlab_lo[4], nlab_hi[4];                              // first / last label of the 4 chunks of the next tile
 #pragma unroll
@@ -889,6 +904,7 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
     return PCL_ERR_ARG;
   }
   a.k1 = tc::LOG2E / d->temperature;
+  a.tail_count = tail;
   const int sms = num_sms();
   const int col_tiles = (int)ceil_div64(a.n_cols > 0 ? a.n_cols : 1, tc::BN);
   int splits = sms / p->row_tiles;
@@ -943,8 +959,23 @@ extern "C" int pcl_to_bf16(const float* src, void* dst, int64_t n_real, int64_t 
   return PCL_OK;
 }
 
+int pcl::tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale) {
+  TcPlan p;
+  int st = make_tc_plan(d, &p);
+  if (st != PCL_OK) return st;
+  *n_slot_rows = (int64_t)p.a.slots * p.a.a_pad;
+  const float cbound = d->contrast_norm_bound > 0.f ? d->contrast_norm_bound : 1.0f;
+  *m2_scale = cbound * p.a.k1 * 1.0001f;
+  return PCL_OK;
+}
+
 extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
                                   void* stream) {
+  return pcl::tc_fwd_ex(d, row_m2, partials, rowstats, loss, stream, false);
+}
+
+int pcl::tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
+                   bool skip_prep) {
   TcPlan p;
   int st = make_tc_plan(d, &p);
   if (st != PCL_OK) return st;
@@ -956,10 +987,12 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   // 1. bf16 anchors (if fp32 given) + row stabilisers
   const float cbound = d->contrast_norm_bound > 0.f ? d->contrast_norm_bound : 1.0f;
   const int64_t n_slot_rows = (int64_t)a.slots * a.a_pad;
-  tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
-                                                     (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, cbound,
-                                                     a.k1, row_m2, partials, n_slot_rows);
-  PCL_LAUNCH_CHECK();
+  if (!skip_prep) {       // (the step path has the anchor selection kernel write row_m2 and initialise the partial slots)
+    tc::k_tc_prep<<<ceil_div(a.a_pad, 8), 256, 0, s>>>(d->anchors_f32, d->anchors_f32 ? (__nv_bfloat16*)d->anchors_bf16 : nullptr,
+                                                       (const __nv_bfloat16*)d->anchors_bf16, d->a_rows, a.a_pad, cbound,
+                                                       a.k1, row_m2, partials, n_slot_rows);
+    PCL_LAUNCH_CHECK();
+  }
   if (d->mode == 2 && a.sorted) {
     int32_t* cls_start = reinterpret_cast<int32_t*>(row_m2 + a.a_pad);       // scratch tail: PCL_MAX_CLASSES + 1 ints
     tc::k_cls_bounds_init<<<2, 256, 0, s>>>(cls_start, (int)a.n_cols);
@@ -997,8 +1030,7 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
   PCL_LAUNCH_CHECK();
   a.persistent = 0;
   if ((variant & 8) || d->neg_only) return PCL_OK;     // similarity + negative-sum sweep only (roofline measurement)
-  k_combine_neg<<<ceil_div(d->a_rows, 256), 256, 0, s>>>(p.sw, partials, rowstats);
-  PCL_LAUNCH_CHECK();
+  // (the NEG partials are combined by the POS sweep's row prologue: no separate pass)
   tc::k_tc_fwd<tc::TC_POS, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
   PCL_LAUNCH_CHECK();
   k_finalize<<<1, 1024, 0, s>>>(p.sw, partials, rowstats, loss);
@@ -1036,10 +1068,16 @@ extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* du
 
 extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
                                   float* dpartials, float* dA, void* stream) {
+  return pcl::tc_bwd_ex(d, row_m2, rowstats, grad_loss, dpartials, dA, stream, nullptr, nullptr);
+}
+
+// dA == nullptr: leave the per-split partials for a fused consumer (splits_out / a_pad_out describe their layout)
+int pcl::tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
+                   float* dpartials, float* dA, void* stream, int* splits_out, int* a_pad_out) {
   TcPlan p;
   int st = make_tc_plan(d, &p);
   if (st != PCL_OK) return st;
-  PCL_REQUIRE(row_m2 && rowstats && dpartials && dA && d->anchors_bf16);
+  PCL_REQUIRE(row_m2 && rowstats && dpartials && d->anchors_bf16);
   if (d->mode != 0) PCL_REQUIRE(d->contrast_bf16);
   cudaStream_t s = (cudaStream_t)stream;
   tc::TcBwdArgs ba;
@@ -1066,6 +1104,9 @@ extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, con
   dim3 grid(p.row_tiles, splits);
   tc::k_tc_bwd<<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmC, ba, dpartials);
   PCL_LAUNCH_CHECK();
+  if (splits_out) *splits_out = splits;
+  if (a_pad_out) *a_pad_out = ba.t.a_pad;
+  if (dA == nullptr) return PCL_OK;
   const int64_t total = (int64_t)d->a_rows * tc::DDIM;
   k_reduce_dA<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(p.sw, dpartials, grad_loss, dA);
   PCL_LAUNCH_CHECK();

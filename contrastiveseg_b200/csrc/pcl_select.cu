@@ -166,15 +166,26 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
          const int32_t* __restrict__ chunk_pref, const int32_t* __restrict__ plan,
          const int32_t* __restrict__ ranks, uint64_t seed, int normalize, int32_t* __restrict__ meta,
          float* __restrict__ anchors, __nv_bfloat16* __restrict__ anchors_bf16, float* __restrict__ inv_norm,
-         float* __restrict__ norm_max) {
+         float* __restrict__ norm_max, float* __restrict__ row_m2, float m2_scale, float* __restrict__ partials,
+         int64_t n_slot_rows) {
+  // tensor-path fusion: initialise the partial-statistic slots (m = -inf, sums = 0) while we are here
+  if (partials != nullptr) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_slot_rows; k += (int64_t)gridDim.x * blockDim.x) {
+      partials[k] = -CUDART_INF_F;
+#pragma unroll
+      for (int q = 1; q < 5; ++q) partials[q * n_slot_rows + k] = 0.f;
+    }
+  }
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int TC = plan[PCL_PLAN_TC], V = plan[PCL_PLAN_V];
   const int D = g.D, ms = g.max_samples;
   if (i >= ms) {
     // padding rows of the bf16 copy (rounded up to 128 rows for the 128-row TMA boxes)
-    if (anchors_bf16 != nullptr && i < ((ms + 127) / 128) * 128)
+    if (anchors_bf16 != nullptr && i < ((ms + 127) / 128) * 128) {
       for (int d = lane; d < D; d += 32) anchors_bf16[(int64_t)i * D + d] = __float2bfloat16(0.f);
+      if (row_m2 != nullptr && lane == 0) row_m2[i] = 0.f;
+    }
     return;
   }
   if (V <= 0 || i >= TC * V) {
@@ -183,7 +194,10 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
       anchors[(int64_t)i * D + d] = 0.f;
       if (anchors_bf16 != nullptr) anchors_bf16[(int64_t)i * D + d] = __float2bfloat16(0.f);
     }
-    if (lane == 0) { meta[i] = -1; meta[ms + i] = -1; meta[2 * ms + i] = -1; meta[3 * ms + i] = -1; inv_norm[i] = 0.f; }
+    if (lane == 0) {
+      meta[i] = -1; meta[ms + i] = -1; meta[2 * ms + i] = -1; meta[3 * ms + i] = -1; inv_norm[i] = 0.f;
+      if (row_m2 != nullptr) row_m2[i] = 0.f;
+    }
     return;
   }
   const int t = i / V, v = i - t * V;
@@ -266,10 +280,20 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
   ss = warp_sum(ss);
   const float nrm = sqrtf(ss);
   const float inv = normalize ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
+  float ss16 = 0.f;                           // squared norm of the bf16-rounded row (tensor-path stabiliser)
   for (int d = lane; d < D; d += 32) {
     float y = dst[d] * inv;
     if (normalize) dst[d] = y;
-    if (anchors_bf16 != nullptr) anchors_bf16[(int64_t)s * D + d] = __float2bfloat16(y);
+    if (anchors_bf16 != nullptr) {
+      const __nv_bfloat16 hb = __float2bfloat16(y);
+      anchors_bf16[(int64_t)s * D + d] = hb;
+      const float f = __bfloat162float(hb);
+      ss16 += f * f;
+    }
+  }
+  if (row_m2 != nullptr) {
+    ss16 = warp_sum(ss16);
+    if (lane == 0) row_m2[s] = sqrtf(ss16) * m2_scale;
   }
   if (lane == 0) {
     meta[s] = pix;
@@ -337,9 +361,48 @@ k_zero_scatter(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __re
     if (meta[ms + s] == b) dst[meta[s]] = dA[(int64_t)s * D + d];
 }
 
+// Same, with the reduction of the backward sweep's per-split partial gradients folded in (step path: the (A, D)
+// gradient matrix is never written): value = scale * sum_p dpartials[p][s][d].
+__global__ void __launch_bounds__(256)
+k_zero_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restrict__ meta,
+                      const float* __restrict__ dpartials, int splits, int a_pad, float inv_T,
+                      const float* __restrict__ grad_loss, float* __restrict__ grad) {
+  const int plane = blockIdx.x;
+  const int D = g.D, ms = g.max_samples;
+  const int b = plane / D, d = plane - b * D;
+  const int64_t HW = (int64_t)g.h * g.w;
+  float* dst = grad + (int64_t)plane * HW;
+  if ((HW & 3) == 0) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = threadIdx.x; i < HW / 4; i += blockDim.x) d4[i] = z;
+  } else {
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) dst[i] = 0.f;
+  }
+  __syncthreads();
+  const int A = min(plan[PCL_PLAN_A], ms);
+  const float scale = inv_T * (grad_loss ? grad_loss[0] : 1.f);
+  for (int s = threadIdx.x; s < A; s += blockDim.x) {
+    if (meta[ms + s] == b) {
+      float v = 0.f;
+      for (int p = 0; p < splits; ++p) v += dpartials[((int64_t)p * a_pad + s) * D + d];    // fixed order
+      dst[meta[s]] = v * scale;
+    }
+  }
+}
+
 }  // namespace pcl
 
 using namespace pcl;
+
+int pcl::zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
+                             int splits, int a_pad, float inv_T, const float* grad_loss, float* grad_embed, void* stream) {
+  if (!g || !plan || !anchor_meta || !dpartials || !grad_embed) return PCL_ERR_ARG;
+  k_zero_scatter_reduce<<<(unsigned)(g->B * g->D), 256, 0, (cudaStream_t)stream>>>(*g, plan, anchor_meta, dpartials, splits,
+                                                                                 a_pad, inv_T, grad_loss, grad_embed);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
 
 // ==================================================================================================
 // C ABI
@@ -395,10 +458,10 @@ extern "C" int pcl_plan_anchors(const pcl_geom* g, const int32_t* counts, int32_
   return PCL_OK;
 }
 
-extern "C" int pcl_select_gather(const pcl_geom* g, const float* embed, const uint16_t* keys,
-                                 const int32_t* chunk_pref, const int32_t* plan, const int32_t* ranks,
-                                 uint64_t seed, int normalize, int32_t* anchor_meta, float* anchors_f32,
-                                 void* anchors_bf16, float* inv_norm, float* norm_max, void* stream) {
+int pcl::select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t* keys, const int32_t* chunk_pref,
+                          const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize, int32_t* anchor_meta,
+                          float* anchors_f32, void* anchors_bf16, float* inv_norm, float* norm_max, float* row_m2,
+                          float m2_scale, float* partials, int64_t n_slot_rows, void* stream) {
   int st = check_geom(g);
   if (st != PCL_OK) return st;
   PCL_REQUIRE(embed && keys && chunk_pref && plan && anchor_meta && anchors_f32 && inv_norm);
@@ -412,9 +475,18 @@ extern "C" int pcl_select_gather(const pcl_geom* g, const float* embed, const ui
   const int rows = anchors_bf16 ? ceil_div(ms, 128) * 128 : ms;
   k_select<<<ceil_div(rows, warps), warps * 32, 0, s>>>(*g, nchunk, embed, keys, chunk_pref, plan, ranks, seed,
                                                        normalize, anchor_meta, anchors_f32,
-                                                       (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max);
+                                                       (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max, row_m2, m2_scale,
+                                                       partials, n_slot_rows);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
+}
+
+extern "C" int pcl_select_gather(const pcl_geom* g, const float* embed, const uint16_t* keys,
+                                 const int32_t* chunk_pref, const int32_t* plan, const int32_t* ranks,
+                                 uint64_t seed, int normalize, int32_t* anchor_meta, float* anchors_f32,
+                                 void* anchors_bf16, float* inv_norm, float* norm_max, void* stream) {
+  return pcl::select_gather_ex(g, embed, keys, chunk_pref, plan, ranks, seed, normalize, anchor_meta, anchors_f32,
+                               anchors_bf16, inv_norm, norm_max, nullptr, 0.f, nullptr, 0, stream);
 }
 
 extern "C" int pcl_scatter_grad(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,

@@ -48,15 +48,24 @@ extern "C" int pcl_step_stats(const pcl_step_desc* d, void* stream) {
 
 extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {
   if (!d) return PCL_ERR_ARG;
-  int st = pcl_select_gather(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
-                             d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, d->norm_max, stream);
-  if (st != PCL_OK) return st;
   if (d->precision == 1) {
+    // tensor path: the selection kernel also writes the row stabilisers and initialises the partial slots
     if (!d->anchors_bf16 || !d->row_m2 || (d->mode == 1 && !d->shadow_bf16)) return PCL_ERR_ARG;
     pcl_tc_desc t;
     fill_tc(d, &t);
-    return pcl_infonce_tc_fwd(&t, d->row_m2, d->partials, d->rowstats, d->loss, stream);
+    int64_t n_slot_rows = 0;
+    float m2_scale = 0.f;
+    int st = pcl::tc_query(&t, &n_slot_rows, &m2_scale);
+    if (st != PCL_OK) return st;
+    st = pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
+                               d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, nullptr, d->row_m2, m2_scale,
+                               d->partials, n_slot_rows, stream);
+    if (st != PCL_OK) return st;
+    return pcl::tc_fwd_ex(&t, d->row_m2, d->partials, d->rowstats, d->loss, stream, true);
   }
+  int st = pcl_select_gather(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
+                             d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, d->norm_max, stream);
+  if (st != PCL_OK) return st;
   pcl_sweep_desc w;
   fill_sweep(d, &w);
   return pcl_infonce_fwd(&w, d->partials, d->rowstats, d->loss, stream);
@@ -68,6 +77,14 @@ extern "C" int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss,
   if (d->precision == 1) {
     pcl_tc_desc t;
     fill_tc(d, &t);
+    if (!d->normalize) {
+      // fused tail: the dense-gradient writer sums the per-split partials itself (no (A, D) gradient round trip)
+      int splits = 0, a_pad = 0;
+      st = pcl::tc_bwd_ex(&t, d->row_m2, d->rowstats, grad_loss, d->dpartials, nullptr, stream, &splits, &a_pad);
+      if (st != PCL_OK) return st;
+      return pcl::zero_scatter_reduce(&d->g, d->plan, d->anchor_meta, d->dpartials, splits, a_pad, 1.f / d->temperature,
+                                      grad_loss, d->grad_embed, stream);
+    }
     st = pcl_infonce_tc_bwd(&t, d->row_m2, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
   } else {
     pcl_sweep_desc w;
