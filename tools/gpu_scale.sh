@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+N=${1:-4}
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+timeout 300 python -m contrastiveseg_b200.build > gpurun_out/build.log 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 \
+  bench.py --gpus $N --steps 200 --warmup 10 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "exit $?" >> gpurun_out/bench_n$N.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 \
+  bench.py --gpus $N --steps 200 --warmup 10 --workload s2 > gpurun_out/bench_s2_n$N.json 2> gpurun_out/bench_s2_n$N.err; echo "exit $?" >> gpurun_out/bench_s2_n$N.err
+grep -h "^{" gpurun_out/bench_n$N.json | cut -c1-330; tail -2 gpurun_out/bench_n$N.err; grep -h "^{" gpurun_out/bench_s2_n$N.json | cut -c1-330; tail -2 gpurun_out/bench_s2_n$N.err
