@@ -499,6 +499,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict(S1 if args.workload == "s1" else S2)
     bank = args.workload == "s2"
+    if os.environ.get("PCL_BENCH_TINY"):            # contract tests on small hosts: same code path, toy geometry
+        cfg.update(B=2, D=32, h=16, w=16, K=5, stride=2, block=8, max_samples=32, max_views=4)
+        if bank:
+            cfg.update(M=8, F=2, net_stride=2)
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:      # defaults are sized for the GPU arm
             args.steps, args.warmup = 3, 1

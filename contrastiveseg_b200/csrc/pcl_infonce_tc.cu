@@ -16,6 +16,7 @@
 #include "pcl_sweep.cuh"
 #include "ptx_sm100.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace pcl {
 namespace tc {
@@ -439,16 +440,6 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-// slots that no CTA writes must read as "nothing seen": m = -inf, sums = 0
-__global__ void k_fill_partials(float* __restrict__ partials, int64_t n_slot_rows) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_slot_rows) {
-    partials[i] = -CUDART_INF_F;
-#pragma unroll
-    for (int k = 1; k < 5; ++k) partials[k * n_slot_rows + i] = 0.f;
-  }
-}
-
 // =====================================================================================================
 // Backward: dA = G . C / T with G formed on the fly (closed form) — FlashAttention-backward
 // shaped: MMA1 S = A.C^T (128 x 128 tile, K = 256) -> epilogue turns S into the bf16 gradient tile G in shared
@@ -836,8 +827,21 @@ static PFN_tmapEncodeTiled get_encode() {
   return fn;
 }
 
-// bf16 row-major (rows, 256) matrix, box = 64 columns (128 B) x box_rows, 128-byte swizzle, OOB rows read as zero
+// bf16 row-major (rows, 256) matrix, box = 64 columns (128 B) x box_rows, 128-byte swizzle, OOB rows read as zero.
+// Encoding costs ~2 us of host time and the step re-uses the same few (pointer, rows, box) triples every call, so a
+// small read-mostly cache keeps them (a tensor map only describes addresses/shapes: no lifetime coupling).
+struct TmapKey { const void* base; uint64_t rows; uint32_t box_rows; };
+struct TmapEntry { TmapKey k; CUtensorMap m; bool used; };
+static TmapEntry g_tmaps[16];
+static unsigned g_tmap_next = 0;
+static std::mutex g_tmap_mu;
+
 static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    for (auto& e : g_tmaps)
+      if (e.used && e.k.base == base && e.k.rows == rows && e.k.box_rows == box_rows) { *m = e.m; return PCL_OK; }
+  }
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) return PCL_ERR_CUDA;
   cuuint64_t gdim[2] = {(cuuint64_t)tc::DDIM, rows};
@@ -847,7 +851,13 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t b
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? PCL_OK : PCL_ERR_CUDA;
+  if (r != CUDA_SUCCESS) return PCL_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  TmapEntry& e = g_tmaps[g_tmap_next++ % 16];
+  e.k = TmapKey{base, rows, box_rows};
+  e.m = *m;
+  e.used = true;
+  return PCL_OK;
 }
 
 struct TcPlan {

@@ -7,8 +7,9 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer owned by the caller unless the name starts with h_;
- *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, keeps no
- *     global mutable state and never throws; the return value is 0 or a negative pcl_status;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and never throws; the
+ *     library keeps no state between calls (apart from a mutex-protected cache of encoded TMA descriptors, which
+ *     describe addresses/shapes only); the return value is 0 or a negative pcl_status;
  *   - scratch comes from caller-provided buffers (sizes: pcl_select_sizes / pcl_sweep_sizes), so the
  *     caller's allocator owns all memory and the sequence is CUDA-graph capturable;
  *   - there is NO CPU fallback: without a CUDA device every compute call returns PCL_ERR_CUDA.
