@@ -384,8 +384,12 @@ extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* 
   PCL_REQUIRE(partials && rowstats && loss);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = sweep_smem(a.D, false);
-  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_fwd = 0;                   // raise the opt-in shared memory limit once per size
+  if (smem > attr_fwd) {
+    PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_fwd = smem;
+  }
   // every (split, live row) slot is written by its CTA (empty column ranges write "nothing seen"),
   // so the partial buffers need no initialisation
   dim3 grid(a.row_tiles, a.splits);
@@ -408,7 +412,11 @@ extern "C" int pcl_infonce_bwd(const pcl_sweep_desc* d, const float* rowstats, c
   PCL_REQUIRE(rowstats && dpartials && dA);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = sweep_smem(a.D, true);
-  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t attr_bwd = 0;
+  if (smem > attr_bwd) {
+    PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bwd = smem;
+  }
   dim3 grid(a.row_tiles, a.splits);
   k_sweep<MODE_BWD><<<grid, SWEEP_THREADS, smem, s>>>(a, nullptr, rowstats, dpartials);
   PCL_LAUNCH_CHECK();

@@ -29,7 +29,9 @@ __device__ __forceinline__ void src_coord(int o, float r, int in_size, int& i0, 
 }
 
 constexpr int CE_THREADS = 256;
-constexpr int BT = 32;                 // tile edge (label pixels): one CTA = 32 x 32 label pixels of one image
+constexpr int BT = 32;                 // tile width  (label pixels)
+constexpr int BTY = 8;                 // tile height: 32 x 8 = 256 threads per CTA -> several CTAs per SM hide the
+                                       // load latency of the bulk-synchronous phases (a 32 x 32 tile ran 1 CTA/SM)
 constexpr int KC_FWD_MAX = 32;         // classes staged per pass in the forward (one pass for K <= 32: one exposed load latency)
 
 // Source patch geometry of a tile (identical for every thread of the CTA).
@@ -39,28 +41,30 @@ struct TileGeo {
 
 // Forward, tile formulation: the <= (32*ry+2) x (32*rx+2) source logits of the tile are staged in shared memory per class
 // chunk; every thread (one label pixel) runs an online log-sum-exp over the classes from shared memory.
-__global__ void __launch_bounds__(BT * BT)
+__global__ void __launch_bounds__(BT * BTY)
 k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_nll, float* __restrict__ part_w, int pitch,
             int kc) {
   extern __shared__ float sm[];                    // [kc][pitch] source patch
-  __shared__ float s_n[BT * BT / 32], s_w[BT * BT / 32];
-  __shared__ int s_y0[BT], s_y1[BT], s_x0[BT], s_x1[BT];
-  __shared__ float s_ly[BT], s_lx[BT];
+  __shared__ float s_n[BT * BTY / 32], s_w[BT * BTY / 32];
+  __shared__ int s_y0[BTY], s_y1[BTY], s_x0[BT], s_x1[BT];
+  __shared__ float s_ly[BTY], s_lx[BT];
   const int tx = threadIdx.x & (BT - 1), ty = threadIdx.x >> 5;
   const int b = blockIdx.z;
-  const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BT;
+  const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BTY;
   const int x = X0 + tx, y = Y0 + ty;
   const int64_t hw = (int64_t)a.h * a.w, HWo = (int64_t)a.H * a.W;
   if (threadIdx.x < BT) {
     int i0, i1; float l;
-    src_coord(min(Y0 + (int)threadIdx.x, a.H - 1), a.ry, a.h, i0, i1, l);
-    s_y0[threadIdx.x] = i0; s_y1[threadIdx.x] = i1; s_ly[threadIdx.x] = l;
+    if (threadIdx.x < BTY) {
+      src_coord(min(Y0 + (int)threadIdx.x, a.H - 1), a.ry, a.h, i0, i1, l);
+      s_y0[threadIdx.x] = i0; s_y1[threadIdx.x] = i1; s_ly[threadIdx.x] = l;
+    }
     src_coord(min(X0 + (int)threadIdx.x, a.W - 1), a.rx, a.w, i0, i1, l);
     s_x0[threadIdx.x] = i0; s_x1[threadIdx.x] = i1; s_lx[threadIdx.x] = l;
   }
   __syncthreads();
   const int ys_base = s_y0[0], xs_base = s_x0[0];
-  const int ny = min(Y0 + BT, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;
+  const int ny = min(Y0 + BTY, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;
   const int ys_n = s_y1[ny - 1] - ys_base + 1, xs_n = s_x1[nx - 1] - xs_base + 1;
   const bool inside = x < a.W && y < a.H;
   const int ly0 = s_y0[ty] - ys_base, ly1 = s_y1[ty] - ys_base, lx0 = s_x0[tx] - xs_base, lx1 = s_x1[tx] - xs_base;
@@ -73,7 +77,7 @@ k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_n
   for (int c0 = 0; c0 < a.K; c0 += kc) {
     const int cn = min(kc, a.K - c0);
     const int patch = ys_n * xs_n;
-    for (int i = threadIdx.x; i < cn * patch; i += BT * BT) {
+    for (int i = threadIdx.x; i < cn * patch; i += BT * BTY) {
       const int cc = i / patch, r = i - cc * patch;
       const int yy = r / xs_n, xx = r - yy * xs_n;
       sm[cc * pitch + r] = a.seg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)(ys_base + yy) * a.w + xs_base + xx];
@@ -103,7 +107,7 @@ k_segce_fwd(SegCeArgs a, float* __restrict__ lse_out, float* __restrict__ part_n
   __syncthreads();
   if (threadIdx.x == 0) {
     float an = 0.f, aw = 0.f;
-    for (int i = 0; i < BT * BT / 32; ++i) { an += s_n[i]; aw += s_w[i]; }      // fixed order
+    for (int i = 0; i < BT * BTY / 32; ++i) { an += s_n[i]; aw += s_w[i]; }      // fixed order
     const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     part_nll[blk] = an;
     part_w[blk] = aw;
@@ -136,30 +140,32 @@ k_segce_finalize(const float* __restrict__ part_nll, const float* __restrict__ p
 // label columns / rows inside the footprint of their source cell.
 constexpr int SRC_MAX = 34;            // source cells per tile edge (scale >= 1: up to 32 + 2)
 
-__global__ void __launch_bounds__(BT * BT)
+__global__ void __launch_bounds__(BT * BTY)
 k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __restrict__ fin,
                  const float* __restrict__ grad_out, float* __restrict__ dseg, int kc, int pitch) {
   extern __shared__ float sm[];
-  float* G = sm;                                   // [kc][BT][BT]
-  float* Hx = G + (size_t)kc * BT * BT;            // [kc][BT][SRC_MAX]
-  float* S = Hx + (size_t)kc * BT * SRC_MAX;       // [kc][pitch] source patch
-  __shared__ int s_y0[BT], s_y1[BT], s_x0[BT], s_x1[BT];
-  __shared__ float s_ly[BT], s_lx[BT];
+  float* G = sm;                                   // [kc][BTY][BT]
+  float* Hx = G + (size_t)kc * BTY * BT;           // [kc][BTY][SRC_MAX]
+  float* S = Hx + (size_t)kc * BTY * SRC_MAX;      // [kc][pitch] source patch
+  __shared__ int s_y0[BTY], s_y1[BTY], s_x0[BT], s_x1[BT];
+  __shared__ float s_ly[BTY], s_lx[BT];
   const int tx = threadIdx.x & (BT - 1), ty = threadIdx.x >> 5;
   const int b = blockIdx.z;
-  const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BT;
+  const int X0 = blockIdx.x * BT, Y0 = blockIdx.y * BTY;
   const int x = X0 + tx, y = Y0 + ty;
   const int64_t hw = (int64_t)a.h * a.w, HWo = (int64_t)a.H * a.W;
   if (threadIdx.x < BT) {
     int i0, i1; float l;
-    src_coord(min(Y0 + (int)threadIdx.x, a.H - 1), a.ry, a.h, i0, i1, l);
-    s_y0[threadIdx.x] = i0; s_y1[threadIdx.x] = i1; s_ly[threadIdx.x] = l;
+    if (threadIdx.x < BTY) {
+      src_coord(min(Y0 + (int)threadIdx.x, a.H - 1), a.ry, a.h, i0, i1, l);
+      s_y0[threadIdx.x] = i0; s_y1[threadIdx.x] = i1; s_ly[threadIdx.x] = l;
+    }
     src_coord(min(X0 + (int)threadIdx.x, a.W - 1), a.rx, a.w, i0, i1, l);
     s_x0[threadIdx.x] = i0; s_x1[threadIdx.x] = i1; s_lx[threadIdx.x] = l;
   }
   __syncthreads();
   const int ys_base = s_y0[0], xs_base = s_x0[0];
-  const int ny = min(Y0 + BT, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;          // valid rows / cols of the tile
+  const int ny = min(Y0 + BTY, a.H) - Y0, nx = min(X0 + BT, a.W) - X0;         // valid rows / cols of the tile
   const int ys_n = s_y1[ny - 1] - ys_base + 1, xs_n = s_x1[nx - 1] - xs_base + 1;
   const int patch = ys_n * xs_n;
   const bool inside = x < a.W && y < a.H;
@@ -182,7 +188,7 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
   const float inv_rx = a.rx > 0.f ? 1.f / a.rx : 0.f, inv_ry = a.ry > 0.f ? 1.f / a.ry : 0.f;
   for (int c0 = 0; c0 < a.K; c0 += kc) {
     const int cn = min(kc, a.K - c0);
-    for (int i = threadIdx.x; i < cn * patch; i += BT * BT) {
+    for (int i = threadIdx.x; i < cn * patch; i += BT * BTY) {
       const int cc = i / patch, r = i - cc * patch;
       const int yy = r / xs_n, xx = r - yy * xs_n;
       S[cc * pitch + r] = a.seg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)(ys_base + yy) * a.w + xs_base + xx];
@@ -196,19 +202,19 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
         const float v = w00 * p[i00] + w01 * p[i01] + w10 * p[i10] + w11 * p[i11];
         g = coef * (__expf(v - lse_p) - ((c0 + cc) == (int)t ? 1.f : 0.f));
       }
-      G[((size_t)cc * BT + ty) * BT + tx] = g;
+      G[((size_t)cc * BTY + ty) * BT + tx] = g;
     }
     __syncthreads();
     // ---- B: x direction (only the label columns whose footprint touches source column xg) ----
-    for (int i = threadIdx.x; i < cn * BT * xs_n; i += BT * BT) {
-      const int xs = i % xs_n, row = (i / xs_n) % BT, cc = i / (xs_n * BT);
+    for (int i = threadIdx.x; i < cn * BTY * xs_n; i += BT * BTY) {
+      const int xs = i % xs_n, row = (i / xs_n) % BTY, cc = i / (xs_n * BTY);
       const int xg = xs_base + xs;
       int klo = 0, khi = nx - 1;
       if (a.rx > 0.f) {
         klo = max(0, (int)floorf(((float)xg - 1.f) * inv_rx) - 1 - X0);
         khi = min(nx - 1, (int)ceilf(((float)xg + 1.f) * inv_rx) + 1 - X0);
       }
-      const float* gr = G + ((size_t)cc * BT + row) * BT;
+      const float* gr = G + ((size_t)cc * BTY + row) * BT;
       float acc = 0.f;
       for (int k = klo; k <= khi; ++k) {
         float wgt = 0.f;
@@ -216,11 +222,11 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
         if (s_x1[k] == xg) wgt += s_lx[k];
         acc += wgt * gr[k];
       }
-      Hx[((size_t)cc * BT + row) * SRC_MAX + xs] = acc;
+      Hx[((size_t)cc * BTY + row) * SRC_MAX + xs] = acc;
     }
     __syncthreads();
     // ---- C: y direction, flush ----
-    for (int i = threadIdx.x; i < cn * ys_n * xs_n; i += BT * BT) {
+    for (int i = threadIdx.x; i < cn * ys_n * xs_n; i += BT * BTY) {
       const int xs = i % xs_n, ysl = (i / xs_n) % ys_n, cc = i / (xs_n * ys_n);
       const int yg = ys_base + ysl;
       int klo = 0, khi = ny - 1;
@@ -233,7 +239,7 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
         float wgt = 0.f;
         if (s_y0[k] == yg) wgt += 1.f - s_ly[k];
         if (s_y1[k] == yg) wgt += s_ly[k];
-        acc += wgt * Hx[((size_t)cc * BT + k) * SRC_MAX + xs];
+        acc += wgt * Hx[((size_t)cc * BTY + k) * SRC_MAX + xs];
       }
       if (acc != 0.f) atomicAdd(&dseg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)yg * a.w + xs_base + xs], acc);
     }
@@ -310,13 +316,13 @@ static int make_ce(const float* seg, const int64_t* target, const float* weight,
 }
 
 static int patch_pitch(const SegCeArgs& a) {
-  // upper bound of the source cells a 32 x 32 label tile touches (ys_n * xs_n), + 1 to de-phase the class planes
-  const int py = (int)(31.f * a.ry) + 3, px = (int)(31.f * a.rx) + 3;
+  // upper bound of the source cells a 32 x BTY label tile touches (ys_n * xs_n), + 1 to de-phase the class planes
+  const int py = (int)((float)(BTY - 1) * a.ry) + 3, px = (int)(31.f * a.rx) + 3;
   return (py < a.h + 1 ? py : a.h + 1) * (px < a.w + 1 ? px : a.w + 1) + 1;
 }
 
 extern "C" int64_t pcl_seg_ce_scratch_floats(int32_t B, int32_t H, int32_t W) {
-  const int64_t blocks = (int64_t)ceil_div(H, 32) * ceil_div(W, 32) * B;
+  const int64_t blocks = (int64_t)ceil_div(H, BTY) * ceil_div(W, BT) * B;
   return (int64_t)B * H * W + 2 * blocks + 2;            // lse | partial nll | partial weight | (loss, weight sum)
 }
 
@@ -329,7 +335,7 @@ extern "C" int pcl_seg_ce_fwd(const float* seg, const int64_t* target, const flo
   PCL_REQUIRE(scratch && loss);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t HWo = (int64_t)H * W;
-  const int64_t blocks = (int64_t)ceil_div(H, BT) * ceil_div(W, BT) * B;
+  const int64_t blocks = (int64_t)ceil_div(H, BTY) * ceil_div(W, BT) * B;
   float* lse = scratch;
   float* pn = scratch + (int64_t)B * HWo;
   float* pw = pn + blocks;
@@ -340,7 +346,7 @@ extern "C" int pcl_seg_ce_fwd(const float* seg, const int64_t* target, const flo
   const size_t smem = (size_t)kc * pitch * sizeof(float);
   if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
   PCL_CUDA(cudaFuncSetAttribute(k_segce_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_segce_fwd<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, pn, pw, pitch, kc);
+  k_segce_fwd<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BTY), B), BT * BTY, smem, s>>>(a, lse, pn, pw, pitch, kc);
   PCL_LAUNCH_CHECK();
   k_segce_finalize<<<1, 1024, 0, s>>>(pn, pw, blocks, fin);
   PCL_LAUNCH_CHECK();
@@ -357,7 +363,7 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
   PCL_REQUIRE(scratch && dseg);
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t HWo = (int64_t)H * W;
-  const int64_t blocks = (int64_t)ceil_div(H, BT) * ceil_div(W, BT) * B;
+  const int64_t blocks = (int64_t)ceil_div(H, BTY) * ceil_div(W, BT) * B;
   const float* lse = scratch;
   const float* fin = scratch + (int64_t)B * HWo + 2 * blocks;
   const int64_t hw = (int64_t)h * w;
@@ -370,11 +376,11 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
   // classes per pass: G (kc*32*32) + Hx (kc*32*34) + source patch (kc*pitch) floats, two CTAs per SM when possible
   const int pitch = patch_pitch(a);
   int kc = K < 24 ? K : 24;                  // one pass for K <= 24 (fewer bulk-synchronous phases per CTA)
-  while (kc > 1 && (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float) > 200 * 1024) --kc;
-  const size_t smem = (size_t)kc * (BT * BT + BT * SRC_MAX + pitch) * sizeof(float);
+  while (kc > 1 && (size_t)kc * (BTY * BT + BTY * SRC_MAX + pitch) * sizeof(float) > 200 * 1024) --kc;
+  const size_t smem = (size_t)kc * (BTY * BT + BTY * SRC_MAX + pitch) * sizeof(float);
   if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
   PCL_CUDA(cudaFuncSetAttribute(k_segce_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_segce_bwd_tile<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BT), B), BT * BT, smem, s>>>(a, lse, fin, grad_loss,
+  k_segce_bwd_tile<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BTY), B), BT * BTY, smem, s>>>(a, lse, fin, grad_loss,
                                                                                                      dseg, kc, pitch);
   PCL_LAUNCH_CHECK();
   return PCL_OK;

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import weakref
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -112,6 +113,7 @@ class ContrastWorkspace:
         self.ranks = torch.zeros(ms, **i32)
         self.ranks_host = torch.zeros(ms, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self.busy = False
+        self.token = 0               # generation counter: a stale autograd node must not release a re-used workspace
         d = _abi.StepDesc()
         d.g = geom
         d.mode, d.bank_K, d.bank_M0, d.bank_M1 = mode, bank_K, bank_M0, bank_M1
@@ -149,6 +151,11 @@ def clear_workspaces() -> None:
 
 
 _step_counter = [0]
+
+
+def _release_workspace(ws, token) -> None:
+    if ws.token == token:
+        ws.busy = False
 
 
 class _PixelContrastFn(torch.autograd.Function):
@@ -265,6 +272,10 @@ class _PixelContrastFn(torch.autograd.Function):
         ctx.keep = (embed_c, labels_c, seg_c, pred_c, segq_c, pixq_c, shadow_c)   # keep inputs alive until kernels ran
         if embed.requires_grad and torch.is_grad_enabled():
             ws.busy = True
+            ws.token += 1
+            ctx.token = ws.token
+            # if the graph is dropped without a backward (e.g. a loss that is only logged) give the workspace back
+            weakref.finalize(ctx, _release_workspace, ws, ws.token)
         return out
 
     @staticmethod
@@ -281,7 +292,7 @@ class _PixelContrastFn(torch.autograd.Function):
         d.grad_embed = grad.data_ptr()
         with _on_device(device):
             _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
-        ws.busy = False
+        _release_workspace(ws, getattr(ctx, "token", ws.token))
         ctx.keep = None
         return grad, None, None, None, None, None, None, None
 

@@ -597,3 +597,22 @@ def test_fused_seg_ce_full_size_and_wrapper_toggle():
         crit.contrast_criterion.perm_fn = P.PermRecorder(rec_seed)
         losses.append(crit({"seg": seg, "embed": data["embed"].to(DEV)}, tgt, with_embed=True).item())
     assert rel_err(losses[0], losses[1]) < 5e-6
+
+
+def test_workspace_is_released_when_the_graph_is_dropped_without_backward():
+    g = load_golden("nomem_small")
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    crit = cs.PixelContrastLoss(_cfg(T, bT, ms, mv, K))
+    embed = torch.from_numpy(g["embed"]).to(DEV).requires_grad_(True)
+    target, predict = torch.from_numpy(g["target"]).to(DEV), torch.from_numpy(g["predict"]).to(DEV)
+    seen = set()
+    for _ in range(6):
+        loss = crit(embed, target, predict)          # logged only: no backward
+        seen.add(id(Fn.last_workspace(embed.device)))
+        del loss
+    assert len(seen) <= 2                            # no workspace leak
+    l1 = crit(embed, target, predict)
+    l2 = crit(embed, target, predict)                # two pending graphs -> two distinct workspaces
+    w2 = Fn.last_workspace(embed.device)
+    l1.backward(); l2.backward()
+    assert torch.isfinite(embed.grad).all() and not w2.busy
