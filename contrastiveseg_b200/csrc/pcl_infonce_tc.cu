@@ -43,6 +43,7 @@ struct TcArgs {
   int splits;                  // 2-D grid: column splits per row tile
   int slots;                   // partial slots per row (stride of the partial arrays)
   int tail_count;              // analytic all-zero columns of label 0 (bank mode: R)
+  int neg_grid;                // CTAs of the persistent NEG sweep (bounds the partial slots a row tile can own)
   int persistent;              // 1: grid = CTAs, each walks a contiguous range of (row tile, column tile) pairs
 };
 
@@ -290,8 +291,12 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         // zero tail of the flattened bank (Q3).  The CTA of split 0 publishes (m, Neg) for the backward.
         if (valid) {
           const int64_t stride = (int64_t)a.slots * a.a_pad;
+          // a row tile is touched by at most T/U + 2 CTAs of the persistent NEG walk (U = pairs per CTA)
+          const long long Pn = (long long)((A + BM - 1) / BM) * T_all;
+          const long long Un = max(1LL, Pn / max(1, a.neg_grid));
+          const int used = (int)min((long long)a.slots, T_all / Un + 2);
           float n = 0.f;
-          for (int pslot = 0; pslot < a.slots; ++pslot) n += partials[stride + (int64_t)pslot * a.a_pad + row];
+          for (int pslot = 0; pslot < used; ++pslot) n += partials[stride + (int64_t)pslot * a.a_pad + row];
           if (a.tail_count > 0 && rcls != 0) n += (float)a.tail_count * ptx::ex2_approx(-m2);
           neg_i = n;
           if (sg.slot == 0 && rowstats_out != nullptr) {
@@ -924,6 +929,7 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   // persistent NEG sweep: G CTAs walk contiguous ranges of the row_tiles x col_tiles pair list
   const long long P = (long long)p->row_tiles * col_tiles;
   p->grid_persistent = (int)(P < sms ? P : sms);
+  a.neg_grid = p->grid_persistent;
   const long long U = P / p->grid_persistent;                      // pairs per CTA (floor, >= 1)
   long long slots_neg = d->plan ? (long long)p->grid_persistent : (col_tiles / U + 2);   // live A unknown on the host
   if (slots_neg > p->grid_persistent) slots_neg = p->grid_persistent;
@@ -942,6 +948,7 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   s.n_cols = a.n_cols; s.tail_count = tail;
   s.inv_T = 1.f / d->temperature; s.T_over_bT = d->temperature / d->base_temperature;
   s.nan_safe = d->nan_safe; s.row_tiles = p->row_tiles; s.splits = a.slots; s.a_pad = a.a_pad; s.col_tiles = col_tiles;
+  s.pos_splits = a.splits;                 // the POS sweep runs on the 2-D grid: only its `splits` slots are written
   return PCL_OK;
 }
 

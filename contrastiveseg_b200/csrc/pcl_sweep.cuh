@@ -18,6 +18,7 @@ struct SweepArgs {
   float inv_T, T_over_bT;
   int nan_safe;
   int row_tiles, splits, a_pad, col_tiles;
+  int pos_splits;          // live slots of the POS partial arrays (0 = same as splits)
 };
 
 __device__ __forceinline__ int live_rows(const SweepArgs& a) {
@@ -54,7 +55,8 @@ k_finalize(SweepArgs a, const float* __restrict__ partials, float* __restrict__ 
   for (int r = threadIdx.x; r < a.a_rows; r += blockDim.x) {
     float ps = 0.f, s = 0.f, c = 0.f, rl = 0.f;
     if (r < A) {
-      for (int p = 0; p < a.splits; ++p) {
+      const int npos = a.pos_splits > 0 ? a.pos_splits : a.splits;
+      for (int p = 0; p < npos; ++p) {
         ps += partials[((int64_t)2 * a.splits + p) * a.a_pad + r];
         s += partials[((int64_t)3 * a.splits + p) * a.a_pad + r];
         c += partials[((int64_t)4 * a.splits + p) * a.a_pad + r];
