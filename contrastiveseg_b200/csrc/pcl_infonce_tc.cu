@@ -492,10 +492,11 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
   const int split = blockIdx.y;
   const int64_t ncols = a.mode == 0 ? (int64_t)A : a.n_cols;
   const int t_hi = (int)((ncols + BNB - 1) / BNB);
-  const int per = (t_hi + a.splits - 1) / a.splits;
-  const int my_lo = split * per;
-  const int my_hi = min(t_hi, my_lo + per);
-  const int ntiles = my_hi > my_lo ? my_hi - my_lo : 0;
+  // Column tiles are dealt round-robin to the splits (tile = split + it * splits): the tiles that hold a row tile's
+  // positives (2 MUFU ops per logit, divergent rows) are spread over all its CTAs instead of landing on two or three
+  // of them (contiguous ranges left 30 % of the SM time idle behind the slowest CTAs: profiles/r1_s2_bwd_*).
+  const int my_lo = split, tstep = a.splits;
+  const int ntiles = t_hi > split ? (t_hi - split + a.splits - 1) / a.splits : 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -525,7 +526,7 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         ptx::mbar_arrive_expect_tx(&sm.c_full[stage], C_STAGE_BYTES);
         for (int kb = 0; kb < NKB; ++kb)
           ptx::tma_load_2d(sm.c + stage * C_STAGE_BYTES + kb * C_KB_BYTES, &tmC, &sm.c_full[stage], kb * BK,
-                           (my_lo + it) * BNB);
+                           (my_lo + it * tstep) * BNB);
       }
     }
   } else if (warp == 1) {
@@ -619,7 +620,7 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
     }
     for (int it = 0; it < ntiles; ++it) {
-      const int ct = my_lo + it;
+      const int ct = my_lo + it * tstep;
       const uint32_t acc = it & 1, phase = (it >> 1) & 1;
       const int col0 = ct * BNB + half * 64;
       int clab[2];
@@ -633,7 +634,7 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       if (it + 1 < ntiles) {                       // labels of the next tile: loads fly while this tile is processed
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          const int cb = (ct + 1) * BNB + half * 64 + ch * 32;
+          const int cb = (ct + tstep) * BNB + half * 64 + ch * 32;
           const bool in = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
           nlab_lo[ch] = in ? col_label(a, cb) : -2;
           nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
