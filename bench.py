@@ -391,7 +391,14 @@ def run_engine(args, cfg, bank, rank, world, dev):
     sampler.stop()
     t_ms = ev[0].elapsed_time(ev[1])
     tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # diagnostics: every rank's device time and host enqueue time per step (which rank sets the max, and why)
+        mine = torch.tensor([t_ms / args.steps, t_enqueue / args.steps * 1e3], dtype=torch.float64, device=dev)
+        allv = torch.empty(2 * world, dtype=torch.float64, device=dev)
+        torch.distributed.all_gather_into_tensor(allv, mine)
+        per_rank = {"ms_per_step": [round(v, 5) for v in allv.view(world, 2)[:, 0].tolist()],
+                    "host_enqueue_ms_per_step": [round(v, 5) for v in allv.view(world, 2)[:, 1].tolist()]}
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
     t_ms = float(tt.item())
     value = world * cfg["B"] * args.steps / (t_ms / 1e3)
@@ -499,7 +506,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "precision": args.precision, "impl": "engine"}
+            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "per_rank": per_rank, "precision": args.precision, "impl": "engine"}
 
 
 def main():
