@@ -75,12 +75,15 @@ class StepDesc(C.Structure):
                 ("loss", c_vp), ("grad_embed", c_vp)]
 
 
+ABI_STRUCTS = (Geom, SelectSizes, SweepDesc, SweepSizes, BankGeom, TcDesc, StepDesc)   # pcl_abi_sizeof ids 0..6
+
 # name -> (restype, argtypes); every symbol declared in include/pcl.h
 SIGNATURES = {
     "pcl_version": (c_i32, []),
     "pcl_strerror": (C.c_char_p, [c_i32]),
     "pcl_last_cuda_error": (C.c_char_p, []),
     "pcl_device_count": (c_i32, []),
+    "pcl_abi_sizeof": (c_i64, [c_i32]),
     "pcl_select_sizes": (c_i32, [C.POINTER(Geom), C.POINTER(SelectSizes)]),
     "pcl_class_stats": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_plan_anchors": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp]),
@@ -141,6 +144,10 @@ def load(build_if_missing: bool = False):
             fn.argtypes = args
         if lib.pcl_version() // 100 != 1:
             raise PclError(f"ABI version mismatch: library reports {lib.pcl_version()}")
+        for sid, st in enumerate(ABI_STRUCTS):       # struct layouts as compiled vs as declared here
+            if lib.pcl_abi_sizeof(sid) != C.sizeof(st):
+                raise PclError(f"ABI layout mismatch: {st.__name__} is {C.sizeof(st)} bytes here, "
+                               f"{lib.pcl_abi_sizeof(sid)} in {path}")
         _lib = lib
     return _lib
 

@@ -25,6 +25,19 @@ extern "C" const char* pcl_strerror(int status) {
 
 extern "C" const char* pcl_last_cuda_error(void) { return pcl::g_last_error; }
 
+extern "C" int64_t pcl_abi_sizeof(int struct_id) {
+  switch (struct_id) {
+    case 0: return (int64_t)sizeof(pcl_geom);
+    case 1: return (int64_t)sizeof(pcl_select_sizes_t);
+    case 2: return (int64_t)sizeof(pcl_sweep_desc);
+    case 3: return (int64_t)sizeof(pcl_sweep_sizes_t);
+    case 4: return (int64_t)sizeof(pcl_bank_geom);
+    case 5: return (int64_t)sizeof(pcl_tc_desc);
+    case 6: return (int64_t)sizeof(pcl_step_desc);
+    default: return -1;
+  }
+}
+
 extern "C" int pcl_device_count(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

@@ -47,6 +47,10 @@ int         pcl_version(void);
 const char* pcl_strerror(int status);
 const char* pcl_last_cuda_error(void);          /* text of the last CUDA error seen by this thread */
 int         pcl_device_count(void);             /* 0 without a usable CUDA device */
+/* FFI layout self-check: sizeof() of a host struct as this library was compiled.  struct_id: 0 pcl_geom,
+ * 1 pcl_select_sizes_t, 2 pcl_sweep_desc, 3 pcl_sweep_sizes_t, 4 pcl_bank_geom, 5 pcl_tc_desc, 6 pcl_step_desc;
+ * -1 for an unknown id.  A binding compares these with its own struct definitions before the first call. */
+int64_t     pcl_abi_sizeof(int struct_id);
 
 /* ------------------------------------------------------------------------------------------------
  * Geometry of one loss call (host struct, passed by pointer).

@@ -47,6 +47,11 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_abi.BankGeom) == 40
     assert C.sizeof(_abi.SelectSizes) == 48
     assert C.sizeof(_abi.SweepSizes) == 40
+    # every host struct, against the sizes the compiled library reports
+    lib = _abi.load(build_if_missing=True)
+    for sid, st in enumerate(_abi.ABI_STRUCTS):
+        assert lib.pcl_abi_sizeof(sid) == C.sizeof(st), st.__name__
+    assert lib.pcl_abi_sizeof(len(_abi.ABI_STRUCTS)) == -1
 
 
 def test_no_cpu_fallback():
