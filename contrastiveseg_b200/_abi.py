@@ -92,6 +92,9 @@ SIGNATURES = {
     "pcl_sweep_sizes": (c_i32, [C.POINTER(SweepDesc), C.POINTER(SweepSizes)]),
     "pcl_infonce_fwd": (c_i32, [C.POINTER(SweepDesc), c_vp, c_vp, c_vp, c_vp]),
     "pcl_infonce_bwd": (c_i32, [C.POINTER(SweepDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_topk_scratch_u32": (c_i64, [C.POINTER(SweepDesc)]),
+    "pcl_infonce_topk_fwd": (c_i32, [C.POINTER(SweepDesc), c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_infonce_topk_bwd": (c_i32, [C.POINTER(SweepDesc), c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_scatter_grad": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pcl_l2norm_fwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i64, c_vp]),
     "pcl_l2norm_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp]),

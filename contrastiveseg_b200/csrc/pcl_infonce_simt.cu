@@ -12,42 +12,9 @@
 // This is the exact path (fp32 FMA); the bf16 tcgen05 path lives in pcl_infonce_tc.cu.
 #include "pcl_common.cuh"
 #include "pcl_sweep.cuh"
+#include "pcl_simt_tile.cuh"
 
 namespace pcl {
-
-constexpr int TM = 64, TN = 64, LDT = 68;     // tile rows/cols, padded leading dim of transposed tiles
-constexpr int SWEEP_THREADS = 256;
-constexpr int QMAX = 16;                      // D/16 accumulators per row in BWD (D <= 256)
-
-__device__ __forceinline__ const float* col_row(const SweepArgs& a, int64_t n, int& label) {
-  if (a.mode == 1) {
-    int c = (int)(n / a.R);
-    int q = (int)(n - (int64_t)c * a.R);
-    label = c + 1;
-    return q < a.M0 ? a.segq + ((int64_t)(c + 1) * a.M0 + q) * a.D
-                    : a.pixq + ((int64_t)(c + 1) * a.M1 + (q - a.M0)) * a.D;
-  }
-  if (a.mode == 0) { label = a.acls[n]; return a.anchors + n * a.D; }
-  label = a.ccls[n];
-  return a.contrast + n * a.D;
-}
-
-// Load a 64 x D row-major block (row pointers in s_ptr, nullptr = zero row) transposed into dst[k*LDT + r].
-__device__ __forceinline__ void load_tile_T(float* __restrict__ dst, const float* const* s_ptr, int D) {
-  const int r = threadIdx.x & 63, kq = threadIdx.x >> 6;
-  const float* src = s_ptr[r];
-  for (int kk = kq * 8; kk < D; kk += 32) {
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (src != nullptr) {
-      v0 = *reinterpret_cast<const float4*>(src + kk);
-      v1 = *reinterpret_cast<const float4*>(src + kk + 4);
-    }
-    dst[(kk + 0) * LDT + r] = v0.x; dst[(kk + 1) * LDT + r] = v0.y;
-    dst[(kk + 2) * LDT + r] = v0.z; dst[(kk + 3) * LDT + r] = v0.w;
-    dst[(kk + 4) * LDT + r] = v1.x; dst[(kk + 5) * LDT + r] = v1.y;
-    dst[(kk + 6) * LDT + r] = v1.z; dst[(kk + 7) * LDT + r] = v1.w;
-  }
-}
 
 enum { MODE_NEG = 0, MODE_POS = 1, MODE_BWD = 2 };
 
@@ -316,7 +283,7 @@ k_sweep(SweepArgs a, float* __restrict__ partials, const float* __restrict__ row
 
 using namespace pcl;
 
-static int make_args(const pcl_sweep_desc* d, SweepArgs* a) {
+int pcl::simt_make_args(const pcl_sweep_desc* d, SweepArgs* a) {
   if (!d || !d->anchors || !d->anchor_cls) return PCL_ERR_ARG;
   if (d->a_rows <= 0 || d->D <= 0) return PCL_ERR_ARG;
   if (d->D % 32 != 0 || d->D > 256) return PCL_ERR_UNSUPPORTED;
@@ -352,7 +319,7 @@ static int make_args(const pcl_sweep_desc* d, SweepArgs* a) {
   return PCL_OK;
 }
 
-static size_t sweep_smem(int D, bool bwd) {
+size_t pcl::simt_sweep_smem(int D, bool bwd) {
   return (size_t)(2 * D * LDT + (bwd ? TM * LDT : 0)) * sizeof(float) + 64 * sizeof(void*) + 64 * 3 * sizeof(int) +
          64 * 8 * sizeof(float);
 }
@@ -366,7 +333,7 @@ extern "C" int pcl_sweep_sizes(const pcl_sweep_desc* d, pcl_sweep_sizes_t* out) 
   tmp.anchors = &dummy_f; tmp.anchor_cls = &dummy_i;
   if (tmp.mode == 1) { tmp.segment_queue = &dummy_f; tmp.pixel_queue = &dummy_f; }
   if (tmp.mode == 2) { tmp.contrast = &dummy_f; tmp.contrast_cls = &dummy_i; }
-  int st = make_args(&tmp, &a);
+  int st = simt_make_args(&tmp, &a);
   if (st != PCL_OK || !out) return st != PCL_OK ? st : PCL_ERR_ARG;
   out->n_real_cols = a.n_cols;
   out->row_tiles = a.row_tiles;
@@ -379,11 +346,11 @@ extern "C" int pcl_sweep_sizes(const pcl_sweep_desc* d, pcl_sweep_sizes_t* out) 
 
 extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream) {
   SweepArgs a;
-  int st = make_args(d, &a);
+  int st = simt_make_args(d, &a);
   if (st != PCL_OK) return st;
   PCL_REQUIRE(partials && rowstats && loss);
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = sweep_smem(a.D, false);
+  const size_t smem = simt_sweep_smem(a.D, false);
   static size_t attr_fwd = 0;                   // raise the opt-in shared memory limit once per size
   if (smem > attr_fwd) {
     PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -404,14 +371,23 @@ extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* 
   return PCL_OK;
 }
 
+int pcl::simt_launch_pos(const SweepArgs& a, float* partials, const float* rowstats, cudaStream_t s) {
+  const size_t smem = simt_sweep_smem(a.D, false);
+  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(a.row_tiles, a.splits);
+  k_sweep<MODE_POS><<<grid, SWEEP_THREADS, smem, s>>>(a, partials, rowstats, nullptr);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
 extern "C" int pcl_infonce_bwd(const pcl_sweep_desc* d, const float* rowstats, const float* grad_loss,
                                float* dpartials, float* dA, void* stream) {
   SweepArgs a;
-  int st = make_args(d, &a);
+  int st = simt_make_args(d, &a);
   if (st != PCL_OK) return st;
   PCL_REQUIRE(rowstats && dpartials && dA);
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = sweep_smem(a.D, true);
+  const size_t smem = simt_sweep_smem(a.D, true);
   static size_t attr_bwd = 0;
   if (smem > attr_bwd) {
     PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

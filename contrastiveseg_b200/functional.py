@@ -31,6 +31,7 @@ class ContrastOptions:
     seed: int = 304
     precision: str = "fp32"                # "fp32" exact SIMT sweep | "bf16" tcgen05 sweep (bank / large problems)
     contrast_norm_bound: float = 1.0       # bound of the contrast rows' L2 norm (tensor path stabiliser; 1 = normalised)
+    topk_negatives: Optional[int] = None   # a10 extension: keep only the k hardest negatives per anchor (None = reference)
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -158,6 +159,54 @@ def _release_workspace(ws, token) -> None:
         ws.busy = False
 
 
+def _step_sweep_desc(ws, d) -> "_abi.SweepDesc":
+    """pcl_sweep_desc of the step's exact sweep (what pcl_step.cu:fill_sweep builds on the C side)."""
+    ms = ws.geom.max_samples
+    sw = _abi.SweepDesc()
+    sw.anchors = ws.anchors_f32.data_ptr()
+    sw.anchor_cls = ws.anchor_meta.data_ptr() + 4 * 2 * ms
+    sw.diag_col = ws.anchor_meta.data_ptr() + 4 * 3 * ms
+    sw.plan = ws.plan.data_ptr()
+    sw.a_rows, sw.D, sw.mode = ms, ws.geom.D, d.mode
+    sw.segment_queue, sw.pixel_queue = d.segment_queue, d.pixel_queue
+    sw.bank_K, sw.bank_M0, sw.bank_M1 = d.bank_K, d.bank_M0, d.bank_M1
+    sw.temperature, sw.base_temperature, sw.nan_safe = d.temperature, d.base_temperature, d.nan_safe
+    return sw
+
+
+def _topk_step_forward(lib, ws, d, opts, stream):
+    """a10: selection + gather as usual, then the top-k InfoNCE sweep (exact fp32 path only)."""
+    if opts.precision != "fp32":
+        raise _abi.PclError("topk_negatives runs on the exact fp32 sweep: use precision='fp32'")
+    k = int(opts.topk_negatives)
+    if k < 1:
+        raise _abi.PclError("topk_negatives must be >= 1 (None disables the selection)")
+    g = ws.geom
+    _abi.check(lib.pcl_select_gather(C.byref(g), d.embed, ws.keys.data_ptr(), ws.chunk_pref.data_ptr(),
+                                     ws.plan.data_ptr(), d.ranks, d.seed, d.normalize, ws.anchor_meta.data_ptr(),
+                                     ws.anchors_f32.data_ptr(), ws.anchors_bf16.data_ptr(), ws.inv_norm.data_ptr(),
+                                     ws.norm_max.data_ptr(), stream), "pcl_select_gather")
+    sw = _step_sweep_desc(ws, d)
+    n = lib.pcl_topk_scratch_u32(C.byref(sw))
+    if n < 0:
+        _abi.check(int(n), "pcl_topk_scratch_u32")
+    scratch = getattr(ws, "topk_scratch", None)
+    if scratch is None or scratch.numel() < n:
+        scratch = ws.topk_scratch = torch.empty(n, dtype=torch.int32, device=ws.device)
+    _abi.check(lib.pcl_infonce_topk_fwd(C.byref(sw), k, scratch.data_ptr(), ws.partials.data_ptr(),
+                                        ws.rowstats.data_ptr(), d.loss, stream), "pcl_infonce_topk_fwd")
+    return sw, k, scratch
+
+
+def _topk_step_backward(lib, ws, d, topk, go, stream):
+    sw, k, scratch = topk
+    _abi.check(lib.pcl_infonce_topk_bwd(C.byref(sw), k, scratch.data_ptr(), ws.rowstats.data_ptr(), go.data_ptr(),
+                                        ws.dpartials.data_ptr(), ws.dA.data_ptr(), stream), "pcl_infonce_topk_bwd")
+    _abi.check(lib.pcl_scatter_grad(C.byref(ws.geom), ws.plan.data_ptr(), ws.anchor_meta.data_ptr(), ws.dA.data_ptr(),
+                                    ws.anchors_f32.data_ptr(), ws.inv_norm.data_ptr(), d.normalize, d.grad_embed,
+                                    stream), "pcl_scatter_grad")
+
+
 class _PixelContrastFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, embed, labels, seg, predict, segq, pixq, shadow, opts: ContrastOptions):
@@ -266,11 +315,15 @@ class _PixelContrastFn(torch.autograd.Function):
                 d.ranks = None
             else:
                 raise _abi.PclError(f"unknown rng mode {opts.rng!r}")
-            _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
+            if opts.topk_negatives:
+                ctx.topk = _topk_step_forward(lib, ws, d, opts, stream)
+            else:
+                ctx.topk = None
+                _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
         ctx.ws = ws
         ctx.embed_shape = tuple(embed_c.shape)
         ctx.keep = (embed_c, labels_c, seg_c, pred_c, segq_c, pixq_c, shadow_c)   # keep inputs alive until kernels ran
-        if embed.requires_grad and torch.is_grad_enabled():
+        if ctx.needs_input_grad[0]:          # (grad mode is always off inside forward: ask the ctx, not torch)
             ws.busy = True
             ws.token += 1
             ctx.token = ws.token
@@ -291,7 +344,10 @@ class _PixelContrastFn(torch.autograd.Function):
         d = ws.desc
         d.grad_embed = grad.data_ptr()
         with _on_device(device):
-            _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
+            if ctx.topk is not None:
+                _topk_step_backward(lib, ws, d, ctx.topk, go, _stream_ptr(device))
+            else:
+                _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
         _release_workspace(ws, getattr(ctx, "token", ws.token))
         ctx.keep = None
         return grad, None, None, None, None, None, None, None
@@ -320,9 +376,10 @@ def last_workspace(embed_device: torch.device):
 def infonce_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast: Optional[torch.Tensor] = None,
                     contrast_cls: Optional[torch.Tensor] = None, queues: Optional[Tuple[torch.Tensor, ...]] = None,
                     diag_col: Optional[torch.Tensor] = None, temperature: float = 0.1, base_temperature: float = 0.07,
-                    nan_safe: bool = False):
+                    nan_safe: bool = False, topk: Optional[int] = None):
     """Returns (loss (1,), rowstats (6, A), desc-state) for the exact fp32 sweep.
-    Modes: self-contrast (contrast None, queues None), explicit matrix (contrast given), bank (queues given)."""
+    Modes: self-contrast (contrast None, queues None), explicit matrix (contrast given), bank (queues given).
+    topk=k keeps only the k hardest negatives of every anchor (a10 extension; None = all, the reference)."""
     lib = _abi.load()
     _require_cuda(anchors, "anchors")
     dev = anchors.device
@@ -358,18 +415,43 @@ def infonce_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast
     partials = torch.empty(5 * ss.partial_f32, dtype=torch.float32, device=dev)
     rowstats = torch.empty(6 * ss.rowstat_f32, dtype=torch.float32, device=dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    if topk is not None:
+        n = lib.pcl_topk_scratch_u32(C.byref(sw))
+        if n < 0:
+            _abi.check(int(n), "pcl_topk_scratch_u32")
+        scratch = torch.empty(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _abi.check(lib.pcl_infonce_topk_fwd(C.byref(sw), int(topk), scratch.data_ptr(), partials.data_ptr(),
+                                                rowstats.data_ptr(), loss.data_ptr(), _stream_ptr(dev)),
+                       "pcl_infonce_topk_fwd")
+        return loss, rowstats.view(6, A), (sw, ss, keep, int(topk), scratch)
     with torch.cuda.device(dev):
         _abi.check(lib.pcl_infonce_fwd(C.byref(sw), partials.data_ptr(), rowstats.data_ptr(), loss.data_ptr(),
                                        _stream_ptr(dev)), "pcl_infonce_fwd")
     return loss, rowstats.view(6, A), (sw, ss, keep)
 
 
+def topk_selection(state, a_rows: int):
+    """Selection result of a topk forward (diagnostics/tests): (tau_key uint32 as int64, tie_weight f32, n_above, n_ties)."""
+    scratch = state[4]
+    sel = scratch[scratch.numel() - 4 * a_rows:].view(4, a_rows)
+    key = sel[0].to(torch.int64) & 0xFFFFFFFF
+    return key, sel[1].view(torch.float32), sel[2].to(torch.int64) & 0xFFFFFFFF, sel[3].to(torch.int64) & 0xFFFFFFFF
+
+
 def infonce_backward(state, rowstats: torch.Tensor, grad_loss: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _abi.load()
-    sw, ss, keep = state
+    sw, ss, keep = state[:3]
     dev = keep[0].device
     dpart = torch.empty(ss.dpartial_f32, dtype=torch.float32, device=dev)
     dA = torch.empty((sw.a_rows, sw.D), dtype=torch.float32, device=dev)
+    if len(state) == 5:                          # forward ran with topk: same scratch (selection result) in the backward
+        k, scratch = state[3], state[4]
+        with torch.cuda.device(dev):
+            _abi.check(lib.pcl_infonce_topk_bwd(C.byref(sw), k, scratch.data_ptr(), rowstats.contiguous().data_ptr(),
+                                                _abi.ptr(grad_loss), dpart.data_ptr(), dA.data_ptr(), _stream_ptr(dev)),
+                       "pcl_infonce_topk_bwd")
+        return dA
     with torch.cuda.device(dev):
         _abi.check(lib.pcl_infonce_bwd(C.byref(sw), rowstats.contiguous().data_ptr(), _abi.ptr(grad_loss),
                                        dpart.data_ptr(), dA.data_ptr(), _stream_ptr(dev)), "pcl_infonce_bwd")

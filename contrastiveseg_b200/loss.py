@@ -1,9 +1,10 @@
 """Drop-in loss modules: same class names, constructor ``(configer)``, forward signatures and registry keys
 as the reference (lib/loss/loss_contrast.py, lib/loss/loss_contrast_mem.py, lib/loss/loss_manager.py:36-41).
 
-The contrast term runs on the B200 engine (functional.pixel_contrast_loss); the segmentation CE stays
-PyTorch (out of the hot path).  Engine-only knobs are read from optional config keys under ``contrast``:
-``rng`` ("device" | "torch_cpu"), ``nan_safe``, ``precision`` ("fp32" | "bf16"), ``skip_warmup_contrast``.
+The contrast term runs on the B200 engine (functional.pixel_contrast_loss); the plain segmentation CE runs on
+the fused up-sample + CE kernels (``contrast.fused_seg_ce``, default on).  Engine-only knobs are read from
+optional config keys under ``contrast``: ``rng`` ("device" | "torch_cpu"), ``nan_safe``, ``precision``
+("fp32" | "bf16"), ``skip_warmup_contrast``, ``topk_negatives`` (a10 extension, default off).
 """
 from __future__ import annotations
 
@@ -44,6 +45,7 @@ class PixelContrastLoss(nn.Module):
         self.nan_safe = bool(_opt(configer, "nan_safe", False))
         self.precision = _opt(configer, "precision", "fp32")
         self.seed = int(_opt(configer, "seed", 304))
+        self.topk_negatives = _opt(configer, "topk_negatives", None)    # a10 extension, None = all negatives (reference)
         self.perm_fn = None            # tests inject recorded permutations here
 
     def options(self, normalize: bool = False) -> ContrastOptions:
@@ -51,7 +53,7 @@ class PixelContrastLoss(nn.Module):
                                max_samples=self.max_samples, max_views=self.max_views,
                                ignore_label=self.ignore_label, num_classes=self.num_classes, normalize=normalize,
                                nan_safe=self.nan_safe, rng=self.rng, perm_fn=self.perm_fn, seed=self.seed,
-                               precision=self.precision)
+                               precision=self.precision, topk_negatives=self.topk_negatives)
 
     def forward(self, feats, labels=None, predict=None, queue=None, seg=None, normalize: bool = False,
                 bank_shadow=None):

@@ -159,6 +159,25 @@ int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* rowstats, f
 int pcl_infonce_bwd(const pcl_sweep_desc* d, const float* rowstats, const float* grad_loss, float* dpartials,
                     float* dA, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * a10: per-anchor top-k hard-negative selection on the exact fp32 sweep — an extension the
+ * reference code does not have (lib/loss/loss_contrast.py:116-117 and loss_contrast_mem.py:140-141 sum ALL
+ * negatives), default off.  Neg_i = sum of exp(l - m_i) over the k negatives of anchor i with the largest
+ * logits; ties at the k-th value share the remaining slots equally (order independent); rows with <= k
+ * negatives keep all of them (== pcl_infonce_fwd).  Exact 3-level radix select on the fp32 logits, streamed:
+ * three histogram sweeps + the weighted NEG sweep + the stock POS sweep; the A x N logits are never stored.
+ *   scratch  uint32 words, pcl_topk_scratch_u32(d) of them (negative = pcl_status): per-row radix bins followed by
+ *            the selection result sel[4][a_rows] = tau key (order-preserving integer image of the k-th largest
+ *            negative logit; 0 = all kept), tie weight (float bits), G = #negatives above tau, E = #ties at tau.
+ *            The SAME scratch must be passed to the backward.
+ *   partials / rowstats / loss / dpartials / dA: as pcl_infonce_fwd / pcl_infonce_bwd.
+ * ----------------------------------------------------------------------------------------------*/
+int64_t pcl_topk_scratch_u32(const pcl_sweep_desc* d);
+int pcl_infonce_topk_fwd(const pcl_sweep_desc* d, int32_t k, uint32_t* scratch, float* partials, float* rowstats,
+                         float* loss, void* stream);
+int pcl_infonce_topk_bwd(const pcl_sweep_desc* d, int32_t k, uint32_t* scratch, const float* rowstats,
+                         const float* grad_loss, float* dpartials, float* dA, void* stream);
+
 /* dA -> dense NCHW gradient of the embedding (zero fill + scatter; with normalize == 1 the
  * projection-normalise backward of the touched columns is fused in: dx = (g - y (y.g)) / ||x||).
  * Replaces the autograd backward of loss_contrast.py:83-85,:141-142 (152 SelectBackward0 zero fills). */

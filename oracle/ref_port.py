@@ -188,6 +188,83 @@ def infonce_closed_form(anchors: torch.Tensor, ya: torch.Tensor, contrast: torch
     return dict(loss=loss, dA=dA, row_loss=row_loss[:, 0], m=m[:, 0], neg=neg[:, 0], s=s[:, 0], npos=npos[:, 0], G=G)
 
 
+def topk_negative_weights(l: torch.Tensor, neg_mask: torch.Tensor, k: Optional[int]):
+    """a10 selection weights (EXTENSION — the reference has no top-k code; semantics defined by SURVEY §8 a10 and
+    contrastiveseg_b200/csrc/pcl_topk.cu).  l (A,N) logits, neg_mask (A,N) bool.  Per row: tau = k-th largest
+    negative logit, weight 1 above tau, (k - G)/E on the E ties at tau, 0 below; rows with <= k negatives keep all.
+    Returns (w, tau, G, E) with tau = -inf / E = 0 for rows that keep everything."""
+    A, N = l.shape
+    w = neg_mask.to(l.dtype)
+    n_neg = neg_mask.sum(1)
+    tau = torch.full((A,), float("-inf"), dtype=l.dtype)
+    G = n_neg.clone()
+    E = torch.zeros_like(n_neg)
+    if k is None:
+        return w, tau, G, E
+    lneg = torch.where(neg_mask, l, torch.full_like(l, float("-inf")))
+    srt = torch.sort(lneg, dim=1, descending=True).values
+    for i in range(A):
+        if int(n_neg[i]) <= k:
+            continue
+        t = srt[i, k - 1]
+        gt = neg_mask[i] & (l[i] > t)
+        eq = neg_mask[i] & (l[i] == t)
+        g, e = int(gt.sum()), int(eq.sum())
+        w[i] = gt.to(l.dtype) + eq.to(l.dtype) * ((k - g) / e)
+        tau[i], G[i], E[i] = t, g, e
+    return w, tau, G, E
+
+
+def infonce_dense_topk(anchors: torch.Tensor, ya: torch.Tensor, contrast: torch.Tensor, yc: torch.Tensor,
+                       temperature: float, base_temperature: float, k: Optional[int]) -> torch.Tensor:
+    """infonce_dense (autograd-capable, (i,i) removed from the positives) with the a10 selection weights on the
+    negatives; the weights are computed from the detached logits (piecewise-constant selection)."""
+    A = anchors.shape[0]
+    same = torch.eq(ya.view(-1, 1), yc.view(1, -1))
+    logits = torch.matmul(anchors, contrast.t()) / temperature
+    w, _, _, _ = topk_negative_weights(logits.detach(), ~same, k)
+    logits = logits - logits.max(dim=1, keepdim=True).values.detach()
+    keep = torch.ones_like(logits)
+    keep[torch.arange(A), torch.arange(A)] = 0
+    pos = same.to(anchors.dtype) * keep
+    e = torch.exp(logits)
+    neg_sum = (e * w).sum(1, keepdim=True)
+    log_prob = logits - torch.log(e + neg_sum)
+    mean_log_prob_pos = (pos * log_prob).sum(1) / pos.sum(1)
+    return (-(temperature / base_temperature) * mean_log_prob_pos).mean()
+
+
+def infonce_topk(anchors: torch.Tensor, ya: torch.Tensor, contrast: torch.Tensor, yc: torch.Tensor,
+                 temperature: float, base_temperature: float, k: Optional[int], self_contrast: bool,
+                 diag_cols: Optional[torch.Tensor] = None):
+    """infonce_closed_form with the a10 top-k hard-negative selection on Neg_i (k=None == the reference).
+    The selection is piecewise constant: the gradient treats the weights as constants."""
+    A = anchors.shape[0]
+    if diag_cols is None:
+        diag_cols = torch.arange(A)
+    l = (anchors @ contrast.t()) / temperature
+    m = l.max(1, keepdim=True).values
+    e = torch.exp(l - m)
+    same = ya.view(-1, 1) == yc.view(1, -1)
+    w, tau, Gc, Ec = topk_negative_weights(l, ~same, k)
+    neg = (e * w).sum(1, keepdim=True)
+    pos = same.clone()
+    pos[torch.arange(A), diag_cols] = False
+    npos = pos.sum(1, keepdim=True).to(anchors.dtype)
+    logp = (l - m) - torch.log(e + neg)
+    row_loss = -(temperature / base_temperature) * (logp * pos).sum(1, keepdim=True) / npos
+    loss = row_loss.mean()
+    c = (temperature / base_temperature) / (A * npos)
+    inv = 1.0 / (e + neg)
+    s = (pos * inv).sum(1, keepdim=True)
+    G = torch.where(pos, -c * (1 - e * inv), torch.zeros_like(e)) + w * c * e * s
+    dA = (G @ contrast) / temperature
+    if self_contrast:
+        dA = dA + (G.t() @ anchors) / temperature
+    return dict(loss=loss, dA=dA, row_loss=row_loss[:, 0], m=m[:, 0], neg=neg[:, 0], s=s[:, 0], npos=npos[:, 0],
+                tau=tau, n_above=Gc, n_ties=Ec, w=w)
+
+
 # --------------------------------------------------------------------------------------------
 # a3+a4+a6: PixelContrastLoss.forward — loss_contrast.py:130-147, loss_contrast_mem.py:154-171
 # --------------------------------------------------------------------------------------------

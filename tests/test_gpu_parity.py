@@ -612,7 +612,9 @@ def test_workspace_is_released_when_the_graph_is_dropped_without_backward():
         del loss
     assert len(seen) <= 2                            # no workspace leak
     l1 = crit(embed, target, predict)
+    w1 = Fn.last_workspace(embed.device)
     l2 = crit(embed, target, predict)                # two pending graphs -> two distinct workspaces
     w2 = Fn.last_workspace(embed.device)
+    assert w1 is not w2 and w1.busy and w2.busy
     l1.backward(); l2.backward()
-    assert torch.isfinite(embed.grad).all() and not w2.busy
+    assert torch.isfinite(embed.grad).all() and not w1.busy and not w2.busy

@@ -1,0 +1,186 @@
+"""Host-side wiring of the autograd entry points, checked on CPU: the real library answers the size queries (pure
+host code), every compute entry point is replaced by a recorder that returns PCL_OK.  Verifies the call sequence and
+the pointer / scalar arguments the Python layer hands to the C ABI (no arithmetic runs; outputs are uninitialised)."""
+import ctypes as C
+
+import pytest
+import torch
+
+import contrastiveseg_b200 as cs
+from contrastiveseg_b200 import _abi, functional as Fn
+
+HOST_ONLY = {"pcl_version", "pcl_strerror", "pcl_last_cuda_error", "pcl_abi_sizeof", "pcl_select_sizes",
+             "pcl_sweep_sizes", "pcl_tc_sizes", "pcl_topk_scratch_u32", "pcl_seg_ce_scratch_floats",
+             "pcl_bank_packet_floats", "pcl_bank_scratch_floats"}
+
+
+class RecordingLib:
+    def __init__(self, real):
+        self._real = real
+        self.calls = []
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if name in HOST_ONLY:
+            return fn
+
+        def rec(*args):
+            snap = []
+            for a in args:
+                obj = getattr(a, "_obj", None)          # ctypes.byref(struct) -> copy of the struct at call time
+                if obj is not None:
+                    cp = type(obj)()
+                    C.memmove(C.byref(cp), C.byref(obj), C.sizeof(obj))
+                    snap.append(cp)
+                else:
+                    snap.append(a)
+            self.calls.append((name, snap))
+            return 0
+        return rec
+
+
+class _NoCtx:
+    def __init__(self, *a):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+@pytest.fixture
+def rec(monkeypatch):
+    lib = RecordingLib(_abi.load(build_if_missing=True))
+    monkeypatch.setattr(Fn._abi, "load", lambda *a, **k: lib)
+    monkeypatch.setattr(Fn, "_require_cuda", lambda t, name: None)
+    monkeypatch.setattr(Fn, "_stream_ptr", lambda device: 0x5EED)
+    monkeypatch.setattr(Fn, "_on_device", _NoCtx)
+    Fn.clear_workspaces()
+    yield lib
+    Fn.clear_workspaces()
+
+
+def _inputs(B=2, D=32, h=8, w=8, K=5, s=2):
+    g = torch.Generator().manual_seed(0)
+    embed = torch.randn(B, D, h, w, generator=g).requires_grad_(True)
+    labels = torch.randint(0, K, (B, h * s, w * s), generator=g)
+    seg = torch.randn(B, K, h, w, generator=g)
+    return embed, labels, seg
+
+
+def test_default_step_call_sequence(rec):
+    embed, labels, seg = _inputs()
+    opts = cs.ContrastOptions(max_samples=64, max_views=4, temperature=0.2, base_temperature=0.1)
+    loss = cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+    assert loss.shape == () and loss.requires_grad
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_forward"]
+    d = rec.calls[1][1][0]
+    ws = Fn.last_workspace(embed.device)
+    assert (d.g.B, d.g.D, d.g.h, d.g.w, d.g.Himg, d.g.Wimg, d.g.K) == (2, 32, 8, 8, 16, 16, 5)
+    assert (d.g.max_samples, d.g.max_views, d.g.ignore_label) == (64, 4, -1)
+    assert d.embed == embed.data_ptr() and d.labels == labels.data_ptr() and d.seg == seg.data_ptr()
+    assert d.predict is None and d.ranks is None and d.mode == 0 and d.precision == 0
+    assert d.loss == loss.data_ptr()
+    assert abs(d.temperature - 0.2) < 1e-7 and abs(d.base_temperature - 0.1) < 1e-7
+    for name in ("keys", "chunk_pref", "counts", "plan", "anchor_meta", "anchors_f32", "anchors_bf16", "inv_norm",
+                 "partials", "rowstats", "dpartials", "dA", "row_m2"):
+        assert getattr(d, name) == getattr(ws, name).data_ptr(), name
+    assert rec.calls[1][1][1] == 0x5EED
+    assert ws.busy
+    loss.backward()
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_forward", "pcl_step_backward"]
+    db = rec.calls[2][1][0]
+    assert db.grad_embed == embed.grad.data_ptr() and embed.grad.shape == embed.shape
+    assert not ws.busy                                    # workspace handed back by the backward
+
+
+def test_pending_graphs_get_distinct_workspaces(rec):
+    """A workspace holds the row statistics its backward needs: a second forward before the first backward must not
+    reuse it; dropping a graph without backward hands the workspace back (weakref finalizer)."""
+    embed, labels, seg = _inputs()
+    opts = cs.ContrastOptions(max_samples=64, max_views=4)
+    l1 = cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+    w1 = Fn.last_workspace(embed.device)
+    l2 = cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+    w2 = Fn.last_workspace(embed.device)
+    assert w1 is not w2 and w1.busy and w2.busy
+    d1, d2 = rec.calls[1][1][0], rec.calls[3][1][0]
+    assert d1.rowstats != d2.rowstats and d1.partials != d2.partials
+    l1.backward()
+    assert not w1.busy and w2.busy
+    assert rec.calls[-1][1][0].rowstats == w1.rowstats.data_ptr()      # l1's backward read l1's statistics
+    l2.backward()
+    assert not w2.busy
+    assert rec.calls[-1][1][0].rowstats == w2.rowstats.data_ptr()
+    seen = set()
+    for _ in range(6):                                    # logged only: no backward
+        loss = cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+        seen.add(id(Fn.last_workspace(embed.device)))
+        del loss
+    assert len(seen) <= 2
+    with torch.no_grad():
+        cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+    assert not Fn.last_workspace(embed.device).busy
+
+
+def test_bank_step_passes_queues_and_seed_changes(rec):
+    embed, labels, seg = _inputs()
+    segq, pixq = torch.randn(5, 6, 32), torch.randn(5, 6, 32)
+    opts = cs.ContrastOptions(max_samples=64, max_views=4)
+    for _ in range(2):
+        cs.pixel_contrast_loss(embed.detach(), labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    d0, d1 = rec.calls[1][1][0], rec.calls[3][1][0]
+    assert d0.mode == 1 and (d0.bank_K, d0.bank_M0, d0.bank_M1) == (5, 6, 6)
+    assert d0.segment_queue == segq.data_ptr() and d0.pixel_queue == pixq.data_ptr()
+    assert d0.seed != d1.seed                             # a fresh sampling stream every call
+    assert not Fn.last_workspace(embed.device).busy       # no grad requested: workspace never locked
+
+
+def test_topk_step_call_sequence(rec):
+    embed, labels, seg = _inputs()
+    opts = cs.ContrastOptions(max_samples=64, max_views=4, topk_negatives=7, normalize=True)
+    loss = cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+    names = [c[0] for c in rec.calls]
+    assert names == ["pcl_step_stats", "pcl_select_gather", "pcl_infonce_topk_fwd"]
+    ws = Fn.last_workspace(embed.device)
+    ms = 64
+    sg = rec.calls[1][1]
+    assert sg[1] == embed.data_ptr() and sg[2] == ws.keys.data_ptr() and sg[3] == ws.chunk_pref.data_ptr()
+    assert sg[4] == ws.plan.data_ptr() and sg[5] is None and sg[7] == 1            # ranks NULL (device rng), normalize
+    assert sg[8] == ws.anchor_meta.data_ptr() and sg[9] == ws.anchors_f32.data_ptr() and sg[-1] == 0x5EED
+    sw, k, scratch = rec.calls[2][1][0], rec.calls[2][1][1], rec.calls[2][1][2]
+    assert k == 7 and scratch == ws.topk_scratch.data_ptr()
+    assert sw.anchors == ws.anchors_f32.data_ptr() and sw.plan == ws.plan.data_ptr()
+    assert sw.anchor_cls == ws.anchor_meta.data_ptr() + 4 * 2 * ms          # class column of anchor_meta (int32)
+    assert sw.diag_col == ws.anchor_meta.data_ptr() + 4 * 3 * ms            # reference row index (Q1)
+    assert (sw.a_rows, sw.D, sw.mode) == (ms, 32, 0)
+    assert ws.topk_scratch.numel() == 64 * 2048 + 4 * ms
+    assert rec.calls[2][1][3] == ws.partials.data_ptr() and rec.calls[2][1][4] == ws.rowstats.data_ptr()
+    assert rec.calls[2][1][5] == loss.data_ptr()
+    loss.backward()
+    names = [c[0] for c in rec.calls]
+    assert names[3:] == ["pcl_infonce_topk_bwd", "pcl_scatter_grad"]
+    bw = rec.calls[3][1]
+    assert bw[1] == 7 and bw[2] == ws.topk_scratch.data_ptr() and bw[3] == ws.rowstats.data_ptr()
+    assert bw[5] == ws.dpartials.data_ptr() and bw[6] == ws.dA.data_ptr()
+    sc = rec.calls[4][1]
+    assert sc[1] == ws.plan.data_ptr() and sc[3] == ws.dA.data_ptr() and sc[6] == 1 and sc[7] == embed.grad.data_ptr()
+
+
+def test_topk_rejects_tensor_precision_and_bad_k(rec):
+    embed, labels, seg = _inputs(D=256)
+    with pytest.raises(_abi.PclError):
+        cs.pixel_contrast_loss(embed, labels, seg=seg,
+                               options=cs.ContrastOptions(max_samples=64, max_views=4, topk_negatives=3, precision="bf16"))
+    with pytest.raises(_abi.PclError):
+        cs.pixel_contrast_loss(embed, labels, seg=seg,
+                               options=cs.ContrastOptions(max_samples=64, max_views=4, topk_negatives=-2))
+
+
+def test_loss_module_reads_topk_key():
+    cfg = cs.Configer(cs.cityscapes_contrast_config())
+    assert cs.PixelContrastLoss(cfg).options().topk_negatives is None
+    cfg.add(["contrast", "topk_negatives"], 32)
+    assert cs.PixelContrastLoss(cfg).options().topk_negatives == 32
