@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
 import weakref
 from typing import Callable, Optional, Tuple
 
@@ -128,14 +129,26 @@ class ContrastWorkspace:
         return self.plan[:_abi.PLAN_HEADER].tolist()
 
 
-_WS_CACHE = {}
+_WS_CACHE = {}                   # (device index, geometry key) -> [workspaces]; insertion order = age of the geometry
+_WS_CACHE_MAX = int(os.environ.get("PCL_WS_CACHE_MAX", "8"))    # geometries kept (multi-scale / random-crop training)
 
 
 _LAST_WS = {}
 
 
 def _get_workspace(device, key, geom, mode, bank_K, bank_M0, bank_M1) -> ContrastWorkspace:
-    lst = _WS_CACHE.setdefault((device.index, key), [])
+    ck = (device.index, key)
+    lst = _WS_CACHE.get(ck)
+    if lst is None:
+        # a new geometry: forget the oldest idle ones first (their scratch goes back to the torch allocator; a
+        # workspace still referenced by a pending autograd graph stays alive through that graph)
+        if len(_WS_CACHE) >= _WS_CACHE_MAX:
+            for old in list(_WS_CACHE):
+                if len(_WS_CACHE) < _WS_CACHE_MAX:
+                    break
+                if not any(w.busy for w in _WS_CACHE[old]):
+                    del _WS_CACHE[old]
+        lst = _WS_CACHE[ck] = []
     for ws in lst:
         if not ws.busy:
             _LAST_WS[device.index] = ws

@@ -184,3 +184,25 @@ def test_loss_module_reads_topk_key():
     assert cs.PixelContrastLoss(cfg).options().topk_negatives is None
     cfg.add(["contrast", "topk_negatives"], 32)
     assert cs.PixelContrastLoss(cfg).options().topk_negatives == 32
+
+
+def test_workspace_cache_is_bounded(rec, monkeypatch):
+    """Varying geometries (multi-scale training) must not pile up scratch buffers: idle geometries beyond the bound
+    are dropped oldest first, busy ones survive."""
+    monkeypatch.setattr(Fn, "_WS_CACHE_MAX", 3)
+    opts = cs.ContrastOptions(max_samples=64, max_views=4)
+    held = None
+    for i, hw in enumerate((8, 10, 12, 14, 16, 18)):
+        embed, labels, seg = _inputs(h=hw, w=hw)
+        loss = cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+        if i == 0:
+            held, held_ws = loss, Fn.last_workspace(embed.device)      # pending graph: its workspace must survive
+        else:
+            loss.backward()
+        assert len(Fn._WS_CACHE) <= 3 + 1
+    assert any(held_ws in lst for lst in Fn._WS_CACHE.values())
+    held.backward()
+    assert not held_ws.busy
+    embed, labels, seg = _inputs(h=20, w=20)
+    cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
+    assert len(Fn._WS_CACHE) <= 3
