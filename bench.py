@@ -347,7 +347,23 @@ def run_engine(args, cfg, bank, rank, world, dev):
     embed = inp["embed"].clone().requires_grad_(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if cfg["B"] < 4 else None
 
+    graphed = {}
+
     def step(e, tgt, seg):
+        if args.graph:
+            # one CUDA-graph replay per step (GraphedContrastStep: static tensors, device-side sampling counter)
+            key = (e.data_ptr(), tgt.data_ptr(), seg.data_ptr())
+            g = graphed.get(key)
+            if g is None:
+                kw = dict(segment_queue=mbank.segment_queue, pixel_queue=mbank.pixel_queue,
+                          bank_shadow=mbank.shadow) if bank else {}
+                opts = crit.options()
+                opts.num_classes = cfg["K"]
+                g = graphed[key] = cs.GraphedContrastStep(e.detach(), tgt, seg=seg, options=opts, **kw)
+            loss, _ = g.replay()
+            if bank:
+                mbank.enqueue(e.detach(), tgt, network_stride=cfg["net_stride"], pixel_update_freq=cfg["F"])
+            return loss
         e.grad = None
         queue = (mbank.segment_queue, mbank.pixel_queue) if bank else None
         loss = crit(e, tgt, seg=seg, queue=queue, bank_shadow=mbank.shadow if bank else None)
@@ -499,6 +515,8 @@ def run_engine(args, cfg, bank, rank, world, dev):
             torch.cuda.synchronize(dev)
             wrapper[name] = e0.elapsed_time(e1) / 30
     launches_per_step = (8 if args.precision == "bf16" else 10) + (4 if bank else 0)   # our kernels per step (memsets not counted)
+    if args.graph:
+        launches_per_step += 1                       # + the device-side rank draw (pcl_step_ranks); one graph launch per step
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
@@ -506,7 +524,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "per_rank": per_rank, "precision": args.precision, "impl": "engine"}
+            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "per_rank": per_rank, "precision": args.precision, "cuda_graph": bool(args.graph), "impl": "engine"}
 
 
 def main():
@@ -517,6 +535,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="s1", choices=["s1", "s2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="run the step as one CUDA-graph replay (GraphedContrastStep) instead of the eager autograd call")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="InfoNCE sweeps: bf16 operands on tcgen05 tensor cores (default) or the exact fp32 SIMT sweep")
     args = ap.parse_args()

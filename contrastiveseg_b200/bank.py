@@ -7,6 +7,9 @@
   (Q2, Q4, Q5, Q6).  Several ranks: every rank builds a fixed-size packet of its new rows, ONE NCCL
   all_gather merges them and every rank applies all packets in rank order, so all banks stay identical
   (replaces the 194.6 MB rank-0 buffer broadcast of DDP, Q9).
+  Called between a loss that read the bank and its ``backward()`` (the trainer's order, trainer_contrastive.py:241-255)
+  the in-place write is held back until right after that backward: the reference's autograd keeps a copy of the bank
+  for its backward, the engine re-reads the bank instead.  Final bank and gradient equal the reference's.
 """
 from __future__ import annotations
 
@@ -18,7 +21,12 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _abi
+from . import functional as _fn
 from . import rng as _rng
+
+
+def _is_cuda(t: torch.Tensor) -> bool:
+    return t.is_cuda
 
 
 def shadow_rows(num_classes: int, memory_size: int) -> int:
@@ -97,9 +105,10 @@ def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue:
                         segment_queue_ptr: torch.Tensor, pixel_queue: torch.Tensor, pixel_queue_ptr: torch.Tensor, *,
                         network_stride: int, memory_size: int, pixel_update_freq: int,
                         perm_fn: Optional[Callable[[int], torch.Tensor]] = None, rng: str = "device", seed: int = 304,
-                        shadow: Optional[torch.Tensor] = None, group=None, distributed: bool = True) -> None:
+                        shadow: Optional[torch.Tensor] = None, group=None, distributed: bool = True,
+                        defer_to_backward: bool = True) -> None:
     lib = _abi.load()
-    if not keys.is_cuda:
+    if not _is_cuda(keys):
         raise _abi.PclError("keys must be a CUDA tensor: the engine has no CPU path")
     dev = keys.device
     keys_c = keys.detach().to(torch.float32).contiguous()
@@ -109,10 +118,10 @@ def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue:
     if M != memory_size:
         raise _abi.PclError("memory_size differs from the queue shape")
     for t, name in ((segment_queue, "segment_queue"), (pixel_queue, "pixel_queue")):
-        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        if not (_is_cuda(t) and t.dtype == torch.float32 and t.is_contiguous()):
             raise _abi.PclError(f"{name} must be a contiguous fp32 CUDA tensor (updated in place)")
     for t, name in ((segment_queue_ptr, "segment_queue_ptr"), (pixel_queue_ptr, "pixel_queue_ptr")):
-        if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
+        if not (_is_cuda(t) and t.dtype == torch.int64 and t.is_contiguous()):
             raise _abi.PclError(f"{name} must be a contiguous int64 CUDA tensor (updated in place)")
     g = _abi.BankGeom(B, D, h, w, labels_c.shape[1], labels_c.shape[2], K, M, network_stride, pixel_update_freq)
     n_packet = lib.pcl_bank_packet_floats(C.byref(g))
@@ -131,11 +140,22 @@ def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue:
         ranks = table.to(dev)
     _enqueue_counter[0] += 1
     s = (int(seed) * 0xD1B54A32D192ED03 + _enqueue_counter[0]) & 0xFFFFFFFFFFFFFFFF
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
+    with _fn._on_device(dev):
         _abi.check(lib.pcl_bank_packet(C.byref(g), keys_c.data_ptr(), labels_c.data_ptr(), _abi.ptr(ranks), s,
-                                       scratch.data_ptr(), packet.data_ptr(), stream), "pcl_bank_packet")
+                                       scratch.data_ptr(), packet.data_ptr(), _fn._stream_ptr(dev)), "pcl_bank_packet")
         packets = gather_packets(packet, group) if distributed else packet.view(1, -1)
-        _abi.check(lib.pcl_bank_apply(C.byref(g), packets.data_ptr(), packets.shape[0], segment_queue.data_ptr(),
-                                      segment_queue_ptr.data_ptr(), pixel_queue.data_ptr(), pixel_queue_ptr.data_ptr(),
-                                      _abi.ptr(shadow), stream), "pcl_bank_apply")
+
+    def apply_packets():           # the in-place write (rows, pointers, bf16 shadow): ordered, rank-major
+        with _fn._on_device(dev):
+            _abi.check(lib.pcl_bank_apply(C.byref(g), packets.data_ptr(), packets.shape[0], segment_queue.data_ptr(),
+                                          segment_queue_ptr.data_ptr(), pixel_queue.data_ptr(),
+                                          pixel_queue_ptr.data_ptr(), _abi.ptr(shadow), _fn._stream_ptr(dev)),
+                       "pcl_bank_apply")
+
+    # A loss that read this bank and has not run its backward yet will re-read the bank in that backward (the reference
+    # holds a copy instead, loss_contrast_mem.py:221): hold the write back until right after it.
+    reader = _fn.bank_reader(dev.index, segment_queue.data_ptr()) if defer_to_backward else None
+    if reader is not None:
+        reader.deferred.append(apply_packets)
+    else:
+        apply_packets()

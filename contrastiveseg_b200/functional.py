@@ -116,6 +116,8 @@ class ContrastWorkspace:
         self.ranks_host = torch.zeros(ms, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
         self.busy = False
         self.token = 0               # generation counter: a stale autograd node must not release a re-used workspace
+        self.bank_key = None         # (device index, segment_queue address) while a backward that re-reads that bank is pending
+        self.deferred = []           # bank writes held back until that backward has run (see bank.dequeue_and_enqueue)
         d = _abi.StepDesc()
         d.g = geom
         d.mode, d.bank_K, d.bank_M0, d.bank_M1 = mode, bank_K, bank_M0, bank_M1
@@ -167,8 +169,51 @@ def clear_workspaces() -> None:
 _step_counter = [0]
 
 
+# ---- banks with a pending reader -------------------------------------------------------------------------------
+# The reference's autograd keeps its own copy of the bank for the backward (torch.cat in loss_contrast_mem.py:221), so
+# the trainer may overwrite bank rows between the loss and loss.backward() (trainer_contrastive.py:241-255).  The engine
+# keeps no copy: its backward sweep re-reads the bank.  A bank write that arrives while such a backward is pending is
+# therefore held back and applied right after it (same final bank, same gradient as the reference).
+_BANK_READERS = {}               # (device index, segment_queue address) -> [workspaces with a pending backward]
+
+
+def bank_reader(device_index, segq_ptr):
+    """The most recent loss whose pending backward will re-read the bank at this address, or None."""
+    lst = _BANK_READERS.get((device_index, segq_ptr))
+    return lst[-1] if lst else None
+
+
+def _run_deferred(ws) -> None:
+    calls, ws.deferred = ws.deferred, []
+    for fn in calls:
+        fn()
+
+
+def _drop_bank_reader(ws) -> None:
+    key, ws.bank_key = ws.bank_key, None
+    if key is not None:
+        lst = _BANK_READERS.get(key)
+        if lst is not None:
+            if ws in lst:
+                lst.remove(ws)
+            if not lst:
+                del _BANK_READERS[key]
+    _run_deferred(ws)
+
+
+def _flush_bank(device_index, segq_ptr) -> None:
+    """A new forward is about to read this bank: writes still held back for older pending losses go in first."""
+    lst = _BANK_READERS.pop((device_index, segq_ptr), None)
+    if lst:
+        for ws in lst:
+            ws.bank_key = None
+            _run_deferred(ws)
+
+
 def _release_workspace(ws, token) -> None:
     if ws.token == token:
+        if ws.bank_key is not None or ws.deferred:
+            _drop_bank_reader(ws)
         ws.busy = False
 
 
@@ -261,6 +306,8 @@ class _PixelContrastFn(torch.autograd.Function):
                 M1 = pixq_c.shape[1]
             if segq_c.shape[2] != D:
                 raise _abi.PclError("bank feature dim differs from the embedding dim")
+            if _BANK_READERS:
+                _flush_bank(device.index, segq_c.data_ptr())
         K = opts.num_classes or (seg_c.shape[1] if seg_c is not None else (bank_K if mode == 1 else _abi.MAX_CLASSES))
         if seg_c is not None and seg_c.shape[1] != K:
             raise _abi.PclError("num_classes differs from the number of seg planes")
@@ -340,8 +387,11 @@ class _PixelContrastFn(torch.autograd.Function):
             ws.busy = True
             ws.token += 1
             ctx.token = ws.token
+            if mode == 1:
+                ws.bank_key = (device.index, segq_c.data_ptr())
+                _BANK_READERS.setdefault(ws.bank_key, []).append(ws)
             # if the graph is dropped without a backward (e.g. a loss that is only logged) give the workspace back
-            weakref.finalize(ctx, _release_workspace, ws, ws.token)
+            weakref.finalize(ctx, _release_workspace, ws, ws.token).atexit = False
         return out
 
     @staticmethod
@@ -361,7 +411,7 @@ class _PixelContrastFn(torch.autograd.Function):
                 _topk_step_backward(lib, ws, d, ctx.topk, go, _stream_ptr(device))
             else:
                 _abi.check(lib.pcl_step_backward(C.byref(d), go.data_ptr(), _stream_ptr(device)), "pcl_step_backward")
-        _release_workspace(ws, getattr(ctx, "token", ws.token))
+        _release_workspace(ws, getattr(ctx, "token", ws.token))     # also applies bank writes held back for this backward
         ctx.keep = None
         return grad, None, None, None, None, None, None, None
 

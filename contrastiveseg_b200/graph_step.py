@@ -1,0 +1,177 @@
+"""One pixel-contrast loss step captured in a single CUDA graph.
+
+The eager step costs ~0.14 ms of host time (Python + autograd + 8 kernel launches) against ~0.13-0.16 ms of GPU
+time at the Cityscapes shape, so it is host-launch-bound as soon as the host slows down (8 ranks on one box).  The C
+ABI neither allocates nor synchronises and all scratch is caller-owned, so the whole sequence
+
+    pcl_step_stats -> pcl_step_ranks -> pcl_step_forward -> pcl_step_backward
+
+is capturable: a replay is ONE graph launch.  Constraints of a captured graph, made explicit here:
+
+* static shapes and static addresses: the tensors given to the constructor are read in place on every replay —
+  refill them (``embed.copy_(...)`` or let the producer write into them), do not replace them;
+* sampling stays fresh: kernel arguments are frozen in a graph, so the anchor ranks are drawn on the device from a
+  counter in device memory (``pcl_step_ranks``) instead of the by-value seed of the eager path;
+* the upstream gradient is a device scalar (``grad_scale``, default 1) folded into the dense gradient by the
+  backward kernels, not an autograd input: use it for the loss weight (``contrast.loss_weight``).
+
+The reference RNG stream (``rng='torch_cpu'`` / injected permutations) needs a host round trip and is not capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _abi
+from . import functional as _fn
+from .functional import ContrastOptions, ContrastWorkspace
+
+
+def _canonical(t: Optional[torch.Tensor], dtype: torch.dtype, name: str, device: torch.device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.device != device or t.dtype != dtype or not t.is_contiguous():
+        raise _abi.PclError(f"{name} must be a contiguous {dtype} tensor on {device}: a captured graph reads it in "
+                            "place on every replay, so no converted copy can be made")
+    return t
+
+
+class GraphedContrastStep:
+    """loss, d loss/d embed of ``pixel_contrast_loss`` for fixed tensors, as one CUDA-graph replay.
+
+    >>> step = GraphedContrastStep(embed, labels, seg=seg, options=opts, grad_scale=loss_weight)
+    >>> loss, grad = step.replay()          # 0-dim loss and (B,D,h,w) gradient, both static buffers
+    """
+
+    def __init__(self, embed: torch.Tensor, labels: torch.Tensor, *, seg: Optional[torch.Tensor] = None,
+                 predict: Optional[torch.Tensor] = None, segment_queue: Optional[torch.Tensor] = None,
+                 pixel_queue: Optional[torch.Tensor] = None, bank_shadow: Optional[torch.Tensor] = None,
+                 options: Optional[ContrastOptions] = None, grad_scale: float = 1.0, capture: bool = True,
+                 warmup: int = 2):
+        self.lib = _abi.load()
+        opts = options or ContrastOptions()
+        _fn._require_cuda(embed, "embed")
+        device = embed.device
+        if opts.rng != "device" or opts.perm_fn is not None:
+            raise _abi.PclError("a captured step draws its anchors on the device: rng must be 'device'")
+        if opts.topk_negatives:
+            raise _abi.PclError("topk_negatives is not wired into the captured step yet")
+        self.embed = _canonical(embed.detach(), torch.float32, "embed", device)
+        self.labels = _canonical(labels, torch.int64, "labels", device)
+        self.seg = _canonical(None if seg is None else seg.detach(), torch.float32, "seg", device)
+        self.predict = _canonical(predict, torch.int64, "predict", device)
+        if self.seg is None and self.predict is None:
+            raise _abi.PclError("either seg or predict is required")
+        self.segq = _canonical(None if segment_queue is None else segment_queue.detach(), torch.float32, "segment_queue", device)
+        self.pixq = _canonical(None if pixel_queue is None else pixel_queue.detach(), torch.float32, "pixel_queue", device)
+        B, D, h, w = self.embed.shape
+        if self.labels.dim() != 3 or self.labels.shape[0] != B:
+            raise _abi.PclError("labels must be (B, Himg, Wimg)")
+        mode, bank_K, M0, M1 = 0, 0, 0, 0
+        if self.segq is not None:
+            mode, bank_K, M0 = 1, self.segq.shape[0], self.segq.shape[1]
+            M1 = self.pixq.shape[1] if self.pixq is not None else 0
+            if self.segq.shape[2] != D:
+                raise _abi.PclError("bank feature dim differs from the embedding dim")
+        K = opts.num_classes or (self.seg.shape[1] if self.seg is not None else (bank_K if mode == 1 else _abi.MAX_CLASSES))
+        if self.seg is not None and (self.seg.shape[1] != K or self.seg.shape[0] != B or tuple(self.seg.shape[2:]) != (h, w)):
+            raise _abi.PclError("seg must be (B, K, h, w) at the embedding resolution with K == num_classes")
+        geom = _abi.Geom(B, D, h, w, self.labels.shape[1], self.labels.shape[2], K, opts.max_samples, opts.max_views,
+                         opts.ignore_label)
+        self.ws = ContrastWorkspace(device, geom, mode, bank_K, M0, M1)        # owned by this object, never shared
+        self.device = device
+        self.loss = torch.zeros((), dtype=torch.float32, device=device)
+        self.grad = torch.empty_like(self.embed)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=device)         # replay index, lives on the device
+        self.scale = torch.full((1,), float(grad_scale), dtype=torch.float32, device=device)
+        d = self.ws.desc
+        d.embed, d.labels = self.embed.data_ptr(), self.labels.data_ptr()
+        d.seg, d.predict = _abi.ptr(self.seg), _abi.ptr(self.predict if self.seg is None else None)
+        d.segment_queue, d.pixel_queue = _abi.ptr(self.segq), _abi.ptr(self.pixq)
+        d.temperature, d.base_temperature = opts.temperature, opts.base_temperature
+        d.nan_safe, d.normalize = int(opts.nan_safe), int(opts.normalize)
+        d.precision = 0
+        self.shadow = None
+        if opts.precision == "bf16":
+            if not self.ws.tc_ok:
+                raise _abi.PclError("precision='bf16' (tcgen05 sweep) needs proj_dim == 256")
+            d.precision = 1
+            d.contrast_norm_bound = float(opts.contrast_norm_bound)
+            if mode == 1:
+                if self.pixq is None or M0 != M1:
+                    raise _abi.PclError("the tensor sweep reads the bank as (segment_queue, pixel_queue) of equal size")
+                if bank_shadow is None:
+                    raise _abi.PclError("pass the bank's maintained bf16 shadow (MemoryBank(with_shadow=True).shadow): "
+                                        "a captured step cannot rebuild it")
+                self.shadow = bank_shadow
+                d.shadow_bf16, d.shadow_rows = bank_shadow.data_ptr(), bank_shadow.shape[0]
+        elif opts.precision != "fp32":
+            raise _abi.PclError(f"unknown precision {opts.precision!r}")
+        d.seed = int(opts.seed) & 0xFFFFFFFFFFFFFFFF          # base seed; the per-replay part is the device counter
+        d.ranks = self.ws.ranks.data_ptr()
+        d.loss, d.grad_embed = self.loss.data_ptr(), self.grad.data_ptr()
+        self.graph = None
+        self.replays = 0
+        if capture:
+            self._capture(max(1, int(warmup)))
+
+    # the launch sequence (also usable eagerly: capture=False)
+    def _enqueue(self, stream: int) -> None:
+        lib, d = self.lib, self.ws.desc
+        _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
+        _abi.check(lib.pcl_step_ranks(C.byref(d), self.counter.data_ptr(), self.ws.ranks.data_ptr(), stream), "pcl_step_ranks")
+        _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
+        _abi.check(lib.pcl_step_backward(C.byref(d), self.scale.data_ptr(), stream), "pcl_step_backward")
+
+    def _capture(self, warmup: int) -> None:
+        dev = self.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(side):
+            for _ in range(warmup):            # first calls set function attributes and encode the TMA descriptors
+                self._enqueue(side.cuda_stream)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.counter.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev), torch.cuda.graph(graph, stream=side):
+            self._enqueue(torch.cuda.current_stream(dev).cuda_stream)
+        self.graph = graph
+
+    def set_grad_scale(self, value: float) -> None:
+        self.scale.fill_(float(value))
+
+    def replay(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Run one step on the current stream.  Returns (loss, grad_embed): static buffers, overwritten by the next
+        replay; grad_embed = grad_scale * d loss / d embed."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            with _fn._on_device(self.device):
+                self._enqueue(_fn._stream_ptr(self.device))
+        self.replays += 1
+        return self.loss, self.grad
+
+    def apply(self, embed: torch.Tensor) -> torch.Tensor:
+        """Autograd hand-off: replays the graph and returns the loss connected to ``embed`` (which must be the tensor
+        the graph was captured on); its backward returns the pre-computed static gradient.  Valid when the returned
+        loss enters the total loss with coefficient 1 and ``backward`` starts from gradient 1 (fold weights into
+        ``grad_scale``): the upstream gradient is NOT multiplied in (that would cost another pass over the dense
+        gradient)."""
+        if embed.data_ptr() != self.embed.data_ptr():
+            raise _abi.PclError("apply() must receive the tensor the step was captured on")
+        return _GraphedFn.apply(embed, self)
+
+
+class _GraphedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, embed, step: GraphedContrastStep):
+        loss, _ = step.replay()
+        ctx.step = step
+        return loss.view(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        return ctx.step.grad, None

@@ -319,6 +319,17 @@ int pcl_step_stats(const pcl_step_desc* d, void* stream);      /* pcl_class_stat
 int pcl_step_forward(const pcl_step_desc* d, void* stream);    /* pcl_select_gather + pcl_infonce_fwd     */
 int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss, void* stream); /* bwd + scatter     */
 
+/* CUDA-graph capture of a step.  The three calls above neither allocate nor synchronise, so a
+ * stats -> forward -> backward sequence can be captured with cudaStreamBeginCapture / replayed with cudaGraphLaunch.
+ * Kernel arguments are frozen in a captured graph, so the by-value sampling seed (pcl_step_desc.seed) would repeat:
+ * call pcl_step_ranks between pcl_step_stats and pcl_step_forward and pass its output as pcl_step_desc.ranks.  It
+ * draws the anchor ranks with the selection's own device RNG from (d->seed, *step_counter) and increments the
+ * counter in device memory, so every replay samples a fresh anchor set (replaces torch.randperm of
+ * lib/loss/loss_contrast.py:79-82 exactly like the eager device RNG does).
+ *   step_counter  1 uint64 in device memory (caller-initialised, e.g. 0), read and incremented on the stream
+ *   ranks         max_samples int32 */
+int pcl_step_ranks(const pcl_step_desc* d, uint64_t* step_counter, int32_t* ranks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,9 +57,13 @@ def rec(monkeypatch):
     monkeypatch.setattr(Fn, "_require_cuda", lambda t, name: None)
     monkeypatch.setattr(Fn, "_stream_ptr", lambda device: 0x5EED)
     monkeypatch.setattr(Fn, "_on_device", _NoCtx)
+    from contrastiveseg_b200 import bank as bank_mod
+    monkeypatch.setattr(bank_mod, "_is_cuda", lambda t: True)
     Fn.clear_workspaces()
+    Fn._BANK_READERS.clear()
     yield lib
     Fn.clear_workspaces()
+    Fn._BANK_READERS.clear()
 
 
 def _inputs(B=2, D=32, h=8, w=8, K=5, s=2):
@@ -206,3 +210,127 @@ def test_workspace_cache_is_bounded(rec, monkeypatch):
     embed, labels, seg = _inputs(h=20, w=20)
     cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
     assert len(Fn._WS_CACHE) <= 3
+
+
+def test_graphed_step_launch_sequence(rec):
+    """GraphedContrastStep (capture=False: the same launch sequence, eagerly): stats -> device rank draw -> forward
+    -> backward on static buffers, the upstream gradient as a device scalar, the rank table wired into the step."""
+    embed, labels, seg = _inputs()
+    opts = cs.ContrastOptions(max_samples=64, max_views=4, seed=77)
+    step = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, grad_scale=0.1, capture=False)
+    loss, grad = step.replay()
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_ranks", "pcl_step_forward", "pcl_step_backward"]
+    d = rec.calls[2][1][0]
+    assert d.ranks == step.ws.ranks.data_ptr() and d.seed == 77
+    assert d.loss == loss.data_ptr() and d.grad_embed == grad.data_ptr() and grad.shape == embed.shape
+    assert d.embed == embed.data_ptr() and d.labels == labels.data_ptr() and d.seg == seg.data_ptr()
+    rk = rec.calls[1][1]
+    assert rk[1] == step.counter.data_ptr() and rk[2] == step.ws.ranks.data_ptr()
+    assert rec.calls[3][1][1] == step.scale.data_ptr() and abs(step.scale.item() - 0.1) < 1e-7
+    l2, g2 = step.replay()
+    assert l2.data_ptr() == loss.data_ptr() and g2.data_ptr() == grad.data_ptr() and step.replays == 2
+    # autograd hand-off: the static gradient comes back for the captured tensor only
+    e = embed.detach().requires_grad_(True)
+    with pytest.raises(_abi.PclError):
+        step.apply(torch.zeros_like(e))
+    step2 = cs.GraphedContrastStep(e, labels, seg=seg, options=opts, capture=False)
+    out = step2.apply(e)
+    out.backward()
+    assert e.grad.shape == e.shape
+    with pytest.raises(_abi.PclError):
+        cs.GraphedContrastStep(embed.detach(), labels, seg=seg, capture=False,
+                               options=cs.ContrastOptions(max_samples=64, max_views=4, rng="torch_cpu"))
+    with pytest.raises(_abi.PclError):
+        cs.GraphedContrastStep(embed.detach(), labels.to(torch.int32), seg=seg, options=opts, capture=False)
+
+
+def _bank(K=5, M=6, D=32):
+    return (torch.randn(K, M, D), torch.zeros(K, dtype=torch.long), torch.randn(K, M, D), torch.zeros(K, dtype=torch.long))
+
+
+def _names(rec):
+    return [c[0] for c in rec.calls]
+
+
+def test_bank_write_waits_for_the_pending_backward(rec):
+    """Trainer order (trainer_contrastive.py:241-255): loss -> enqueue -> backward.  The engine's backward re-reads the
+    bank, so the in-place write must land after it; without a pending reader it is immediate."""
+    embed, labels, seg = _inputs()
+    segq, sp, pixq, pp = _bank()
+    opts = cs.ContrastOptions(max_samples=64, max_views=4)
+    kw = dict(network_stride=2, memory_size=6, pixel_update_freq=3, distributed=False)
+    cs.dequeue_and_enqueue(embed.detach(), labels, segq, sp, pixq, pp, **kw)
+    assert _names(rec) == ["pcl_bank_packet", "pcl_bank_apply"]                 # nobody is reading: write at once
+    rec.calls.clear()
+    loss = cs.pixel_contrast_loss(embed, labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    ws = Fn.last_workspace(embed.device)
+    assert Fn.bank_reader(embed.device.index, segq.data_ptr()) is ws
+    cs.dequeue_and_enqueue(embed.detach(), labels, segq, sp, pixq, pp, **kw)
+    assert _names(rec) == ["pcl_step_stats", "pcl_step_forward", "pcl_bank_packet"] and len(ws.deferred) == 1
+    loss.backward()
+    assert _names(rec)[3:] == ["pcl_step_backward", "pcl_bank_apply"]
+    ap = rec.calls[-1][1]
+    assert ap[3] == segq.data_ptr() and ap[4] == sp.data_ptr() and ap[5] == pixq.data_ptr() and ap[6] == pp.data_ptr()
+    assert not ws.deferred and ws.bank_key is None and not ws.busy and not Fn._BANK_READERS
+    # a different bank is not held back by this reader
+    rec.calls.clear()
+    loss = cs.pixel_contrast_loss(embed, labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    other = _bank()
+    cs.dequeue_and_enqueue(embed.detach(), labels, *other, **kw)
+    assert _names(rec)[-2:] == ["pcl_bank_packet", "pcl_bank_apply"]
+    # opt-out writes immediately
+    cs.dequeue_and_enqueue(embed.detach(), labels, segq, sp, pixq, pp, defer_to_backward=False, **kw)
+    assert _names(rec)[-1] == "pcl_bank_apply"
+    loss.backward()
+    assert not Fn._BANK_READERS
+
+
+def test_held_back_bank_write_is_never_lost(rec):
+    embed, labels, seg = _inputs()
+    segq, sp, pixq, pp = _bank()
+    opts = cs.ContrastOptions(max_samples=64, max_views=4)
+    kw = dict(network_stride=2, memory_size=6, pixel_update_freq=3, distributed=False)
+    # graph dropped without backward: the write lands when the graph dies
+    loss = cs.pixel_contrast_loss(embed, labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    cs.dequeue_and_enqueue(embed.detach(), labels, segq, sp, pixq, pp, **kw)
+    assert "pcl_bank_apply" not in _names(rec)
+    del loss
+    assert _names(rec)[-1] == "pcl_bank_apply" and not Fn._BANK_READERS
+    # a new forward on the same bank first lets the held-back write in (it must see the updated bank)
+    rec.calls.clear()
+    l1 = cs.pixel_contrast_loss(embed, labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    cs.dequeue_and_enqueue(embed.detach(), labels, segq, sp, pixq, pp, **kw)
+    l2 = cs.pixel_contrast_loss(embed, labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    assert _names(rec) == ["pcl_step_stats", "pcl_step_forward", "pcl_bank_packet", "pcl_bank_apply",
+                           "pcl_step_stats", "pcl_step_forward"]
+    l1.backward(); l2.backward()
+    assert _names(rec).count("pcl_bank_apply") == 1 and not Fn._BANK_READERS
+    # evaluation (no grad): nothing pending, immediate
+    rec.calls.clear()
+    with torch.no_grad():
+        cs.pixel_contrast_loss(embed, labels, seg=seg, segment_queue=segq, pixel_queue=pixq, options=opts)
+    cs.dequeue_and_enqueue(embed.detach(), labels, segq, sp, pixq, pp, **kw)
+    assert _names(rec)[-1] == "pcl_bank_apply"
+
+
+def test_trainer_hook_order_with_bank(rec):
+    """ContrastTrainerHook.loss_step + backward: loss (fused seg CE + contrast on the bank), packet build at the
+    reference's point of the iteration, bank write right after the contrast backward."""
+    K, D = 5, 32
+    cfg = cs.Configer({"data": {"num_classes": K}, "network": {"stride": 2},
+                       "loss": {"loss_type": "mem_contrast_ce_loss", "params": {"ce_ignore_index": -1}},
+                       "contrast": {"temperature": 0.07, "base_temperature": 0.07, "max_samples": 64, "max_views": 4,
+                                    "loss_weight": 0.1, "use_rmi": False, "use_lovasz": False, "warmup_iters": 0,
+                                    "with_memory": True, "memory_size": 6, "pixel_update_freq": 3,
+                                    "fused_seg_ce": False}})
+    bank = cs.MemoryBank(K, 6, D)
+    hook = cs.ContrastTrainerHook(cfg, bank)
+    embed, labels, seg = _inputs()
+    seg = seg.requires_grad_(True)
+    out = {"seg": seg, "embed": embed, "key": embed.detach(), "lb_key": labels}
+    loss = hook.loss_step(out, labels, iters=3, distributed=True)
+    assert _names(rec) == ["pcl_step_stats", "pcl_step_forward", "pcl_bank_packet"]
+    loss.backward()
+    assert _names(rec)[3:] == ["pcl_step_backward", "pcl_bank_apply"]
+    assert rec.calls[-1][1][3] == bank.segment_queue.data_ptr()
+    assert seg.grad is not None and embed.grad is not None

@@ -7,13 +7,14 @@ mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 timeout 300 python -m contrastiveseg_b200.build > gpurun_out/build.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-PCL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_topk.py -m gpu -q > gpurun_out/pytest_topk.log 2>&1
-echo "topk exit $?" >> gpurun_out/pytest_topk.log
+PCL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_topk.py tests/test_gpu_pending.py -m gpu -q > gpurun_out/pytest_topk.log 2>&1
+echo "experimental exit $?" >> gpurun_out/pytest_topk.log
 PCL_TEST_EXPERIMENTAL=1 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 \
   --print-limit 30 python -m pytest tests/test_gpu_topk.py -m gpu -q -x -k "exact_data or zero_tail" \
   > gpurun_out/sanitize_topk.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitize_topk.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
+timeout 600 python bench.py --steps 200 --warmup 10 --graph --no-cpu-baseline > gpurun_out/bench_graph.json 2> gpurun_out/bench_graph.err; echo "bench --graph exit $?" >> gpurun_out/bench_graph.err
 tail -15 gpurun_out/pytest_gpu.log; tail -30 gpurun_out/pytest_topk.log
 grep -E "ERROR SUMMARY|Invalid|out of bounds|misaligned|passed|failed|exit" gpurun_out/sanitize_topk.log | tail -10
-tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err; cat gpurun_out/bench_graph.json; tail -3 gpurun_out/bench_graph.err
