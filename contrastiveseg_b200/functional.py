@@ -162,6 +162,8 @@ def _get_workspace(device, key, geom, mode, bank_K, bank_M0, bank_M1) -> Contras
 
 
 def clear_workspaces() -> None:
+    for key in list(_BANK_READERS):          # bank writes still held back go in before the bookkeeping is dropped
+        _flush_bank(*key)
     _WS_CACHE.clear()
     _LAST_WS.clear()
 
