@@ -334,3 +334,30 @@ def test_trainer_hook_order_with_bank(rec):
     assert _names(rec)[3:] == ["pcl_step_backward", "pcl_bank_apply"]
     assert rec.calls[-1][1][3] == bank.segment_queue.data_ptr()
     assert seg.grad is not None and embed.grad is not None
+
+
+def test_fused_seg_ce_wiring(rec):
+    g = torch.Generator().manual_seed(1)
+    seg = torch.randn(2, 5, 8, 8, generator=g).requires_grad_(True)
+    target = torch.randint(-1, 5, (2, 16, 16), generator=g)
+    weight = torch.rand(5, generator=g)
+    loss = cs.upsample_cross_entropy(seg, target, weight, ignore_index=-1)
+    assert _names(rec) == ["pcl_seg_ce_fwd"]
+    a = rec.calls[0][1]
+    assert a[0] == seg.data_ptr() and a[1] == target.data_ptr() and a[2] == weight.data_ptr()
+    assert tuple(a[3:10]) == (2, 5, 8, 8, 16, 16, -1) and a[11] == loss.data_ptr() and a[12] == 0x5EED
+    loss.backward()
+    b = rec.calls[1][1]
+    assert rec.calls[1][0] == "pcl_seg_ce_bwd" and b[0] == seg.data_ptr() and b[10] == a[10]      # same scratch
+    assert b[12] == seg.grad.data_ptr() and seg.grad.shape == seg.shape
+    # the wrapper takes the fused path for the reference's plain CE configuration
+    cfg = cs.Configer(cs.cityscapes_contrast_config())
+    crit = cs.ContrastCELoss(cfg)
+    rec.calls.clear()
+    import unittest.mock as um
+    with um.patch.object(type(crit), "_can_fuse", lambda self, ce, s: self.fused_seg_ce):
+        embed, labels, sg = _inputs(K=19)
+        out = crit({"seg": sg.requires_grad_(True), "embed": embed}, labels, with_embed=True)
+    assert _names(rec) == ["pcl_seg_ce_fwd", "pcl_step_stats", "pcl_step_forward"]
+    out.backward()
+    assert sorted(_names(rec)[3:]) == ["pcl_seg_ce_bwd", "pcl_step_backward"]
