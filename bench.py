@@ -286,6 +286,60 @@ def stage_timings(cfg, inp, dev, precision, iters=20):
     return out, A
 
 
+def train_iter_bench(cfg, inp, dev, precision, iters=10):
+    """BASELINE.json's second figure, "train iters/sec": one synthetic training iteration = producer fwd -> ContrastCELoss
+    (fused seg CE + pixel contrast) -> backward -> SGD step.  The reference's HRNet-W48 cannot travel to the GPU box and
+    is outside the hot-path scope, so the producer is a stand-in with the same output contract and tensor sizes
+    (lib/models/nets/hrnet.py:76-95: 720-channel stride-4 features -> 19-class head + 720->720->256 projection head
+    with the engine's L2-normalise): the number shows the loss step's share of an iteration, not HRNet's speed."""
+    import torch.nn as nn
+    import contrastiveseg_b200 as cs
+
+    class StandIn(nn.Module):
+        def __init__(self, K, D, C=720):
+            super().__init__()
+            self.body = nn.Sequential(nn.Conv2d(3, 64, 3, 2, 1), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                                      nn.Conv2d(64, C, 3, 2, 1), nn.BatchNorm2d(C), nn.ReLU(inplace=True))
+            self.cls = nn.Conv2d(C, K, 1)
+            self.proj = cs.ProjectionHead(C, D, proj="convmlp", bn_type="torchbn")
+
+        def forward(self, x):
+            f = self.body(x)
+            return {"seg": self.cls(f), "embed": self.proj(f)}
+
+    torch.manual_seed(304)
+    net = StandIn(cfg["K"], cfg["D"]).to(dev)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    crit = cs.ContrastCELoss(engine_configer(cfg, False, precision)).to(dev)
+    H, W = inp["target"].shape[1], inp["target"].shape[2]
+    x = torch.randn(cfg["B"], 3, H, W, device=dev)
+
+    def it():
+        out = net(x)
+        loss = crit(out, inp["target"], with_embed=True)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(3):
+        it()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(iters):
+        loss = it()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    ok = bool(torch.isfinite(loss).item())
+    del net, opt, x
+    torch.cuda.empty_cache()
+    return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "global_batch": cfg["B"], "finite_loss": ok,
+            "producer": "stand-in conv stem -> 720ch stride-4 features -> 19-class head + 720-720-256 projection head "
+                        "(engine L2-normalise); fp32, SGD momentum 0.9; not HRNet-W48",
+            "loss": "ContrastCELoss (fused seg CE + pixel contrast, with_embed=True)"}
+
+
 def tensor_sweep_roofline(dev, peaks, A=16384, N=65536, iters=5):
     """The dense contraction alone (similarity + negative-sum sweep on tcgen05) at one S4 point (BASELINE configs[4]):
     algorithmic FLOPs 2*A*N*D over the CUDA-event time, vs the measured bf16 peak."""
@@ -514,6 +568,16 @@ def run_engine(args, cfg, bank, rank, world, dev):
             e1.record()
             torch.cuda.synchronize(dev)
             wrapper[name] = e0.elapsed_time(e1) / 30
+    # "train iters/sec" half of BASELINE.json's metric (N=1, stand-in producer); never allowed to break the bench line
+    train = None
+    if world == 1 and not bank and not os.environ.get("PCL_BENCH_NO_TRAIN_ITER"):
+        try:
+            train = train_iter_bench(cfg, inp, dev, args.precision)
+            if wrapper:
+                train["loss_step_ms"] = wrapper.get("fused_seg_ce_ms")
+                train["loss_step_share"] = wrapper.get("fused_seg_ce_ms") / train["ms_per_iter"]
+        except Exception as exc:                      # noqa: BLE001
+            train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     launches_per_step = (8 if args.precision == "bf16" else 10) + (4 if bank else 0)   # our kernels per step (memsets not counted)
     if args.graph:
         launches_per_step += 1                       # + the device-side rank draw (pcl_step_ranks); one graph launch per step
@@ -524,7 +588,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
             "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "per_rank": per_rank, "precision": args.precision, "cuda_graph": bool(args.graph), "impl": "engine"}
+            "stage_ms": stages, "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "per_rank": per_rank, "train_iter": train, "precision": args.precision, "cuda_graph": bool(args.graph), "impl": "engine"}
 
 
 def main():
