@@ -115,6 +115,7 @@ SIGNATURES = {
     "pcl_step_stats": (c_i32, [C.POINTER(StepDesc), c_vp]),
     "pcl_step_forward": (c_i32, [C.POINTER(StepDesc), c_vp]),
     "pcl_step_backward": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp]),
+    "pcl_step_backward_prezeroed": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp]),
     "pcl_step_ranks": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp, c_vp]),
 }
 

@@ -42,6 +42,9 @@ int tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, 
 int zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
                         int splits, int a_pad, float inv_T, const float* grad_loss, float* grad_embed, void* stream);
 
+int scatter_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
+                 const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed, void* stream);
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

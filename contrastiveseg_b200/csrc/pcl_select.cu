@@ -404,6 +404,19 @@ int pcl::zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32
   return PCL_OK;
 }
 
+// Scatter-only variant for callers that zero-fill the dense gradient themselves (e.g. overlapped with the forward on a
+// second stream): drops the A gradient rows into an already-zero (B,D,h,w) buffer.
+int pcl::scatter_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
+                      const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed, void* stream) {
+  if (!g || !plan || !anchor_meta || !dA || !grad_embed) return PCL_ERR_ARG;
+  if (normalize && (!anchors_f32 || !inv_norm)) return PCL_ERR_ARG;
+  const int warps = 8;
+  k_scatter<<<ceil_div(g->max_samples, warps), warps * 32, 0, (cudaStream_t)stream>>>(*g, plan, anchor_meta, dA, anchors_f32,
+                                                                                     inv_norm, normalize, grad_embed);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
 // ==================================================================================================
 // C ABI
 // ==================================================================================================

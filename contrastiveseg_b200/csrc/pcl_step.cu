@@ -95,3 +95,23 @@ extern "C" int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss,
   return pcl_scatter_grad(&d->g, d->plan, d->anchor_meta, d->dA, d->anchors_f32, d->inv_norm, d->normalize,
                           d->grad_embed, stream);
 }
+
+// Backward for a dense-gradient buffer the caller has ALREADY zero-filled (the 268 MB fill is the HBM floor of the
+// step; a caller that starts it on a second stream at the beginning of the forward hides it behind the latency-bound
+// selection and sweep kernels): backward sweep -> (A, D) gradient rows -> scatter of those rows only.
+extern "C" int pcl_step_backward_prezeroed(const pcl_step_desc* d, const float* grad_loss, void* stream) {
+  if (!d) return PCL_ERR_ARG;
+  int st;
+  if (d->precision == 1) {
+    pcl_tc_desc t;
+    fill_tc(d, &t);
+    st = pcl_infonce_tc_bwd(&t, d->row_m2, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
+  } else {
+    pcl_sweep_desc w;
+    fill_sweep(d, &w);
+    st = pcl_infonce_bwd(&w, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
+  }
+  if (st != PCL_OK) return st;
+  return pcl::scatter_rows(&d->g, d->plan, d->anchor_meta, d->dA, d->anchors_f32, d->inv_norm, d->normalize,
+                           d->grad_embed, stream);
+}

@@ -4,9 +4,11 @@ The eager step costs ~0.14 ms of host time (Python + autograd + 8 kernel launche
 time at the Cityscapes shape, so it is host-launch-bound as soon as the host slows down (8 ranks on one box).  The C
 ABI neither allocates nor synchronises and all scratch is caller-owned, so the whole sequence
 
-    pcl_step_stats -> pcl_step_ranks -> pcl_step_forward -> pcl_step_backward
+    pcl_step_stats -> pcl_step_ranks -> pcl_step_forward -> pcl_step_backward[_prezeroed]
 
-is capturable: a replay is ONE graph launch.  Constraints of a captured graph, made explicit here:
+is capturable: a replay is ONE graph launch.  The zero-fill of the dense gradient (the HBM floor of the step) runs as
+a parallel branch of the graph from the start of the step (``overlap_zero_fill``), hidden behind the latency-bound
+selection and sweep kernels; the backward then scatters only the sampled columns.  Constraints of a captured graph, made explicit here:
 
 * static shapes and static addresses: the tensors given to the constructor are read in place on every replay —
   refill them (``embed.copy_(...)`` or let the producer write into them), do not replace them;
@@ -49,7 +51,7 @@ class GraphedContrastStep:
                  predict: Optional[torch.Tensor] = None, segment_queue: Optional[torch.Tensor] = None,
                  pixel_queue: Optional[torch.Tensor] = None, bank_shadow: Optional[torch.Tensor] = None,
                  options: Optional[ContrastOptions] = None, grad_scale: float = 1.0, capture: bool = True,
-                 warmup: int = 2):
+                 warmup: int = 2, overlap_zero_fill: bool = True):
         self.lib = _abi.load()
         opts = options or ContrastOptions()
         _fn._require_cuda(embed, "embed")
@@ -114,28 +116,52 @@ class GraphedContrastStep:
         d.loss, d.grad_embed = self.loss.data_ptr(), self.grad.data_ptr()
         self.graph = None
         self.replays = 0
+        # The zero-fill of the dense gradient (B*D*h*w*4 bytes, the HBM floor of the step) does not depend on anything
+        # the step computes: run it on a second stream from the start of the step, behind the latency-bound selection
+        # and sweep kernels, and let the backward scatter only the sampled columns (pcl_step_backward_prezeroed).
+        self.overlap_zero_fill = bool(overlap_zero_fill)
+        self.side = None
         if capture:
             self._capture(max(1, int(warmup)))
+
+    # fork / join of the overlapped zero-fill (torch streams + events; inside a capture these become graph edges)
+    def _fork_zero_fill(self) -> None:
+        main = torch.cuda.current_stream(self.device)
+        if self.side is None:
+            self.side = torch.cuda.Stream(self.device)
+        self.side.wait_stream(main)                  # the previous consumer of `grad` is ordered before the fill
+        with torch.cuda.stream(self.side):
+            self.grad.zero_()
+
+    def _join_zero_fill(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
 
     # the launch sequence (also usable eagerly: capture=False)
     def _enqueue(self, stream: int) -> None:
         lib, d = self.lib, self.ws.desc
+        if self.overlap_zero_fill:
+            self._fork_zero_fill()
         _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
         _abi.check(lib.pcl_step_ranks(C.byref(d), self.counter.data_ptr(), self.ws.ranks.data_ptr(), stream), "pcl_step_ranks")
         _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
-        _abi.check(lib.pcl_step_backward(C.byref(d), self.scale.data_ptr(), stream), "pcl_step_backward")
+        if self.overlap_zero_fill:
+            self._join_zero_fill()
+            _abi.check(lib.pcl_step_backward_prezeroed(C.byref(d), self.scale.data_ptr(), stream),
+                       "pcl_step_backward_prezeroed")
+        else:
+            _abi.check(lib.pcl_step_backward(C.byref(d), self.scale.data_ptr(), stream), "pcl_step_backward")
 
     def _capture(self, warmup: int) -> None:
         dev = self.device
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.device(dev), torch.cuda.stream(side):
-            for _ in range(warmup):            # first calls set function attributes and encode the TMA descriptors
-                self._enqueue(side.cuda_stream)
-        torch.cuda.current_stream(dev).wait_stream(side)
+        cap = torch.cuda.Stream(dev)           # capture stream (graphs cannot be captured on the default stream)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(cap):
+            for _ in range(warmup):            # eager runs first: kernels get loaded, function attributes set, TMA
+                self._enqueue(cap.cuda_stream)  # descriptors encoded — none of that may happen under capture
+        torch.cuda.current_stream(dev).wait_stream(cap)
         self.counter.zero_()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.device(dev), torch.cuda.graph(graph, stream=side):
+        with torch.cuda.device(dev), torch.cuda.graph(graph, stream=cap):
             self._enqueue(torch.cuda.current_stream(dev).cuda_stream)
         self.graph = graph
 

@@ -318,6 +318,10 @@ typedef struct {
 int pcl_step_stats(const pcl_step_desc* d, void* stream);      /* pcl_class_stats + pcl_plan_anchors      */
 int pcl_step_forward(const pcl_step_desc* d, void* stream);    /* pcl_select_gather + pcl_infonce_fwd     */
 int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss, void* stream); /* bwd + scatter     */
+/* Same backward for a grad_embed buffer the caller has already zero-filled (e.g. on a second stream, overlapped with
+ * the forward: the 268 MB fill is the HBM floor of the step, the selection and sweep kernels are latency-bound): runs
+ * the backward sweep and scatters only the sampled columns.  Nothing else of grad_embed is written. */
+int pcl_step_backward_prezeroed(const pcl_step_desc* d, const float* grad_loss, void* stream);
 
 /* CUDA-graph capture of a step.  The three calls above neither allocate nor synchronise, so a
  * stats -> forward -> backward sequence can be captured with cudaStreamBeginCapture / replayed with cudaGraphLaunch.

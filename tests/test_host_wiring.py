@@ -217,7 +217,8 @@ def test_graphed_step_launch_sequence(rec):
     -> backward on static buffers, the upstream gradient as a device scalar, the rank table wired into the step."""
     embed, labels, seg = _inputs()
     opts = cs.ContrastOptions(max_samples=64, max_views=4, seed=77)
-    step = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, grad_scale=0.1, capture=False)
+    step = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, grad_scale=0.1, capture=False,
+                                  overlap_zero_fill=False)
     loss, grad = step.replay()
     assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_ranks", "pcl_step_forward", "pcl_step_backward"]
     d = rec.calls[2][1][0]
@@ -233,7 +234,7 @@ def test_graphed_step_launch_sequence(rec):
     e = embed.detach().requires_grad_(True)
     with pytest.raises(_abi.PclError):
         step.apply(torch.zeros_like(e))
-    step2 = cs.GraphedContrastStep(e, labels, seg=seg, options=opts, capture=False)
+    step2 = cs.GraphedContrastStep(e, labels, seg=seg, options=opts, capture=False, overlap_zero_fill=False)
     out = step2.apply(e)
     out.backward()
     assert e.grad.shape == e.shape
@@ -242,6 +243,15 @@ def test_graphed_step_launch_sequence(rec):
                                options=cs.ContrastOptions(max_samples=64, max_views=4, rng="torch_cpu"))
     with pytest.raises(_abi.PclError):
         cs.GraphedContrastStep(embed.detach(), labels.to(torch.int32), seg=seg, options=opts, capture=False)
+    # overlapped zero-fill: fork before the first kernel, join before the scatter-only backward
+    rec.calls.clear()
+    step3 = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, capture=False)
+    step3._fork_zero_fill = lambda: rec.calls.append(("fork", []))
+    step3._join_zero_fill = lambda: rec.calls.append(("join", []))
+    step3.replay()
+    assert _names(rec) == ["fork", "pcl_step_stats", "pcl_step_ranks", "pcl_step_forward", "join",
+                           "pcl_step_backward_prezeroed"]
+    assert rec.calls[-1][1][0].grad_embed == step3.grad.data_ptr() and rec.calls[-1][1][1] == step3.scale.data_ptr()
 
 
 def _bank(K=5, M=6, D=32):
