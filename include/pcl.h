@@ -12,7 +12,10 @@
  *     describe addresses/shapes only); the return value is 0 or a negative pcl_status;
  *   - scratch comes from caller-provided buffers (sizes: pcl_select_sizes / pcl_sweep_sizes), so the
  *     caller's allocator owns all memory and the sequence is CUDA-graph capturable;
- *   - there is NO CPU fallback: without a CUDA device every compute call returns PCL_ERR_CUDA.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns PCL_ERR_CUDA;
+ *   - one device per process (the one-process-per-GPU model of the reference's DDP launcher,
+ *     lib/utils/distributed.py): opt-in shared-memory limits are raised once per process with cudaFuncSetAttribute,
+ *     which is a per-device setting, so driving a second device from the same process is not supported.
  */
 #ifndef PCL_H_
 #define PCL_H_
