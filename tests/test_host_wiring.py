@@ -371,3 +371,35 @@ def test_fused_seg_ce_wiring(rec):
     assert _names(rec) == ["pcl_seg_ce_fwd", "pcl_step_stats", "pcl_step_forward"]
     out.backward()
     assert sorted(_names(rec)[3:]) == ["pcl_seg_ce_bwd", "pcl_step_backward"]
+
+
+def test_explicit_operand_entry_points(rec, monkeypatch):
+    """infonce_forward / infonce_backward on explicit operands, stock and top-k variants (torch.cuda.device stubbed)."""
+    monkeypatch.setattr(torch.cuda, "device", _NoCtx)
+    g = torch.Generator().manual_seed(2)
+    a, c = torch.randn(70, 32, generator=g), torch.randn(200, 32, generator=g)
+    ya, yc = torch.randint(0, 4, (70,), generator=g), torch.randint(0, 4, (200,), generator=g)
+    loss, rowstats, st = Fn.infonce_forward(a, ya, contrast=c, contrast_cls=yc, temperature=0.1, base_temperature=0.07)
+    assert _names(rec) == ["pcl_infonce_fwd"] and rowstats.shape == (6, 70) and len(st) == 3
+    sw = rec.calls[0][1][0]
+    assert (sw.a_rows, sw.D, sw.mode, sw.n_cols) == (70, 32, 2, 200)
+    dA = Fn.infonce_backward(st, rowstats)
+    assert _names(rec)[-1] == "pcl_infonce_bwd" and dA.shape == (70, 32)
+    rec.calls.clear()
+    loss, rowstats, st = Fn.infonce_forward(a, ya, contrast=c, contrast_cls=yc, topk=9)
+    assert _names(rec) == ["pcl_infonce_topk_fwd"] and len(st) == 5 and rec.calls[0][1][1] == 9
+    scratch = st[4]
+    assert scratch.numel() == 128 * 2048 + 4 * 70 and rec.calls[0][1][2] == scratch.data_ptr()
+    key, tw, G, E = Fn.topk_selection(st, 70)
+    assert key.shape == tw.shape == G.shape == E.shape == (70,)
+    dA = Fn.infonce_backward(st, rowstats)
+    bw = rec.calls[-1]
+    assert bw[0] == "pcl_infonce_topk_bwd" and bw[1][1] == 9 and bw[1][2] == scratch.data_ptr() and dA.shape == (70, 32)
+    # self-contrast and bank modes build the descriptor they claim
+    rec.calls.clear()
+    Fn.infonce_forward(a, ya)
+    assert rec.calls[0][1][0].mode == 0
+    segq, pixq = torch.randn(4, 6, 32), torch.randn(4, 6, 32)
+    Fn.infonce_forward(a, ya, queues=(segq, pixq))
+    d = rec.calls[1][1][0]
+    assert d.mode == 1 and (d.bank_K, d.bank_M0, d.bank_M1) == (4, 6, 6)
