@@ -27,6 +27,11 @@ import torch  # noqa: E402
 S1 = dict(B=8, D=256, h=128, w=256, K=19, stride=4, block=32, T=0.1, bT=0.07, max_samples=1024, max_views=100)
 S2 = dict(B=1, D=256, h=128, w=256, K=19, stride=4, block=32, T=0.07, bT=0.07, max_samples=1024, max_views=100,
           M=5000, F=10, net_stride=4)
+# BASELINE configs[3], opt-in: ResNet-101 DeepLab-V3 + region memory on COCO-Stuff 520x520, 171 classes,
+# 2 images per rank; the dilated-8 backbone yields a 66x66 embedding (nearest label index floor(dst*520/66), not ::8) and
+# the bank's labels[:, ::8, ::8] grid (65x65) is flat-index-misaligned with the 4356 feature columns (Q6)
+S3 = dict(B=2, D=256, h=66, w=66, K=171, stride=8, block=40, himg=520, wimg=520, T=0.07, bT=0.07, max_samples=1024,
+          max_views=100, M=5000, F=10, net_stride=8)
 
 
 def load_peaks():
@@ -118,7 +123,8 @@ def pin_to_gpu_local_cpus(dev_index: int):
 def make_inputs(cfg, seed, device=None, bank=False):
     from contrastiveseg_b200.synth import make_bank, make_contrast_batch
     d = make_contrast_batch(B=cfg["B"], D=cfg["D"], h=cfg["h"], w=cfg["w"], num_classes=cfg["K"],
-                            img_stride=cfg["stride"], block=cfg["block"], seed=seed)
+                            img_stride=cfg["stride"], block=cfg["block"], seed=seed, himg=cfg.get("himg"),
+                            wimg=cfg.get("wimg"))
     out = dict(embed=d["embed"], seg=d["seg"], target=d["target"])
     if bank:
         out.update(make_bank(cfg["K"], cfg["M"], cfg["D"], seed + 1000))
@@ -213,7 +219,10 @@ def run_reference(args, cfg, bank, rank, budget_s=150.0):
 
 def workload_config(cfg, bank, B=None):
     name = ("HRNet-W48 pixel-contrast + pixel/region memory bank" if bank else "HRNet-W48 pixel-contrast (no memory bank)")
-    return {"workload": f"{name}, synthetic Cityscapes 1024x512 19-class -> embed {cfg['D']}x{cfg['h']}x{cfg['w']}, "
+    data = "synthetic Cityscapes 1024x512 19-class"
+    if cfg["K"] == 171:
+        name, data = "ResNet-101 DeepLab-V3 pixel-contrast + region memory", "synthetic COCO-Stuff 520x520 171-class"
+    return {"workload": f"{name}, {data} -> embed {cfg['D']}x{cfg['h']}x{cfg['w']}, "
                         f"batch {B or cfg['B']} per GPU, max_samples {cfg['max_samples']}, max_views {cfg['max_views']}",
             "per_gpu_batch": B or cfg["B"], "parallelism": "dp (images sharded, no data-path collective)" if not bank
             else "dp + one NCCL all_gather of the bank enqueue packet per step",
@@ -597,7 +606,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--workload", default="s1", choices=["s1", "s2"])
+    ap.add_argument("--workload", default="s1", choices=["s1", "s2", "s3"],
+                    help="s1 = BASELINE configs[1] (headline), s2 = configs[2] (memory bank), s3 = configs[3] (171 classes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
                     help="run the step as one CUDA-graph replay (GraphedContrastStep) instead of the eager autograd call")
@@ -607,8 +617,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = dict(S1 if args.workload == "s1" else S2)
-    bank = args.workload == "s2"
+    cfg = dict({"s1": S1, "s2": S2, "s3": S3}[args.workload])
+    bank = args.workload in ("s2", "s3")
     if os.environ.get("PCL_BENCH_TINY"):            # contract tests on small hosts: same code path, toy geometry
         cfg.update(B=2, D=32, h=16, w=16, K=5, stride=2, block=8, max_samples=32, max_views=4)
         if bank:
