@@ -1,0 +1,114 @@
+"""CPU execution of the engine's REAL SIMT kernel sources (tests/emu: the .cu files compiled for host fibers): the GPU
+parity tests of test_gpu_parity.py / test_gpu_topk.py / test_gpu_pending.py that do not need the tcgen05 tensor path are
+re-run here with DEV = "cpu", through the same Python layer and the same C ABI.  This covers the kernel logic (indices,
+barriers, reductions, selection, sampling, bank update, top-k select, graph rank draw) on machines without a GPU; it
+proves nothing about the hardware build (that is what `-m gpu` is for) and floating point differs from the GPU in the
+last bits (no FMA contraction), which the parity tolerances absorb.  TEST INFRASTRUCTURE: the product never loads the
+emulation library (`_abi.load` refuses it)."""
+import pytest
+import torch
+
+import contrastiveseg_b200 as cs
+import emu_harness
+import test_gpu_parity as G
+import test_gpu_pending as PD
+import test_gpu_topk as TK
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    lib = emu_harness.use_emulation(monkeypatch)
+    for m in (G, TK, PD):
+        monkeypatch.setattr(m, "DEV", "cpu")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    # the GPU tests rely on `.to(DEV)` producing a NEW tensor (host -> device copy); `.to("cpu")` would alias the source
+    orig_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        r = orig_to(self, *a, **k)
+        if r is self and len(a) == 1 and not k and isinstance(a[0], str) and a[0] == "cpu":
+            return self.clone()
+        return r
+
+    monkeypatch.setattr(torch.Tensor, "to", to)
+    return lib
+
+
+def _case(fn, **kw):
+    ident = fn.__name__.replace("test_", "") + ("[" + "-".join(str(v) for v in kw.values()) + "]" if kw else "")
+    return pytest.param(fn, kw, id=ident)
+
+
+PARITY = (
+    [_case(G.test_loss_and_grad_match_reference, name=n)
+     for n in ("nomem_small", "nomem_oddv", "nomem_mv1", "nomem_nondiv", "mem_small")] +
+    [_case(G.test_concatenated_queue_tensor_is_accepted, name="mem_small")] +
+    [_case(G.test_contrast_ce_wrapper, name=n, mem=m) for n, m in (("wrapper_nomem_embed", False),
+                                                                   ("wrapper_nomem_warmup", False),
+                                                                   ("wrapper_mem_embed", True))] +
+    [_case(G.test_bank_enqueue_matches_reference, name=n) for n in ("enqueue_aligned", "enqueue_q6")] +
+    [_case(G.test_bank_enqueue_shape_error_like_reference)] +
+    [_case(G.test_l2_normalize_matches_torch, shape=s) for s in ((2, 256, 16, 32), (1, 32, 7, 9), (3, 320, 5, 8))] +
+    [_case(G.test_fused_normalize_path_equals_normalise_then_loss)] +
+    [_case(G.test_device_rng_sampling_is_valid_and_loss_matches_oracle_on_same_indices, mem=m) for m in (False, True)] +
+    [_case(G.test_device_rng_changes_between_steps_and_is_seed_reproducible),
+     _case(G.test_explicit_infonce_modes_and_nan_semantics),
+     _case(G.test_empty_inputs_give_zero_loss_not_a_crash),
+     _case(G.test_torch_cpu_rng_mode_draws_the_reference_stream),
+     _case(G.test_trainer_hook_end_to_end_with_bank),
+     _case(G.test_workspace_is_released_when_the_graph_is_dropped_without_backward)] +
+    [_case(G.test_fused_upsample_cross_entropy, B=b, K=k, h=h, w=w, H=H, W=W, weighted=wt)
+     for b, k, h, w, H, W, wt in ((2, 5, 16, 20, 32, 40, False), (1, 19, 13, 10, 50, 37, True), (2, 7, 8, 8, 8, 8, False),
+                                  (1, 3, 5, 7, 1, 9, True))]
+)
+
+
+@pytest.mark.parametrize("fn,kw", PARITY)
+def test_gpu_parity_cases_on_emulated_kernels(emu, fn, kw):
+    fn(**kw)
+
+
+TOPK = (
+    [_case(TK.test_topk_explicit_exact_data, A=a, N=n, k=k) for a, n, k in ((70, 333, 9), (130, 1000, 1), (64, 200, 64),
+                                                                            (200, 129, 40))] +
+    [_case(TK.test_topk_self_contrast_exact_data, k=k) for k in (3, 50)] +
+    [_case(TK.test_topk_bank_mode_with_zero_tail, k=k) for k in (5, 37, 10 ** 6)] +
+    [_case(TK.test_topk_through_the_loss_module, name=n) for n in ("nomem_small", "mem_small")]
+)
+
+
+@pytest.mark.parametrize("fn,kw", TOPK)
+def test_topk_kernels_on_emulation(emu, fn, kw):
+    """a10: the radix-select / weighted-sweep kernels of csrc/pcl_topk.cu against the sort-based oracle."""
+    fn(**kw)
+
+
+def test_topk_normalised_embeddings_on_emulation(emu):
+    TK.test_topk_normalised_embeddings_loss()
+
+
+def test_bank_write_waits_for_backward_on_emulation(emu):
+    """Gradient bit-identical with / without an enqueue between loss and backward; final bank equals an immediate enqueue."""
+    PD.test_enqueue_between_loss_and_backward_does_not_change_the_gradient("fp32")
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_graphed_step_sequence_on_emulation(emu, monkeypatch, overlap):
+    """GraphedContrastStep's launch sequence run eagerly (no CUDA graph on a CPU): the device-side rank draw
+    (csrc/pcl_graph.cu) reproduces the eager sampling stream, the scatter-only backward equals the fused writer."""
+    from contrastiveseg_b200 import graph_step
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
+    PD.test_graphed_step_equals_eager_step("fp32", False, overlap)
+
+
+def test_product_refuses_the_emulation_library(monkeypatch):
+    """No CPU path in the product: pointing the loader at the emulation build is an error, not a fallback."""
+    import emu_harness as H
+    from contrastiveseg_b200 import _abi
+    H.emu_library()
+    monkeypatch.setenv("PCL_B200_LIB", H.build_emu.LIB)
+    monkeypatch.setattr(_abi, "_lib", None)
+    with pytest.raises(_abi.PclError, match="emulation"):
+        _abi.load()
