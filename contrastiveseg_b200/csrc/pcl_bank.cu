@@ -229,6 +229,10 @@ static int make_dims(const pcl_bank_geom* g, BankDims* d) {
   d->HW = (int64_t)g->h * g->w;
   d->slot_f32 = 2 + g->D + g->pixel_update_freq * g->D;
   if ((int64_t)d->T > d->HW) return PCL_ERR_SHAPE;     // the reference would index past the feature map
+  // K' = min(n, pixel_update_freq) rows go into a ring of M rows: with K' > M the reference's slice assignment
+  // pixel_queue[lb, -K':, :] = feat raises (trainer_contrastive.py:133-135).  That needs n > M and freq > M; the engine
+  // refuses the configuration up front instead of depending on the data (the wrap branch would write before row 0).
+  if (g->pixel_update_freq > g->M) return PCL_ERR_SHAPE;
   return PCL_OK;
 }
 

@@ -112,3 +112,22 @@ def test_product_refuses_the_emulation_library(monkeypatch):
     monkeypatch.setattr(_abi, "_lib", None)
     with pytest.raises(_abi.PclError, match="emulation"):
         _abi.load()
+
+
+def test_update_freq_larger_than_memory_is_refused(emu):
+    """Found by differential fuzzing on the emulator: with pixel_update_freq > memory_size the wrap branch of the bank
+    write would start before row 0 (the reference raises once a class has more than memory_size pixels).  The engine
+    refuses the configuration up front — also in the real library, where the check runs before any CUDA call."""
+    import ctypes as C
+    from contrastiveseg_b200 import _abi
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    data = make_contrast_batch(B=1, D=32, h=8, w=8, num_classes=4, img_stride=1, block=8, seed=1)
+    b = make_bank(4, 3, 32, 2)
+    with pytest.raises(_abi.PclError, match="shape"):
+        cs.dequeue_and_enqueue(data["embed"], data["target"], b["segment_queue"], b["segment_queue_ptr"], b["pixel_queue"],
+                               b["pixel_queue_ptr"], network_stride=1, memory_size=3, pixel_update_freq=5, distributed=False)
+    import contrastiveseg_b200.build as build
+    real = C.CDLL(build.library_path())
+    real.pcl_bank_packet.restype = C.c_int32
+    g = _abi.BankGeom(1, 32, 8, 8, 8, 8, 4, 3, 1, 5)
+    assert real.pcl_bank_packet(C.byref(g), None, None, None, C.c_uint64(0), None, None, None) == -4
