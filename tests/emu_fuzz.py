@@ -1,0 +1,274 @@
+"""TEST INFRASTRUCTURE: differential fuzzing of the engine (real SIMT kernel sources on the host-fiber emulator,
+tests/emu) against the oracle over random geometries.  Used by tests/test_emu_fuzz.py (bounded) and
+tools/emu_fuzz.py (long runs).  Every fuzzer returns a list of failure descriptions (empty = clean).
+
+It found the out-of-bounds wrap write for pixel_update_freq > memory_size (now refused, csrc/pcl_bank.cu: make_dims)."""
+import math
+import random
+
+import torch
+import torch.nn.functional as F
+
+import contrastiveseg_b200 as cs
+from contrastiveseg_b200 import _abi, functional as Fn
+from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+from oracle import ref_port as P
+
+
+def _cfg(T, bT, ms, mv, K):
+    return cs.Configer({"data": {"num_classes": K},
+                        "contrast": {"temperature": T, "base_temperature": bT, "max_samples": ms, "max_views": mv,
+                                     "loss_weight": 0.1},
+                        "loss": {"params": {"ce_ignore_index": -1}}, "network": {"stride": 8}})
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-9)
+
+
+def fuzz_loss(seed: int, n: int):
+    """PixelContrastLoss (exact path, injected permutations) vs the float64 oracle: random batch / embedding / image
+    sizes (divisible and not), class counts, sampling limits, with and without bank, seg logits or predictions.
+    Degenerate inputs: the reference raises (no class qualifies, zero views) -> the engine returns an exact zero;
+    rows without positives -> NaN on both sides."""
+    rng = random.Random(seed)
+    bad = []
+    for it in range(n):
+        B, D, h, w = rng.randint(1, 3), rng.choice([32, 64]), rng.randint(3, 36), rng.randint(3, 36)
+        K, ms, mv = rng.randint(2, 12), rng.randint(4, 160), rng.randint(1, 16)
+        block, boost = rng.choice([2, 3, 5, 8, 16]), rng.choice([0.0, 1.0, 2.0, 4.0])
+        if rng.random() < 0.5:
+            st = rng.choice([1, 2, 4])
+            himg, wimg = h * st, w * st
+        else:
+            himg, wimg = rng.randint(h, 4 * h + 3), rng.randint(w, 4 * w + 3)
+        mem, M = rng.random() < 0.4, rng.randint(2, 24)
+        T, bT, s = rng.choice([0.07, 0.1, 0.5]), rng.choice([0.07, 0.1]), rng.randint(0, 10 ** 6)
+        use_seg = rng.random() < 0.5
+        desc = (f"loss seed={seed} it={it} B={B} D={D} hw={h}x{w} img={himg}x{wimg} K={K} ms={ms} mv={mv} block={block} "
+                f"boost={boost} mem={mem} M={M} T={T} seg={use_seg}")
+        data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=1, block=block, boost=boost, seed=s,
+                                   himg=himg, wimg=wimg)
+        bank = make_bank(K, M, D, s + 1) if mem else None
+        rec = P.PermRecorder(torch.Generator().manual_seed(s))
+        e64 = data["embed"].double().requires_grad_(True)
+        q = torch.cat((bank["segment_queue"], bank["pixel_queue"]), 1).double() if mem else None
+        predict = data["seg"].argmax(1)
+        why = None
+        try:
+            ref = P.pixel_contrast_loss(e64, data["target"], predict, temperature=T, base_temperature=bT, max_samples=ms,
+                                        max_views=mv, queue=q, perm_fn=rec)
+            ref.backward()
+        except (RuntimeError, IndexError, ValueError) as ex:
+            why = type(ex).__name__
+        crit = cs.PixelContrastLoss(_cfg(T, bT, ms, mv, K))
+        crit.perm_fn = P.PermReplay(rec.draws) if why is None else (lambda k: torch.randperm(k))
+        embed = data["embed"].clone().requires_grad_(True)
+        queue = (bank["segment_queue"].clone(), bank["pixel_queue"].clone()) if mem else None
+        loss = crit(embed, data["target"], predict=None if use_seg else predict, seg=data["seg"] if use_seg else None,
+                    queue=queue)
+        loss.backward()
+        if why == "IndexError":
+            continue          # more anchors than bank columns (Q1): the reference crashes, the engine masks nothing
+        if why is not None:
+            if not (loss.item() == 0.0 and embed.grad.abs().max().item() == 0.0):
+                bad.append(f"degenerate input not answered with an exact zero: {desc} ({why}) loss={loss.item()}")
+            continue
+        lv, rv = loss.item(), ref.item()
+        if math.isnan(rv):
+            if not math.isnan(lv):
+                bad.append(f"reference NaN, engine {lv}: {desc}")
+            continue
+        gerr = (embed.grad.double() - e64.grad).abs().max().item() / max(e64.grad.abs().max().item(), 1e-9)
+        if _rel(lv, rv) > 5e-6 or gerr > 2e-5:
+            bad.append(f"mismatch rel={_rel(lv, rv):.2e} gerr={gerr:.2e}: {desc}")
+    return bad
+
+
+def fuzz_bank(seed: int, n: int):
+    """dequeue_and_enqueue over several steps (wrap-around, stride mismatch Q6, overlapping writes Q4) vs the oracle:
+    pointers exact, rows to rounding; configurations the reference rejects must be rejected too."""
+    rng = random.Random(seed)
+    bad = []
+    names = ("segment_queue", "segment_queue_ptr", "pixel_queue", "pixel_queue_ptr")
+    for it in range(n):
+        B, D, h, w, K = rng.randint(1, 3), rng.choice([32, 64]), rng.randint(3, 30), rng.randint(3, 30), rng.randint(2, 10)
+        M, Fq, s, img_s = rng.randint(2, 20), rng.randint(1, 12), rng.choice([1, 2, 3, 4, 8]), rng.choice([1, 2, 4])
+        block, steps, sd = rng.choice([2, 4, 8, 16]), rng.randint(1, 5), rng.randint(0, 10 ** 6)
+        desc = f"bank seed={seed} it={it} B={B} D={D} hw={h}x{w} K={K} M={M} F={Fq} stride={s} img_stride={img_s} steps={steps}"
+        b0 = make_bank(K, M, D, sd)
+        ref = [b0[k].clone() for k in names]
+        mine = [b0[k].clone() for k in names]
+        done = True
+        for st in range(steps):
+            data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=img_s, block=block, seed=sd + st)
+            rec = P.PermRecorder(torch.Generator().manual_seed(sd + st))
+            r_ok = True
+            try:
+                P.dequeue_and_enqueue(data["embed"], data["target"], *ref, network_stride=s, memory_size=M,
+                                      pixel_update_freq=Fq, perm_fn=rec)
+            except (RuntimeError, IndexError):
+                r_ok = False
+            m_ok = True
+            try:
+                cs.dequeue_and_enqueue(data["embed"].clone(), data["target"], *mine, network_stride=s, memory_size=M,
+                                       pixel_update_freq=Fq, distributed=False,
+                                       perm_fn=P.PermReplay(rec.draws) if r_ok else (lambda k: torch.randperm(k)))
+            except _abi.PclError:
+                m_ok = False
+            if r_ok and not m_ok and Fq > M:
+                done = False          # pixel_update_freq > memory_size is refused up front (documented)
+                break
+            if r_ok != m_ok:
+                bad.append(f"refusal differs (reference ok={r_ok}, engine ok={m_ok}): {desc}")
+                done = False
+                break
+            if not r_ok:
+                done = False
+                break
+        if not done:
+            continue
+        if not (torch.equal(ref[1], mine[1]) and torch.equal(ref[3], mine[3])):
+            bad.append(f"pointers differ: {desc}")
+            continue
+        e_seg, e_pix = (ref[0] - mine[0]).abs().max().item(), (ref[2] - mine[2]).abs().max().item()
+        if e_seg > 2e-6 or e_pix > 2e-7:
+            bad.append(f"rows differ seg={e_seg:.1e} pix={e_pix:.1e}: {desc}")
+    return bad
+
+
+def fuzz_segce(seed: int, n: int):
+    """Fused bilinear(align_corners) up/down-sampling + weighted CE with ignore vs the float64 torch ops."""
+    rng = random.Random(seed)
+    bad = []
+    for it in range(n):
+        B, K, h, w = rng.randint(1, 3), rng.randint(2, 21), rng.randint(1, 20), rng.randint(1, 24)
+        H, W, weighted, ign = rng.randint(1, 60), rng.randint(1, 60), rng.random() < 0.5, rng.choice([-1, 255, 0])
+        g = torch.Generator().manual_seed(rng.randint(0, 10 ** 6))
+        seg = torch.randn(B, K, h, w, generator=g) * 2
+        target = torch.randint(0, K, (B, H, W), generator=g)
+        target[torch.rand(B, H, W, generator=g) < 0.2] = ign
+        weight = (torch.rand(K, generator=g) + 0.5) if weighted else None
+        desc = f"segce seed={seed} it={it} B={B} K={K} {h}x{w}->{H}x{W} weighted={weighted} ignore={ign}"
+        s1 = seg.clone().requires_grad_(True)
+        loss = cs.upsample_cross_entropy(s1, target, weight, ign)
+        loss.backward(torch.tensor(0.7))
+        s2 = seg.clone().double().requires_grad_(True)
+        ref = P.seg_cross_entropy(s2, target, ign, weight.double() if weighted else None)
+        ref.backward(torch.tensor(0.7, dtype=torch.float64))
+        if math.isnan(ref.item()):
+            if not math.isnan(loss.item()):
+                bad.append(f"reference NaN, engine {loss.item()}: {desc}")
+            continue
+        gerr = (s1.grad.double() - s2.grad).abs().max().item() / max(s2.grad.abs().max().item(), 1e-9)
+        if _rel(loss.item(), ref.item()) > 3e-6 or gerr > 2e-5:
+            bad.append(f"mismatch rel={_rel(loss.item(), ref.item()):.2e} gerr={gerr:.2e}: {desc}")
+    return bad
+
+
+def fuzz_device_sampling(seed: int, n: int, check_sampling):
+    """Device RNG (keyed bijection, no injected permutations), optional fused normalise: every anchor a valid distinct
+    pixel of its (image, class, hard|easy) group; loss / gradient vs the oracle evaluated on exactly those anchors."""
+    rng = random.Random(seed)
+    bad = []
+    for it in range(n):
+        B, D, h, w = rng.randint(1, 3), rng.choice([32, 64]), rng.randint(4, 40), rng.randint(4, 40)
+        K, ms, mv = rng.randint(2, 10), rng.randint(4, 200), rng.randint(1, 16)
+        block, st, boost = rng.choice([2, 4, 8, 16]), rng.choice([1, 2, 4]), rng.choice([0.0, 2.0, 4.0])
+        mem, norm, sd = rng.random() < 0.4, rng.random() < 0.4, rng.randint(0, 10 ** 6)
+        desc = f"devrng seed={seed} it={it} B={B} D={D} {h}x{w} K={K} ms={ms} mv={mv} block={block} st={st} mem={mem} norm={norm}"
+        data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=st, block=block, boost=boost, seed=sd)
+        bank = make_bank(K, rng.randint(8, 30), D, sd + 1)
+        crit = cs.PixelContrastLoss(_cfg(0.1, 0.07, ms, mv, K))
+        embed = (data["embed_raw"] if norm else data["embed"]).clone().requires_grad_(True)
+        queue = (bank["segment_queue"].clone(), bank["pixel_queue"].clone()) if mem else None
+        loss = crit(embed, data["target"], seg=data["seg"], queue=queue, normalize=norm)
+        loss.backward()
+        ws = Fn.last_workspace(embed.device)
+        TC, V, A = ws.plan_header()[:3]
+        lab = P.downsample_labels(data["target"], h, w).reshape(B, -1)
+        prd = data["seg"].argmax(1).reshape(B, -1)
+        if TC == 0 or V == 0:
+            if loss.item() != 0.0:
+                bad.append(f"degenerate input, loss {loss.item()}: {desc}")
+            continue
+        try:
+            _, _, A2, meta = check_sampling(ws, lab, prd, ms, mv)
+        except AssertionError as ex:
+            bad.append(f"invalid sample set ({str(ex)[:120]}): {desc}")
+            continue
+        pix, img, cls, refrow = meta
+        if mem and A > bank["segment_queue"].shape[0] * 2 * bank["segment_queue"].shape[1]:
+            continue
+        e64 = (data["embed_raw"] if norm else data["embed"]).double().requires_grad_(True)
+        Xf = (F.normalize(e64, dim=1) if norm else e64).permute(0, 2, 3, 1).reshape(B, -1, D)
+        inv = torch.empty(A, dtype=torch.long)
+        inv[refrow] = torch.arange(A)
+        anchors, ya = Xf[img, pix][inv], cls[inv].double()
+        if mem:
+            contrast, yc = P.flatten_queue(torch.cat((bank["segment_queue"], bank["pixel_queue"]), 1).double())
+            lo = P.infonce_dense(anchors, ya, contrast, yc, 0.1, 0.07)
+        else:
+            lo = P.infonce_dense(anchors, ya, anchors, ya, 0.1, 0.07)
+        lo.backward()
+        if math.isnan(lo.item()):
+            if not math.isnan(loss.item()):
+                bad.append(f"reference NaN, engine {loss.item()}: {desc}")
+            continue
+        gerr = (embed.grad.double() - e64.grad).abs().max().item() / max(e64.grad.abs().max().item(), 1e-9)
+        if _rel(loss.item(), lo.item()) > 5e-6 or gerr > 3e-5:
+            bad.append(f"mismatch rel={_rel(loss.item(), lo.item()):.2e} gerr={gerr:.2e}: {desc}")
+    return bad
+
+
+def fuzz_topk(seed: int, n: int):
+    """a10 top-k kernels vs the sort-based oracle: explicit / self / bank (zero tail) operands; exact dyadic data (ties,
+    strict gradient check) and unit-norm data (near-ties: loss strict, gradient in norm)."""
+    rng = random.Random(seed)
+    bad = []
+    for it in range(n):
+        A, N, D, ncls = rng.randint(2, 150), rng.randint(2, 400), rng.choice([32, 64]), rng.randint(2, 8)
+        k, exact, mode = rng.randint(1, 60), rng.random() < 0.5, rng.choice(["explicit", "self", "bank"])
+        g = torch.Generator().manual_seed(rng.randint(0, 10 ** 6))
+        desc = f"topk seed={seed} it={it} A={A} N={N} D={D} classes={ncls} k={k} exact={exact} mode={mode}"
+        if exact:
+            den = 4 if D == 32 else 8                       # keeps exp(l - m) inside the fp32 range
+            mk = lambda *s: torch.randint(-3, 4, s, generator=g).double() / den      # noqa: E731
+            T, bT = 0.125, 0.25
+        else:
+            mk = lambda *s: F.normalize(torch.randn(*s, generator=g), dim=-1).double()   # noqa: E731
+            T, bT = 0.1, 0.07
+        a, ya = mk(A, D), torch.randint(0, ncls, (A,), generator=g)
+        if mode == "explicit":
+            c, yc, diag = mk(N, D), torch.randint(0, ncls, (N,), generator=g), torch.arange(A) % N
+            o = P.infonce_topk(a, ya, c, yc, T, bT, k, False, diag_cols=diag)
+            loss, rs, st = Fn.infonce_forward(a.float(), ya, contrast=c.float(), contrast_cls=yc, diag_col=diag,
+                                              temperature=T, base_temperature=bT, topk=k)
+        elif mode == "self":
+            o = P.infonce_topk(a, ya, a, ya, T, bT, k, True)
+            loss, rs, st = Fn.infonce_forward(a.float(), ya, temperature=T, base_temperature=bT, topk=k)
+        else:
+            K, M = ncls, rng.randint(1, 12)
+            if A > K * 2 * M:
+                continue
+            segq, pixq = mk(K, M, D), mk(K, M, D)
+            if exact:
+                pixq[:, ::3] = 0
+            ya = ya[torch.argsort(torch.where(ya == 0, K, ya), stable=True)]
+            contrast, yc = P.flatten_queue(torch.cat((segq, pixq), 1))
+            o = P.infonce_topk(a, ya, contrast, yc.long(), T, bT, k, False)
+            loss, rs, st = Fn.infonce_forward(a.float(), ya, queues=(segq.float(), pixq.float()),
+                                              diag_col=torch.arange(A), temperature=T, base_temperature=bT, topk=k)
+        dA = Fn.infonce_backward(st, rs).double()
+        lo = o["loss"].item()
+        if math.isnan(lo):
+            if not math.isnan(loss.item()):
+                bad.append(f"reference NaN, engine {loss.item()}: {desc}")
+            continue
+        if exact:
+            gerr, tol = (dA - o["dA"]).abs().max().item() / max(o["dA"].abs().max().item(), 1e-9), 2e-5
+        else:
+            gerr, tol = (torch.linalg.norm(dA - o["dA"]) / max(torch.linalg.norm(o["dA"]).item(), 1e-9)).item(), 5e-2
+        if _rel(loss.item(), lo) > 1e-5 or gerr > tol:
+            bad.append(f"mismatch rel={_rel(loss.item(), lo):.2e} gerr={gerr:.2e}: {desc}")
+    return bad

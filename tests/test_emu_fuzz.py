@@ -1,0 +1,34 @@
+"""Bounded differential fuzzing of the real SIMT kernel sources (host-fiber emulation, tests/emu) against the oracle:
+random geometries per component, fixed seeds.  `python tools/emu_fuzz.py` runs the same fuzzers for as long as wanted."""
+import pytest
+import torch
+
+import emu_fuzz
+import emu_harness
+import test_gpu_parity as G
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    return emu_harness.use_emulation(monkeypatch)
+
+
+def test_fuzz_pixel_contrast_loss(emu):
+    assert emu_fuzz.fuzz_loss(seed=11, n=60) == []
+
+
+def test_fuzz_bank_enqueue(emu):
+    assert emu_fuzz.fuzz_bank(seed=12, n=40) == []
+
+
+def test_fuzz_fused_seg_ce(emu):
+    assert emu_fuzz.fuzz_segce(seed=13, n=60) == []
+
+
+def test_fuzz_device_sampling(emu):
+    assert emu_fuzz.fuzz_device_sampling(seed=14, n=40, check_sampling=G._check_device_sampling) == []
+
+
+def test_fuzz_topk(emu):
+    assert emu_fuzz.fuzz_topk(seed=15, n=50) == []
