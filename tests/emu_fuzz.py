@@ -116,8 +116,12 @@ def fuzz_bank(seed: int, n: int):
                                        perm_fn=P.PermReplay(rec.draws) if r_ok else (lambda k: torch.randperm(k)))
             except _abi.PclError:
                 m_ok = False
-            if r_ok and not m_ok and Fq > M:
-                done = False          # pixel_update_freq > memory_size is refused up front (documented)
+            grid = -(-h * img_s // s) * -(-w * img_s // s)          # positions of labels[:, ::s, ::s]
+            if r_ok and not m_ok and (Fq > M or grid > h * w):
+                # refused up front from the geometry alone (documented): pixel_update_freq > memory_size, or a label
+                # grid with more positions than feature columns (Q6) — the reference only fails there when the data
+                # happens to put a labelled position / a large class beyond the limit
+                done = False
                 break
             if r_ok != m_ok:
                 bad.append(f"refusal differs (reference ok={r_ok}, engine ok={m_ok}): {desc}")
