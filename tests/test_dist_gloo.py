@@ -1,6 +1,7 @@
 """world_size-2 gloo tests (CPU) of the bank merge plumbing: one all_gather of the fixed-size enqueue packet,
-rank-major order, identical result on every rank; world 1 is a pass-through.  The packet application itself is
-a CUDA kernel (GPU test: tests/test_gpu_parity.py + tools/dist_bank_check.py)."""
+rank-major order, identical result on every rank; world 1 is a pass-through.  The packet build / application are
+CUDA kernels (GPU: tests/test_gpu_parity.py + tools/dist_bank_check.py over NCCL); the last test here runs their
+sources on the host-fiber emulator (tests/emu) on both ranks with the real gloo all_gather in between."""
 import os
 import socket
 
@@ -77,3 +78,45 @@ def test_rank_ordered_merge_gives_identical_banks(tmp_path):
     b0, b1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
     for x, y in zip(b0, b1):
         assert torch.equal(x, y)
+
+
+def _emu_bank_worker(rank, world, port, out_dir):
+    """The real enqueue kernels (host-fiber emulation of csrc/pcl_bank.cu) on every rank + the real all_gather (gloo):
+    what tools/dist_bank_check.py checks on GPUs with NCCL."""
+    import pytest
+    import emu_harness
+    import contrastiveseg_b200 as cs
+    from oracle import ref_port as P
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    emu_harness.use_emulation(pytest.MonkeyPatch())
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, D, M, F, steps = 6, 32, 9, 4, 3
+    names = ("segment_queue", "segment_queue_ptr", "pixel_queue", "pixel_queue_ptr")
+    bank0 = make_bank(K, M, D, 11)
+    mine = [bank0[k].clone() for k in names]
+    ref = [bank0[k].clone() for k in names]
+    for s in range(steps):
+        datas = [make_contrast_batch(B=2, D=D, h=12, w=16, num_classes=K, img_stride=2, block=4, seed=1000 * s + r)
+                 for r in range(world)]
+        perms = []
+        for r in range(world):                  # sequential oracle: rank 0's images, then rank 1's
+            rec = P.PermRecorder(torch.Generator().manual_seed(77 * s + r))
+            P.dequeue_and_enqueue(datas[r]["embed"], datas[r]["target"], *ref, network_stride=2, memory_size=M,
+                                  pixel_update_freq=F, perm_fn=rec)
+            perms.append(rec.draws)
+        cs.dequeue_and_enqueue(datas[rank]["embed"].clone(), datas[rank]["target"], *mine, network_stride=2,
+                               memory_size=M, pixel_update_freq=F, perm_fn=P.PermReplay(perms[rank]))
+    assert torch.equal(mine[1], ref[1]) and torch.equal(mine[3], ref[3])
+    assert (mine[0] - ref[0]).abs().max().item() <= 2e-6 and (mine[2] - ref[2]).abs().max().item() <= 2e-7
+    torch.save(mine, os.path.join(out_dir, f"e{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_emulated_enqueue_kernels_merge_across_two_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_emu_bank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    b0, b1 = torch.load(tmp_path / "e0.pt"), torch.load(tmp_path / "e1.pt")
+    for x, y in zip(b0, b1):
+        assert torch.equal(x, y)                    # bit-identical banks on both ranks
