@@ -61,7 +61,7 @@ class MemoryBank(nn.Module):
         """Rebuild the bf16 shadow from the fp32 queues (after load_state_dict or an external write)."""
         lib = _abi.load()
         dev = self.segment_queue.device
-        if not self.segment_queue.is_cuda:
+        if not _is_cuda(self.segment_queue):
             raise _abi.PclError("the bank shadow lives on the GPU")
         if self.shadow is None or self.shadow.device != dev:
             self.shadow = torch.empty((shadow_rows(self.num_classes, self.memory_size), self.dim),

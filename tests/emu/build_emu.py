@@ -4,7 +4,9 @@ threads (fibers) with g++, so CPU-only test runs execute the real kernel code.  
 Source rewriting (text level, the .cu files themselves are untouched):
   kernel<<<grid, block, smem, stream>>>(args)   ->  emu::cfg(grid, block, smem, stream).bind(kernel)(args)
   extern __shared__ [__align__(n)] T name[];     ->  T* name = reinterpret_cast<T*>(emu::dyn_smem());
-The tensor path (pcl_infonce_tc.cu: tcgen05/TMA inline PTX) is replaced by stubs (emu_tc_stubs.cpp).
+  asm volatile("bar.sync id, %0;" :: "n"(N) ...) ->  emu::named_barrier(id, N);
+The tensor path (pcl_infonce_tc.cu) compiles against shim/ptx_sm100.cuh, a functional model of the mbarrier / TMA /
+tcgen05 primitives with the product header's names (found first on the include path).
 """
 from __future__ import annotations
 
@@ -19,14 +21,16 @@ CSRC = os.path.join(ROOT, "contrastiveseg_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libpcl_emu.so")
 SOURCES = ["pcl_api.cu", "pcl_select.cu", "pcl_infonce_simt.cu", "pcl_topk.cu", "pcl_graph.cu", "pcl_bank.cu",
-           "pcl_norm.cu", "pcl_segce.cu", "pcl_step.cu"]
+           "pcl_norm.cu", "pcl_segce.cu", "pcl_step.cu", "pcl_infonce_tc.cu"]
 
 LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>", re.S)
+NAMED_BARRIER = re.compile(r'asm volatile\("bar\.sync (\d+), %0;" ::"n"\((\w+)\) : "memory"\);')
 EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w ]*?)\s+(\w+)\s*\[\s*\]\s*;")
 
 
 def rewrite(text: str) -> str:
     text = EXTERN_SHARED.sub(lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>(emu::dyn_smem());", text)
+    text = NAMED_BARRIER.sub(lambda m: f"emu::named_barrier({m.group(1)}, {m.group(2)});", text)
     return LAUNCH.sub(lambda m: f"emu::cfg({m.group(2)}).bind({m.group(1)})", text)
 
 

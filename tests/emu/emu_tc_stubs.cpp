@@ -1,27 +1,29 @@
-// TEST INFRASTRUCTURE: entry points of the tcgen05/TMA tensor path (inline PTX, not emulated) for the host-thread build
-// of the SIMT kernels — every one reports PCL_ERR_UNSUPPORTED — plus the marker that keeps this build out of the product.
-#include "pcl_common.cuh"
+// TEST INFRASTRUCTURE: the marker that keeps the emulation build out of the product, and the host-side model of
+// cuTensorMapEncodeTiled that pairs with the TMA model in shim/ptx_sm100.cuh.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+#include "ptx_sm100.cuh"
 
 extern "C" int pcl_emulated(void) { return 1; }      // contrastiveseg_b200._abi.load refuses a library that exports this
 
-namespace pcl {
-int tc_fwd_ex(const pcl_tc_desc*, float*, float*, float*, float*, void*, bool) { return PCL_ERR_UNSUPPORTED; }
-int tc_query(const pcl_tc_desc*, int64_t*, float*) { return PCL_ERR_UNSUPPORTED; }
-int tc_bwd_ex(const pcl_tc_desc*, const float*, const float*, const float*, float*, float*, void*, int*, int*) {
-  return PCL_ERR_UNSUPPORTED;
+static CUresult emu_encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* gdim,
+                                 const cuuint64_t* gstride, const cuuint32_t* box, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  if (!m || rank != 2 || dt != CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 || sw != CU_TENSOR_MAP_SWIZZLE_128B) return CUDA_ERROR_INVALID_VALUE;
+  if (((uintptr_t)base & 15) != 0 || (gstride[0] & 15) != 0 || box[0] * 2 != 128 || box[1] > 256) return CUDA_ERROR_INVALID_VALUE;
+  memset(m, 0, sizeof(*m));
+  ptx::TmapModel t{(const uint8_t*)base, gdim[1], gstride[0], box[0], box[1], 0x7A3Du};
+  memcpy(m, &t, sizeof(t));
+  return CUDA_SUCCESS;
 }
-}  // namespace pcl
 
-// sizing only: reports "no extra scratch" so that D == 256 workspaces can be built and used on the exact fp32 path
-extern "C" int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out) {
-  if (!d || !out) return PCL_ERR_ARG;
-  memset(out, 0, sizeof(*out));
-  out->rowstat_f32 = d->a_rows;
-  return PCL_OK;
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+  if (symbol && strcmp(symbol, "cuTensorMapEncodeTiled") == 0) {
+    *fn = (void*)emu_encode_tiled;
+    if (q) *q = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
+  if (q) *q = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorInvalidValue;
 }
-extern "C" int pcl_to_bf16(const float*, void*, int64_t, int64_t, void*) { return PCL_ERR_UNSUPPORTED; }
-extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc*, float*, float*, float*, float*, void*) { return PCL_ERR_UNSUPPORTED; }
-extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc*, const float*, const float*, const float*, float*, float*, void*) {
-  return PCL_ERR_UNSUPPORTED;
-}
-extern "C" int pcl_tc_dump_logits(const pcl_tc_desc*, float*, float*, void*) { return PCL_ERR_UNSUPPORTED; }

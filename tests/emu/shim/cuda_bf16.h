@@ -12,3 +12,5 @@ static inline __nv_bfloat16 __float2bfloat16(float f) {
   return r;
 }
 static inline float __bfloat162float(__nv_bfloat16 h) { uint32_t u = (uint32_t)h.x << 16; float f; memcpy(&f, &u, 4); return f; }
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };      // .x = low half-word
+static inline __nv_bfloat162 __floats2bfloat162_rn(float lo, float hi) { return __nv_bfloat162{__float2bfloat16(lo), __float2bfloat16(hi)}; }

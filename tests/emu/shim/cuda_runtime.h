@@ -66,7 +66,7 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) {
 
 namespace emu {
 
-enum { RUNNABLE = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3 };
+enum { RUNNABLE = 0, WAIT_BLOCK = 1, WAIT_WARP = 2, DONE = 3, WAIT_NAMED = 4 };
 constexpr size_t STACK_BYTES = 256 * 1024;
 
 struct Fiber {
@@ -74,6 +74,7 @@ struct Fiber {
   int state;
   unsigned lin;        // linear thread index in the block
   uint3 t3;
+  int named_id = 0, named_n = 0;     // bar.sync id, n (named barrier the fiber waits at)
 };
 struct Warp { uint64_t buf[32]; };
 struct Block {
@@ -83,6 +84,8 @@ struct Block {
   Fiber* cur = nullptr;
   uint3 bid{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
   void* dyn = nullptr;
+  size_t dyn_bytes = 0;
+  std::vector<float> tmem;           // tensor memory of the block: 128 lanes x 512 columns (tcgen05 model, ptx_sm100.cuh)
   std::function<void()> body;
 };
 inline Block* g_blk = nullptr;
@@ -153,6 +156,15 @@ inline void run_block(Block& B) {
         progressed = true;
       }
     }
+    // bar.sync id, n: released when n live threads wait at the same id
+    for (int id = 1; id < 16; ++id) {
+      size_t cnt = 0; int need = 0;
+      for (size_t i = 0; i < n; ++i) if (B.fibers[i].state == WAIT_NAMED && B.fibers[i].named_id == id) { ++cnt; need = B.fibers[i].named_n; }
+      if (cnt && (int)cnt >= need) {
+        for (size_t i = 0; i < n; ++i) if (B.fibers[i].state == WAIT_NAMED && B.fibers[i].named_id == id) B.fibers[i].state = RUNNABLE;
+        progressed = true;
+      }
+    }
     if (!progressed) { fprintf(stderr, "emu: deadlock (divergent barrier) in block (%u,%u,%u)\n", B.bid.x, B.bid.y, B.bid.z); abort(); }
   }
 }
@@ -169,8 +181,9 @@ inline void launch(const Cfg& c, std::function<void()> body) {
   B.bdim = uint3{c.b.x, c.b.y, c.b.z};
   B.gdim = uint3{c.g.x, c.g.y, c.g.z};
   B.body = std::move(body);
-  std::vector<char> dyn(c.smem + 64);
-  B.dyn = (void*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
+  std::vector<char> dyn(c.smem + 2048);
+  B.dyn = (void*)(((uintptr_t)dyn.data() + 1023) & ~(uintptr_t)1023);      // 1024-aligned like the shared window
+  B.dyn_bytes = c.smem + 1024;
   for (unsigned i = 0; i < nt; ++i) {
     B.fibers[i].lin = i;
     B.fibers[i].t3 = uint3{i % c.b.x, (i / c.b.x) % c.b.y, i / (c.b.x * c.b.y)};
@@ -204,6 +217,13 @@ template <class G, class Bk>
 inline CfgBinder cfg(G g, Bk b, size_t smem = 0, cudaStream_t s = nullptr) { return CfgBinder{cfg_make(dim3(g), dim3(b), smem, s)}; }
 
 inline void* dyn_smem() { return g_blk->dyn; }
+inline void named_barrier(int id, int nthreads) {
+  Fiber* f = g_blk->cur;
+  f->named_id = id; f->named_n = nthreads;
+  yield(WAIT_NAMED);
+}
+// cooperative spin (polling loops on mbarriers): stay runnable, let the other fibers of the block run
+inline void spin_yield() { yield(RUNNABLE); }
 inline unsigned lane_id() { return g_blk->cur->lin & 31u; }
 inline Warp& my_warp() { return g_blk->warps[g_blk->cur->lin >> 5]; }
 inline bool lane_live(unsigned lane) {
@@ -279,6 +299,14 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline long long __float2ll_rn(float x) { return llrintf(x); }
 static inline int __float2int_rn(float x) { return (int)lrintf(x); }
+static inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
+#define __grid_constant__
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+// a small "GPU" keeps persistent grids short under emulation and still exercises multi-CTA work splitting
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 6; return cudaSuccess; }
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum { cudaEnableDefault = 0 };
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long flags, cudaDriverEntryPointQueryResult* q);
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }

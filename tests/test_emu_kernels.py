@@ -1,6 +1,7 @@
-"""CPU execution of the engine's REAL SIMT kernel sources (tests/emu: the .cu files compiled for host fibers): the GPU
-parity tests of test_gpu_parity.py / test_gpu_topk.py / test_gpu_pending.py that do not need the tcgen05 tensor path are
-re-run here with DEV = "cpu", through the same Python layer and the same C ABI.  This covers the kernel logic (indices,
+"""CPU execution of the engine's REAL kernel sources (tests/emu: the .cu files compiled for host fibers; the tensor path
+against a functional model of mbarrier / TMA / tcgen05): the GPU tests of test_gpu_parity.py / test_gpu_topk.py /
+test_gpu_pending.py are re-run here with DEV = "cpu", through the same Python layer and the same C ABI (all but the
+full-size ones).  This covers the kernel logic (indices,
 barriers, reductions, selection, sampling, bank update, top-k select, graph rank draw) on machines without a GPU; it
 proves nothing about the hardware build (that is what `-m gpu` is for) and floating point differs from the GPU in the
 last bits (no FMA contraction), which the parity tolerances absorb.  TEST INFRASTRUCTURE: the product never loads the
@@ -81,6 +82,37 @@ TOPK = (
 def test_topk_kernels_on_emulation(emu, fn, kw):
     """a10: the radix-select / weighted-sweep kernels of csrc/pcl_topk.cu against the sort-based oracle."""
     fn(**kw)
+
+
+TENSOR = (
+    [_case(G.test_tc_pipeline_raw_logits, A=a, N=n) for a, n in ((128, 256), (200, 1000))] +
+    [_case(G.test_tc_forward_matches_oracle, A=a, N=n, T=t, self_mode=sm) for a, n, t, sm in ((200, 1000, 0.1, False),
+                                                                                          (912, 912, 0.1, True))] +
+    [_case(G.test_tc_backward_matches_oracle, A=a, N=n, T=t, self_mode=sm) for a, n, t, sm in ((200, 1000, 0.1, False),
+                                                                                           (912, 912, 0.1, True))] +
+    [_case(G.test_loss_module_on_tensor_path, name=n) for n in ("nomem_d256", "mem_d256")] +
+    [_case(G.test_bank_shadow_tracks_enqueue_and_tensor_path_uses_it),
+     _case(G.test_coco_stuff_shape_171_classes_with_bank, precision="bf16"),
+     _case(PD.test_enqueue_between_loss_and_backward_does_not_change_the_gradient, precision="bf16")]
+)
+
+
+@pytest.mark.parametrize("fn,kw", TENSOR)
+def test_tensor_path_on_the_functional_tcgen05_model(emu, fn, kw):
+    """csrc/pcl_infonce_tc.cu (TMA-fed tcgen05 sweeps) compiled against tests/emu/shim/ptx_sm100.cuh, a functional model
+    of mbarrier / TMA (SWIZZLE_128B) / tcgen05.mma (shared-memory descriptors, K- and MN-major) / tensor memory: the
+    warp-specialised pipelines, descriptor arithmetic, class tests and epilogues run on the CPU.  The kernels are the
+    ones verified on the B200, so a pass also confirms that the model reads descriptors the way the hardware does."""
+    fn(**kw)
+
+
+@pytest.mark.parametrize("mem,overlap", [(False, False), (False, True), (True, True)])
+def test_graphed_step_tensor_path_on_emulation(emu, monkeypatch, mem, overlap):
+    from contrastiveseg_b200 import graph_step
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
+    PD.test_graphed_step_equals_eager_step("bf16", mem, overlap)
 
 
 def test_topk_normalised_embeddings_on_emulation(emu):
