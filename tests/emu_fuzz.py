@@ -276,3 +276,70 @@ def fuzz_topk(seed: int, n: int):
         if _rel(loss.item(), lo) > 1e-5 or gerr > tol:
             bad.append(f"mismatch rel={_rel(loss.item(), lo):.2e} gerr={gerr:.2e}: {desc}")
     return bad
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def fuzz_tensor_path(seed: int, n: int):
+    """tcgen05 sweeps (functional model) on explicit operands: self-contrast, explicit contrast set (sorted / unsorted
+    labels), bank through the bf16 shadow; ragged A and N (not multiples of the 128 x 256 tile), few / many classes.
+    Loss and positive counts against the float64 closed form on the bf16-rounded operands; gradient within the bf16
+    tolerance of the path (max-abs 6e-3 * max|g|, relative Frobenius 3e-3)."""
+    from contrastiveseg_b200.bank import shadow_rows
+    rng = random.Random(seed)
+    bad = []
+    lib = _abi.load()
+    for it in range(n):
+        A, N, ncls = rng.randint(1, 420), rng.randint(1, 1500), rng.randint(1, 20)
+        T, mode, clustered = rng.choice([0.07, 0.1, 0.5]), rng.choice(["self", "sorted", "unsorted", "bank"]), rng.choice([0.0, 0.5])
+        g = torch.Generator().manual_seed(rng.randint(0, 10 ** 6))
+        desc = f"tensor seed={seed} it={it} A={A} N={N} classes={ncls} T={T} mode={mode} clustered={clustered}"
+        centers = F.normalize(torch.randn(ncls + 1, 256, generator=g), dim=1)
+        ya = torch.randint(0, ncls, (A,), generator=g)
+        a = F.normalize(torch.randn(A, 256, generator=g) + clustered * 16 * centers[ya], dim=1)
+        if mode == "self":
+            loss, st, state = Fn.infonce_tc_forward(a, ya, temperature=T, base_temperature=0.07)
+            cf = P.infonce_closed_form(_bf(a).double(), ya, _bf(a).double(), ya, T, 0.07, self_contrast=True)
+        elif mode in ("sorted", "unsorted"):
+            yc = torch.randint(0, ncls, (N,), generator=g)
+            if mode == "sorted":
+                yc = torch.sort(yc).values
+            c = F.normalize(torch.randn(N, 256, generator=g) + clustered * 16 * centers[yc], dim=1)
+            c16 = Fn.to_bf16_rows(c, -(-N // 256) * 256)
+            diag = torch.arange(A) % N
+            loss, st, state = Fn.infonce_tc_forward(a, ya, contrast_bf16=c16, contrast_cls=yc, n_cols=N, diag_col=diag,
+                                                    temperature=T, base_temperature=0.07, sorted_cols=(mode == "sorted"))
+            cf = P.infonce_closed_form(_bf(a).double(), ya, _bf(c).double(), yc, T, 0.07, self_contrast=False, diag_cols=diag)
+        else:
+            K, M = max(ncls, 2), rng.randint(1, 40)
+            if A > K * 2 * M:
+                continue
+            ya = torch.randint(0, K, (A,), generator=g)
+            ya = ya[torch.argsort(torch.where(ya == 0, K, ya), stable=True)]
+            a = F.normalize(torch.randn(A, 256, generator=g) + clustered * 16 * centers[ya], dim=1)
+            segq = F.normalize(torch.randn(K, M, 256, generator=g), dim=2)
+            pixq = F.normalize(torch.randn(K, M, 256, generator=g), dim=2)
+            shadow = torch.empty((shadow_rows(K, M), 256), dtype=torch.bfloat16)
+            _abi.check(lib.pcl_bank_shadow_rebuild(segq.data_ptr(), pixq.data_ptr(), K, M, 256, shadow.data_ptr(), None))
+            loss, st, state = Fn.infonce_tc_forward(a, ya, bank=(shadow, K, 2 * M), diag_col=torch.arange(A),
+                                                    temperature=T, base_temperature=0.07)
+            contrast, yc = P.flatten_queue(torch.cat((_bf(segq), _bf(pixq)), 1).double())
+            cf = P.infonce_closed_form(_bf(a).double(), ya, contrast, yc.long(), T, 0.07, self_contrast=False)
+        dA = Fn.infonce_tc_backward(state, st).double()
+        lo = cf["loss"].item()
+        if math.isnan(lo):
+            if not math.isnan(loss.item()):
+                bad.append(f"reference NaN, engine {loss.item()}: {desc}")
+            continue
+        if not torch.equal(st[4].double(), cf["npos"]):
+            bad.append(f"positive counts differ: {desc}")
+            continue
+        # the gradient reference uses the same bf16-rounded operands (the rounding of the operands is not under test)
+        gmax = cf["dA"].abs().max().item()
+        gabs = (dA - cf["dA"]).abs().max().item() / max(gmax, 1e-9)
+        gfro = ((dA - cf["dA"]).norm() / max(cf["dA"].norm().item(), 1e-9)).item()
+        if _rel(loss.item(), lo) > 5e-5 or gabs > 6e-3 or gfro > 3e-3:
+            bad.append(f"mismatch rel={_rel(loss.item(), lo):.2e} gabs={gabs:.2e} gfro={gfro:.2e}: {desc}")
+    return bad

@@ -32,3 +32,7 @@ def test_fuzz_device_sampling(emu):
 
 def test_fuzz_topk(emu):
     assert emu_fuzz.fuzz_topk(seed=15, n=50) == []
+
+
+def test_fuzz_tensor_path(emu):
+    assert emu_fuzz.fuzz_tensor_path(seed=16, n=14) == []

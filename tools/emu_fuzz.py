@@ -25,7 +25,8 @@ if __name__ == "__main__":
     for r in range(rounds):
         for name, fn in (("loss", lambda s: emu_fuzz.fuzz_loss(s, n)), ("bank", lambda s: emu_fuzz.fuzz_bank(s, n)),
                          ("segce", lambda s: emu_fuzz.fuzz_segce(s, n)), ("topk", lambda s: emu_fuzz.fuzz_topk(s, n)),
-                         ("devrng", lambda s: emu_fuzz.fuzz_device_sampling(s, n, G._check_device_sampling))):
+                         ("devrng", lambda s: emu_fuzz.fuzz_device_sampling(s, n, G._check_device_sampling)),
+                         ("tensor", lambda s: emu_fuzz.fuzz_tensor_path(s, max(1, n // 5)))):
             bad = fn(1000 * r + 7)
             total += len(bad)
             print(f"round {r} {name}: {n} cases, {len(bad)} failures", flush=True)
