@@ -343,3 +343,48 @@ def fuzz_tensor_path(seed: int, n: int):
         if _rel(loss.item(), lo) > 5e-5 or gabs > 6e-3 or gfro > 3e-3:
             bad.append(f"mismatch rel={_rel(loss.item(), lo):.2e} gabs={gabs:.2e} gfro={gfro:.2e}: {desc}")
     return bad
+
+
+def fuzz_graphed_step(seed: int, n: int):
+    """GraphedContrastStep's launch sequence (device-side rank draw, optional pre-zeroed scatter-only backward) against the
+    eager autograd step over random geometries: replay r must sample, and compute, exactly what eager step r+1 does."""
+    from contrastiveseg_b200 import graph_step
+    rng = random.Random(seed)
+    bad = []
+    saved = (graph_step.GraphedContrastStep._capture, graph_step.GraphedContrastStep._fork_zero_fill,
+             graph_step.GraphedContrastStep._join_zero_fill)
+    graph_step.GraphedContrastStep._capture = lambda self, warmup: None            # no CUDA graphs on a CPU: run eagerly
+    graph_step.GraphedContrastStep._fork_zero_fill = lambda self: self.grad.zero_()
+    graph_step.GraphedContrastStep._join_zero_fill = lambda self: None
+    try:
+        for it in range(n):
+            B, D, h, w = rng.randint(1, 3), rng.choice([32, 64]), rng.randint(4, 30), rng.randint(4, 30)
+            K, ms, mv = rng.randint(2, 9), rng.randint(4, 150), rng.randint(1, 12)
+            st, block, mem = rng.choice([1, 2, 4]), rng.choice([2, 4, 8]), rng.random() < 0.4
+            norm, overlap, sd = rng.random() < 0.3, rng.random() < 0.5, rng.randint(0, 10 ** 6)
+            desc = f"graph seed={seed} it={it} B={B} D={D} {h}x{w} K={K} ms={ms} mv={mv} mem={mem} norm={norm} overlap={overlap}"
+            data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=st, block=block, seed=sd)
+            bank = make_bank(K, rng.randint(4, 20), D, sd + 1)
+            kw = dict(segment_queue=bank["segment_queue"], pixel_queue=bank["pixel_queue"]) if mem else {}
+            opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=ms, max_views=mv, seed=sd % 1000,
+                                      num_classes=K, normalize=norm)
+            src = data["embed_raw"] if norm else data["embed"]
+            step = cs.GraphedContrastStep(src.clone(), data["target"], seg=data["seg"], options=opts,
+                                          overlap_zero_fill=overlap, **kw)
+            for r in range(2):
+                loss, grad = step.replay()
+                meta, lv, gv = step.ws.anchor_meta.clone(), loss.clone(), grad.clone()
+                Fn._step_counter[0] = r
+                e = src.clone().requires_grad_(True)
+                l2 = cs.pixel_contrast_loss(e, data["target"], seg=data["seg"], options=opts, **kw)
+                ws = Fn.last_workspace(e.device)
+                l2.backward()
+                same_l = torch.equal(l2.detach(), lv) or (torch.isnan(l2) and torch.isnan(lv))
+                ok_g = torch.allclose(e.grad, gv, rtol=3e-6, atol=0, equal_nan=True)
+                if not (torch.equal(ws.anchor_meta, meta) and same_l and ok_g):
+                    bad.append(f"replay {r} differs from the eager step: {desc}")
+                    break
+    finally:
+        (graph_step.GraphedContrastStep._capture, graph_step.GraphedContrastStep._fork_zero_fill,
+         graph_step.GraphedContrastStep._join_zero_fill) = saved
+    return bad

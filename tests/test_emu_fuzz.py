@@ -36,3 +36,7 @@ def test_fuzz_topk(emu):
 
 def test_fuzz_tensor_path(emu):
     assert emu_fuzz.fuzz_tensor_path(seed=16, n=14) == []
+
+
+def test_fuzz_graphed_step(emu):
+    assert emu_fuzz.fuzz_graphed_step(seed=17, n=25) == []
