@@ -388,3 +388,70 @@ def fuzz_graphed_step(seed: int, n: int):
         (graph_step.GraphedContrastStep._capture, graph_step.GraphedContrastStep._fork_zero_fill,
          graph_step.GraphedContrastStep._join_zero_fill) = saved
     return bad
+
+
+def fuzz_trainer_hook(seed: int, n: int):
+    """The whole hook of trainer_contrastive.py:209-255 over several iterations with an evolving bank, reference RNG
+    stream (rng='torch_cpu', same torch seed on both sides): loss -> enqueue -> backward.  Loss, d/d seg, d/d embed and
+    the bank after every iteration against the oracle — in particular the gradient must not see the rows the enqueue
+    of the same iteration writes (the reference's autograd holds a copy of the bank; the engine holds the write back)."""
+    rng = random.Random(seed)
+    bad = []
+    names = ("segment_queue", "segment_queue_ptr", "pixel_queue", "pixel_queue_ptr")
+    for it in range(n):
+        B, D, h, w, K = rng.randint(1, 2), rng.choice([32, 64]), rng.randint(6, 20), rng.randint(6, 20), rng.randint(3, 7)
+        st, block, M, Fq = rng.choice([1, 2]), rng.choice([2, 4, 8]), rng.randint(6, 16), rng.randint(1, 5)
+        ms, mv, warm, iters, sd = rng.randint(8, 80), rng.randint(1, 6), rng.randint(0, 2), rng.randint(2, 4), rng.randint(0, 10 ** 6)
+        T, lw = rng.choice([0.07, 0.1]), 0.1
+        desc = f"hook seed={seed} it={it} B={B} D={D} {h}x{w} K={K} stride={st} M={M} F={Fq} ms={ms} mv={mv} warmup={warm} iters={iters}"
+        cfg = cs.Configer({"data": {"num_classes": K}, "network": {"stride": st},
+                           "loss": {"loss_type": "mem_contrast_ce_loss", "params": {"ce_ignore_index": -1}},
+                           "contrast": {"temperature": T, "base_temperature": 0.07, "max_samples": ms, "max_views": mv,
+                                        "loss_weight": lw, "use_rmi": False, "use_lovasz": False, "warmup_iters": warm,
+                                        "with_memory": True, "memory_size": M, "pixel_update_freq": Fq, "rng": "torch_cpu"}})
+        bank = cs.MemoryBank(K, M, D)
+        b0 = make_bank(K, M, D, sd)
+        for k in names:
+            getattr(bank, k).copy_(b0[k])
+        ref = [b0[k].clone().double() if "ptr" not in k else b0[k].clone() for k in names]
+        hook = cs.ContrastTrainerHook(cfg, bank)
+        ok = True
+        for step in range(iters):
+            data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=st, block=block, seed=sd + step)
+            with_embed = step >= warm
+            # reference side (float64), torch RNG stream seeded
+            torch.manual_seed(sd + step)
+            s64, e64 = data["seg"].double().requires_grad_(True), data["embed"].double().requires_grad_(True)
+            try:
+                lo = P.contrast_ce_loss({"seg": s64, "embed": e64, "segment_queue": ref[0], "pixel_queue": ref[2]},
+                                        data["target"], with_embed=with_embed, loss_weight=lw, temperature=T,
+                                        base_temperature=0.07, max_samples=ms, max_views=mv, with_memory=True)
+                P.dequeue_and_enqueue(data["embed"].double(), data["target"], *ref, network_stride=st, memory_size=M,
+                                      pixel_update_freq=Fq)
+                lo.backward()
+            except (RuntimeError, IndexError, ValueError):
+                ok = None                       # degenerate draw (no class qualifies, A > bank columns, ...): skip the case
+                break
+            # engine side, same stream
+            torch.manual_seed(sd + step)
+            seg, emb = data["seg"].clone().requires_grad_(True), data["embed"].clone().requires_grad_(True)
+            out = {"seg": seg, "embed": emb, "key": emb.detach(), "lb_key": data["target"]}
+            loss = hook.loss_step(out, data["target"], iters=step)
+            loss.backward()
+            if math.isnan(lo.item()):
+                if not math.isnan(loss.item()):
+                    bad.append(f"reference NaN, engine {loss.item()} at iteration {step}: {desc}")
+                ok = None
+                break
+            ge = (emb.grad.double() - e64.grad).abs().max().item() / max(e64.grad.abs().max().item(), 1e-9)
+            gs = (seg.grad.double() - s64.grad).abs().max().item() / max(s64.grad.abs().max().item(), 1e-9)
+            eb = max((bank.segment_queue.double() - ref[0]).abs().max().item(), (bank.pixel_queue.double() - ref[2]).abs().max().item())
+            ptr_ok = torch.equal(bank.segment_queue_ptr, ref[1]) and torch.equal(bank.pixel_queue_ptr, ref[3])
+            if _rel(loss.item(), lo.item()) > 5e-6 or ge > 3e-5 or gs > 3e-5 or eb > 3e-6 or not ptr_ok:
+                bad.append(f"iteration {step}: rel={_rel(loss.item(), lo.item()):.1e} d_embed={ge:.1e} d_seg={gs:.1e} bank={eb:.1e} "
+                           f"ptr_ok={ptr_ok}: {desc}")
+                ok = False
+                break
+            # fp32 bank rows drift from the float64 reference by rounding only; re-align so the drift cannot accumulate
+            ref[0], ref[2] = bank.segment_queue.double().clone(), bank.pixel_queue.double().clone()
+    return bad

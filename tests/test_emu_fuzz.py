@@ -40,3 +40,16 @@ def test_fuzz_tensor_path(emu):
 
 def test_fuzz_graphed_step(emu):
     assert emu_fuzz.fuzz_graphed_step(seed=17, n=25) == []
+
+
+def test_fuzz_trainer_hook(emu):
+    assert emu_fuzz.fuzz_trainer_hook(seed=18, n=25) == []
+
+
+def test_trainer_hook_fuzz_detects_an_early_bank_write(emu, monkeypatch):
+    """Negative control: with the bank write applied immediately (before the pending backward, the behaviour of the
+    first GPU-verified build) the embedding gradient of the hook flow deviates from the reference by tens of percent."""
+    from contrastiveseg_b200 import functional as Fn
+    monkeypatch.setattr(Fn, "bank_reader", lambda *a: None)
+    bad = emu_fuzz.fuzz_trainer_hook(seed=18, n=12)
+    assert len(bad) >= 6 and all("d_embed" in b for b in bad)
