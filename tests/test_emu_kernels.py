@@ -163,3 +163,10 @@ def test_update_freq_larger_than_memory_is_refused(emu):
     real.pcl_bank_packet.restype = C.c_int32
     g = _abi.BankGeom(1, 32, 8, 8, 8, 8, 4, 3, 1, 5)
     assert real.pcl_bank_packet(C.byref(g), None, None, None, C.c_uint64(0), None, None, None) == -4
+
+
+def test_full_size_cityscapes_batch_on_emulation(emu):
+    """BASELINE configs[1] at full size (B=8, 256 x 128 x 256 embedding, 19 classes, up to 1024 anchors) through the
+    emulated kernels: the size-independent properties of the GPU test (valid distinct anchors, loss == oracle on the same
+    anchors, dense gradient zero outside the sampled columns)."""
+    G.test_full_size_cityscapes_batch_properties()
