@@ -122,9 +122,24 @@ inline void run_block(Block& B) {
     f.state = RUNNABLE;
   }
   size_t live = n;
+  // Scheduling order between synchronisation points is unspecified on the GPU.  PCL_EMU_SCHED=reverse | random[:seed]
+  // permutes it (per pass): a result that changes with the order means a missing barrier / a data race.
+  static const int sched_mode = [] { const char* e = getenv("PCL_EMU_SCHED"); return !e ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : 2; }();
+  static uint64_t rng_state = [] { const char* e = getenv("PCL_EMU_SCHED"); const char* c = e ? strchr(e, ':') : nullptr;
+                                   return (uint64_t)(c ? atoll(c + 1) : 1) * 0x9E3779B97F4A7C15ull + 1; }();
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
   while (live) {
     bool progressed = false;
-    for (size_t i = 0; i < n; ++i) {
+    if (sched_mode == 1) { for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)(n - 1 - i); }
+    else if (sched_mode == 2) {
+      for (size_t i = n; i > 1; --i) {
+        rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
+        std::swap(order[i - 1], order[rng_state % i]);
+      }
+    }
+    for (size_t oi = 0; oi < n; ++oi) {
+      const size_t i = order[oi];
       Fiber& f = B.fibers[i];
       if (f.state != RUNNABLE) continue;
       B.cur = &f;

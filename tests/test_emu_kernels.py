@@ -170,3 +170,19 @@ def test_full_size_cityscapes_batch_on_emulation(emu):
     emulated kernels: the size-independent properties of the GPU test (valid distinct anchors, loss == oracle on the same
     anchors, dense gradient zero outside the sampled columns)."""
     G.test_full_size_cityscapes_batch_properties()
+
+
+def test_results_do_not_depend_on_the_thread_schedule():
+    """Between synchronisation points the GPU may run the threads of a block in any order; the emulator's default is
+    ascending.  Re-run a cross-section of the emulated cases (SIMT sweeps, selection, bank, top-k, the tcgen05 pipelines,
+    the bit-exact graph/eager comparison) with a randomly permuted order: a failure here means a missing barrier."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PCL_EMU_SCHED="random:20260923")
+    sel = ("loss_and_grad_match_reference and mem_small or bank_enqueue_matches_reference or topk_explicit_exact_data and 333 "
+           "or tc_backward_matches_oracle and 1000 or graphed_step_sequence_on_emulation or fused_upsample and 19")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", sel], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
