@@ -205,12 +205,22 @@ inline void launch(const Cfg& c, std::function<void()> body) {
   }
   Block* saved = g_blk;
   g_blk = &B;
-  for (unsigned z = 0; z < c.g.z; ++z)
-    for (unsigned y = 0; y < c.g.y; ++y)
-      for (unsigned x = 0; x < c.g.x; ++x) {
-        B.bid = uint3{x, y, z};
-        run_block(B);
-      }
+  // blocks of a grid run one after another; with PCL_EMU_SCHED set their order is reversed / shuffled as well (no kernel
+  // may depend on the order in which its blocks are scheduled)
+  const size_t nb = (size_t)c.g.x * c.g.y * c.g.z;
+  std::vector<size_t> border(nb);
+  for (size_t i = 0; i < nb; ++i) border[i] = i;
+  const char* sched = getenv("PCL_EMU_SCHED");
+  if (sched && sched[0] == 'r' && sched[1] == 'e') { for (size_t i = 0; i < nb; ++i) border[i] = nb - 1 - i; }
+  else if (sched) {
+    uint64_t st = 0x9E3779B97F4A7C15ull * (nb + 1) + (uint64_t)c.b.x;
+    for (size_t i = nb; i > 1; --i) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; std::swap(border[i - 1], border[st % i]); }
+  }
+  for (size_t bi = 0; bi < nb; ++bi) {
+    const size_t lin = border[bi];
+    B.bid = uint3{(unsigned)(lin % c.g.x), (unsigned)((lin / c.g.x) % c.g.y), (unsigned)(lin / ((size_t)c.g.x * c.g.y))};
+    run_block(B);
+  }
   g_blk = saved;
 }
 
