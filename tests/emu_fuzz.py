@@ -455,3 +455,63 @@ def fuzz_trainer_hook(seed: int, n: int):
             # fp32 bank rows drift from the float64 reference by rounding only; re-align so the drift cannot accumulate
             ref[0], ref[2] = bank.segment_queue.double().clone(), bank.pixel_queue.double().clone()
     return bad
+
+
+def fuzz_wrappers(seed: int, n: int):
+    """ContrastCELoss / MemContrastCELoss end to end (fused up-sample + CE kernels for the seg half, pixel contrast on the
+    reference RNG stream), warm-up and post-warm-up, optional class weights: loss, d/d seg, d/d embed vs the oracle."""
+    from contrastiveseg_b200 import loss as loss_mod
+    rng = random.Random(seed)
+    bad = []
+    saved = loss_mod.ContrastCELoss._can_fuse
+    loss_mod.ContrastCELoss._can_fuse = lambda self, ce, s: self.fused_seg_ce and ce.ce_loss.reduction == "mean"
+    try:
+        for it in range(n):
+            B, D, h, w, K = rng.randint(1, 2), rng.choice([32, 64]), rng.randint(5, 18), rng.randint(5, 18), rng.randint(2, 8)
+            mem, with_embed, weighted = rng.random() < 0.5, rng.random() < 0.7, rng.random() < 0.4
+            ms, mv, M, sd = rng.randint(8, 90), rng.randint(1, 8), rng.randint(4, 14), rng.randint(0, 10 ** 6)
+            if rng.random() < 0.5:
+                st = rng.choice([2, 4])
+                himg, wimg = h * st, w * st
+            else:
+                himg, wimg = rng.randint(h, 3 * h + 2), rng.randint(w, 3 * w + 2)
+            T, lw = rng.choice([0.07, 0.1]), rng.choice([0.1, 1.0])
+            desc = (f"wrapper seed={seed} it={it} B={B} D={D} {h}x{w}->{himg}x{wimg} K={K} mem={mem} with_embed={with_embed} "
+                    f"weighted={weighted} ms={ms} mv={mv}")
+            data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=1, block=rng.choice([2, 4, 8]), seed=sd,
+                                       himg=himg, wimg=wimg)
+            bank = make_bank(K, M, D, sd + 1)
+            g = torch.Generator().manual_seed(sd)
+            cew = (torch.rand(K, generator=g) + 0.5) if weighted else None
+            params = {"ce_ignore_index": -1, "ce_reduction": "elementwise_mean"}
+            if weighted:
+                params["ce_weight"] = cew.tolist()
+            cfg = cs.Configer({"data": {"num_classes": K}, "network": {"stride": 8}, "loss": {"params": params},
+                               "contrast": {"temperature": T, "base_temperature": 0.07, "max_samples": ms, "max_views": mv,
+                                            "loss_weight": lw, "use_rmi": False, "use_lovasz": False, "rng": "torch_cpu"}})
+            crit = (cs.MemContrastCELoss if mem else cs.ContrastCELoss)(cfg)
+            extra = {"segment_queue": bank["segment_queue"], "pixel_queue": bank["pixel_queue"]} if mem else {}
+            torch.manual_seed(sd)
+            s64, e64 = data["seg"].double().requires_grad_(True), data["embed"].double().requires_grad_(True)
+            try:
+                lo = P.contrast_ce_loss(dict({"seg": s64, "embed": e64}, **{k: v.double() for k, v in extra.items()}),
+                                        data["target"], with_embed=with_embed, loss_weight=lw, temperature=T, base_temperature=0.07,
+                                        max_samples=ms, max_views=mv, with_memory=mem, ce_weight=cew.double() if weighted else None)
+                lo.backward()
+            except (RuntimeError, IndexError, ValueError):
+                continue
+            torch.manual_seed(sd)
+            seg, emb = data["seg"].clone().requires_grad_(True), data["embed"].clone().requires_grad_(True)
+            loss = crit(dict({"seg": seg, "embed": emb}, **extra), data["target"], with_embed=with_embed)
+            loss.backward()
+            if math.isnan(lo.item()):
+                if not math.isnan(loss.item()):
+                    bad.append(f"reference NaN, engine {loss.item()}: {desc}")
+                continue
+            ge = (emb.grad.double() - e64.grad).abs().max().item() / max(e64.grad.abs().max().item(), 1e-9)
+            gs = (seg.grad.double() - s64.grad).abs().max().item() / max(s64.grad.abs().max().item(), 1e-9)
+            if _rel(loss.item(), lo.item()) > 5e-6 or ge > 3e-5 or gs > 3e-5:
+                bad.append(f"mismatch rel={_rel(loss.item(), lo.item()):.1e} d_embed={ge:.1e} d_seg={gs:.1e}: {desc}")
+    finally:
+        loss_mod.ContrastCELoss._can_fuse = saved
+    return bad

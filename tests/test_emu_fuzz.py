@@ -53,3 +53,7 @@ def test_trainer_hook_fuzz_detects_an_early_bank_write(emu, monkeypatch):
     monkeypatch.setattr(Fn, "bank_reader", lambda *a: None)
     bad = emu_fuzz.fuzz_trainer_hook(seed=18, n=12)
     assert len(bad) >= 6 and all("d_embed" in b for b in bad)
+
+
+def test_fuzz_loss_wrappers(emu):
+    assert emu_fuzz.fuzz_wrappers(seed=19, n=40) == []

@@ -28,7 +28,8 @@ if __name__ == "__main__":
                          ("devrng", lambda s: emu_fuzz.fuzz_device_sampling(s, n, G._check_device_sampling)),
                          ("tensor", lambda s: emu_fuzz.fuzz_tensor_path(s, max(1, n // 5))),
                          ("graph", lambda s: emu_fuzz.fuzz_graphed_step(s, max(1, n // 2))),
-                         ("hook", lambda s: emu_fuzz.fuzz_trainer_hook(s, max(1, n // 2)))):
+                         ("hook", lambda s: emu_fuzz.fuzz_trainer_hook(s, max(1, n // 2))),
+                         ("wrappers", lambda s: emu_fuzz.fuzz_wrappers(s, n))):
             bad = fn(1000 * r + 7)
             total += len(bad)
             print(f"round {r} {name}: {n} cases, {len(bad)} failures", flush=True)
