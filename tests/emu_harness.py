@@ -54,6 +54,22 @@ def use_emulation(monkeypatch):
         self.ranks_host = torch.zeros_like(self.ranks)          # pinned staging buffer on a CUDA box
 
     monkeypatch.setattr(Fn.ContrastWorkspace, "__init__", init)
+    if os.environ.get("PCL_EMU_POISON"):
+        # uninitialised-read check: every torch.empty / empty_like buffer (scratch AND outputs) starts as NaN / a large
+        # integer instead of whatever the allocator returns; a kernel that reads scratch it never wrote poisons its result
+        real_empty, real_empty_like = torch.empty, torch.empty_like
+
+        def _poison(t):
+            if t.numel():
+                with torch.no_grad():
+                    if t.dtype.is_floating_point:
+                        t.fill_(float("nan"))
+                    elif t.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+                        t.fill_(torch.iinfo(t.dtype).max - 7)
+            return t
+
+        monkeypatch.setattr(torch, "empty", lambda *a, **k: _poison(real_empty(*a, **k)))
+        monkeypatch.setattr(torch, "empty_like", lambda *a, **k: _poison(real_empty_like(*a, **k)))
     Fn.clear_workspaces()
     Fn._BANK_READERS.clear()
     return lib
