@@ -340,7 +340,9 @@ def fuzz_tensor_path(seed: int, n: int):
         gmax = cf["dA"].abs().max().item()
         gabs = (dA - cf["dA"]).abs().max().item() / max(gmax, 1e-9)
         gfro = ((dA - cf["dA"]).norm() / max(cf["dA"].norm().item(), 1e-9)).item()
-        if _rel(loss.item(), lo) > 5e-5 or gabs > 6e-3 or gfro > 3e-3:
+        # (a loss that is exactly 0 in real arithmetic — a single class, no negatives — comes out as ~1e-8 of ex2/lg2
+        # approximation noise on the tensor path: absolute floor next to the relative bound)
+        if abs(loss.item() - lo) > 5e-5 * abs(lo) + 1e-6 or gabs > 6e-3 or gfro > 3e-3:
             bad.append(f"mismatch rel={_rel(loss.item(), lo):.2e} gabs={gabs:.2e} gfro={gfro:.2e}: {desc}")
     return bad
 
