@@ -43,7 +43,7 @@ def test_fuzz_graphed_step(emu):
 
 
 def test_fuzz_trainer_hook(emu):
-    assert emu_fuzz.fuzz_trainer_hook(seed=18, n=14) == []
+    assert emu_fuzz.fuzz_trainer_hook(seed=18, n=10) == []
 
 
 def test_trainer_hook_fuzz_detects_an_early_bank_write(emu, monkeypatch):

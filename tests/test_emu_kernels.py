@@ -88,11 +88,9 @@ TENSOR = (
     [_case(G.test_tc_pipeline_raw_logits, A=a, N=n) for a, n in ((128, 256), (200, 1000))] +
     [_case(G.test_tc_forward_matches_oracle, A=a, N=n, T=t, self_mode=sm) for a, n, t, sm in ((200, 1000, 0.1, False),
                                                                                           (912, 912, 0.1, True))] +
-    [_case(G.test_tc_backward_matches_oracle, A=a, N=n, T=t, self_mode=sm) for a, n, t, sm in ((200, 1000, 0.1, False),
-                                                                                           (912, 912, 0.1, True))] +
+    [_case(G.test_tc_backward_matches_oracle, A=200, N=1000, T=0.1, self_mode=False)] +      # self mode: fuzz_tensor_path
     [_case(G.test_loss_module_on_tensor_path, name=n) for n in ("nomem_d256", "mem_d256")] +
     [_case(G.test_bank_shadow_tracks_enqueue_and_tensor_path_uses_it),
-     _case(G.test_coco_stuff_shape_171_classes_with_bank, precision="bf16"),
      _case(PD.test_enqueue_between_loss_and_backward_does_not_change_the_gradient, precision="bf16")]
 )
 
@@ -113,10 +111,6 @@ def test_graphed_step_tensor_path_on_emulation(emu, monkeypatch, mem, overlap):
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_graphed_step_equals_eager_step("bf16", mem, overlap)
-
-
-def test_topk_normalised_embeddings_on_emulation(emu):
-    TK.test_topk_normalised_embeddings_loss()
 
 
 def test_bank_write_waits_for_backward_on_emulation(emu):
@@ -180,8 +174,8 @@ def test_results_do_not_depend_on_the_thread_schedule():
     import subprocess
     import sys
     env = dict(os.environ, PCL_EMU_SCHED="random:20260923")
-    sel = ("loss_and_grad_match_reference and mem_small or bank_enqueue_matches_reference or topk_explicit_exact_data and 333 "
-           "or tc_backward_matches_oracle and 1000 or graphed_step_sequence_on_emulation or fused_upsample and 19")
+    sel = ("loss_and_grad_match_reference and mem_small or bank_enqueue_matches_reference and q6 or topk_explicit_exact_data and 333 "
+           "or tc_backward_matches_oracle or graphed_step_sequence_on_emulation and True or fused_upsample and 19")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
                         "-k", sel], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
