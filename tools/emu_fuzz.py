@@ -1,6 +1,6 @@
 """Long-running differential fuzz of the SIMT kernel sources on the CPU emulator (see tests/emu_fuzz.py).
 
-    python tools/emu_fuzz.py [rounds=5] [iterations per fuzzer and round=200]
+    python tools/emu_fuzz.py [rounds=5] [iterations per fuzzer and round=200] [seed offset=7]
 """
 import os
 import sys
@@ -18,6 +18,7 @@ import test_gpu_parity as G  # noqa: E402
 if __name__ == "__main__":
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    base = int(sys.argv[3]) if len(sys.argv) > 3 else 7
     mp = pytest.MonkeyPatch()
     mp.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     emu_harness.use_emulation(mp)
@@ -30,9 +31,9 @@ if __name__ == "__main__":
                          ("graph", lambda s: emu_fuzz.fuzz_graphed_step(s, max(1, n // 2))),
                          ("hook", lambda s: emu_fuzz.fuzz_trainer_hook(s, max(1, n // 2))),
                          ("wrappers", lambda s: emu_fuzz.fuzz_wrappers(s, n))):
-            bad = fn(1000 * r + 7)
+            bad = fn(1000 * r + base)
             total += len(bad)
-            print(f"round {r} {name}: {n} cases, {len(bad)} failures", flush=True)
+            print(f"round {r} {name}: {len(bad)} failures", flush=True)
             for b in bad[:10]:
                 print("   ", b)
     sys.exit(1 if total else 0)
