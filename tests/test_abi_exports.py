@@ -69,3 +69,13 @@ def test_product_never_imports_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/pcl.h must compile as C99 with nothing but the standard headers."""
+    import subprocess
+    src = tmp_path / "chk.c"
+    src.write_text('#include "pcl.h"\nint main(void) { pcl_geom g; (void)g; return pcl_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I",
+                        os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
