@@ -592,7 +592,7 @@ def run_engine(args, cfg, bank, rank, world, dev):
         launches_per_step += 1                       # + the device-side rank draw (pcl_step_ranks); one graph launch per step
     return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic", "config": workload_config(cfg, bank), "clocks": dict(sampler.summary(), window=clock_window),
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e_steps},
@@ -609,6 +609,9 @@ def main():
     ap.add_argument("--workload", default="s1", choices=["s1", "s2", "s3"],
                     help="s1 = BASELINE configs[1] (headline), s2 = configs[2] (memory bank), s3 = configs[3] (171 classes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): the workload's batch per GPU; strong: the workload's batch split over the ranks "
+                         "(global batch fixed, as lib/datasets/data_loader.py:137 does), SURVEY §8d asks for both")
     ap.add_argument("--graph", action="store_true",
                     help="run the step as one CUDA-graph replay (GraphedContrastStep) instead of the eager autograd call")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
@@ -619,6 +622,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict({"s1": S1, "s2": S2, "s3": S3}[args.workload])
     bank = args.workload in ("s2", "s3")
+    if args.scaling == "strong":
+        if cfg["B"] % world != 0:
+            raise SystemExit(f"--scaling strong: global batch {cfg['B']} is not divisible by {world} ranks")
+        cfg["B"] //= world
     if os.environ.get("PCL_BENCH_TINY"):            # contract tests on small hosts: same code path, toy geometry
         cfg.update(B=2, D=32, h=16, w=16, K=5, stride=2, block=8, max_samples=32, max_views=4)
         if bank:
