@@ -120,3 +120,71 @@ def test_emulated_enqueue_kernels_merge_across_two_ranks(tmp_path):
     b0, b1 = torch.load(tmp_path / "e0.pt"), torch.load(tmp_path / "e1.pt")
     for x, y in zip(b0, b1):
         assert torch.equal(x, y)                    # bit-identical banks on both ranks
+
+
+def _ddp_hook_worker(rank, world, port, out_dir):
+    """C3-style plumbing on CPU: a tiny DDP-wrapped producer ({'seg','embed','key','lb_key'} contract), the drop-in hook
+    (MemContrastCELoss + bank enqueue) on the emulated kernels, SGD.  Two warm-up iterations (contrast weighted 0 but the
+    projection head stays in the graph, loss_contrast.py:189) and two contrast iterations."""
+    import pytest
+    import torch.nn as nn
+    import emu_harness
+    import contrastiveseg_b200 as cs
+    from contrastiveseg_b200.synth import make_contrast_batch
+    emu_harness.use_emulation(pytest.MonkeyPatch())
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, D = 5, 32
+
+    class TinyNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = nn.Sequential(nn.Conv2d(3, 8, 3, stride=2, padding=1), nn.ReLU())
+            self.cls = nn.Conv2d(8, K, 1)
+            self.proj = cs.ProjectionHead(8, D, proj="convmlp", bn_type="torchbn")
+
+        def forward(self, x, targets):
+            f = self.body(x)
+            emb = self.proj(f)
+            return {"seg": self.cls(f), "embed": emb, "key": emb.detach(), "lb_key": targets}
+
+    torch.manual_seed(0)                                   # identical initial weights on both ranks
+    net = nn.parallel.DistributedDataParallel(TinyNet(), find_unused_parameters=True, broadcast_buffers=False)
+    cfg = cs.Configer({"data": {"num_classes": K}, "network": {"stride": 2},
+                       "loss": {"loss_type": "mem_contrast_ce_loss", "params": {"ce_ignore_index": -1}},
+                       "contrast": {"temperature": 0.1, "base_temperature": 0.07, "max_samples": 48, "max_views": 4,
+                                    "loss_weight": 0.1, "use_rmi": False, "use_lovasz": False, "warmup_iters": 2,
+                                    "with_memory": True, "memory_size": 12, "pixel_update_freq": 3}})
+    torch.manual_seed(1)
+    bank = cs.MemoryBank(K, 12, D)                         # same initial bank on both ranks
+    hook = cs.ContrastTrainerHook(cfg, bank)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05)
+    losses = []
+    for it in range(4):
+        data = make_contrast_batch(B=2, D=D, h=12, w=12, num_classes=K, img_stride=2, block=4, seed=50 * it + rank)
+        x = torch.randn(2, 3, 24, 24, generator=torch.Generator().manual_seed(7 * it + rank))
+        out = net(x, data["target"])
+        loss = hook.loss_step(out, data["target"], iters=it)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(l == l and abs(l) < 1e4 for l in losses)
+    proj_w = net.module.proj.proj[0].weight
+    assert proj_w.grad is not None                          # the head received a (possibly zero-weighted) gradient
+    state = {"params": [p.detach().clone() for p in net.parameters()],
+             "bank": [b.clone() for b in (bank.segment_queue, bank.segment_queue_ptr, bank.pixel_queue, bank.pixel_queue_ptr)]}
+    torch.save(state, os.path.join(out_dir, f"d{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_training_iterations_with_the_hook_on_two_ranks(tmp_path):
+    port = _free_port()
+    mp.spawn(_ddp_hook_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    s0, s1 = torch.load(tmp_path / "d0.pt"), torch.load(tmp_path / "d1.pt")
+    for a, b in zip(s0["params"], s1["params"]):
+        assert torch.equal(a, b)                            # DDP kept the replicas in step through the custom backward
+    for a, b in zip(s0["bank"], s1["bank"]):
+        assert torch.equal(a, b)                            # one all_gather per step kept the banks identical
+    assert not torch.equal(s0["bank"][3], torch.zeros_like(s0["bank"][3]))     # and the bank advanced
