@@ -180,3 +180,29 @@ def test_results_do_not_depend_on_the_thread_schedule():
                         "-k", sel], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_baseline_config0_geometry_on_emulation(emu, monkeypatch):
+    """BASELINE configs[0] (the CPU plumbing case): bs 2, 256 x 256 input, stride 8 -> 32 x 32 x 256 embedding, 19 classes,
+    the reference's default sampling limits — the whole ContrastCELoss (fused seg CE + pixel contrast) on the emulated
+    kernels against the oracle on the reference's RNG stream."""
+    from contrastiveseg_b200 import loss as loss_mod
+    from contrastiveseg_b200.synth import make_contrast_batch
+    monkeypatch.setattr(loss_mod.ContrastCELoss, "_can_fuse", lambda self, ce, s: self.fused_seg_ce)
+    data = make_contrast_batch(B=2, D=256, h=32, w=32, num_classes=19, img_stride=8, block=96, seed=304)
+    cfgd = cs.cityscapes_contrast_config()
+    cfgd["contrast"]["rng"] = "torch_cpu"
+    crit = cs.ContrastCELoss(cs.Configer(cfgd))
+    torch.manual_seed(304)
+    s64, e64 = data["seg"].double().requires_grad_(True), data["embed"].double().requires_grad_(True)
+    ref = G.P.contrast_ce_loss({"seg": s64, "embed": e64}, data["target"], with_embed=True, loss_weight=0.1, temperature=0.1,
+                               base_temperature=0.07, max_samples=1024, max_views=100)
+    ref.backward()
+    torch.manual_seed(304)
+    seg, emb = data["seg"].clone().requires_grad_(True), data["embed"].clone().requires_grad_(True)
+    loss = crit({"seg": seg, "embed": emb}, data["target"], with_embed=True)
+    loss.backward()
+    assert G.rel_err(loss.item(), ref.item()) < 2e-6
+    assert (emb.grad.double() - e64.grad).abs().max().item() <= 1e-5 * e64.grad.abs().max().item()
+    assert (seg.grad.double() - s64.grad).abs().max().item() <= 1e-5 * s64.grad.abs().max().item()
+    assert emb.grad.abs().max().item() > 0
