@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <vector>
 
@@ -86,6 +87,8 @@ struct Block {
   void* dyn = nullptr;
   size_t dyn_bytes = 0;
   std::vector<float> tmem;           // tensor memory of the block: 128 lanes x 512 columns (tcgen05 model, ptx_sm100.cuh)
+  struct AsyncOp { int engine; std::function<void()> run; };   // engine 0 = TMA (may complete out of order), 1 = tensor pipe (in order)
+  std::deque<AsyncOp> async_q;       // issued-but-not-yet-executed asynchronous operations
   std::function<void()> body;
 };
 inline Block* g_blk = nullptr;
@@ -146,6 +149,36 @@ inline void run_block(Block& B) {
       swapcontext(&B.sched, &f.ctx);
       progressed = true;
       if (f.state == DONE) --live;
+    }
+    // asynchronous engines (TMA / tensor core model): what was issued during this pass executes now, in issue order —
+    // i.e. strictly AFTER the issuing thread moved on, so a consumer that does not wait on the mbarrier reads stale data
+    // and a producer that refills a stage before its MMAs were committed corrupts their operands (both are caught by
+    // the parity checks).  PCL_EMU_ASYNC_DELAY=k executes only every k-th pass (longer in-flight windows).
+    if (!B.async_q.empty()) {
+      static const int delay = [] { const char* e = getenv("PCL_EMU_ASYNC_DELAY"); int d = e ? atoi(e) : 1; return d < 1 ? 1 : d; }();
+      static thread_local unsigned pass_no = 0;
+      if (++pass_no % delay == 0 || !progressed) {
+        if (sched_mode == 2) {
+          // random mode: the tensor pipe retires everything in order; every pending TMA copy completes with probability
+          // 1/2, in random order (bulk copies are independent of each other) — at least one operation per drain
+          std::deque<Block::AsyncOp> keep;
+          std::vector<Block::AsyncOp> tma;
+          size_t ran = 0;
+          while (!B.async_q.empty()) {
+            Block::AsyncOp op = std::move(B.async_q.front()); B.async_q.pop_front();
+            if (op.engine == 1) { op.run(); ++ran; } else tma.push_back(std::move(op));
+          }
+          for (size_t i = tma.size(); i > 1; --i) { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; std::swap(tma[i - 1], tma[rng_state % i]); }
+          for (auto& op : tma) {
+            rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
+            if ((rng_state & 1) || (ran == 0 && !progressed)) { op.run(); ++ran; } else keep.push_back(std::move(op));
+          }
+          B.async_q = std::move(keep);
+        } else {
+          while (!B.async_q.empty()) { Block::AsyncOp op = std::move(B.async_q.front()); B.async_q.pop_front(); op.run(); }
+        }
+        progressed = true;
+      }
     }
     // __syncthreads: released when every thread that has not exited waits at it
     bool any = false, all = true;

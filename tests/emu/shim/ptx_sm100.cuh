@@ -78,20 +78,27 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- TMA ----
 struct TmapModel { const uint8_t* base; uint64_t rows; uint64_t row_bytes; uint32_t box_cols; uint32_t box_rows; uint32_t magic; };
 inline void prefetch_tmap(const CUtensorMap*) {}
+inline bool async_eager() { static const bool e = [] { const char* v = getenv("PCL_EMU_ASYNC"); return v && v[0] == 'e'; }(); return e; }
+template <class F> inline void issue_async(int engine, F&& op) {     // engine 0 = TMA, 1 = tensor pipe
+  if (async_eager()) op();                                   // PCL_EMU_ASYNC=eager: complete at issue time
+  else emu::g_blk->async_q.push_back(emu::Block::AsyncOp{engine, std::function<void()>(std::forward<F>(op))});
+}
 inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
-  const TmapModel& t = *reinterpret_cast<const TmapModel*>(m);
+  const TmapModel t = *reinterpret_cast<const TmapModel*>(m);
   if (t.magic != 0x7A3Du || t.box_cols * 2 != 128) { fprintf(stderr, "emu: bad tensor map\n"); abort(); }
   if (((uintptr_t)smem_dst & 1023) != 0) { fprintf(stderr, "emu: TMA destination not 1024-byte aligned\n"); abort(); }
   uint8_t* dst = (uint8_t*)smem_dst;
-  for (uint32_t r = 0; r < t.box_rows; ++r) {
-    const int64_t row = (int64_t)c1 + r;
-    for (uint32_t c = 0; c < 8; ++c) {
-      uint8_t* d = dst + (size_t)r * 128 + ((c ^ (r & 7u)) * 16);
-      if (row >= 0 && (uint64_t)row < t.rows) memcpy(d, t.base + (size_t)row * t.row_bytes + ((size_t)c0 + c * 8) * 2, 16);
-      else memset(d, 0, 16);
+  issue_async(0, [=]() {
+    for (uint32_t r = 0; r < t.box_rows; ++r) {
+      const int64_t row = (int64_t)c1 + r;
+      for (uint32_t c = 0; c < 8; ++c) {
+        uint8_t* d = dst + (size_t)r * 128 + ((c ^ (r & 7u)) * 16);
+        if (row >= 0 && (uint64_t)row < t.rows) memcpy(d, t.base + (size_t)row * t.row_bytes + ((size_t)c0 + c * 8) * 2, 16);
+        else memset(d, 0, 16);
+      }
     }
-  }
-  mbar_complete_tx(bar, t.box_rows * 128);
+    mbar_complete_tx(bar, t.box_rows * 128);
+  });
 }
 
 // ---- tcgen05 ----
@@ -119,7 +126,11 @@ inline float operand(uint64_t desc, bool mn_major, uint32_t idx, uint32_t k) {
   memcpy(&h, smem_ptr(P), 2);
   return __bfloat162float(h);
 }
+inline void mma_execute(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate);
 inline void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  issue_async(1, [=]() { mma_execute(tmem_d, desc_a, desc_b, idesc, accumulate); });   // operands are read at execution time
+}
+inline void mma_execute(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   const uint32_t M = ((idesc >> 24) & 0x1F) << 4, N = ((idesc >> 17) & 0x3F) << 3;
   const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
   const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xFFFF;
@@ -135,7 +146,7 @@ inline void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32
       tmem_at(lane0 + m, col0 + n) = acc;
     }
 }
-inline void mma_commit(uint64_t* bar) { mbar_arrive(bar); }       // the model executes every MMA at issue time
+inline void mma_commit(uint64_t* bar) { issue_async(1, [=]() { mbar_arrive(bar); }); }   // arrives after every MMA issued before it
 inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   const uint32_t lane = (taddr >> 16) + emu::lane_id(), col = taddr & 0xFFFF;
   for (uint32_t j = 0; j < 32; ++j) r[j] = __float_as_uint(tmem_at(lane, col + j));
