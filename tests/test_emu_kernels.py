@@ -1,6 +1,6 @@
 """CPU execution of the engine's REAL kernel sources (tests/emu: the .cu files compiled for host fibers; the tensor path
 against a functional model of mbarrier / TMA / tcgen05): the GPU tests of test_gpu_parity.py / test_gpu_topk.py /
-test_gpu_pending.py are re-run here with DEV = "cpu", through the same Python layer and the same C ABI (all but the
+test_gpu_zpending.py are re-run here with DEV = "cpu", through the same Python layer and the same C ABI (all but the
 full-size ones).  This covers the kernel logic (indices,
 barriers, reductions, selection, sampling, bank update, top-k select, graph rank draw) on machines without a GPU; it
 proves nothing about the hardware build (that is what `-m gpu` is for) and floating point differs from the GPU in the
@@ -12,7 +12,7 @@ import torch
 import contrastiveseg_b200 as cs
 import emu_harness
 import test_gpu_parity as G
-import test_gpu_pending as PD
+import test_gpu_zpending as PD
 import test_gpu_topk as TK
 
 

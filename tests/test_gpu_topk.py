@@ -2,9 +2,8 @@
 sort-based definition.  a10 is not in the reference code, default off and excluded from the reference parity bar
 (SURVEY §8 a10); these tests pin the kernels to the oracle semantics.
 
-STATUS: written when the round's GPU budget was already spent — the kernels compile for sm_100a and the streamed
-select is verified step by step on CPU (tests/test_topk_logic.py), but this file has not run on hardware yet.
-It is therefore opt-in (PCL_TEST_EXPERIMENTAL=1) so that the verified `-m gpu` suite stays a clean signal."""
+STATUS: written when the round's GPU budget was already spent — the kernels compile for sm_100a and pass these very
+tests on the CPU emulator (tests/test_emu_kernels.py), but the file has not run on hardware yet: see `pytestmark`."""
 import os
 
 import numpy as np
@@ -16,9 +15,12 @@ from contrastiveseg_b200 import functional as Fn
 from oracle import ref_port as P
 from helpers import load_golden, unpack_perms, rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("PCL_TEST_EXPERIMENTAL"),
-                                 reason="a10 top-k kernels not yet run on hardware: set PCL_TEST_EXPERIMENTAL=1")]
+# Not yet run on hardware when committed (the kernels and the host logic pass on the CPU emulator of tests/emu).  Until
+# they have passed once on a B200 (then: PCL_TEST_EXPERIMENTAL=1 makes them strict) a failure is reported as "xfailed"
+# and a success as "xpassed" — the verified `-m gpu` suite stays a clean signal either way; the timeout bounds a surprise.
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(condition=not os.environ.get("PCL_TEST_EXPERIMENTAL"), strict=False,
+                                reason="first hardware run pending (passes on the CPU emulator, tests/test_emu_kernels.py)")]
 DEV = "cuda:0"
 
 

@@ -1,6 +1,7 @@
-"""GPU tests of features written after the round-1 GPU budget was spent (opt-in: PCL_TEST_EXPERIMENTAL=1, see
-tools/gpu_round2_first.sh).  Their host-side logic is covered on CPU by tests/test_host_wiring.py; what is left to
-confirm on hardware is listed per test.  Once they have passed on a B200 they move into test_gpu_parity.py."""
+"""GPU tests of features written after the round-1 GPU budget was spent (the file sorts last among the GPU tests on
+purpose: it contains the CUDA-graph capture).  They pass on the CPU emulator (tests/test_emu_kernels.py) and the host
+logic is covered by tests/test_host_wiring.py; what is left to confirm on hardware is listed per test.  Once they have
+passed on a B200 they move into test_gpu_parity.py.  See `pytestmark` for how they are reported until then."""
 import os
 
 import pytest
@@ -10,9 +11,12 @@ import contrastiveseg_b200 as cs
 from contrastiveseg_b200 import functional as Fn
 from contrastiveseg_b200.synth import make_bank, make_contrast_batch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("PCL_TEST_EXPERIMENTAL"),
-                                 reason="not yet run on hardware: set PCL_TEST_EXPERIMENTAL=1")]
+# Not yet run on hardware when committed (the kernels and the host logic pass on the CPU emulator of tests/emu).  Until
+# they have passed once on a B200 (then: PCL_TEST_EXPERIMENTAL=1 makes them strict) a failure is reported as "xfailed"
+# and a success as "xpassed" — the verified `-m gpu` suite stays a clean signal either way; the timeout bounds a surprise.
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(condition=not os.environ.get("PCL_TEST_EXPERIMENTAL"), strict=False,
+                                reason="first hardware run pending (passes on the CPU emulator, tests/test_emu_kernels.py)")]
 DEV = "cuda:0"
 
 

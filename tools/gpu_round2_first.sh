@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 timeout 300 python -m contrastiveseg_b200.build > gpurun_out/build.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-PCL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_topk.py tests/test_gpu_pending.py -m gpu -q > gpurun_out/pytest_topk.log 2>&1
+PCL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_topk.py tests/test_gpu_zpending.py -m gpu -q > gpurun_out/pytest_topk.log 2>&1
 echo "experimental exit $?" >> gpurun_out/pytest_topk.log
 PCL_TEST_EXPERIMENTAL=1 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 \
   --print-limit 30 python -m pytest tests/test_gpu_topk.py -m gpu -q -x -k "exact_data or zero_tail" \
@@ -15,7 +15,7 @@ PCL_TEST_EXPERIMENTAL=1 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-san
 # the CPU emulator executes blocks sequentially: shared-memory races and barrier divergence of the NEW kernels can only
 # show up on the hardware -> racecheck + synccheck over the top-k / rank-draw / scatter-only paths (small shapes)
 PCL_TEST_EXPERIMENTAL=1 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 \
-  --print-limit 20 python -m pytest tests/test_gpu_topk.py tests/test_gpu_pending.py -m gpu -q -x -k "exact_data or zero_tail or fp32" \
+  --print-limit 20 python -m pytest tests/test_gpu_topk.py tests/test_gpu_zpending.py -m gpu -q -x -k "exact_data or zero_tail or fp32" \
   > gpurun_out/racecheck_new.log 2>&1; echo "racecheck exit $?" >> gpurun_out/racecheck_new.log
 PCL_TEST_EXPERIMENTAL=1 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool synccheck --error-exitcode 7 \
   --print-limit 20 python -m pytest tests/test_gpu_topk.py -m gpu -q -x -k "exact_data" \
