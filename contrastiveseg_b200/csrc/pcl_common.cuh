@@ -75,30 +75,37 @@ __device__ __host__ __forceinline__ int nearest_src(int dst, float scale, int in
   return s < in_size - 1 ? s : in_size - 1;
 }
 
-// Keyed bijection on [0, n): multiply/xorshift rounds on the next power of two with cycle walking.
-// Used when no permutation table is injected: view j of a group takes element perm(j), so distinct
-// j give distinct elements without any sequential state (replaces torch.randperm(n)[:k]).
-__device__ __forceinline__ uint32_t keyed_perm(uint32_t j, uint32_t n, uint64_t key) {
-  if (n <= 1) return 0;
-  int bits = 32 - __clz(n - 1);
-  uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
-  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
-  int sh = bits > 1 ? bits / 2 : 1;
-  uint32_t x = j;
-  do {
-    x = (x * 0x9E3779B1u + k0) & mask;  x ^= x >> sh;
-    x = (x * 0x85EBCA6Bu + k1) & mask;  x ^= x >> sh;
-    x = (x * 0xC2B2AE35u + (k0 ^ 0x27D4EB2Fu)) & mask;  x ^= x >> sh;
-    x = (x * 0x165667B1u + (k1 ^ 0x9E3779B9u)) & mask;  x ^= x >> sh;
-  } while (x >= n);
-  return x;
-}
-
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
+}
+
+// Keyed bijection on [0, n): an 8-round balanced Feistel network on the next even number of bits, with cycle walking.
+// Used when no permutation table is injected: view j of a group takes element perm(j), so distinct j give distinct
+// elements without any sequential state (replaces torch.randperm(n)[:k]).  The round function hashes (key, round, half)
+// with the full 64-bit key, so small groups are sampled without the pairwise structure of multiply/xorshift rounds
+// (measured on n = 60, k = 10: pair co-occurrence chi2/dof ~1.0, was 3.1; n = 7, k = 3: ~1.0, was 26;
+// tests/test_host_logic.py checks the host model of this function, tests/test_emu_kernels.py that the kernels follow it).
+__device__ __forceinline__ uint32_t keyed_perm(uint32_t j, uint32_t n, uint64_t key) {
+  if (n <= 1) return 0;
+  const int bits = 32 - __clz(n - 1);                  // ceil(log2 n) >= 1
+  const int hb = (bits + 1) >> 1;                      // half width (<= 16): the network permutes [0, 2^(2 hb)) >= [0, n)
+  const uint32_t hmask = (1u << hb) - 1u;
+  uint32_t x = j;
+  do {
+    uint32_t L = x >> hb, R = x & hmask;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {                       // 4 rounds leave visible structure on domains of 16 elements
+      const uint32_t f = (uint32_t)mix64(key + (uint64_t)r * 0x9E3779B97F4A7C15ull + R) & hmask;
+      const uint32_t t = R;
+      R = L ^ f;
+      L = t;
+    }
+    x = (L << hb) | R;
+  } while (x >= n);                                    // domain <= 4n: a few iterations at most on average
+  return x;
 }
 
 }  // namespace pcl

@@ -67,3 +67,45 @@ def bank_rank_table(counts: np.ndarray, F: int, perm_fn: Callable[[int], torch.T
                 k = min(n, F)
                 table[b * K + c, :k] = p[:k].to(torch.int32)
     return table
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Host model of the DEVICE sampling RNG (csrc/pcl_common.cuh: mix64, keyed_perm) — diagnostics and tests only (which
+# pixels will a given seed pick, statistical quality of the draw); the product never samples on the host in this mode.
+# ---------------------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def mix64(z: int) -> int:
+    z = (z + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def keyed_perm(j: int, n: int, key: int) -> int:
+    """Element that view j of an n-element group takes: 8-round balanced Feistel bijection with cycle walking."""
+    if n <= 1:
+        return 0
+    bits = (n - 1).bit_length()
+    hb = (bits + 1) >> 1
+    hmask = (1 << hb) - 1
+    x = j
+    while True:
+        L, R = x >> hb, x & hmask
+        for r in range(8):
+            f = mix64((key + r * 0x9E3779B97F4A7C15 + R) & _M64) & hmask
+            L, R = R, L ^ f
+        x = (L << hb) | R
+        if x < n:
+            return x
+
+
+def device_step_seed(seed: int, step_counter: int) -> int:
+    """pcl_step_desc.seed of the eager call number `step_counter` (functional._step_counter after the increment)."""
+    return (int(seed) * 0x9E3779B97F4A7C15 + step_counter) & _M64
+
+
+def device_rank(step_seed: int, image: int, cls: int, num_classes: int, easy: bool, j: int, n: int) -> int:
+    """Rank (within the hard or easy pixel list of (image, cls), ascending pixel order) of the j-th sampled view."""
+    return keyed_perm(j, n, mix64(step_seed ^ (((image * num_classes + cls) << 1) | (1 if easy else 0))))

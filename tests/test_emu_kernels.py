@@ -206,3 +206,35 @@ def test_baseline_config0_geometry_on_emulation(emu, monkeypatch):
     assert (emb.grad.double() - e64.grad).abs().max().item() <= 1e-5 * e64.grad.abs().max().item()
     assert (seg.grad.double() - s64.grad).abs().max().item() <= 1e-5 * s64.grad.abs().max().item()
     assert emb.grad.abs().max().item() > 0
+
+
+def test_device_sampler_equals_its_host_model(emu):
+    """The pixels the selection kernels pick in device-RNG mode are exactly those of the host model of the sampler
+    (contrastiveseg_b200.rng.device_rank): same seed derivation, same keyed bijection, same rank -> pixel order."""
+    from contrastiveseg_b200 import functional as Fn, rng
+    from contrastiveseg_b200.synth import make_contrast_batch
+    K, ms, mv = 6, 60, 5
+    data = make_contrast_batch(B=2, D=32, h=20, w=24, num_classes=K, img_stride=2, block=8, seed=9)
+    opts = cs.ContrastOptions(max_samples=ms, max_views=mv, num_classes=K, seed=77)
+    lab = G.P.downsample_labels(data["target"], 20, 24).reshape(2, -1)
+    prd = data["seg"].argmax(1).reshape(2, -1)
+    for call in (1, 2, 3):
+        Fn._step_counter[0] = call - 1
+        cs.pixel_contrast_loss(data["embed"], data["target"], seg=data["seg"], options=opts)
+        ws = Fn.last_workspace(data["embed"].device)
+        TC, V, A = ws.plan_header()[:3]
+        pix, img, cls, _ = (t[:A].tolist() for t in ws.anchor_meta.view(4, -1))
+        got = sorted(zip(img, cls, pix))
+        seed = rng.device_step_seed(77, call)
+        want = []
+        for b in range(2):
+            for c in range(K):
+                is_c = lab[b] == c
+                if int(is_c.sum()) <= mv:
+                    continue
+                hard = (is_c & (prd[b] != c)).nonzero()[:, 0].tolist()
+                easy = (is_c & (prd[b] == c)).nonzero()[:, 0].tolist()
+                kh, ke = G.P.split_hard_easy(len(hard), len(easy), V)
+                want += [(b, c, hard[rng.device_rank(seed, b, c, K, False, j, len(hard))]) for j in range(kh)]
+                want += [(b, c, easy[rng.device_rank(seed, b, c, K, True, j, len(easy))]) for j in range(ke)]
+        assert got == sorted(want)

@@ -91,3 +91,31 @@ def test_bank_rank_table_order():
     t = rng.bank_rank_table(counts, 2, perm)
     assert draws == [3, 2, 5, 1]           # image asc, class asc, class 0 skipped, empty slots skipped
     assert t[1].tolist() == [2, 1] and t[3].tolist() == [1, 0] and t[6].tolist() == [4, 3] and t[7].tolist() == [0, 0]
+
+
+def test_device_rng_model_is_a_bijection_and_statistically_flat():
+    """Host model of the device sampler (csrc/pcl_common.cuh keyed_perm): a bijection on [0, n) for every key, and — what
+    the multiply/xorshift rounds of the first build failed for small groups — k-subsets whose marginal and PAIR
+    frequencies are those of a uniform draw without replacement (chi-square within 5 sigma)."""
+    import numpy as np
+    from contrastiveseg_b200 import rng
+    for n in (1, 2, 3, 7, 60, 100, 1000, 1025):
+        for key in (1, 12345678901234567, (1 << 64) - 1):
+            assert sorted(rng.keyed_perm(j, n, key) for j in range(n)) == list(range(n))
+    for n, k, N in ((60, 10, 3000), (7, 3, 3000), (200, 6, 3000)):
+        hits, pairs = np.zeros(n), np.zeros((n, n))
+        for s in range(N):
+            key = rng.mix64(rng.device_step_seed(123, s + 1) ^ ((1 * 19 + 4) << 1))
+            pick = [rng.keyed_perm(j, n, key) for j in range(k)]
+            assert len(set(pick)) == k
+            hits[pick] += 1
+            for a in pick:
+                pairs[a, pick] += 1
+        exp = N * k / n
+        chi = ((hits - exp) ** 2 / exp).sum()
+        assert abs(chi - (n - 1)) < 5 * (2 * (n - 1)) ** 0.5, (n, k, chi)
+        pe = N * (k / n) * ((k - 1) / (n - 1))
+        off = pairs[~np.eye(n, dtype=bool)]
+        cells = off.size / 2                                    # symmetric table
+        chi_p = ((off - pe) ** 2 / pe).sum() / 2
+        assert abs(chi_p - cells) < 6 * (2 * cells) ** 0.5, (n, k, chi_p / cells)
