@@ -161,7 +161,9 @@ class GraphedContrastStep:
         torch.cuda.current_stream(dev).wait_stream(cap)
         self.counter.zero_()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.device(dev), torch.cuda.graph(graph, stream=cap):
+        # thread_local: only this thread's CUDA calls are policed during the capture (the NCCL watchdog of a DDP job polls
+        # events from another thread)
+        with torch.cuda.device(dev), torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
             self._enqueue(torch.cuda.current_stream(dev).cuda_stream)
         self.graph = graph
 

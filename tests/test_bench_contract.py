@@ -31,3 +31,40 @@ def test_reference_arm_json_line():
 def test_reference_arm_bank_workload():
     d = _run(["--workload", "s2"])
     assert d["impl"] == "reference" and "memory bank" in d["config"]["workload"]
+
+
+def test_graph_arm_protocol_never_blocks_the_parent(tmp_path):
+    """bench.py's CUDA-graph arm runs in a child process per rank (READY / GO / one JSON line).  Whatever the child does —
+    refuses (no GPU here), answers after unrelated output, dies, or stays silent — the parent gets a definite answer."""
+    import subprocess
+    import sys
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+
+    def arm_for(cmd):
+        arm = bench.GraphArm.__new__(bench.GraphArm)
+        arm.result, arm._buf = None, b""
+        arm.proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        return arm
+
+    args = types.SimpleNamespace(steps=3, warmup=3, precision="bf16", workload="s1", scaling="weak")
+    real = bench.GraphArm(args, 0, 0)                       # the real child: no CUDA device on this box -> a refusal, not READY
+    assert real.wait_ready(180) is False and real.result["ok"] is False and real.result["why"]
+    real.close()
+    fake = tmp_path / "child.py"
+    fake.write_text('import sys, json\nprint("library noise")\nprint("READY", flush=True)\n'
+                    'assert sys.stdin.readline().strip() == "GO"\n'
+                    'print(json.dumps({"ok": True, "ms_per_step": 0.1, "e2e_s_per_step": 0.007, "finite": True}), flush=True)\n')
+    arm = arm_for([sys.executable, str(fake)])
+    assert arm.wait_ready(60) is True
+    assert arm.go(60) == {"ok": True, "ms_per_step": 0.1, "e2e_s_per_step": 0.007, "finite": True}
+    arm.close()
+    assert arm.proc.poll() == 0
+    arm = arm_for([sys.executable, "-c", "import sys; sys.exit(3)"])
+    assert arm.wait_ready(60) is False and arm.result["ok"] is False
+    arm.close()
+    arm = arm_for([sys.executable, "-c", "import time; time.sleep(120)"])
+    assert arm.wait_ready(1.0) is False
+    arm.close()
+    assert arm.proc.poll() is not None                      # the silent child was terminated (exact pid)
