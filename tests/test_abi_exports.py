@@ -79,3 +79,17 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I",
                         os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_c_client_links_and_runs(tmp_path):
+    """examples/c_abi_sizes.c: a plain C program against include/pcl.h + libpcl_b200.so (host-only entry points)."""
+    import subprocess
+    lib = build.build_library()
+    exe = tmp_path / "c_abi_sizes"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_sizes.c"), "-L", os.path.dirname(lib), "-lpcl_b200",
+                        f"-Wl,-rpath,{os.path.dirname(lib)}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "selection scratch: keys 262144 u16" in r.stdout and "pcl 100" in r.stdout
