@@ -11,7 +11,7 @@ from .loss import (ContrastAuxCELoss, ContrastCELoss, MemContrastCELoss, PixelCo
                    get_seg_loss)
 from .bank import MemoryBank, dequeue_and_enqueue, gather_packets      # noqa: F401
 from .projection import ProjectionHead                                  # noqa: F401
-from .trainer_hook import ContrastTrainerHook                           # noqa: F401
+from .trainer_hook import ContrastTrainerHook, LossStepTimer            # noqa: F401
 from .graph_step import GraphedContrastStep                             # noqa: F401
 
 __version__ = "0.1.0"

@@ -403,3 +403,39 @@ def test_explicit_operand_entry_points(rec, monkeypatch):
     Fn.infonce_forward(a, ya, queues=(segq, pixq))
     d = rec.calls[1][1][0]
     assert d.mode == 1 and (d.bank_K, d.bank_M0, d.bank_M1) == (4, 6, 6)
+
+
+def test_loss_step_timer_never_blocks(rec, monkeypatch):
+    """LossStepTimer: events recorded around loss_step, read() only reports steps whose events have completed."""
+    clock = {"t": 0.0}
+
+    class FakeEvent:
+        done_after = 2                                   # becomes 'complete' two queries after it was recorded
+
+        def __init__(self, enable_timing=False):
+            self.t, self.q = None, 0
+
+        def record(self):
+            clock["t"] += 1.5
+            self.t = clock["t"]
+
+        def query(self):
+            self.q += 1
+            return self.q >= FakeEvent.done_after
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    timer = cs.LossStepTimer(depth=3)
+    cfg = cs.Configer(cs.cityscapes_contrast_config())
+    cfg.add(["contrast", "warmup_iters"], 0)
+    cfg.add(["contrast", "fused_seg_ce"], False)
+    hook = cs.ContrastTrainerHook(cfg, timer=timer)
+    embed, labels, seg = _inputs(K=19)
+    assert timer.read() is None
+    hook.loss_step({"seg": seg.requires_grad_(True), "embed": embed}, labels, iters=1)
+    assert timer.read() is None                          # recorded, not complete yet: no value, no waiting
+    assert timer.read() == 1.5                           # complete now
+    hook.loss_step({"seg": seg, "embed": embed}, labels, iters=2)
+    assert timer.read() == 1.5                           # the newest step is still in flight: last completed value
