@@ -520,6 +520,46 @@ class GraphArm:
                 pass
 
 
+def graph_arm_measure(args, cfg, rank, world, dev, barrier):
+    """Run the CUDA-graph arm (one child per rank, see run_graph_child / GraphArm) and reduce its result over the ranks.
+    Every rank takes part in every collective below whatever happens to its own child (no rank may wait alone).
+    Returns {"ok": True, value, ms_per_step, e2e_value, ...} or {"ok": False, "why": ...}."""
+    arm, ready, why = None, False, None
+    try:
+        arm = GraphArm(args, rank, dev.index)
+        ready = arm.wait_ready()
+        if not ready:
+            why = (arm.result or {}).get("why", "graph child did not get ready")
+    except Exception as exc:                         # noqa: BLE001
+        why = f"{type(exc).__name__}: {exc}"[:200]
+    flag = torch.tensor([1.0 if ready else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    if float(flag.item()) > 0.5:
+        barrier()                                    # all children are warmed up and wait for GO: start them together
+        res = arm.go()
+        ok = bool(res.get("ok")) and bool(res.get("finite", False)) and (res.get("ms_per_step") or 0.0) > 1e-3 \
+            and (res.get("e2e_s_per_step") or 0.0) > 1e-6
+        vals = torch.tensor([1.0 if ok else 0.0, -(res.get("ms_per_step") or 0.0), -(res.get("e2e_s_per_step") or 0.0),
+                             -(res.get("host_enqueue_ms_per_step") or 0.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MIN)          # MIN of negatives = MAX over ranks
+        if float(vals[0].item()) > 0.5:
+            g_ms, g_e2e = -float(vals[1].item()), -float(vals[2].item())
+            graph = {"ok": True, "ms_per_step": g_ms, "value": world * cfg["B"] / (g_ms / 1e3),
+                     "e2e_value": world * cfg["B"] / g_e2e, "e2e_steps": res.get("e2e_steps"),
+                     "host_enqueue_ms_per_step": -float(vals[3].item()), "clocks": res.get("clocks"),
+                     "check": "on every rank's GPU, before timing: replay == eager autograd step (same anchors, same loss "
+                              "bits, gradient within 3e-6 relative: scatter-only backward vs fused writer)"}
+        else:
+            graph = {"ok": False, "why": res.get("why", "a rank's graph child failed")}
+    else:
+        graph = {"ok": False, "why": why or "another rank's graph child did not get ready"}
+    if arm is not None:
+        arm.close()
+    return graph
+
+
 def tensor_sweep_roofline(dev, peaks, A=16384, N=65536, iters=5):
     """The dense contraction alone (similarity + negative-sum sweep on tcgen05) at one S4 point (BASELINE configs[4]):
     algorithmic FLOPs 2*A*N*D over the CUDA-event time, vs the measured bf16 peak."""
@@ -680,42 +720,9 @@ def run_engine(args, cfg, bank, rank, world, dev):
     e2e_val = world * cfg["B"] * e_steps / float(et.item())
 
     # ---- CUDA-graph arm (child process per rank; the eager numbers above are already final) ----
-    # Every rank takes part in every collective below whatever happens to its own child (no rank may wait alone).
     graph = None
     if not bank and not args.graph and not args.no_graph_arm and not os.environ.get("PCL_BENCH_NO_GRAPH_ARM"):
-        arm, ready, why = None, False, None
-        try:
-            arm = GraphArm(args, rank, dev.index)
-            ready = arm.wait_ready()
-            if not ready:
-                why = (arm.result or {}).get("why", "graph child did not get ready")
-        except Exception as exc:                         # noqa: BLE001
-            why = f"{type(exc).__name__}: {exc}"[:200]
-        flag = torch.tensor([1.0 if ready else 0.0], dtype=torch.float64, device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
-        if float(flag.item()) > 0.5:
-            barrier()                                    # all children are warmed up and wait for GO: start them together
-            res = arm.go()
-            ok = bool(res.get("ok")) and bool(res.get("finite", False)) and (res.get("ms_per_step") or 0.0) > 1e-3 \
-                and (res.get("e2e_s_per_step") or 0.0) > 1e-6
-            vals = torch.tensor([1.0 if ok else 0.0, -(res.get("ms_per_step") or 0.0), -(res.get("e2e_s_per_step") or 0.0),
-                                 -(res.get("host_enqueue_ms_per_step") or 0.0)], dtype=torch.float64, device=dev)
-            if world > 1:
-                torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MIN)          # MIN of negatives = MAX over ranks
-            if float(vals[0].item()) > 0.5:
-                g_ms, g_e2e = -float(vals[1].item()), -float(vals[2].item())
-                graph = {"ok": True, "ms_per_step": g_ms, "value": world * cfg["B"] / (g_ms / 1e3),
-                         "e2e_value": world * cfg["B"] / g_e2e, "e2e_steps": res.get("e2e_steps"),
-                         "host_enqueue_ms_per_step": -float(vals[3].item()), "clocks": res.get("clocks"),
-                         "check": "on every rank's GPU, before timing: replay == eager autograd step (same anchors, same loss "
-                                  "bits, gradient within 3e-6 relative: scatter-only backward vs fused writer)"}
-            else:
-                graph = {"ok": False, "why": res.get("why", "a rank's graph child failed")}
-        else:
-            graph = {"ok": False, "why": why or "another rank's graph child did not get ready"}
-        if arm is not None:
-            arm.close()
+        graph = graph_arm_measure(args, cfg, rank, world, dev, barrier)
     if rank != 0:
         return None
     # ---- per-stage times + roofline of the dominant stage (rank 0, N-independent) ----

@@ -68,3 +68,73 @@ def test_graph_arm_protocol_never_blocks_the_parent(tmp_path):
     assert arm.wait_ready(1.0) is False
     arm.close()
     assert arm.proc.poll() is not None                      # the silent child was terminated (exact pid)
+
+
+_FAKE_OK = ('import sys, json\nprint("READY", flush=True)\nassert sys.stdin.readline().strip() == "GO"\n'
+            'print(json.dumps({"ok": True, "ms_per_step": %s, "e2e_s_per_step": 0.008, "host_enqueue_ms_per_step": 0.01, '
+            '"e2e_steps": 50, "clocks": None, "finite": True}), flush=True)\n')
+
+
+def _fake_arm_factory(bench, script_for_rank):
+    import subprocess
+
+    class FakeArm(bench.GraphArm):
+        def __init__(self, args, rank, local):
+            self.result, self._buf = None, b""
+            self.proc = subprocess.Popen([sys.executable, script_for_rank(rank)], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL)
+    return FakeArm
+
+
+def test_graph_arm_reduction_single_rank(tmp_path, monkeypatch):
+    import types
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    ok, bad = tmp_path / "ok.py", tmp_path / "bad.py"
+    ok.write_text(_FAKE_OK % "0.1")
+    bad.write_text('import json\nprint(json.dumps({"ok": False, "why": "replay 0 differs from the eager step"}), flush=True)\n')
+    args = types.SimpleNamespace(steps=200, warmup=10, precision="bf16", workload="s1", scaling="weak")
+    cfg = {"B": 8}
+    monkeypatch.setattr(bench, "GraphArm", _fake_arm_factory(bench, lambda r: str(ok)))
+    g = bench.graph_arm_measure(args, cfg, 0, 1, torch.device("cpu"), lambda: None)
+    assert g["ok"] and abs(g["ms_per_step"] - 0.1) < 1e-12 and abs(g["value"] - 8 / 0.1e-3) < 1e-6
+    assert abs(g["e2e_value"] - 8 / 0.008) < 1e-6 and g["e2e_steps"] == 50
+    monkeypatch.setattr(bench, "GraphArm", _fake_arm_factory(bench, lambda r: str(bad)))
+    g = bench.graph_arm_measure(args, cfg, 0, 1, torch.device("cpu"), lambda: None)
+    assert g == {"ok": False, "why": "replay 0 differs from the eager step"}
+
+
+def _graph_arm_worker(rank, world, port, out_dir, scripts):
+    import types
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bench.GraphArm = _fake_arm_factory(bench, lambda r: scripts[r])
+    args = types.SimpleNamespace(steps=200, warmup=10, precision="bf16", workload="s1", scaling="weak")
+    g = bench.graph_arm_measure(args, {"B": 8}, rank, world, torch.device("cpu"), dist.barrier)
+    with open(os.path.join(out_dir, f"g{rank}.json"), "w") as f:
+        json.dump(g, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_graph_arm_reduction_two_ranks(tmp_path):
+    """Max over ranks when both children succeed; when one rank's child refuses, BOTH ranks fall back (and nobody hangs)."""
+    import socket
+    import torch.multiprocessing as mp
+    fast, slow, bad = tmp_path / "fast.py", tmp_path / "slow.py", tmp_path / "bad.py"
+    fast.write_text(_FAKE_OK % "0.10")
+    slow.write_text(_FAKE_OK % "0.13")
+    bad.write_text('import json\nprint(json.dumps({"ok": False, "why": "CUDA error"}), flush=True)\n')
+    for scripts, expect_ok in (([str(fast), str(slow)], True), ([str(fast), str(bad)], False)):
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        mp.spawn(_graph_arm_worker, args=(2, port, str(tmp_path), scripts), nprocs=2, join=True)
+        g0, g1 = (json.load(open(tmp_path / f"g{r}.json")) for r in (0, 1))
+        assert g0["ok"] == g1["ok"] == expect_ok
+        if expect_ok:
+            assert abs(g0["ms_per_step"] - 0.13) < 1e-12 and g0["value"] == g1["value"]
+            assert abs(g0["value"] - 2 * 8 / 0.13e-3) < 1e-6            # max over ranks sets the whole-job throughput
