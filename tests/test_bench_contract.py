@@ -138,3 +138,66 @@ def test_graph_arm_reduction_two_ranks(tmp_path):
         if expect_ok:
             assert abs(g0["ms_per_step"] - 0.13) < 1e-12 and g0["value"] == g1["value"]
             assert abs(g0["value"] - 2 * 8 / 0.13e-3) < 1e-6            # max over ranks sets the whole-job throughput
+
+
+def _run_engine_on_emulator(monkeypatch, fake_graph_ms=None):
+    """bench.run_engine end to end on the CPU: the engine's kernels on the host-fiber emulator (tests/emu), CUDA events /
+    pinned memory stubbed, toy geometry.  Exercises everything between argument parsing and the JSON line."""
+    import types
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    import emu_harness
+    emu_harness.use_emulation(monkeypatch)
+
+    class Ev:
+        def __init__(self, **k):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 2.0
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    if fake_graph_ms is not None:
+        monkeypatch.setattr(bench, "graph_arm_measure", lambda *a, **k: {
+            "ok": True, "ms_per_step": fake_graph_ms, "value": 2 / (fake_graph_ms / 1e3), "e2e_value": 123.0, "e2e_steps": 50,
+            "host_enqueue_ms_per_step": 0.01, "clocks": {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 4},
+            "check": "stub"})
+    args = types.SimpleNamespace(steps=4, warmup=3, precision="fp32", workload="s1", scaling="weak", graph=False,
+                                 no_graph_arm=False, no_cpu_baseline=False, gpus=1)
+    cfg = dict(bench.S1)
+    cfg.update(B=2, D=32, h=16, w=16, K=5, stride=2, block=8, max_samples=32, max_views=4)
+    res = bench.run_engine(args, cfg, False, 0, 1, torch.device("cpu"))
+    return json.loads(json.dumps(res))                     # must be JSON-serialisable as is
+
+
+REQUIRED = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline")
+
+
+def test_engine_arm_line_on_the_emulator_eager_fallback(monkeypatch):
+    res = _run_engine_on_emulator(monkeypatch)                      # the real graph child refuses (no GPU here) -> eager line
+    for k in REQUIRED:
+        assert k in res, k
+    assert res["impl"] == "engine" and res["cuda_graph"] is False and res["graph_arm"]["ok"] is False
+    assert res["value"] == res["eager"]["value"] and res["config"]["step"].startswith("eager")
+    assert res["ms_per_step"] == 0.5 and res["value"] == 2 * 4 / 2e-3          # 4 steps in the stubbed 2 ms
+    assert res["roofline"]["bound"] == "hbm" and res["cpu_baseline"]["kind"] == "port"
+    assert res["train_iter"] and "error" not in res["train_iter"] and res["train_iter"]["finite_loss"] is True
+    assert set(res["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+
+
+def test_engine_arm_line_on_the_emulator_graph_headline(monkeypatch):
+    monkeypatch.setenv("PCL_BENCH_NO_TRAIN_ITER", "1")              # covered by the test above
+    res = _run_engine_on_emulator(monkeypatch, fake_graph_ms=0.2)   # a verified, faster graph arm becomes the headline
+    assert res["cuda_graph"] is True and res["ms_per_step"] == 0.2 and res["value"] == 2 / 0.2e-3
+    assert res["eager"]["ms_per_step"] == 0.5 and res["e2e"]["value"] == 123.0 and res["e2e"]["steps"] == 50
+    assert res["config"]["step"].startswith("one CUDA-graph replay") and res["clocks"]["samples"] == 4
+    slower = _run_engine_on_emulator(monkeypatch, fake_graph_ms=0.9)            # a slower one does not
+    assert slower["cuda_graph"] is False and slower["ms_per_step"] == 0.5 and slower["graph_arm"]["ok"] is True
