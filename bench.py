@@ -509,7 +509,7 @@ class GraphArm:
         try:
             if self.proc.poll() is None:
                 self.proc.stdin.close()
-                self.proc.wait(timeout=10)
+                self.proc.wait(timeout=4)                # a child that has printed its line exits at once
         except Exception:                                # noqa: BLE001
             pass
         if self.proc.poll() is None:
