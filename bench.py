@@ -458,9 +458,19 @@ class GraphArm:
                "--steps", str(args.steps),
                "--warmup", str(args.warmup), "--precision", args.precision, "--workload", args.workload, "--scaling", args.scaling,
                "--child-world", str(int(os.environ.get("WORLD_SIZE", "1")))]
-        self.proc = subprocess.Popen(cmd, env=env, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        import tempfile
+        self._err = tempfile.TemporaryFile()             # the child's stderr, quoted in `why` when it dies without an answer
+        self.proc = subprocess.Popen(cmd, env=env, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=self._err)
         self.result = None
         self._buf = b""
+
+    def _stderr_tail(self, n=240):
+        try:
+            self._err.seek(0)
+            txt = self._err.read().decode("utf-8", "replace").strip().replace("\n", " | ")
+            return txt[-n:]
+        except Exception:                                # noqa: BLE001
+            return ""
 
     def _readline(self, timeout_s):
         """Next protocol line of the child (READY or one JSON object); anything else a library printed is skipped.
@@ -490,7 +500,8 @@ class GraphArm:
         if line == "READY":
             return True
         try:
-            self.result = json.loads(line) if line else {"ok": False, "why": "no answer from the graph child (timeout or exit)"}
+            self.result = json.loads(line) if line else {"ok": False, "why": "no answer from the graph child (timeout or exit)"
+                                                         + (": " + self._stderr_tail() if getattr(self, "_err", None) else "")}
         except ValueError:
             self.result = {"ok": False, "why": f"unexpected output from the graph child: {line[:120]!r}"}
         return False
@@ -500,7 +511,8 @@ class GraphArm:
             self.proc.stdin.write(b"GO\n")
             self.proc.stdin.flush()
             line = self._readline(timeout_s)
-            self.result = json.loads(line) if line else {"ok": False, "why": "graph child timed out"}
+            self.result = json.loads(line) if line else {"ok": False, "why": "graph child timed out or died"
+                                                         + (": " + self._stderr_tail() if getattr(self, "_err", None) else "")}
         except Exception as exc:                         # noqa: BLE001
             self.result = {"ok": False, "why": f"{type(exc).__name__}: {exc}"[:200]}
         return self.result
