@@ -45,6 +45,16 @@ class MemoryBank(nn.Module):
         self.with_shadow = with_shadow
         self.shadow = None            # bf16 ((K-1)*2M padded to 256, D), engine-internal (not in state_dict)
 
+    def flush(self) -> None:
+        """Apply bank writes still held back for a pending backward (see ``dequeue_and_enqueue``): between ``loss_step``
+        and ``backward()`` the buffers hold the bank the loss read, not yet the rows enqueued since."""
+        if self.segment_queue.is_cuda:
+            _fn._flush_bank(self.segment_queue.device.index, self.segment_queue.data_ptr())
+
+    def state_dict(self, *args, **kwargs):
+        self.flush()                  # a checkpoint taken inside that window must contain the enqueued rows
+        return super().state_dict(*args, **kwargs)
+
     def attach(self, outputs: dict) -> dict:
         """What the trainer does before the loss call (trainer_contrastive.py:214-217)."""
         outputs["pixel_queue"] = self.pixel_queue

@@ -45,6 +45,32 @@ int zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* a
 int scatter_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
                  const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed, void* stream);
 
+// ---- per-device kernel attributes ----------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (function, device) and SETS the limit (a later call with
+// a smaller size lowers it).  Every kernel therefore opts in ONCE per device to the largest size it can ever need
+// (known at compile time: D <= 256); the bit mask is indexed by the current device, so a process that drives several
+// GPUs gets every device configured.
+struct SmemOptIn { unsigned long long mask; };
+template <typename F>
+static inline int smem_opt_in(SmemOptIn& st, F func, size_t max_bytes) {
+  int dev = 0;
+  PCL_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(&st.mask, __ATOMIC_ACQUIRE) & bit) return PCL_OK;
+  PCL_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes));
+  __atomic_fetch_or(&st.mask, bit, __ATOMIC_RELEASE);
+  return PCL_OK;
+}
+#define PCL_SMEM_OPT_IN(func, max_bytes)                                   \
+  do {                                                                      \
+    static ::pcl::SmemOptIn st__ = {0ull};                                  \
+    int rc__ = ::pcl::smem_opt_in(st__, func, (max_bytes));                 \
+    if (rc__ != PCL_OK) return rc__;                                        \
+  } while (0)
+
+// SM count of the current device (cached per device; 148 when sizing on a host without one)
+int num_sms();
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -351,12 +351,8 @@ extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* 
   PCL_REQUIRE(partials && rowstats && loss);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = simt_sweep_smem(a.D, false);
-  static size_t attr_fwd = 0;                   // raise the opt-in shared memory limit once per size
-  if (smem > attr_fwd) {
-    PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_fwd = smem;
-  }
+  PCL_SMEM_OPT_IN(k_sweep<MODE_NEG>, simt_sweep_smem(256, false));
+  PCL_SMEM_OPT_IN(k_sweep<MODE_POS>, simt_sweep_smem(256, false));
   // every (split, live row) slot is written by its CTA (empty column ranges write "nothing seen"),
   // so the partial buffers need no initialisation
   dim3 grid(a.row_tiles, a.splits);
@@ -373,7 +369,9 @@ extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* 
 
 int pcl::simt_launch_pos(const SweepArgs& a, float* partials, const float* rowstats, cudaStream_t s) {
   const size_t smem = simt_sweep_smem(a.D, false);
-  PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (round 1 set the limit to THIS call's size here: a D=64 top-k call lowered it under the D=256 size the forward
+  // believed to be in place -> cudaErrorInvalidValue on the next D=256 POS launch.  Now: one opt-in to the maximum.)
+  PCL_SMEM_OPT_IN(k_sweep<MODE_POS>, simt_sweep_smem(256, false));
   dim3 grid(a.row_tiles, a.splits);
   k_sweep<MODE_POS><<<grid, SWEEP_THREADS, smem, s>>>(a, partials, rowstats, nullptr);
   PCL_LAUNCH_CHECK();
@@ -388,11 +386,7 @@ extern "C" int pcl_infonce_bwd(const pcl_sweep_desc* d, const float* rowstats, c
   PCL_REQUIRE(rowstats && dpartials && dA);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = simt_sweep_smem(a.D, true);
-  static size_t attr_bwd = 0;
-  if (smem > attr_bwd) {
-    PCL_CUDA(cudaFuncSetAttribute(k_sweep<MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bwd = smem;
-  }
+  PCL_SMEM_OPT_IN(k_sweep<MODE_BWD>, simt_sweep_smem(256, true));
   dim3 grid(a.row_tiles, a.splits);
   k_sweep<MODE_BWD><<<grid, SWEEP_THREADS, smem, s>>>(a, nullptr, rowstats, dpartials);
   PCL_LAUNCH_CHECK();

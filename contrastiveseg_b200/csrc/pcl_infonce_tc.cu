@@ -881,16 +881,14 @@ static int tc_variant() {
   return v;
 }
 
-static int num_sms() {
-  static int n = 0;
+int pcl::num_sms() {
+  static int cache[64] = {0};     // per device (a process may drive several GPUs)
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 148; }   // sizing on a host without a device
+  int& n = cache[dev & 63];
   if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else {
-      (void)cudaGetLastError();
-      return 148;                 // sizing on a host without a device (B200)
-    }
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else { (void)cudaGetLastError(); return 148; }
   }
   return n;
 }
@@ -1027,13 +1025,9 @@ int pcl::tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* 
   else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemLayout) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_NEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_NEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_POS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_NEG, true>), smem);
+  PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_NEG, false>), smem);
+  PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_POS, false>), smem);
   dim3 grid(p.row_tiles, a.splits);
   const int variant = tc_variant();
   if (variant & 2) {                                   // tuning knob: 2-D grid instead of the persistent walk
@@ -1077,7 +1071,7 @@ extern "C" int pcl_tc_dump_logits(const pcl_tc_desc* d, float* row_m2, float* du
   else st = make_tmap(&tmB, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::BN);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemLayout) + 1024;
-  PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_fwd<tc::TC_DUMP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_DUMP, false>), smem);
   dim3 grid(p.row_tiles, a.splits);
   tc::k_tc_fwd<tc::TC_DUMP, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, dump, nullptr);
   PCL_LAUNCH_CHECK();
@@ -1114,11 +1108,7 @@ int pcl::tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowst
   else st = make_tmap(&tmC, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : ba.t.n_cols), tc::BNB);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemBwd) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PCL_CUDA(cudaFuncSetAttribute(tc::k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  PCL_SMEM_OPT_IN(tc::k_tc_bwd, smem);
   dim3 grid(p.row_tiles, splits);
   tc::k_tc_bwd<<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmC, ba, dpartials);
   PCL_LAUNCH_CHECK();

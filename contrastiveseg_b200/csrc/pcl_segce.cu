@@ -6,7 +6,10 @@
 //                sum of exp), NLL of the target class, log-sum-exp kept per pixel (B*Himg*Wimg floats) for backward;
 //                per-CTA partial sums -> k_segce_finalize (fixed order: bit-reproducible)
 //   k_segce_bwd  one thread per logit seg[b,c,y,x]: gathers over the label pixels in its bilinear footprint
-//                (weight * (softmax - onehot)), no atomics: deterministic
+//                (weight * (softmax - onehot)), no atomics: deterministic — the gather kernel, used for down-sampling
+//                geometries; the default up-sampling geometry runs k_segce_bwd_tile, which accumulates the source
+//                cells shared by up to 4 neighbouring tiles with fp32 global atomics: its dseg is reproducible only to
+//                the last ulp or two (summation order of <= 4 addends), which the parity tolerance (1e-5 max|g|) covers
 // HBM: reads seg (B*K*h*w*4) + labels (B*Himg*Wimg*8), writes lse (B*Himg*Wimg*4); backward re-reads them and writes
 // dseg.  Everything else stays in L1/L2 (a 4x4 block of label pixels shares its 4 source logits).
 #include "pcl_common.cuh"
@@ -345,7 +348,7 @@ extern "C" int pcl_seg_ce_fwd(const float* seg, const int64_t* target, const flo
   while (kc > 1 && (size_t)kc * pitch * sizeof(float) > 96 * 1024) --kc;
   const size_t smem = (size_t)kc * pitch * sizeof(float);
   if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
-  PCL_CUDA(cudaFuncSetAttribute(k_segce_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCL_SMEM_OPT_IN(k_segce_fwd, 200 * 1024);
   k_segce_fwd<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BTY), B), BT * BTY, smem, s>>>(a, lse, pn, pw, pitch, kc);
   PCL_LAUNCH_CHECK();
   k_segce_finalize<<<1, 1024, 0, s>>>(pn, pw, blocks, fin);
@@ -379,7 +382,7 @@ extern "C" int pcl_seg_ce_bwd(const float* seg, const int64_t* target, const flo
   while (kc > 1 && (size_t)kc * (BTY * BT + BTY * SRC_MAX + pitch) * sizeof(float) > 200 * 1024) --kc;
   const size_t smem = (size_t)kc * (BTY * BT + BTY * SRC_MAX + pitch) * sizeof(float);
   if (smem > 200 * 1024) return PCL_ERR_UNSUPPORTED;
-  PCL_CUDA(cudaFuncSetAttribute(k_segce_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCL_SMEM_OPT_IN(k_segce_bwd_tile, 200 * 1024);
   k_segce_bwd_tile<<<dim3((unsigned)ceil_div(W, BT), (unsigned)ceil_div(H, BTY), B), BT * BTY, smem, s>>>(a, lse, fin, grad_loss,
                                                                                                      dseg, kc, pitch);
   PCL_LAUNCH_CHECK();

@@ -442,14 +442,10 @@ extern "C" int pcl_infonce_topk_fwd(const pcl_sweep_desc* d, int32_t k, uint32_t
   PCL_REQUIRE(partials && rowstats && loss);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = topk_smem(a.D, false);
-  static size_t attr_fwd = 0;
-  if (smem > attr_fwd) {
-    PCL_CUDA(cudaFuncSetAttribute(k_topk_sweep<TK_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(k_topk_sweep<TK_H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(k_topk_sweep<TK_H3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCL_CUDA(cudaFuncSetAttribute(k_topk_sweep<TK_NEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_fwd = smem;
-  }
+  PCL_SMEM_OPT_IN(k_topk_sweep<TK_H1>, topk_smem(256, false));
+  PCL_SMEM_OPT_IN(k_topk_sweep<TK_H2>, topk_smem(256, false));
+  PCL_SMEM_OPT_IN(k_topk_sweep<TK_H3>, topk_smem(256, false));
+  PCL_SMEM_OPT_IN(k_topk_sweep<TK_NEG>, topk_smem(256, false));
   PCL_CUDA(cudaMemsetAsync(tk.hist, 0, (size_t)a.a_pad * TK_BINS * sizeof(uint32_t), s));
   const dim3 grid(a.row_tiles, a.splits);
   const int scan_blocks = ceil_div(a.a_rows, 8);          // 8 warps (rows) per 256-thread block
@@ -485,11 +481,7 @@ extern "C" int pcl_infonce_topk_bwd(const pcl_sweep_desc* d, int32_t k, uint32_t
   PCL_REQUIRE(rowstats && dpartials && dA);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = topk_smem(a.D, true);
-  static size_t attr_bwd = 0;
-  if (smem > attr_bwd) {
-    PCL_CUDA(cudaFuncSetAttribute(k_topk_sweep<TK_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bwd = smem;
-  }
+  PCL_SMEM_OPT_IN(k_topk_sweep<TK_BWD>, topk_smem(256, true));
   const dim3 grid(a.row_tiles, a.splits);
   k_topk_sweep<TK_BWD><<<grid, SWEEP_THREADS, smem, s>>>(a, tk, nullptr, rowstats, dpartials);
   PCL_LAUNCH_CHECK();

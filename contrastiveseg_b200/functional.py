@@ -402,6 +402,12 @@ class _PixelContrastFn(torch.autograd.Function):
         lib = _abi.load()
         ws = ctx.ws
         device = ws.device
+        # The backward sweep re-reads the workspace scratch and the input tensors of THIS forward.  Both are handed back
+        # after the first backward (another forward may have overwritten them since), so a second backward through the
+        # same node (retain_graph=True) cannot be served: fail loudly instead of returning a gradient of something else.
+        if ctx.keep is None or ws.token != getattr(ctx, "token", None):
+            raise _abi.PclError("pixel_contrast_loss: backward ran twice on the same graph (retain_graph=True is not "
+                                "supported: the engine keeps no copy of the forward's scratch); call the loss again")
         grad = torch.empty(ctx.embed_shape, dtype=torch.float32, device=device)
         go = grad_out
         if go.device != device or go.dtype != torch.float32 or not go.is_contiguous():

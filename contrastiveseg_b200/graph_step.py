@@ -202,4 +202,8 @@ class _GraphedFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
+        # the static gradient already contains grad_scale; an upstream factor other than 1 (loss weight applied outside,
+        # AMP loss scaling) would be silently dropped -> asynchronous device-side assertion (no host sync, one tiny kernel)
+        torch._assert_async((grad_out == 1).all(),
+                            "GraphedContrastStep.apply(): upstream gradient != 1; fold the factor into grad_scale")
         return ctx.step.grad, None

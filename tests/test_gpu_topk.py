@@ -2,8 +2,8 @@
 sort-based definition.  a10 is not in the reference code, default off and excluded from the reference parity bar
 (SURVEY §8 a10); these tests pin the kernels to the oracle semantics.
 
-STATUS: written when the round's GPU budget was already spent — the kernels compile for sm_100a and pass these very
-tests on the CPU emulator (tests/test_emu_kernels.py), but the file has not run on hardware yet: see `pytestmark`."""
+STATUS: strict since round 2 (all cases pass on the B200, profiles/r2_02_pytest_full.log); the same cases also run on
+the CPU emulator (tests/test_emu_kernels.py)."""
 import os
 
 import numpy as np
@@ -15,12 +15,7 @@ from contrastiveseg_b200 import functional as Fn
 from oracle import ref_port as P
 from helpers import load_golden, unpack_perms, rel_err
 
-# Not yet run on hardware when committed (the kernels and the host logic pass on the CPU emulator of tests/emu).  Until
-# they have passed once on a B200 (then: PCL_TEST_EXPERIMENTAL=1 makes them strict) a failure is reported as "xfailed"
-# and a success as "xpassed" — the verified `-m gpu` suite stays a clean signal either way; the timeout bounds a surprise.
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(condition=not os.environ.get("PCL_TEST_EXPERIMENTAL"), strict=False,
-                                reason="first hardware run pending (passes on the CPU emulator, tests/test_emu_kernels.py)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]      # strict: verified on the B200 (profiles/r2_01_*)
 DEV = "cuda:0"
 
 

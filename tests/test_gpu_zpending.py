@@ -1,7 +1,9 @@
-"""GPU tests of features written after the round-1 GPU budget was spent (the file sorts last among the GPU tests on
-purpose: it contains the CUDA-graph capture).  They pass on the CPU emulator (tests/test_emu_kernels.py) and the host
-logic is covered by tests/test_host_wiring.py; what is left to confirm on hardware is listed per test.  Once they have
-passed on a B200 they move into test_gpu_parity.py.  See `pytestmark` for how they are reported until then."""
+"""GPU tests of the deferred bank write and the CUDA-graph step (the file sorts last among the GPU tests on purpose: it
+contains the CUDA-graph capture).  Strict since round 2.  The three fp32 cases failed in the round-1 driver run ONLY when
+they ran after tests/test_gpu_topk.py: a D=64 top-k call lowered the dynamic-shared-memory opt-in of k_sweep<POS> below
+the D=256 size (cudaErrorInvalidValue at the next D=256 launch; log: profiles/r2_02_pytest_full_before_fix.log) — fixed
+by the per-device one-time opt-in to the kernel's maximum (PCL_SMEM_OPT_IN, csrc/pcl_common.cuh);
+`test_smem_opt_in_survives_a_smaller_launch` below pins it."""
 import os
 
 import pytest
@@ -11,12 +13,7 @@ import contrastiveseg_b200 as cs
 from contrastiveseg_b200 import functional as Fn
 from contrastiveseg_b200.synth import make_bank, make_contrast_batch
 
-# Not yet run on hardware when committed (the kernels and the host logic pass on the CPU emulator of tests/emu).  Until
-# they have passed once on a B200 (then: PCL_TEST_EXPERIMENTAL=1 makes them strict) a failure is reported as "xfailed"
-# and a success as "xpassed" — the verified `-m gpu` suite stays a clean signal either way; the timeout bounds a surprise.
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(condition=not os.environ.get("PCL_TEST_EXPERIMENTAL"), strict=False,
-                                reason="first hardware run pending (passes on the CPU emulator, tests/test_emu_kernels.py)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]      # strict: verified on the B200 (profiles/r2_01_*)
 DEV = "cuda:0"
 
 
@@ -121,3 +118,47 @@ def test_graphed_step_equals_eager_step(precision, mem, overlap):
     out = step2.apply(e)
     out.backward()
     assert torch.equal(e.grad, step2.grad)
+
+
+def test_smem_opt_in_survives_a_smaller_launch():
+    """Regression (round-1 hidden failure): a small-D launch of a sweep kernel must not lower the shared-memory opt-in a
+    later D=256 launch needs — exact fp32 loss at D=256, then the top-k path (which launches k_sweep<POS>) at D=64, then
+    D=256 again."""
+    def run(D, topk=None):
+        K = 5
+        data = make_contrast_batch(B=2, D=D, h=16, w=32, num_classes=K, img_stride=4, block=16, seed=9)
+        e = data["embed"].to(DEV).requires_grad_(True)
+        opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=64, max_views=4, seed=1,
+                                  precision="fp32", num_classes=K, topk_negatives=topk)
+        Fn._step_counter[0] = 0
+        l = cs.pixel_contrast_loss(e, data["target"].to(DEV), seg=data["seg"].to(DEV), options=opts)
+        l.backward()
+        torch.cuda.synchronize()
+        return l.detach().clone(), e.grad.clone()
+    l0, g0 = run(256)
+    run(64, topk=3)
+    run(64)
+    l1, g1 = run(256)
+    assert torch.equal(l0, l1) and torch.equal(g0, g1)
+
+
+def test_second_backward_is_refused_and_state_dict_flushes_the_pending_write():
+    """(a) the engine keeps no copy of the forward's scratch, so a second backward through the same node
+    (retain_graph=True) must raise instead of returning a gradient computed from overwritten scratch; (b) a checkpoint
+    taken between loss_step and backward must contain the rows enqueued in that window."""
+    from contrastiveseg_b200._abi import PclError
+    K, D, M = 6, 64, 32
+    data = make_contrast_batch(B=2, D=D, h=16, w=32, num_classes=K, img_stride=4, block=16, seed=5)
+    tgt, seg = data["target"].to(DEV), data["seg"].to(DEV)
+    bank = cs.MemoryBank(K, M, D).to(DEV)
+    crit = cs.PixelContrastLoss(_cfg(K, "fp32", seed=11))
+    embed = data["embed"].to(DEV).requires_grad_(True)
+    loss = crit(embed, tgt, seg=seg, queue=(bank.segment_queue, bank.pixel_queue))
+    before = bank.pixel_queue.clone()
+    bank.enqueue(embed.detach(), tgt, network_stride=4, pixel_update_freq=5, seed=3)
+    assert torch.equal(bank.pixel_queue, before)                 # held back
+    sd = bank.state_dict()
+    assert not torch.equal(sd["pixel_queue"], before)            # state_dict() flushed the pending write
+    loss.backward(retain_graph=True)
+    with pytest.raises(PclError, match="backward ran twice"):
+        loss.backward()
