@@ -185,35 +185,76 @@ def calibrate_cpu(cfg, bank):
     return best
 
 
-def run_reference(args, cfg, bank, rank, budget_s=150.0):
+_REF_CACHE = {}
+
+
+def real_reference_step(inp, cfg, bank):
+    """The UNMODIFIED reference modules (lib/loss/loss_contrast*.py, Trainer._dequeue_and_enqueue) when a reference tree
+    is reachable ($CSEG_REF, /root/reference, baseline/_ref): never the case on a stock GPU box, where the port runs."""
+    from oracle import ref_loader as RL
+    import types
+    key = (bank, cfg["T"], cfg["bT"], cfg["max_samples"], cfg["max_views"])
+    if key not in _REF_CACHE:
+        ref = RL.load_reference()
+        d = {"contrast": {"temperature": cfg["T"], "base_temperature": cfg["bT"], "max_samples": cfg["max_samples"],
+                          "max_views": cfg["max_views"], "loss_weight": 0.1, "use_rmi": False, "use_lovasz": False},
+             "loss": {"params": {"ce_ignore_index": -1, "ce_reduction": "elementwise_mean"}}, "network": {"stride": cfg.get("net_stride", 4)}}
+        mod = (ref.mem if bank else ref.nomem).PixelContrastLoss(RL.DictConfiger(d))
+        _REF_CACHE[key] = (ref, mod)
+    ref, mod = _REF_CACHE[key]
+    embed = inp["embed"].clone().requires_grad_(True)
+    predict = inp["seg"].argmax(1)
+    if bank:
+        queue = torch.cat((inp["segment_queue"], inp["pixel_queue"]), 1)
+        loss = mod(embed, inp["target"], predict, queue)
+    else:
+        loss = mod(embed, inp["target"], predict)
+    loss.backward()
+    if bank:
+        me = types.SimpleNamespace(network_stride=cfg["net_stride"], memory_size=cfg["M"], pixel_update_freq=cfg["F"])
+        ref.enqueue(me, inp["embed"], inp["target"], inp["segment_queue"], inp["segment_queue_ptr"], inp["pixel_queue"],
+                    inp["pixel_queue_ptr"])
+    return float(loss.item())
+
+
+def reference_kind():
+    try:
+        from oracle import ref_loader as RL
+        if RL.reference_root() is not None:
+            RL.load_reference()
+            return "reference"
+    except Exception:                                    # noqa: BLE001
+        pass
+    return "port"
+
+
+def run_reference(args, cfg, bank, rank):
+    """Reference arm: the reference's own CPU path on the box's host cores, SAME config as the engine arm (full batch).
+    The reference is Python and does not travel to the GPU box, so there it is the op-for-op port (oracle/ref_port.py,
+    pinned to the reference by golden vectors); where a reference tree is reachable the unmodified modules run."""
     if rank != 0:
         return None
+    kind = reference_kind()
+    step = real_reference_step if kind == "reference" else cpu_port_step
     threads, t1 = calibrate_cpu(cfg, bank)
-    total = args.steps + args.warmup
-    # the reference's backward fills one (B,HW,D) tensor per (image,class) pair: step time grows ~B^2
-    B_ref = 1
-    for b in (cfg["B"], cfg["B"] // 2, cfg["B"] // 4):
-        if b >= 1 and total * t1 * b * b <= budget_s:
-            B_ref = b
-            break
-    c = dict(cfg); c["B"] = B_ref
-    inp = make_inputs(c, 304, None, bank)
+    inp = make_inputs(cfg, 304, None, bank)
     for _ in range(args.warmup):
-        cpu_port_step(inp, c, bank)
+        step(inp, cfg, bank)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_step(inp, c, bank)
+        step(inp, cfg, bank)
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
-    val = B_ref * args.steps / dt
-    sample = (f"{args.steps} steps of the workload geometry at batch {B_ref} (full batch {cfg['B']}; bounded so the run "
-              f"fits ~{budget_s:.0f} s) on {threads} of {os.cpu_count()} host threads (fastest of 8/16/32/64/all), fp32 torch "
-              "CPU, per-(image,class) gather + autograd backward like the reference")
+    val = cfg["B"] * args.steps / dt
+    sample = (f"{args.steps} steps of the full workload (batch {cfg['B']}) after {args.warmup} warm-up on {threads} of "
+              f"{os.cpu_count()} host threads (fastest of 8/16/32/64/all, calibrated on one image), fp32 torch CPU, "
+              + ("the unmodified reference modules" if kind == "reference" else
+                 "per-(image,class) gather + autograd backward like the reference (oracle/ref_port.py)"))
     return {"impl": "reference", "metric": "contrast-loss fwd+bwd throughput", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, bank, B_ref),
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": workload_config(cfg, bank),
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
@@ -225,9 +266,7 @@ def workload_config(cfg, bank, B=None):
     return {"workload": f"{name}, {data} -> embed {cfg['D']}x{cfg['h']}x{cfg['w']}, "
                         f"batch {B or cfg['B']} per GPU, max_samples {cfg['max_samples']}, max_views {cfg['max_views']}",
             "per_gpu_batch": B or cfg["B"], "parallelism": "dp (images sharded, no data-path collective)" if not bank
-            else "dp + one NCCL all_gather of the bank enqueue packet per step",
-            "l2": "inputs larger than L2 (embed 268 MB + grad 268 MB per step vs 126 MB L2)" if (B or cfg["B"]) >= 4
-            else "L2 flushed between iterations"}
+            else "dp + one NCCL all_gather of the bank enqueue packet per step"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -350,226 +389,333 @@ def train_iter_bench(cfg, inp, dev, precision, iters=10):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CUDA-graph arm: the same step as ONE graph replay (GraphedContrastStep), measured in a child process per rank so
-# that nothing it does can touch the process that produced the eager numbers.  The child first proves on the hardware
-# that a replay computes exactly what the eager autograd step computes (anchors, loss, dense gradient), then waits for
-# the parent's "GO" (sent after a barrier over all ranks) and times K replays with CUDA events.
+# engine arm: every workload is measured through the public graphed-step API (GraphedContrastStep): ONE CUDA-graph replay
+# per step (bank steps on several ranks: two replays around the NCCL all_gather of the enqueue packet).
 # ---------------------------------------------------------------------------------------------------
-def run_graph_child(args, cfg):
-    import contrastiveseg_b200 as cs
-    from contrastiveseg_b200 import functional as Fn
-    out = {"ok": False}
-    try:
-        dev = torch.device("cuda:0")                  # the parent narrowed CUDA_VISIBLE_DEVICES to this rank's GPU
-        torch.cuda.set_device(dev)
-        inp_h = make_inputs(cfg, 304 + args.child_rank, None, False)
-        inp = {k: v.to(dev) for k, v in inp_h.items()}
-        crit = cs.PixelContrastLoss(engine_configer(cfg, False, args.precision))
-        opts = crit.options()
+L2_BYTES = 126 << 20
+
+
+def working_set_bytes(cfg, bank):
+    hw = cfg["h"] * cfg["w"]
+    himg, wimg = cfg.get("himg") or cfg["h"] * cfg["stride"], cfg.get("wimg") or cfg["w"] * cfg["stride"]
+    ws = cfg["B"] * (2 * cfg["D"] * hw * 4 + cfg["K"] * hw * 4 + himg * wimg * 8)
+    if bank:
+        ws += (cfg["K"] - 1) * 2 * cfg["M"] * cfg["D"] * 2          # the bf16 shadow the sweeps stream
+    return ws
+
+
+def rotation_sets(cfg, bank):
+    """Timing rule: inputs larger than L2, or flush.  A step's working set (embed + dense gradient + seg + labels
+    [+ bank shadow]) above ~1.2x L2 needs nothing; below that the bench rotates over R independent input/gradient
+    buffer sets (R x working set > 2.2 x L2), so no timed step finds its inputs in L2 and no flush sits in the timed
+    region."""
+    ws = working_set_bytes(cfg, bank)
+    if ws >= 1.2 * L2_BYTES:
+        return 1
+    return max(2, min(8, -(-int(2.2 * L2_BYTES) // ws)))
+
+
+class Workload:
+    """One measured workload: R rotating input sets, one GraphedContrastStep per set (bank steps share the bank)."""
+
+    def __init__(self, args, name, cfg, bank, rank, world, dev):
+        import contrastiveseg_b200 as cs
+        self.args, self.name, self.cfg, self.bank, self.rank, self.world, self.dev = args, name, cfg, bank, rank, world, dev
+        self.R = 1 if os.environ.get("PCL_BENCH_TINY") else rotation_sets(cfg, bank)
+        self.host = [make_inputs(cfg, 304 + rank + 1000 * r, None, bank) for r in range(self.R)]
+        self.inp = [{k: v.to(dev) for k, v in h.items() if k in ("embed", "seg", "target")} for h in self.host]
+        self.crit = cs.PixelContrastLoss(engine_configer(cfg, bank, args.precision))
+        self.mbank = None
+        if bank:
+            self.mbank = cs.MemoryBank(cfg["K"], cfg["M"], cfg["D"], with_shadow=(args.precision == "bf16")).to(dev)
+            self.mbank.segment_queue.copy_(self.host[0]["segment_queue"]); self.mbank.pixel_queue.copy_(self.host[0]["pixel_queue"])
+            if args.precision == "bf16":
+                self.mbank.sync_shadow()
+        self.steps = []
+        self.graph_error = None
+        opts = self.crit.options()
         opts.num_classes = cfg["K"]
-        # ---- 1. replay == eager step, on this GPU, before anything is timed ----
-        probe = cs.GraphedContrastStep(inp["embed"].clone(), inp["target"], seg=inp["seg"], options=opts)
-        for r in range(2):
-            loss_g, grad_g = probe.replay()
-            torch.cuda.synchronize(dev)
-            meta_g, loss_g, grad_g = probe.ws.anchor_meta.clone(), loss_g.clone(), grad_g.clone()
-            Fn._step_counter[0] = r
-            e = inp["embed"].clone().requires_grad_(True)
-            loss_e = cs.pixel_contrast_loss(e, inp["target"], seg=inp["seg"], options=opts)
-            ws = Fn.last_workspace(dev)
-            loss_e.backward()
-            torch.cuda.synchronize(dev)
-            same = (torch.equal(ws.anchor_meta, meta_g) and torch.equal(loss_e.detach(), loss_g) and
-                    torch.allclose(e.grad, grad_g, rtol=3e-6, atol=0))
-            if not same:
-                out["why"] = f"replay {r} differs from the eager step"
-                print(json.dumps(out), flush=True)
-                return
-        del probe, e
-        torch.cuda.empty_cache()
-        # ---- 2. the timed object: static input buffers, one replay per step ----
-        step = cs.GraphedContrastStep(inp["embed"], inp["target"], seg=inp["seg"], options=opts)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if cfg["B"] < 4 else None
-        for _ in range(max(args.warmup, 3)):
-            step.replay()
-        torch.cuda.synchronize(dev)
-        print("READY", flush=True)
-        if sys.stdin.readline().strip() != "GO":
-            return
-        sampler = ClockSampler(args.child_gpu) if args.child_rank == 0 else None      # nvidia-smi takes the physical index / uuid
-        if sampler:
+        try:
+            for r in range(self.R):
+                kw = {}
+                if bank:
+                    kw = dict(segment_queue=self.mbank.segment_queue, pixel_queue=self.mbank.pixel_queue,
+                              bank_shadow=self.mbank.shadow,
+                              enqueue=dict(bank=self.mbank, network_stride=cfg["net_stride"], pixel_update_freq=cfg["F"]))
+                self.steps.append(cs.GraphedContrastStep(self.inp[r]["embed"], self.inp[r]["target"], seg=self.inp[r]["seg"],
+                                                         options=opts, capture=not args.no_graph, **kw))
+        except Exception as exc:                                   # noqa: BLE001  (never lose the whole line)
+            self.graph_error = f"{type(exc).__name__}: {exc}"[:300]
+            self.steps = []
+
+    # ---- the step, two ways ----
+    def replay(self, i):
+        return self.steps[i % self.R].replay()[0]
+
+    def eager(self, i):
+        inp = self.inp[i % self.R]
+        e = inp["embed"].detach().requires_grad_(True)
+        queue = (self.mbank.segment_queue, self.mbank.pixel_queue) if self.bank else None
+        loss = self.crit(e, inp["target"], seg=inp["seg"], queue=queue, bank_shadow=self.mbank.shadow if self.bank else None)
+        if self.bank:
+            self.mbank.enqueue(e.detach(), inp["target"], network_stride=self.cfg["net_stride"], pixel_update_freq=self.cfg["F"])
+        loss.backward()
+        return loss
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def reduce_max(self, values):
+        t = torch.tensor(values, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def time_loop(self, fn, steps, warmup, sampler=None):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks.
+        Returns (device ms per step, host enqueue ms per step, clock window description)."""
+        for i in range(max(warmup, 3)):
+            fn(i)
+        self.barrier()
+        if sampler is not None and self.rank == 0:
             sampler.start()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        torch.cuda.synchronize(dev)
+        self.barrier()
         t0 = time.perf_counter()
         ev[0].record()
-        for _ in range(args.steps):
-            if flush is not None:
-                flush.zero_()
-            step.replay()
+        for i in range(steps):
+            fn(i)
         ev[1].record()
-        t_host = time.perf_counter() - t0
-        torch.cuda.synchronize(dev)
-        while time.perf_counter() - t0 < 0.9:            # keep the GPU under the same load for the clock sampler
+        t_host = time.perf_counter() - t0               # host time to enqueue the K steps (no sync inside)
+        self.barrier()
+        window = "timed region"
+        if sampler is not None:
+            # nvidia-smi samples every 200 ms; a short timed region would see no sample, so the SAME loop keeps running
+            # (untimed) until the sampler has covered >= 0.9 s under load
+            while time.perf_counter() - t0 < 0.9:
+                window = "timed region + untimed continuation of the same step loop to 0.9 s"
+                for i in range(50):
+                    fn(i)
+                torch.cuda.synchronize(self.dev)
+            if self.rank == 0:
+                sampler.stop()
+        ms, host = self.reduce_max([ev[0].elapsed_time(ev[1]) / steps, t_host / steps * 1e3])
+        return ms, host, window
+
+    def e2e(self, fn, steps):
+        """Same step with HOST inputs: pinned embed/seg/target copied H2D every step, loss read back (D2H)."""
+        pin = [{k: h[k].pin_memory() for k in ("embed", "seg", "target")} for h in self.host]
+        h2d = sum(pin[0][k].numel() * pin[0][k].element_size() for k in pin[0])
+
+        def one(i):
+            r = i % self.R
+            for k in pin[r]:
+                self.inp[r][k].copy_(pin[r][k], non_blocking=True)
+            return fn(i).item()
+        for i in range(3):
+            one(i)
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(i)
+        self.barrier()
+        (dt,) = self.reduce_max([time.perf_counter() - t0])
+        return self.world * self.cfg["B"] * steps / dt, h2d
+
+    def kernels_per_step(self):
+        """Kernels of this library per step, counted by the library itself around one eager pass of the step's own launch
+        sequence (what the graph replays)."""
+        from contrastiveseg_b200 import _abi
+        lib = _abi.load()
+        if not self.steps:
+            return None
+        st = self.steps[0]
+        snap = None
+        if self.bank:
+            b = self.mbank
+            snap = [t.clone() for t in (b.segment_queue, b.segment_queue_ptr, b.pixel_queue, b.pixel_queue_ptr)]
+        n0 = lib.pcl_launch_count()
+        with torch.cuda.device(self.dev):
+            st._enqueue(torch.cuda.current_stream(self.dev).cuda_stream)
+        n = int(lib.pcl_launch_count() - n0)
+        torch.cuda.synchronize(self.dev)
+        if snap is not None:                               # this extra step is not part of any measurement
+            for t, v in zip((b.segment_queue, b.segment_queue_ptr, b.pixel_queue, b.pixel_queue_ptr), snap):
+                t.copy_(v)
+            if b.shadow is not None:
+                b.sync_shadow()
+        return n
+
+    def measure(self, sampler=None, with_eager=False, with_e2e=True):
+        a = self.args
+        out = {"workload": workload_config(self.cfg, self.bank)["workload"], "per_gpu_batch": self.cfg["B"],
+               "rotation_sets": self.R, "working_set_mb": round(working_set_bytes(self.cfg, self.bank) / 1e6, 1)}
+        fn, mode = (self.replay, "graph") if self.steps else (self.eager, "eager")
+        if not self.steps:
+            out["graph_error"] = self.graph_error or "disabled (--no-graph)"
+        ms, host, window = self.time_loop(fn, a.steps, a.warmup, sampler)
+        out.update(mode=mode, ms_per_step=ms, value=self.world * self.cfg["B"] / (ms / 1e3), host_ms_per_step=host,
+                   clock_window=window, kernels_per_step=self.kernels_per_step())
+        if with_e2e:
+            e_steps = max(3, min(a.steps, 50))
+            ev, h2d = self.e2e(fn, e_steps)
+            out["e2e"] = {"value": ev, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e_steps}
+        if with_eager and self.steps:
+            ems, ehost, _ = self.time_loop(self.eager, a.steps, a.warmup)
+            out["eager"] = {"ms_per_step": ems, "value": self.world * self.cfg["B"] / (ems / 1e3), "host_ms_per_step": ehost}
+        if self.bank and self.world > 1 and self.steps:
+            # the one data-path collective: NCCL all_gather of the enqueue packet, timed alone on the device
+            st = self.steps[0]
+            for _ in range(5):
+                st._gather()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.barrier()
+            e0.record()
             for _ in range(50):
-                step.replay()
-            torch.cuda.synchronize(dev)
-        clocks = None
-        if sampler:
-            sampler.stop()
-            clocks = sampler.summary()
-        ms = ev[0].elapsed_time(ev[1]) / args.steps
-        # ---- 3. end to end: pinned host inputs copied in every step, loss read back ----
-        pin = {k: inp_h[k].pin_memory() for k in ("embed", "seg", "target")}
-        e_steps = max(3, min(args.steps, 50))
-
-        def e2e_step():
-            for k in pin:
-                inp[k].copy_(pin[k], non_blocking=True)
-            loss, _ = step.replay()
-            return loss.item()
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        t1 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        out.update(ok=True, ms_per_step=ms, host_enqueue_ms_per_step=t_host / args.steps * 1e3,
-                   e2e_s_per_step=(time.perf_counter() - t1) / e_steps, e2e_steps=e_steps, clocks=clocks,
-                   finite=bool(torch.isfinite(step.loss).item()))
-    except Exception as exc:                             # noqa: BLE001
-        out["why"] = f"{type(exc).__name__}: {exc}"[:300]
-    print(json.dumps(out), flush=True)
-
-
-class GraphArm:
-    """Parent side of the CUDA-graph arm: one child per rank on that rank's GPU (see run_graph_child)."""
-
-    def __init__(self, args, rank, local):
-        import subprocess
-        env = dict(os.environ)
-        vis = [v.strip() for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
-        env["CUDA_VISIBLE_DEVICES"] = vis[local] if local < len(vis) else str(local)
-        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
-            env.pop(k, None)
-        self.gpu = env["CUDA_VISIBLE_DEVICES"]
-        cmd = [sys.executable, os.path.abspath(__file__), "--graph-child", "--child-rank", str(rank), "--child-gpu", self.gpu,
-               "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--precision", args.precision, "--workload", args.workload, "--scaling", args.scaling,
-               "--child-world", str(int(os.environ.get("WORLD_SIZE", "1")))]
-        import tempfile
-        self._err = tempfile.TemporaryFile()             # the child's stderr, quoted in `why` when it dies without an answer
-        self.proc = subprocess.Popen(cmd, env=env, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=self._err)
-        self.result = None
-        self._buf = b""
-
-    def _stderr_tail(self, n=240):
-        try:
-            self._err.seek(0)
-            txt = self._err.read().decode("utf-8", "replace").strip().replace("\n", " | ")
-            return txt[-n:]
-        except Exception:                                # noqa: BLE001
-            return ""
-
-    def _readline(self, timeout_s):
-        """Next protocol line of the child (READY or one JSON object); anything else a library printed is skipped.
-        Raw, unbuffered reads: select() must see exactly what has not been consumed yet."""
-        import select
-        deadline = time.perf_counter() + timeout_s
-        fd = self.proc.stdout.fileno()
-        while True:
-            while b"\n" in self._buf:
-                line, self._buf = self._buf.split(b"\n", 1)
-                line = line.decode("utf-8", "replace").strip()
-                if line == "READY" or line.startswith("{"):
-                    return line
-            left = deadline - time.perf_counter()
-            if left <= 0:
-                return None
-            r, _, _ = select.select([fd], [], [], left)
-            if not r:
-                return None
-            chunk = os.read(fd, 65536)
-            if not chunk:
-                return None                              # child closed its stdout (exited)
-            self._buf += chunk
-
-    def wait_ready(self, timeout_s=420.0):
-        line = self._readline(timeout_s)
-        if line == "READY":
-            return True
-        try:
-            self.result = json.loads(line) if line else {"ok": False, "why": "no answer from the graph child (timeout or exit)"
-                                                         + (": " + self._stderr_tail() if getattr(self, "_err", None) else "")}
-        except ValueError:
-            self.result = {"ok": False, "why": f"unexpected output from the graph child: {line[:120]!r}"}
-        return False
-
-    def go(self, timeout_s=300.0):
-        try:
-            self.proc.stdin.write(b"GO\n")
-            self.proc.stdin.flush()
-            line = self._readline(timeout_s)
-            self.result = json.loads(line) if line else {"ok": False, "why": "graph child timed out or died"
-                                                         + (": " + self._stderr_tail() if getattr(self, "_err", None) else "")}
-        except Exception as exc:                         # noqa: BLE001
-            self.result = {"ok": False, "why": f"{type(exc).__name__}: {exc}"[:200]}
-        return self.result
+                st._gather()
+            e1.record()
+            self.barrier()
+            (g_ms,) = self.reduce_max([e0.elapsed_time(e1) / 50])
+            out["allgather_ms"] = g_ms
+            out["packet_bytes_per_rank"] = int(st.enq["packet"].numel() * 4)
+        losses = [float(fn(i).item()) for i in range(2)]
+        out["finite_loss"] = all(x == x and abs(x) < 1e30 for x in losses)
+        return out
 
     def close(self):
-        try:
-            if self.proc.poll() is None:
-                self.proc.stdin.close()
-                self.proc.wait(timeout=4)                # a child that has printed its line exits at once
-        except Exception:                                # noqa: BLE001
-            pass
-        if self.proc.poll() is None:
-            self.proc.kill()                             # exactly the child this object started
+        self.steps = []
+        self.inp = self.host = None
+        from contrastiveseg_b200 import functional as Fn
+        Fn.clear_workspaces()
+        torch.cuda.empty_cache()
+
+
+def step_algorithmic_bytes(cfg, A, bank):
+    """labels at the embedding stride + seg (argmax) + gather + dense-gradient write (+ the bank shadow once per
+    sweep, forward and backward, + the enqueue's pass over the keys)."""
+    hw = cfg["h"] * cfg["w"]
+    b = cfg["B"] * hw * 8 + cfg["B"] * cfg["K"] * hw * 4 + A * cfg["D"] * 4 + cfg["B"] * cfg["D"] * hw * 4
+    if bank:
+        b += 2 * (cfg["K"] - 1) * 2 * cfg["M"] * cfg["D"] * 2 + cfg["B"] * cfg["D"] * hw * 4
+    return b
+
+
+def run_engine(args, cfg, bank, rank, world, dev):
+    import contrastiveseg_b200 as cs
+    from contrastiveseg_b200 import _abi
+    _abi.load()
+    peaks = load_peaks()
+    sampler = ClockSampler(dev.index)
+    # ---- headline: the workload named on the command line (default s1 = BASELINE configs[1]), weak scaling ----
+    head = Workload(args, args.workload, cfg, bank, rank, world, dev)
+    hm = head.measure(sampler=sampler, with_eager=True)
+    A_live = int(head.steps[0].ws.plan[2].item()) if head.steps else 0
+    inp0 = head.inp[0]
+    stages = {}
+    if rank == 0 and not bank and world == 1:
+        stages, A_live = stage_timings(cfg, inp0, dev, args.precision)
+    wrapper = train = tens = None
+    if rank == 0 and world == 1 and not bank and not os.environ.get("PCL_BENCH_HEADLINE_ONLY"):
+        embed = inp0["embed"].detach().requires_grad_(True)
+        wrapper = {}
+        for name, fused in (("fused_seg_ce_ms", True), ("torch_seg_ce_ms", False)):
+            cw = engine_configer(cfg, bank, args.precision)
+            cw.add(["contrast", "fused_seg_ce"], fused)
+            mod = cs.ContrastCELoss(cw).to(dev)
+            seg_l = inp0["seg"].clone().requires_grad_(True)
+
+            def wstep():
+                embed.grad = None; seg_l.grad = None
+                mod({"seg": seg_l, "embed": embed}, inp0["target"], with_embed=True).backward()
+            for _ in range(5):
+                wstep()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(30):
+                wstep()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            wrapper[name] = e0.elapsed_time(e1) / 30
+        if not os.environ.get("PCL_BENCH_NO_TRAIN_ITER"):
             try:
-                self.proc.wait(timeout=10)
-            except Exception:                            # noqa: BLE001
-                pass
-
-
-def graph_arm_measure(args, cfg, rank, world, dev, barrier):
-    """Run the CUDA-graph arm (one child per rank, see run_graph_child / GraphArm) and reduce its result over the ranks.
-    Every rank takes part in every collective below whatever happens to its own child (no rank may wait alone).
-    Returns {"ok": True, value, ms_per_step, e2e_value, ...} or {"ok": False, "why": ...}."""
-    arm, ready, why = None, False, None
-    try:
-        arm = GraphArm(args, rank, dev.index)
-        ready = arm.wait_ready()
-        if not ready:
-            why = (arm.result or {}).get("why", "graph child did not get ready")
-    except Exception as exc:                         # noqa: BLE001
-        why = f"{type(exc).__name__}: {exc}"[:200]
-    flag = torch.tensor([1.0 if ready else 0.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
-    if float(flag.item()) > 0.5:
-        barrier()                                    # all children are warmed up and wait for GO: start them together
-        res = arm.go()
-        ok = bool(res.get("ok")) and bool(res.get("finite", False)) and (res.get("ms_per_step") or 0.0) > 1e-3 \
-            and (res.get("e2e_s_per_step") or 0.0) > 1e-6
-        vals = torch.tensor([1.0 if ok else 0.0, -(res.get("ms_per_step") or 0.0), -(res.get("e2e_s_per_step") or 0.0),
-                             -(res.get("host_enqueue_ms_per_step") or 0.0)], dtype=torch.float64, device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.MIN)          # MIN of negatives = MAX over ranks
-        if float(vals[0].item()) > 0.5:
-            g_ms, g_e2e = -float(vals[1].item()), -float(vals[2].item())
-            graph = {"ok": True, "ms_per_step": g_ms, "value": world * cfg["B"] / (g_ms / 1e3),
-                     "e2e_value": world * cfg["B"] / g_e2e, "e2e_steps": res.get("e2e_steps"),
-                     "host_enqueue_ms_per_step": -float(vals[3].item()), "clocks": res.get("clocks"),
-                     "check": "on every rank's GPU, before timing: replay == eager autograd step (same anchors, same loss "
-                              "bits, gradient within 3e-6 relative: scatter-only backward vs fused writer)"}
-        else:
-            graph = {"ok": False, "why": res.get("why", "a rank's graph child failed")}
-    else:
-        graph = {"ok": False, "why": why or "another rank's graph child did not get ready"}
-    if arm is not None:
-        arm.close()
-    return graph
+                train = train_iter_bench(cfg, inp0, dev, args.precision)
+                train["loss_step_ms"] = wrapper.get("fused_seg_ce_ms")
+                train["loss_step_share"] = wrapper.get("fused_seg_ce_ms") / train["ms_per_iter"]
+            except Exception as exc:                      # noqa: BLE001
+                train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if cfg["D"] == 256:
+            tens = tensor_sweep_roofline(dev, peaks)
+    # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload at the SAME batch ----
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads, t1 = calibrate_cpu(cfg, bank)
+        ih = head.host[0]
+        t0 = time.perf_counter()
+        cpu_port_step(ih, cfg, bank)
+        cdt = time.perf_counter() - t0
+        n_cpu = 1
+        if cdt < 8.0:                                   # small geometries: a few more steps
+            n_cpu = 3
+            t0 = time.perf_counter()
+            for _ in range(n_cpu):
+                cpu_port_step(ih, cfg, bank)
+            cdt = (time.perf_counter() - t0) / n_cpu
+        cpu = {"value": cfg["B"] / cdt, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} step(s) of the full workload (batch {cfg['B']}) after the calibration pass, fp32 torch CPU on "
+                         f"{threads} of {os.cpu_count()} host threads (fastest setting), {cdt * 1e3:.0f} ms/step"}
+    head.close()
+    # ---- the memory-bank step (BASELINE configs[2]: one image per rank + ONE NCCL all_gather of the enqueue packet per
+    #      step) and strong scaling of the headline (global batch fixed), measured in the same run at every N ----
+    blocks = {}
+    if not os.environ.get("PCL_BENCH_HEADLINE_ONLY") and args.workload == "s1":
+        s2 = dict(S2)
+        if os.environ.get("PCL_BENCH_TINY"):
+            s2.update(B=1, D=32, h=16, w=16, K=5, stride=2, block=8, max_samples=32, max_views=4, M=8, F=2, net_stride=2)
+        try:
+            w2 = Workload(args, "s2", s2, True, rank, world, dev)
+            blocks["bank"] = dict(w2.measure(with_e2e=False), config="BASELINE configs[2]: HRNet-W48 + pixel/region memory bank "
+                                  "(19 x (5000+5000) x 256), one image per rank, max_views 100, bank merged by one NCCL "
+                                  "all_gather of the enqueue packet per step; weak scaling (value = world images per step)")
+            w2.close()
+        except Exception as exc:                          # noqa: BLE001
+            blocks["bank"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if world > 1 and cfg["B"] % world == 0:
+            cs_ = dict(cfg); cs_["B"] = cfg["B"] // world
+            try:
+                w3 = Workload(args, "s1-strong", cs_, False, rank, world, dev)
+                blocks["strong"] = dict(w3.measure(with_e2e=False), config=f"headline workload with the global batch {cfg['B']} "
+                                        f"split over {world} ranks (lib/datasets/data_loader.py:137)")
+                w3.close()
+            except Exception as exc:                      # noqa: BLE001
+                blocks["strong"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    if rank != 0:
+        return None
+    # ---- roofline of what was timed: the whole step against the HBM peak (the step is one graph; its kernels are
+    #      latency-bound except the dense-gradient fill, so the per-step fraction is the honest figure) ----
+    alg = step_algorithmic_bytes(cfg, A_live, bank)
+    ach = alg / (hm["ms_per_step"] * 1e-3) / 1e9
+    roof = {"kernel": "whole step (one CUDA-graph replay: all kernels of the loss step)" if hm["mode"] == "graph" else "whole step (eager)",
+            "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+            "traffic": ncu_traffic("step"), "peak_source": peaks["source"], "algorithmic_bytes": alg,
+            "anchors": A_live, "kernels_per_step": hm["kernels_per_step"]}
+    clocks = dict(sampler.summary(), window=hm["clock_window"])
+    kps = hm["kernels_per_step"] or 0
+    conf = dict(workload_config(cfg, bank),
+                step="one CUDA-graph replay per step (GraphedContrastStep)" if hm["mode"] == "graph" else "eager autograd call per step",
+                l2=("inputs larger than L2 (working set %.0f MB vs 126 MB)" % hm["working_set_mb"]) if hm["rotation_sets"] == 1
+                else f"rotating over {hm['rotation_sets']} input/gradient buffer sets ({hm['working_set_mb']:.0f} MB each) so that no step finds its inputs in L2")
+    return {"metric": "contrast-loss fwd+bwd throughput", "value": hm["value"], "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": hm["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": conf, "clocks": clocks,
+            "e2e": hm.get("e2e"), "gpu_launches": kps * args.steps, "roofline": roof, "cpu_baseline": cpu,
+            "stage_ms": stages, "host_enqueue_ms_per_step": hm["host_ms_per_step"], "tensor_roofline": tens,
+            "contrast_ce_wrapper": wrapper, "train_iter": train, "precision": args.precision,
+            "cuda_graph": hm["mode"] == "graph", "graph_error": hm.get("graph_error"), "eager": hm.get("eager"),
+            "bank": blocks.get("bank"), "strong": blocks.get("strong"), "impl": "engine"}
 
 
 def tensor_sweep_roofline(dev, peaks, A=16384, N=65536, iters=5):
@@ -616,231 +762,6 @@ def tensor_sweep_roofline(dev, peaks, A=16384, N=65536, iters=5):
             "forward_tflops": fl / (out["forward"] * 1e-3) / 1e12, "backward_tflops": fl / (out["backward"] * 1e-3) / 1e12}
 
 
-def run_engine(args, cfg, bank, rank, world, dev):
-    import contrastiveseg_b200 as cs
-    from contrastiveseg_b200 import _abi
-    _abi.load()
-    peaks = load_peaks()
-    inp_h = make_inputs(cfg, 304 + rank, None, bank)
-    inp = {k: v.to(dev) for k, v in inp_h.items()}
-    cfgr = engine_configer(cfg, bank, args.precision)
-    crit = cs.PixelContrastLoss(cfgr)
-    mbank = None
-    if bank:
-        mbank = cs.MemoryBank(cfg["K"], cfg["M"], cfg["D"], with_shadow=True).to(dev)
-        mbank.segment_queue.copy_(inp["segment_queue"]); mbank.pixel_queue.copy_(inp["pixel_queue"])
-        mbank.sync_shadow()
-    embed = inp["embed"].clone().requires_grad_(True)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if cfg["B"] < 4 else None
-
-    graphed = {}
-
-    def step(e, tgt, seg):
-        if args.graph:
-            # one CUDA-graph replay per step (GraphedContrastStep: static tensors, device-side sampling counter)
-            key = (e.data_ptr(), tgt.data_ptr(), seg.data_ptr())
-            g = graphed.get(key)
-            if g is None:
-                kw = dict(segment_queue=mbank.segment_queue, pixel_queue=mbank.pixel_queue,
-                          bank_shadow=mbank.shadow) if bank else {}
-                opts = crit.options()
-                opts.num_classes = cfg["K"]
-                g = graphed[key] = cs.GraphedContrastStep(e.detach(), tgt, seg=seg, options=opts, **kw)
-            loss, _ = g.replay()
-            if bank:
-                mbank.enqueue(e.detach(), tgt, network_stride=cfg["net_stride"], pixel_update_freq=cfg["F"])
-            return loss
-        e.grad = None
-        queue = (mbank.segment_queue, mbank.pixel_queue) if bank else None
-        loss = crit(e, tgt, seg=seg, queue=queue, bank_shadow=mbank.shadow if bank else None)
-        if bank:
-            mbank.enqueue(e.detach(), tgt, network_stride=cfg["net_stride"], pixel_update_freq=cfg["F"])
-        loss.backward()
-        return loss
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(max(args.warmup, 3)):
-        step(embed, inp["target"], inp["seg"])
-    # one nvidia-smi poller for the whole job (rank 0, its own GPU): every poll takes driver locks that stall kernel
-    # launches of ALL ranks, so N pollers would perturb a host-launch-bound step
-    sampler = ClockSampler(dev.index)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    ev[0].record()
-    for _ in range(args.steps):
-        if flush is not None:
-            flush.zero_()
-        step(embed, inp["target"], inp["seg"])
-    ev[1].record()
-    t_enqueue = time.perf_counter() - t_wall0        # host time to enqueue the K steps (no sync inside)
-    barrier()
-    # nvidia-smi samples every 200 ms; a short timed region (K steps of ~0.2 ms) would see no sample, so the SAME
-    # step loop keeps running (untimed) until the sampler has covered >= 0.9 s under load
-    clock_window = "timed region"
-    while time.perf_counter() - t_wall0 < 0.9:
-        clock_window = "timed region + untimed continuation of the same step loop to 0.9 s"
-        for _ in range(50):
-            step(embed, inp["target"], inp["seg"])
-        torch.cuda.synchronize(dev)
-    sampler.stop()
-    t_ms = ev[0].elapsed_time(ev[1])
-    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    per_rank = None
-    if world > 1:
-        # diagnostics: every rank's device time and host enqueue time per step (which rank sets the max, and why)
-        mine = torch.tensor([t_ms / args.steps, t_enqueue / args.steps * 1e3], dtype=torch.float64, device=dev)
-        allv = torch.empty(2 * world, dtype=torch.float64, device=dev)
-        torch.distributed.all_gather_into_tensor(allv, mine)
-        per_rank = {"ms_per_step": [round(v, 5) for v in allv.view(world, 2)[:, 0].tolist()],
-                    "host_enqueue_ms_per_step": [round(v, 5) for v in allv.view(world, 2)[:, 1].tolist()]}
-        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-    t_ms = float(tt.item())
-    value = world * cfg["B"] * args.steps / (t_ms / 1e3)
-
-    # ---- e2e: host (pinned) buffers in, loss scalar out, every step ----
-    pin = {k: inp_h[k].pin_memory() for k in ("embed", "seg", "target")}
-    dbuf = {k: torch.empty_like(inp[k]) for k in ("embed", "seg", "target")}
-    h2d = sum(pin[k].numel() * pin[k].element_size() for k in pin)
-
-    def e2e_step():
-        for k in pin:
-            dbuf[k].copy_(pin[k], non_blocking=True)
-        e = dbuf["embed"].requires_grad_(True)
-        loss = step(e, dbuf["target"], dbuf["seg"])
-        dbuf["embed"] = e.detach()
-        return loss.item()                          # D2H read of the step's result
-    e_steps = max(3, min(args.steps, 50))
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        e2e_step()
-    barrier()
-    e_dt = time.perf_counter() - t0
-    et = torch.tensor([e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(et, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = world * cfg["B"] * e_steps / float(et.item())
-
-    # ---- CUDA-graph arm (child process per rank; the eager numbers above are already final) ----
-    graph = None
-    if not bank and not args.graph and not args.no_graph_arm and not os.environ.get("PCL_BENCH_NO_GRAPH_ARM"):
-        graph = graph_arm_measure(args, cfg, rank, world, dev, barrier)
-    if rank != 0:
-        return None
-    # ---- per-stage times + roofline of the dominant stage (rank 0, N-independent) ----
-    roof = None
-    stages = {}
-    if not bank:
-        stages, A = stage_timings(cfg, inp, dev, args.precision)
-        # roofline of the one single-pass bandwidth-bound kernel of the step, the dense-gradient writer (the other
-        # stages are chains of short latency-bound launches at A <= 1024; stage_ms lists them all)
-        dom = "scatter_grad"
-        BDHW4 = cfg["B"] * cfg["D"] * cfg["h"] * cfg["w"] * 4
-        alg_bytes = {
-            "scatter_grad": BDHW4 + 2 * A * cfg["D"] * 4,
-            "class_stats": cfg["B"] * cfg["h"] * cfg["w"] * (cfg["K"] * 4 + 8 + 2),
-            "select_gather": A * cfg["D"] * (4 + 4 + 2) + cfg["B"] * cfg["h"] * cfg["w"] * 2,
-        }
-        if dom in alg_bytes:
-            ach = alg_bytes[dom] / (stages[dom] * 1e-3) / 1e9
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("k_zero_scatter"),
-                    "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes[dom],
-                    "kernel_name": "k_zero_scatter" if dom == "scatter_grad" else dom}
-        else:
-            flops = 2.0 * A * A * cfg["D"] * (2 if dom == "infonce_fwd" else 2)
-            ach = flops / (stages[dom] * 1e-3) / 1e12
-            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "note": "A=N<=1024 is the launch/latency-bound regime of the sweep (SURVEY §8d); tensor_roofline reports the S4 point"}
-    # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same workload ----
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        threads, t1 = calibrate_cpu(cfg, bank)
-        Bc = cfg["B"] if 3 * t1 * cfg["B"] ** 2 <= 40.0 else max(1, cfg["B"] // 2) if 3 * t1 * (cfg["B"] // 2) ** 2 <= 40.0 else 1
-        cc = dict(cfg); cc["B"] = Bc
-        ih = make_inputs(cc, 304, None, bank) if Bc != cfg["B"] else inp_h
-        cpu_port_step(ih, cc, bank)
-        n_cpu = 2
-        t0 = time.perf_counter()
-        for _ in range(n_cpu):
-            cpu_port_step(ih, cc, bank)
-        cdt = time.perf_counter() - t0
-        cpu = {"value": Bc * n_cpu / cdt, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{n_cpu} steps at batch {Bc} (of {cfg['B']}) after 1 warm-up, fp32 torch CPU on {threads} of "
-                         f"{os.cpu_count()} host threads (fastest setting), {cdt / n_cpu * 1e3:.0f} ms/step"}
-    tens = tensor_sweep_roofline(dev, peaks) if (world == 1 and cfg["D"] == 256) else None
-    # whole ContrastCELoss.forward + backward (seg CE + contrast): the reference's "Loss Time" scope, with the fused
-    # up-sample + CE kernels (§8f row 1) and with the PyTorch seg-CE ops
-    wrapper = None
-    if world == 1 and not bank:
-        wrapper = {}
-        for name, fused in (("fused_seg_ce_ms", True), ("torch_seg_ce_ms", False)):
-            cw = engine_configer(cfg, bank, args.precision)
-            cw.add(["contrast", "fused_seg_ce"], fused)
-            mod = cs.ContrastCELoss(cw).to(dev)
-            seg_l = inp["seg"].clone().requires_grad_(True)
-
-            def wstep():
-                embed.grad = None; seg_l.grad = None
-                mod({"seg": seg_l, "embed": embed}, inp["target"], with_embed=True).backward()
-            for _ in range(5):
-                wstep()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(dev)
-            e0.record()
-            for _ in range(30):
-                wstep()
-            e1.record()
-            torch.cuda.synchronize(dev)
-            wrapper[name] = e0.elapsed_time(e1) / 30
-    # "train iters/sec" half of BASELINE.json's metric (N=1, stand-in producer); never allowed to break the bench line
-    train = None
-    if world == 1 and not bank and not os.environ.get("PCL_BENCH_NO_TRAIN_ITER"):
-        try:
-            train = train_iter_bench(cfg, inp, dev, args.precision)
-            if wrapper:
-                train["loss_step_ms"] = wrapper.get("fused_seg_ce_ms")
-                train["loss_step_share"] = wrapper.get("fused_seg_ce_ms") / train["ms_per_iter"]
-        except Exception as exc:                      # noqa: BLE001
-            train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-    launches_per_step = (8 if args.precision == "bf16" else 10) + (4 if bank else 0)   # our kernels per step (memsets not counted)
-    if args.graph:
-        launches_per_step += 1                       # + the device-side rank draw (pcl_step_ranks); one graph launch per step
-    # headline = the faster of the two ways the public API offers to run the step: eager autograd call, or one CUDA-graph
-    # replay (GraphedContrastStep) — the latter only if every rank proved replay == eager on its GPU and finished
-    eager = {"value": value, "ms_per_step": t_ms / args.steps, "e2e_value": e2e_val,
-             "host_enqueue_ms_per_step": t_enqueue / args.steps * 1e3, "kernels_per_step": launches_per_step}
-    use_graph = bool(graph and graph.get("ok") and graph["ms_per_step"] < t_ms / args.steps)
-    clocks_out = dict(sampler.summary(), window=clock_window)
-    if use_graph:
-        value, e2e_val = graph["value"], graph["e2e_value"]
-        e_steps = graph.get("e2e_steps") or e_steps
-        t_ms = graph["ms_per_step"] * args.steps
-        launches_per_step += 2                       # + rank draw, + the reduction kernel of the scatter-only backward
-        if graph.get("clocks") and graph["clocks"].get("samples"):
-            clocks_out = dict(graph["clocks"], window="graph arm: timed region + untimed continuation of the same replay loop to 0.9 s")
-    return {"metric": "contrast-loss fwd+bwd throughput", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
-            "data": "synthetic", "config": dict(workload_config(cfg, bank), step="one CUDA-graph replay per step (GraphedContrastStep)" if use_graph else "eager autograd call per step"), "clocks": clocks_out,
-            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e_steps},
-            "gpu_launches": launches_per_step * args.steps, "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stages, "host_enqueue_ms_per_step": graph["host_enqueue_ms_per_step"] if use_graph else t_enqueue / args.steps * 1e3, "tensor_roofline": tens, "contrast_ce_wrapper": wrapper, "per_rank": per_rank, "train_iter": train, "precision": args.precision, "cuda_graph": bool(args.graph) or use_graph,
-            "eager": eager, "graph_arm": graph, "impl": "engine"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -853,17 +774,12 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): the workload's batch per GPU; strong: the workload's batch split over the ranks "
                          "(global batch fixed, as lib/datasets/data_loader.py:137 does), SURVEY §8d asks for both")
-    ap.add_argument("--no-graph-arm", action="store_true", help="skip the CUDA-graph arm (child process per rank)")
-    ap.add_argument("--graph-child", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--child-rank", type=int, default=0, help=argparse.SUPPRESS)
-    ap.add_argument("--child-world", type=int, default=1, help=argparse.SUPPRESS)
-    ap.add_argument("--child-gpu", default="0", help=argparse.SUPPRESS)
-    ap.add_argument("--graph", action="store_true",
-                    help="run the step as one CUDA-graph replay (GraphedContrastStep) instead of the eager autograd call")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="run GraphedContrastStep's launch sequence eagerly instead of as a captured CUDA graph")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="InfoNCE sweeps: bf16 operands on tcgen05 tensor cores (default) or the exact fp32 SIMT sweep")
     args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1")) if not args.graph_child else args.child_world
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = dict({"s1": S1, "s2": S2, "s3": S3}[args.workload])
@@ -876,9 +792,6 @@ def main():
         cfg.update(B=2, D=32, h=16, w=16, K=5, stride=2, block=8, max_samples=32, max_views=4)
         if bank:
             cfg.update(M=8, F=2, net_stride=2)
-    if args.graph_child:
-        run_graph_child(args, cfg)
-        return
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 10:      # defaults are sized for the GPU arm
             args.steps, args.warmup = 3, 1
@@ -890,9 +803,9 @@ def main():
         raise SystemExit("bench.py --impl engine needs a CUDA device (the engine has no CPU path)")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    pin_to_gpu_local_cpus(dev.index)          # NUMA-local host threads for the launch path, at every N (incl. 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        pin_to_gpu_local_cpus(dev.index)
         torch.distributed.init_process_group("nccl", device_id=dev)
     res = run_engine(args, cfg, bank, rank, world, dev)
     if res is not None:

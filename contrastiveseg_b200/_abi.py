@@ -84,6 +84,7 @@ SIGNATURES = {
     "pcl_last_cuda_error": (C.c_char_p, []),
     "pcl_device_count": (c_i32, []),
     "pcl_abi_sizeof": (c_i64, [c_i32]),
+    "pcl_launch_count": (c_u64, []),
     "pcl_select_sizes": (c_i32, [C.POINTER(Geom), C.POINTER(SelectSizes)]),
     "pcl_class_stats": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_plan_anchors": (c_i32, [C.POINTER(Geom), c_vp, c_vp, c_vp]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "pcl_bank_packet_floats": (c_i64, [C.POINTER(BankGeom)]),
     "pcl_bank_scratch_floats": (c_i64, [C.POINTER(BankGeom)]),
     "pcl_bank_packet": (c_i32, [C.POINTER(BankGeom), c_vp, c_vp, c_vp, c_u64, c_vp, c_vp, c_vp]),
+    "pcl_bank_packet_dev": (c_i32, [C.POINTER(BankGeom), c_vp, c_vp, c_u64, c_vp, c_vp, c_vp, c_vp]),
     "pcl_bank_apply": (c_i32, [C.POINTER(BankGeom), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_bank_shadow_rebuild": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "pcl_tc_sizes": (c_i32, [C.POINTER(TcDesc), C.POINTER(SweepSizes)]),

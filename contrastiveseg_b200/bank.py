@@ -92,15 +92,22 @@ class MemoryBank(nn.Module):
                             pixel_update_freq=pixel_update_freq, shadow=self.shadow, **kw)
 
 
-def gather_packets(packet: torch.Tensor, group=None) -> torch.Tensor:
-    """One all_gather of the fixed-size enqueue packet; returns (world, packet_floats), rank-major."""
+def world_size(group=None) -> int:
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return packet.view(1, -1)
-    world = dist.get_world_size(group)
+        return 1
+    return dist.get_world_size(group)
+
+
+def gather_packets(packet: torch.Tensor, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One all_gather of the fixed-size enqueue packet; returns (world, packet_floats), rank-major.
+    ``out``: optional pre-allocated (world, packet_floats) receive buffer (no allocation per step)."""
+    import torch.distributed as dist
+    world = world_size(group)
     if world == 1:
         return packet.view(1, -1)
-    out = torch.empty((world, packet.numel()), dtype=packet.dtype, device=packet.device)
+    if out is None or out.shape != (world, packet.numel()):
+        out = torch.empty((world, packet.numel()), dtype=packet.dtype, device=packet.device)
     if packet.is_cuda:
         dist.all_gather_into_tensor(out, packet.view(-1).contiguous(), group=group)      # NCCL over NVLink
     else:
@@ -109,6 +116,31 @@ def gather_packets(packet: torch.Tensor, group=None) -> torch.Tensor:
 
 
 _enqueue_counter = [0]
+
+# Per (device, packet geometry, world) scratch / packet / receive buffers, kept across steps: the enqueue allocates
+# nothing in steady state (round 1 drew two torch.empty per call).  Re-use is safe in stream order; the one case where a
+# buffer may still be needed by a held-back bank write is handled by the caller (fresh buffers for that call).
+_ENQ_BUFFERS = {}
+
+
+def enqueue_buffers(dev: torch.device, n_scratch: int, n_packet: int, world: int, fresh: bool = False):
+    key = (dev.index, n_scratch, n_packet, world)
+    bufs = None if fresh else _ENQ_BUFFERS.get(key)
+    if bufs is None:
+        bufs = (torch.empty(n_scratch, dtype=torch.float32, device=dev),
+                torch.empty(n_packet, dtype=torch.float32, device=dev),
+                torch.empty((world, n_packet), dtype=torch.float32, device=dev) if world > 1 else None)
+        if not fresh:
+            if len(_ENQ_BUFFERS) >= 8:
+                _ENQ_BUFFERS.pop(next(iter(_ENQ_BUFFERS)))
+            _ENQ_BUFFERS[key] = bufs
+    return bufs
+
+
+def enqueue_seed(seed: int) -> int:
+    """Base of the device-RNG seed of an enqueue; the per-call counter is added to it (host side here, device side in
+    a captured step: pcl_bank_packet_dev)."""
+    return (int(seed) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
 def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue: torch.Tensor,
@@ -138,8 +170,12 @@ def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue:
     n_scratch = lib.pcl_bank_scratch_floats(C.byref(g))
     if n_packet < 0:
         _abi.check(int(n_packet), "pcl_bank_packet_floats")
-    scratch = torch.empty(n_scratch, dtype=torch.float32, device=dev)
-    packet = torch.empty(n_packet, dtype=torch.float32, device=dev)
+    # a write already held back for a pending backward still reads the cached packet buffers: this (rare) second
+    # enqueue inside the same loss -> backward window gets buffers of its own
+    reader = _fn.bank_reader(dev.index, segment_queue.data_ptr()) if defer_to_backward else None
+    world = world_size(group) if distributed else 1
+    scratch, packet, recv = enqueue_buffers(dev, n_scratch, n_packet, world,
+                                            fresh=reader is not None and bool(reader.deferred))
     ranks = None
     if perm_fn is not None or rng == "torch_cpu":
         sub = labels_c[:, ::network_stride, ::network_stride].reshape(B, -1)
@@ -149,11 +185,11 @@ def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue:
         table = _rng.bank_rank_table(counts.cpu().numpy(), pixel_update_freq, perm_fn or (lambda n: torch.randperm(n)))
         ranks = table.to(dev)
     _enqueue_counter[0] += 1
-    s = (int(seed) * 0xD1B54A32D192ED03 + _enqueue_counter[0]) & 0xFFFFFFFFFFFFFFFF
+    s = (enqueue_seed(seed) + _enqueue_counter[0]) & 0xFFFFFFFFFFFFFFFF
     with _fn._on_device(dev):
         _abi.check(lib.pcl_bank_packet(C.byref(g), keys_c.data_ptr(), labels_c.data_ptr(), _abi.ptr(ranks), s,
                                        scratch.data_ptr(), packet.data_ptr(), _fn._stream_ptr(dev)), "pcl_bank_packet")
-        packets = gather_packets(packet, group) if distributed else packet.view(1, -1)
+        packets = gather_packets(packet, group, out=recv) if distributed else packet.view(1, -1)
 
     def apply_packets():           # the in-place write (rows, pointers, bf16 shadow): ordered, rank-major
         with _fn._on_device(dev):
@@ -164,7 +200,6 @@ def dequeue_and_enqueue(keys: torch.Tensor, labels: torch.Tensor, segment_queue:
 
     # A loss that read this bank and has not run its backward yet will re-read the bank in that backward (the reference
     # holds a copy instead, loss_contrast_mem.py:221): hold the write back until right after it.
-    reader = _fn.bank_reader(dev.index, segment_queue.data_ptr()) if defer_to_backward else None
     if reader is not None:
         reader.deferred.append(apply_packets)
     else:

@@ -8,7 +8,11 @@ void set_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_last_error, sizeof(g_last_error), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file,
            line);
 }
+static unsigned long long g_launches = 0ull;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace pcl
+
+extern "C" uint64_t pcl_launch_count(void) { return __atomic_load_n(&pcl::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int pcl_version(void) { return PCL_VERSION; }
 

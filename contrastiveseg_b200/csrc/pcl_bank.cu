@@ -109,7 +109,8 @@ k_bank_segsum(BankDims d, const float* __restrict__ keys, const int64_t* __restr
 __global__ void __launch_bounds__(256)
 k_bank_rows(BankDims d, const float* __restrict__ keys, const int32_t* __restrict__ counts,
             const unsigned long long* __restrict__ sums, const int32_t* __restrict__ ranks, uint64_t seed,
-            float* __restrict__ packet) {
+            const unsigned long long* __restrict__ seed_offset, float* __restrict__ packet) {
+  if (seed_offset != nullptr) seed += *seed_offset;          // captured sequence: per-replay part lives on the device
   const int slot = blockIdx.x;
   const int K = d.g.K, D = d.g.D, F = d.g.pixel_update_freq;
   const int b = slot / K, c = slot - b * K;
@@ -251,8 +252,8 @@ extern "C" int64_t pcl_bank_scratch_floats(const pcl_bank_geom* g) {
   return (int64_t)g->B * g->K + 2 * (int64_t)g->B * g->K * g->D + 2;
 }
 
-extern "C" int pcl_bank_packet(const pcl_bank_geom* g, const float* keys, const int64_t* labels, const int32_t* ranks,
-                               uint64_t seed, float* scratch, float* packet, void* stream) {
+static int bank_packet_impl(const pcl_bank_geom* g, const float* keys, const int64_t* labels, const int32_t* ranks,
+                            uint64_t seed, const uint64_t* seed_offset, float* scratch, float* packet, void* stream) {
   BankDims d;
   int st = make_dims(g, &d);
   if (st != PCL_OK) return st;
@@ -269,9 +270,20 @@ extern "C" int pcl_bank_packet(const pcl_bank_geom* g, const float* keys, const 
   k_bank_segsum<<<dim3(chunks, ceil_div(g->D, SEG_DG), g->B), 256, (size_t)g->K * SEG_DG * sizeof(unsigned long long), s>>>(
       d, keys, labels, sums);
   PCL_LAUNCH_CHECK();
-  k_bank_rows<<<(unsigned)slots, 256, 0, s>>>(d, keys, counts, sums, ranks, seed, packet);
+  k_bank_rows<<<(unsigned)slots, 256, 0, s>>>(d, keys, counts, sums, ranks, seed,
+                                              reinterpret_cast<const unsigned long long*>(seed_offset), packet);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
+}
+
+extern "C" int pcl_bank_packet(const pcl_bank_geom* g, const float* keys, const int64_t* labels, const int32_t* ranks,
+                               uint64_t seed, float* scratch, float* packet, void* stream) {
+  return bank_packet_impl(g, keys, labels, ranks, seed, nullptr, scratch, packet, stream);
+}
+
+extern "C" int pcl_bank_packet_dev(const pcl_bank_geom* g, const float* keys, const int64_t* labels, uint64_t seed,
+                                   const uint64_t* seed_offset, float* scratch, float* packet, void* stream) {
+  return bank_packet_impl(g, keys, labels, nullptr, seed, seed_offset, scratch, packet, stream);
 }
 
 extern "C" int pcl_bank_apply(const pcl_bank_geom* g, const float* packets, int32_t world, float* segment_queue,

@@ -22,7 +22,12 @@ void set_cuda_error(cudaError_t e, const char* file, int line);
     }                                                                   \
   } while (0)
 
-#define PCL_LAUNCH_CHECK() PCL_CUDA(cudaGetLastError())
+void count_launch();
+#define PCL_LAUNCH_CHECK()          \
+  do {                              \
+    ::pcl::count_launch();          \
+    PCL_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define PCL_REQUIRE(cond)                 \
   do {                                    \

@@ -18,6 +18,12 @@ selection and sweep kernels; the backward then scatters only the sampled columns
   backward kernels, not an autograd input: use it for the loss weight (``contrast.loss_weight``).
 
 The reference RNG stream (``rng='torch_cpu'`` / injected permutations) needs a host round trip and is not capturable.
+
+Memory-bank steps (``enqueue=``): the trainer's order loss -> enqueue -> backward (trainer_contrastive.py:241-255) is part
+of the captured sequence: stats -> ranks -> forward -> enqueue packet | all_gather | backward -> bank write.  One rank: a
+single graph.  Several ranks: two graphs with ONE NCCL all_gather of the packet between them (three host calls per step,
+nothing allocated, no host synchronisation); the bank write comes after the backward sweep that re-reads the bank, so
+gradient and final bank equal the reference's (same property as the eager deferred write).
 """
 from __future__ import annotations
 
@@ -51,7 +57,9 @@ class GraphedContrastStep:
                  predict: Optional[torch.Tensor] = None, segment_queue: Optional[torch.Tensor] = None,
                  pixel_queue: Optional[torch.Tensor] = None, bank_shadow: Optional[torch.Tensor] = None,
                  options: Optional[ContrastOptions] = None, grad_scale: float = 1.0, capture: bool = True,
-                 warmup: int = 2, overlap_zero_fill: bool = True):
+                 warmup: int = 2, overlap_zero_fill: bool = True, enqueue: Optional[dict] = None):
+        """enqueue (bank steps): dict(bank=MemoryBank, keys=(B,D,h,w) fp32 [default: embed], labels=(B,Himg,Wimg) int64
+        [default: labels], network_stride=int, pixel_update_freq=int, seed=int, group=process group or None)."""
         self.lib = _abi.load()
         opts = options or ContrastOptions()
         _fn._require_cuda(embed, "embed")
@@ -115,7 +123,11 @@ class GraphedContrastStep:
         d.ranks = self.ws.ranks.data_ptr()
         d.loss, d.grad_embed = self.loss.data_ptr(), self.grad.data_ptr()
         self.graph = None
+        self.graph_b = None
         self.replays = 0
+        self.enq = None
+        if enqueue is not None:
+            self._init_enqueue(enqueue)
         # The zero-fill of the dense gradient (B*D*h*w*4 bytes, the HBM floor of the step) does not depend on anything
         # the step computes: run it on a second stream from the start of the step, behind the latency-bound selection
         # and sweep kernels, and let the backward scatter only the sampled columns (pcl_step_backward_prezeroed).
@@ -123,6 +135,52 @@ class GraphedContrastStep:
         self.side = None
         if capture:
             self._capture(max(1, int(warmup)))
+
+    def _init_enqueue(self, e: dict) -> None:
+        from . import bank as _bank
+        bank = e["bank"]
+        if self.segq is None or bank.segment_queue.data_ptr() != self.segq.data_ptr():
+            raise _abi.PclError("enqueue=: the step must read the bank it writes (pass bank.segment_queue / pixel_queue)")
+        dev = self.device
+        keys = _canonical(e.get("keys", self.embed).detach(), torch.float32, "keys", dev)
+        labels = _canonical(e.get("labels", self.labels), torch.int64, "lb_key", dev)
+        B, D, h, w = keys.shape
+        g = _abi.BankGeom(B, D, h, w, labels.shape[1], labels.shape[2], bank.num_classes, bank.memory_size,
+                          int(e["network_stride"]), int(e["pixel_update_freq"]))
+        n_packet = self.lib.pcl_bank_packet_floats(C.byref(g))
+        n_scratch = self.lib.pcl_bank_scratch_floats(C.byref(g))
+        if n_packet < 0:
+            _abi.check(int(n_packet), "pcl_bank_packet_floats")
+        group = e.get("group")
+        world = _bank.world_size(group)
+        # buffers owned by this object (a captured graph holds their addresses)
+        scratch, packet, recv = _bank.enqueue_buffers(dev, int(n_scratch), int(n_packet), world, fresh=True)
+        if bank.with_shadow and bank.shadow is None:
+            bank.sync_shadow()
+        self.enq = dict(bank=bank, keys=keys, labels=labels, g=g, scratch=scratch, packet=packet, recv=recv, world=world,
+                        group=group, seed=_bank.enqueue_seed(int(e.get("seed", 304))))
+
+    def _enqueue_packet(self, stream: int) -> None:
+        q = self.enq
+        _abi.check(self.lib.pcl_bank_packet_dev(C.byref(q["g"]), q["keys"].data_ptr(), q["labels"].data_ptr(), q["seed"],
+                                                self.counter.data_ptr(), q["scratch"].data_ptr(), q["packet"].data_ptr(),
+                                                stream), "pcl_bank_packet_dev")
+
+    def _gather(self) -> torch.Tensor:
+        q = self.enq
+        if q["world"] == 1:
+            return q["packet"].view(1, -1)
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(q["recv"], q["packet"], group=q["group"])          # NCCL over NVLink
+        return q["recv"]
+
+    def _enqueue_apply(self, stream: int) -> None:
+        q = self.enq
+        b = q["bank"]
+        pk = q["recv"] if q["world"] > 1 else q["packet"]
+        _abi.check(self.lib.pcl_bank_apply(C.byref(q["g"]), pk.data_ptr(), q["world"], b.segment_queue.data_ptr(),
+                                           b.segment_queue_ptr.data_ptr(), b.pixel_queue.data_ptr(),
+                                           b.pixel_queue_ptr.data_ptr(), _abi.ptr(b.shadow), stream), "pcl_bank_apply")
 
     # fork / join of the overlapped zero-fill (torch streams + events; inside a capture these become graph edges)
     def _fork_zero_fill(self) -> None:
@@ -137,35 +195,81 @@ class GraphedContrastStep:
         torch.cuda.current_stream(self.device).wait_stream(self.side)
 
     # the launch sequence (also usable eagerly: capture=False)
-    def _enqueue(self, stream: int) -> None:
+    def _enqueue_a(self, stream: int) -> None:
+        """First half: (zero-fill branch ||) stats -> ranks -> forward -> this rank's enqueue packet."""
         lib, d = self.lib, self.ws.desc
         if self.overlap_zero_fill:
             self._fork_zero_fill()
         _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
         _abi.check(lib.pcl_step_ranks(C.byref(d), self.counter.data_ptr(), self.ws.ranks.data_ptr(), stream), "pcl_step_ranks")
         _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
+        if self.enq is not None:
+            self._enqueue_packet(stream)
         if self.overlap_zero_fill:
             self._join_zero_fill()
+
+    def _enqueue_b(self, stream: int) -> None:
+        """Second half: backward -> dense gradient -> (after the sweep that re-reads the bank) the bank write."""
+        lib, d = self.lib, self.ws.desc
+        if self.overlap_zero_fill:
             _abi.check(lib.pcl_step_backward_prezeroed(C.byref(d), self.scale.data_ptr(), stream),
                        "pcl_step_backward_prezeroed")
         else:
             _abi.check(lib.pcl_step_backward(C.byref(d), self.scale.data_ptr(), stream), "pcl_step_backward")
+        if self.enq is not None:
+            self._enqueue_apply(stream)
+
+    @property
+    def split(self) -> bool:
+        """Two graphs with the all_gather between them (bank step on several ranks)."""
+        return self.enq is not None and self.enq["world"] > 1
+
+    def _enqueue(self, stream: int) -> None:
+        self._enqueue_a(stream)
+        if self.split:
+            self._gather()
+        self._enqueue_b(stream)
 
     def _capture(self, warmup: int) -> None:
         dev = self.device
         cap = torch.cuda.Stream(dev)           # capture stream (graphs cannot be captured on the default stream)
         cap.wait_stream(torch.cuda.current_stream(dev))
+        if self.enq is not None:               # the warm-up runs write the bank: put it back afterwards
+            b = self.enq["bank"]
+            self._bank_snapshot = [t.clone() for t in (b.segment_queue, b.segment_queue_ptr, b.pixel_queue,
+                                                       b.pixel_queue_ptr)] + ([b.shadow.clone()] if b.shadow is not None else [])
         with torch.cuda.device(dev), torch.cuda.stream(cap):
             for _ in range(warmup):            # eager runs first: kernels get loaded, function attributes set, TMA
                 self._enqueue(cap.cuda_stream)  # descriptors encoded — none of that may happen under capture
         torch.cuda.current_stream(dev).wait_stream(cap)
         self.counter.zero_()
-        graph = torch.cuda.CUDAGraph()
+        if self.enq is not None:
+            torch.cuda.synchronize(dev)
+            self._restore_bank()
         # thread_local: only this thread's CUDA calls are policed during the capture (the NCCL watchdog of a DDP job polls
         # events from another thread)
-        with torch.cuda.device(dev), torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
-            self._enqueue(torch.cuda.current_stream(dev).cuda_stream)
-        self.graph = graph
+        graph = torch.cuda.CUDAGraph()
+        if not self.split:
+            with torch.cuda.device(dev), torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
+                s = torch.cuda.current_stream(dev).cuda_stream
+                self._enqueue_a(s)
+                self._enqueue_b(s)
+            self.graph = graph
+        else:
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.device(dev), torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
+                self._enqueue_a(torch.cuda.current_stream(dev).cuda_stream)
+            with torch.cuda.device(dev), torch.cuda.graph(graph_b, stream=cap, capture_error_mode="thread_local"):
+                self._enqueue_b(torch.cuda.current_stream(dev).cuda_stream)
+            self.graph, self.graph_b = graph, graph_b
+
+    def _restore_bank(self) -> None:
+        b = self.enq["bank"]
+        snap, self._bank_snapshot = self._bank_snapshot, None
+        for t, v in zip((b.segment_queue, b.segment_queue_ptr, b.pixel_queue, b.pixel_queue_ptr), snap):
+            t.copy_(v)
+        if b.shadow is not None:
+            b.shadow.copy_(snap[4])
 
     def set_grad_scale(self, value: float) -> None:
         self.scale.fill_(float(value))
@@ -175,6 +279,9 @@ class GraphedContrastStep:
         replay; grad_embed = grad_scale * d loss / d embed."""
         if self.graph is not None:
             self.graph.replay()
+            if self.graph_b is not None:
+                self._gather()
+                self.graph_b.replay()
         else:
             with _fn._on_device(self.device):
                 self._enqueue(_fn._stream_ptr(self.device))

@@ -47,7 +47,7 @@ class FSCELoss(nn.Module):
 
 
 class FSAuxCELoss(nn.Module):
-    """seg_loss_weight * CE(seg) + aux_loss_weight * CE(aux)  (lib/loss/loss_helper.py:283-303)."""
+    """seg_loss_weight * CE(seg) + aux_loss_weight * CE(aux)  (lib/loss/loss_helper.py:301-313)."""
 
     def __init__(self, configer=None):
         super().__init__()

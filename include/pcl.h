@@ -54,6 +54,9 @@ int         pcl_device_count(void);             /* 0 without a usable CUDA devic
  * 1 pcl_select_sizes_t, 2 pcl_sweep_desc, 3 pcl_sweep_sizes_t, 4 pcl_bank_geom, 5 pcl_tc_desc, 6 pcl_step_desc;
  * -1 for an unknown id.  A binding compares these with its own struct definitions before the first call. */
 int64_t     pcl_abi_sizeof(int struct_id);
+/* Diagnostics: number of kernels this library has launched (or recorded into a stream capture) since it was loaded,
+ * process-wide.  The difference around one eager pass of a call sequence = kernels per step (bench.py: gpu_launches). */
+uint64_t    pcl_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Geometry of one loss call (host struct, passed by pointer).
@@ -231,6 +234,12 @@ int64_t pcl_bank_scratch_floats(const pcl_bank_geom* g);   /* floats of scratch 
 /* ranks: NULL -> device RNG with `seed`; else (B*K, F) int32 table of perm values per slot. */
 int pcl_bank_packet(const pcl_bank_geom* g, const float* keys, const int64_t* labels, const int32_t* ranks,
                     uint64_t seed, float* scratch, float* packet, void* stream);
+
+/* Same for a captured launch sequence (CUDA graph): kernel arguments are frozen at capture, so the per-call part of the
+ * seed is read from device memory: effective seed = seed + *seed_offset (uint64 on the device, e.g. the step counter
+ * pcl_step_ranks advances; NULL -> 0).  Device RNG only. */
+int pcl_bank_packet_dev(const pcl_bank_geom* g, const float* keys, const int64_t* labels, uint64_t seed,
+                        const uint64_t* seed_offset, float* scratch, float* packet, void* stream);
 
 /* Apply `world` packets (contiguous, rank-major) to the queues in place.  shadow_bf16 (optional,
  * ((K-1)*2M rounded up to 256, D) bf16) is the engine's class-blocked bf16 copy used by the tensor path. */

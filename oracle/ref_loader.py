@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference modules for oracle validation / golden generation.
 
 TEST INFRASTRUCTURE.  Works only where the reference tree is reachable (this build container:
-/root/reference, or $CSEG_REF).  It never exists on the GPU box; nothing on the GPU path calls
+/root/reference, $CSEG_REF, or a driver-provided baseline/_ref).  It never exists on the GPU box; nothing on the GPU path calls
 this.  Recipe follows SURVEY.md appendix B.
 """
 from __future__ import annotations
@@ -18,7 +18,8 @@ import torch.nn as nn
 
 
 def reference_root() -> Optional[str]:
-    for cand in (os.environ.get("CSEG_REF"), "/root/reference"):
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("CSEG_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
         if cand and os.path.isfile(os.path.join(cand, "lib", "loss", "loss_contrast.py")):
             return cand
     return None

@@ -383,3 +383,22 @@ def contrast_ce_loss(preds: dict, target: torch.Tensor, *, with_embed: bool, los
     if with_embed:
         return loss + loss_weight * lc
     return loss + 0 * lc
+
+
+def contrast_auxce_loss(preds: dict, target: torch.Tensor, *, with_embed: bool, loss_weight: float,
+                        seg_loss_weight: float, aux_loss_weight: float, temperature: float, base_temperature: float,
+                        max_samples: int, max_views: int, ignore_label: int = -1, ce_weight=None,
+                        perm_fn: Optional[PermFn] = None, per_pair_gather: bool = True) -> torch.Tensor:
+    """ContrastAuxCELoss.forward — lib/loss/loss_contrast.py:213-234: FSAuxCELoss (lib/loss/loss_helper.py:301-313:
+    seg_loss * CE(up(seg)) + aux_loss * CE(up(seg_aux)), both bilinear align_corners=True, :223-225) + the no-bank
+    pixel-contrast term on predict = argmax(seg) (:227-228); `loss + loss_weight * lc` or `loss + 0 * lc` (:230-234)."""
+    seg, seg_aux, embed = preds["seg"], preds["seg_aux"], preds["embed"]
+    loss = (seg_loss_weight * seg_cross_entropy(seg, target, ignore_label, ce_weight) +
+            aux_loss_weight * seg_cross_entropy(seg_aux, target, ignore_label, ce_weight))
+    predict = seg.argmax(dim=1)
+    lc = pixel_contrast_loss(embed, target, predict, temperature=temperature, base_temperature=base_temperature,
+                             max_samples=max_samples, max_views=max_views, ignore_label=ignore_label, queue=None,
+                             perm_fn=perm_fn, per_pair_gather=per_pair_gather)
+    if with_embed:
+        return loss + loss_weight * lc
+    return loss + 0 * lc

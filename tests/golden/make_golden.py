@@ -111,6 +111,38 @@ def wrapper_case(name, *, with_embed, mem, seed=11):
     print(f"{name}: loss={loss.item():.7f}")
 
 
+def aux_wrapper_case(name, *, with_embed, seed=13, weighted=False):
+    """lib/loss/loss_contrast.py:192-234 ContrastAuxCELoss (the class the DeepLab / HRNet-OCR contrast scripts select):
+    FSAuxCELoss (lib/loss/loss_helper.py:301-313) on the bilinearly up-sampled [seg_aux, seg] + the pixel-contrast term."""
+    ref = load_reference()
+    B, D, h, w, K, stride = 2, 32, 13, 17, 6, 4
+    data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=stride, block=8, seed=seed)
+    d = cfg_dict(0.1, 0.07, 48, 5, loss_weight=0.1)
+    d["network"]["loss_weights"] = {"seg_loss": 1.0, "aux_loss": 0.4}
+    ce_w = None
+    if weighted:
+        ce_w = [0.8, 1.1, 0.9, 1.3, 1.0, 0.7]
+        d["loss"]["params"]["ce_weight"] = ce_w
+    cfg = DictConfiger(d)
+    g = torch.Generator().manual_seed(seed + 5)
+    seg = data["seg"].clone().requires_grad_(True)
+    seg_aux = (data["seg"] * 0.5 + torch.randn(data["seg"].shape, generator=g)).requires_grad_(True)
+    embed = data["embed"].clone().requires_grad_(True)
+    crit = ref.nomem.ContrastAuxCELoss(cfg)
+    rec = PermRecorder(torch.Generator().manual_seed(seed + 1))
+    with patched_randperm(rec):
+        loss = crit({"seg": seg, "seg_aux": seg_aux, "embed": embed}, data["target"], with_embed=with_embed)
+    loss.backward()
+    flat, lens = pack_perms(rec.draws)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), embed=data["embed"].numpy(), seg=data["seg"].numpy(),
+                        seg_aux=seg_aux.detach().numpy(), target=data["target"].numpy(), perm_flat=flat, perm_lens=lens,
+                        loss=np.float32(loss.item()), grad_embed=embed.grad.numpy(), grad_seg=seg.grad.numpy(),
+                        grad_seg_aux=seg_aux.grad.numpy(),
+                        ce_weight=np.array(ce_w if ce_w else [], dtype=np.float32),
+                        params=np.array([0.1, 0.07, 48, 5, K, -1, 0.1, float(with_embed), 1.0, 0.4]))
+    print(f"{name}: loss={loss.item():.7f}")
+
+
 def enqueue_case(name, *, B, D, h, w, K, img_stride, net_stride, M, Fq, steps, seed):
     ref = load_reference()
     bank = make_bank(K, M, D, seed + 2)
@@ -136,6 +168,12 @@ def enqueue_case(name, *, B, D, h, w, K, img_stride, net_stride, M, Fq, steps, s
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only == ["aux"]:              # add the round-2 cases without touching the committed round-1 files
+        torch.manual_seed(0)
+        aux_wrapper_case("wrapper_aux_embed", with_embed=True)
+        aux_wrapper_case("wrapper_aux_warmup_weighted", with_embed=False, weighted=True)
+        sys.exit(0)
     torch.manual_seed(0)
     loss_case("nomem_small", B=2, D=32, h=24, w=24, K=5, stride=2, block=8, T=0.1, bT=0.07,
               max_samples=40, max_views=6, seed=1)
@@ -154,6 +192,8 @@ if __name__ == "__main__":
     wrapper_case("wrapper_nomem_embed", with_embed=True, mem=False)
     wrapper_case("wrapper_nomem_warmup", with_embed=False, mem=False)
     wrapper_case("wrapper_mem_embed", with_embed=True, mem=True)
+    aux_wrapper_case("wrapper_aux_embed", with_embed=True)
+    aux_wrapper_case("wrapper_aux_warmup_weighted", with_embed=False, weighted=True)
     enqueue_case("enqueue_aligned", B=2, D=32, h=16, w=16, K=5, img_stride=2, net_stride=2, M=7, Fq=3,
                  steps=6, seed=21)
     enqueue_case("enqueue_q6", B=2, D=32, h=16, w=16, K=5, img_stride=2, net_stride=4, M=9, Fq=4,

@@ -47,6 +47,9 @@ PARITY = (
     [_case(G.test_contrast_ce_wrapper, name=n, mem=m) for n, m in (("wrapper_nomem_embed", False),
                                                                    ("wrapper_nomem_warmup", False),
                                                                    ("wrapper_mem_embed", True))] +
+    [_case(G.test_contrast_auxce_wrapper, name=n, fused=f) for n, f in (("wrapper_aux_embed", True),
+                                                                        ("wrapper_aux_warmup_weighted", True),
+                                                                        ("wrapper_aux_embed", False))] +
     [_case(G.test_bank_enqueue_matches_reference, name=n) for n in ("enqueue_aligned", "enqueue_q6")] +
     [_case(G.test_bank_enqueue_shape_error_like_reference)] +
     [_case(G.test_l2_normalize_matches_torch, shape=s) for s in ((2, 256, 16, 32), (1, 32, 7, 9), (3, 320, 5, 8))] +
@@ -111,6 +114,16 @@ def test_graphed_step_tensor_path_on_emulation(emu, monkeypatch, mem, overlap):
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_graphed_step_equals_eager_step("bf16", mem, overlap)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_graphed_bank_step_on_emulation(emu, monkeypatch, precision):
+    """The bank step's launch sequence incl. the device-seeded enqueue packet (pcl_bank_packet_dev) == the trainer order."""
+    from contrastiveseg_b200 import graph_step
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
+    PD.test_graphed_bank_step_with_enqueue_equals_the_trainer_order(precision)
 
 
 def test_bank_write_waits_for_backward_on_emulation(emu):

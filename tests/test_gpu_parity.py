@@ -116,6 +116,35 @@ def test_contrast_ce_wrapper(name, mem):
     assert (embed.grad.cpu() - gref).abs().max().item() <= 1e-5 * max(gref.abs().max().item(), 1e-12) + 1e-12
 
 
+@pytest.mark.parametrize("name", ["wrapper_aux_embed", "wrapper_aux_warmup_weighted"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_contrast_auxce_wrapper(name, fused):
+    """ContrastAuxCELoss (lib/loss/loss_contrast.py:192-234, registry key 'contrast_auxce_loss': the class the DeepLab
+    and HRNet-OCR contrast scripts select) against goldens produced by the unmodified reference: loss 1e-5, all three
+    gradients; with the fused up-sample + CE kernels (default) and with the PyTorch seg-CE ops."""
+    g = load_golden(name)
+    T, bT, ms, mv, K, ign, lw, with_embed, w_seg, w_aux = g["params"].tolist()
+    cfg = _cfg(T, bT, ms, mv, K, {"loss_weight": lw, "fused_seg_ce": fused})
+    cfg.add(["network", "loss_weights"], {"seg_loss": w_seg, "aux_loss": w_aux})
+    if g["ce_weight"].size:
+        params = dict(cfg.get("loss", "params")); params["ce_weight"] = g["ce_weight"].tolist()
+        cfg.add(["loss", "params"], params)
+    crit = cs.get_seg_loss(cfg, "contrast_auxce_loss").to(DEV)
+    assert isinstance(crit, cs.ContrastAuxCELoss)
+    crit.contrast_criterion.perm_fn = P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"]))
+    seg = torch.from_numpy(g["seg"]).to(DEV).requires_grad_(True)
+    seg_aux = torch.from_numpy(g["seg_aux"]).to(DEV).requires_grad_(True)
+    embed = torch.from_numpy(g["embed"]).to(DEV).requires_grad_(True)
+    loss = crit({"seg": seg, "seg_aux": seg_aux, "embed": embed}, torch.from_numpy(g["target"]).to(DEV),
+                with_embed=bool(with_embed))
+    loss.backward()
+    assert rel_err(loss.item(), g["loss"]) < 1e-5
+    for got, key in ((seg.grad, "grad_seg"), (seg_aux.grad, "grad_seg_aux")):
+        assert torch.allclose(got.cpu(), torch.from_numpy(g[key]), rtol=1e-4, atol=1e-7), key
+    gref = torch.from_numpy(g["grad_embed"])
+    assert (embed.grad.cpu() - gref).abs().max().item() <= 1e-5 * max(gref.abs().max().item(), 1e-12) + 1e-12
+
+
 @pytest.mark.parametrize("name", ["enqueue_aligned", "enqueue_q6"])
 def test_bank_enqueue_matches_reference(name):
     g = load_golden(name)

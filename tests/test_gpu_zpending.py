@@ -162,3 +162,47 @@ def test_second_backward_is_refused_and_state_dict_flushes_the_pending_write():
     loss.backward(retain_graph=True)
     with pytest.raises(PclError, match="backward ran twice"):
         loss.backward()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_graphed_bank_step_with_enqueue_equals_the_trainer_order(precision):
+    """Bank step as ONE graph (world 1): stats -> ranks -> forward -> enqueue packet -> backward -> bank write.  Replay r
+    must equal the eager trainer order (loss -> enqueue -> backward, trainer_contrastive.py:241-255) with counters r+1:
+    same loss bits, same gradient, bit-identical bank (rows, pointers, bf16 shadow) after every step."""
+    from contrastiveseg_b200 import bank as bank_mod
+    K, D, M = 7, 256, 48
+    data = make_contrast_batch(B=2, D=D, h=32, w=32, num_classes=K, img_stride=4, block=16, seed=21)
+    embed, tgt, seg = data["embed"].to(DEV), data["target"].to(DEV), data["seg"].to(DEV)
+    shadow = precision == "bf16"
+    torch.manual_seed(0)
+    bank_g = cs.MemoryBank(K, M, D, with_shadow=shadow).to(DEV)
+    bank_e = cs.MemoryBank(K, M, D, with_shadow=shadow).to(DEV)
+    bank_e.load_state_dict(bank_g.state_dict())
+    if shadow:
+        bank_g.sync_shadow(); bank_e.sync_shadow()
+    opts = cs.ContrastOptions(temperature=0.07, base_temperature=0.07, max_samples=128, max_views=8, seed=5,
+                              precision=precision, num_classes=K)
+    step = cs.GraphedContrastStep(embed, tgt, seg=seg, segment_queue=bank_g.segment_queue, pixel_queue=bank_g.pixel_queue,
+                                  bank_shadow=bank_g.shadow, options=opts,
+                                  enqueue=dict(bank=bank_g, network_stride=4, pixel_update_freq=5, seed=3))
+    names = ("segment_queue", "pixel_queue", "segment_queue_ptr", "pixel_queue_ptr")
+    for name in names:                                           # warm-up runs of the capture left no trace in the bank
+        assert torch.equal(getattr(bank_g, name), getattr(bank_e, name)), name
+    for r in range(3):
+        loss, grad = step.replay()
+        torch.cuda.synchronize()
+        Fn._step_counter[0] = r
+        bank_mod._enqueue_counter[0] = r
+        e = embed.clone().requires_grad_(True)
+        l = cs.pixel_contrast_loss(e, tgt, seg=seg, segment_queue=bank_e.segment_queue, pixel_queue=bank_e.pixel_queue,
+                                   bank_shadow=bank_e.shadow, options=opts)
+        bank_e.enqueue(e.detach(), tgt, network_stride=4, pixel_update_freq=5, seed=3)
+        l.backward()
+        torch.cuda.synchronize()
+        assert torch.equal(l.detach(), loss)
+        assert torch.allclose(e.grad, grad, rtol=2e-6, atol=0)
+        for name in names:
+            assert torch.equal(getattr(bank_g, name), getattr(bank_e, name)), (r, name)
+        if shadow:
+            assert torch.equal(bank_g.shadow, bank_e.shadow)
+    assert not torch.equal(bank_g.pixel_queue_ptr, torch.zeros_like(bank_g.pixel_queue_ptr))

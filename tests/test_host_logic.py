@@ -119,3 +119,24 @@ def test_device_rng_model_is_a_bijection_and_statistically_flat():
         cells = off.size / 2                                    # symmetric table
         chi_p = ((off - pe) ** 2 / pe).sum() / 2
         assert abs(chi_p - cells) < 6 * (2 * cells) ** 0.5, (n, k, chi_p / cells)
+
+
+def test_chunked_bank_closed_form_equals_the_oracle_closed_form():
+    """tests/helpers.bank_infonce_chunked (the checker of the full-size GPU parity tests) against
+    oracle.ref_port.infonce_closed_form on the flattened bank, incl. class-0 anchors (zero-tail positives, Q3) and a
+    diagonal inside the class-1 block (Q1)."""
+    import torch
+    from oracle import ref_port as P
+    from helpers import bank_infonce_chunked
+    g = torch.Generator().manual_seed(5)
+    K, M, D, A = 5, 7, 16, 23
+    segq = torch.nn.functional.normalize(torch.randn(K, M, D, generator=g), dim=2)
+    pixq = torch.nn.functional.normalize(torch.randn(K, M, D, generator=g), dim=2)
+    anchors = torch.nn.functional.normalize(torch.randn(A, D, generator=g), dim=1)
+    ya = torch.randint(0, K, (A,), generator=g)
+    diag = torch.randperm(A, generator=g)
+    contrast, yc = P.flatten_queue(torch.cat((segq, pixq), 1).double())
+    ref = P.infonce_closed_form(anchors.double(), ya.double(), contrast, yc, 0.07, 0.07, False, diag_cols=diag)
+    got = bank_infonce_chunked(anchors, ya, diag, segq, pixq, 0.07, 0.07, chunk=11)
+    assert abs(got["loss"].item() - ref["loss"].item()) <= 1e-12 * abs(ref["loss"].item())
+    assert torch.allclose(got["dA"], ref["dA"], rtol=1e-10, atol=1e-14)

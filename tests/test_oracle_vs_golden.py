@@ -92,3 +92,24 @@ def test_port_wrapper_matches_reference(name, mem):
     assert rel_err(loss.item(), g["loss"]) < 2e-6
     assert torch.allclose(seg.grad, torch.from_numpy(g["grad_seg"]), rtol=1e-5, atol=1e-8)
     assert torch.allclose(embed.grad, torch.from_numpy(g["grad_embed"]), rtol=1e-4, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["wrapper_aux_embed", "wrapper_aux_warmup_weighted"])
+def test_port_aux_wrapper_matches_reference(name):
+    """ContrastAuxCELoss (lib/loss/loss_contrast.py:192-234) golden from the unmodified reference vs the port."""
+    g = load_golden(name)
+    T, bT, ms, mv, K, ign, lw, with_embed, w_seg, w_aux = g["params"].tolist()
+    seg = torch.from_numpy(g["seg"]).requires_grad_(True)
+    seg_aux = torch.from_numpy(g["seg_aux"]).requires_grad_(True)
+    embed = torch.from_numpy(g["embed"]).requires_grad_(True)
+    cw = torch.from_numpy(g["ce_weight"]) if g["ce_weight"].size else None
+    replay = P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"]))
+    loss = P.contrast_auxce_loss({"seg": seg, "seg_aux": seg_aux, "embed": embed}, torch.from_numpy(g["target"]),
+                                 with_embed=bool(with_embed), loss_weight=lw, seg_loss_weight=w_seg, aux_loss_weight=w_aux,
+                                 temperature=T, base_temperature=bT, max_samples=int(ms), max_views=int(mv),
+                                 ignore_label=int(ign), ce_weight=cw, perm_fn=replay)
+    loss.backward()
+    assert rel_err(loss.item(), g["loss"]) < 2e-6
+    assert torch.allclose(seg.grad, torch.from_numpy(g["grad_seg"]), rtol=1e-5, atol=1e-8)
+    assert torch.allclose(seg_aux.grad, torch.from_numpy(g["grad_seg_aux"]), rtol=1e-5, atol=1e-8)
+    assert torch.allclose(embed.grad, torch.from_numpy(g["grad_embed"]), rtol=1e-4, atol=1e-8)

@@ -44,6 +44,46 @@ for a in mine:
     g = [torch.empty_like(a) for _ in range(world)]
     dist.all_gather(g, a)
     ok &= all(torch.equal(g[0], x) for x in g)
+# ---- the graphed bank step on several ranks: two graphs around ONE all_gather of the packet (graph_step.py).  Replay r
+# must equal the eager trainer order (loss -> enqueue [all_gather] -> backward -> deferred write) on every rank, and the
+# banks must stay bit-identical across ranks. ----
+from contrastiveseg_b200 import bank as bank_mod, functional as Fn
+K2, M2 = 7, 48
+data = make_contrast_batch(B=1, D=256, h=32, w=32, num_classes=K2, img_stride=4, block=16, seed=500 + rank)
+embed, tgt, seg = data["embed"].to(dev), data["target"].to(dev), data["seg"].to(dev)
+torch.manual_seed(0)
+bank_g = cs.MemoryBank(K2, M2, 256, with_shadow=True).to(dev)
+bank_e = cs.MemoryBank(K2, M2, 256, with_shadow=True).to(dev)
+bank_e.load_state_dict(bank_g.state_dict())
+bank_g.sync_shadow(); bank_e.sync_shadow()
+opts = cs.ContrastOptions(temperature=0.07, base_temperature=0.07, max_samples=128, max_views=8, seed=5, precision="bf16",
+                          num_classes=K2)
+step = cs.GraphedContrastStep(embed, tgt, seg=seg, segment_queue=bank_g.segment_queue, pixel_queue=bank_g.pixel_queue,
+                              bank_shadow=bank_g.shadow, options=opts,
+                              enqueue=dict(bank=bank_g, network_stride=4, pixel_update_freq=5, seed=3))
+gok = step.split and step.graph_b is not None
+for r in range(3):
+    loss, grad = step.replay()
+    torch.cuda.synchronize()
+    Fn._step_counter[0] = r
+    bank_mod._enqueue_counter[0] = r
+    e = embed.clone().requires_grad_(True)
+    l = cs.pixel_contrast_loss(e, tgt, seg=seg, segment_queue=bank_e.segment_queue, pixel_queue=bank_e.pixel_queue,
+                               bank_shadow=bank_e.shadow, options=opts)
+    bank_e.enqueue(e.detach(), tgt, network_stride=4, pixel_update_freq=5, seed=3)
+    l.backward()
+    torch.cuda.synchronize()
+    gok &= torch.equal(l.detach(), loss) and torch.allclose(e.grad, grad, rtol=2e-6, atol=0)
+    for name in names:
+        gok &= torch.equal(getattr(bank_g, name), getattr(bank_e, name))
+    gok &= torch.equal(bank_g.shadow, bank_e.shadow)
+for name in names:
+    a = getattr(bank_g, name)
+    g = [torch.empty_like(a) for _ in range(world)]
+    dist.all_gather(g, a)
+    gok &= all(torch.equal(g[0], x) for x in g)
+print(f"rank {rank} graphed bank step (2 graphs + 1 all_gather) {'OK' if gok else 'FAILED'}", flush=True)
+ok &= bool(gok)
 print(f"rank {rank} dist bank check {'OK' if ok else 'FAILED'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
