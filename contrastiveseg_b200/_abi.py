@@ -72,7 +72,7 @@ class StepDesc(C.Structure):
                 ("partials", c_vp), ("rowstats", c_vp), ("dpartials", c_vp), ("dA", c_vp),
                 ("precision", c_i32), ("shadow_bf16", c_vp), ("shadow_rows", c_i64), ("contrast_norm_bound", c_f32),
                 ("row_m2", c_vp),
-                ("loss", c_vp), ("grad_embed", c_vp)]
+                ("loss", c_vp), ("grad_embed", c_vp), ("sync", c_vp)]
 
 
 ABI_STRUCTS = (Geom, SelectSizes, SweepDesc, SweepSizes, BankGeom, TcDesc, StepDesc)   # pcl_abi_sizeof ids 0..6
@@ -119,6 +119,10 @@ SIGNATURES = {
     "pcl_step_backward": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp]),
     "pcl_step_backward_prezeroed": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp]),
     "pcl_step_ranks": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp, c_vp]),
+    "pcl_step_fused_supported": (c_i32, [C.POINTER(StepDesc)]),
+    "pcl_step_fused_loss": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp]),
+    "pcl_step_fused_scatter": (c_i32, [C.POINTER(StepDesc), c_vp, c_vp, c_vp]),
+    "pcl_fill_zero": (c_i32, [c_vp, c_u64, c_vp]),
 }
 
 _lib = None

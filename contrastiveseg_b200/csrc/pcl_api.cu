@@ -8,6 +8,7 @@ void set_cuda_error(cudaError_t e, const char* file, int line) {
   snprintf(g_last_error, sizeof(g_last_error), "%s (%s) at %s:%d", cudaGetErrorName(e), cudaGetErrorString(e), file,
            line);
 }
+void set_error_text(const char* text) { snprintf(g_last_error, sizeof(g_last_error), "%s", text); }
 static unsigned long long g_launches = 0ull;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace pcl

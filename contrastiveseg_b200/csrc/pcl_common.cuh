@@ -12,6 +12,7 @@ namespace pcl {
 
 // ---- error plumbing -----------------------------------------------------------------------------
 void set_cuda_error(cudaError_t e, const char* file, int line);
+void set_error_text(const char* text);            // driver-API failures (tensor-map encoding): same per-thread slot
 
 #define PCL_CUDA(expr)                                                  \
   do {                                                                  \
@@ -38,7 +39,8 @@ void count_launch();
 int select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t* keys, const int32_t* chunk_pref,
                      const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize, int32_t* anchor_meta,
                      float* anchors_f32, void* anchors_bf16, float* inv_norm, float* norm_max, float* row_m2,
-                     float m2_scale, float* partials, int64_t n_slot_rows, void* stream);
+                     float m2_scale, float* partials, int64_t n_slot_rows, void* stream,
+                     const unsigned long long* seed_ctr = nullptr);
 int tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
               bool skip_prep);
 int tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale);
@@ -47,6 +49,14 @@ int tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, 
 int zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
                         int splits, int a_pad, float inv_T, const float* grad_loss, float* grad_embed, void* stream);
 
+int self_fused_supported(const pcl_tc_desc* d);
+int self_fused(const pcl_tc_desc* d, const float* row_m2, float* partials, float* rowstats, float* loss, float* dpartials,
+               unsigned int* sync, void* stream);
+int class_stats_plan(const pcl_geom* g, const int64_t* labels, const float* seg, const int64_t* predict, uint16_t* keys,
+                     int32_t* chunk_pref, int32_t* counts, int32_t* plan, unsigned int* done_ctr, void* stream);
+int scatter_reduce_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials, int splits,
+                        int split_cols, int a_pad, float inv_T, const float* grad_scale, float* grad_embed, unsigned long long* step_counter,
+                        void* stream);
 int scatter_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
                  const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed, void* stream);
 

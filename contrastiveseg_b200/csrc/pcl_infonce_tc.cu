@@ -19,6 +19,7 @@
 #include <mutex>
 
 namespace pcl {
+int tc_make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows);
 namespace tc {
 
 // Forward tile = 128 rows x 256 columns (one M128 x N256 x K16 UMMA per K step).  A 256-row x 128-column variant (two
@@ -849,7 +850,7 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t b
       if (e.used && e.k.base == base && e.k.rows == rows && e.k.box_rows == box_rows) { *m = e.m; return PCL_OK; }
   }
   PFN_tmapEncodeTiled enc = get_encode();
-  if (!enc) return PCL_ERR_CUDA;
+  if (!enc) { pcl::set_error_text("cuTensorMapEncodeTiled entry point not found"); return PCL_ERR_CUDA; }
   cuuint64_t gdim[2] = {(cuuint64_t)tc::DDIM, rows};
   cuuint64_t gstride[1] = {(cuuint64_t)tc::DDIM * 2};
   cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
@@ -857,13 +858,23 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t b
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return PCL_ERR_CUDA;
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (CUresult %d): base %p rows %llu box_rows %u", (int)r, base,
+             (unsigned long long)rows, box_rows);
+    pcl::set_error_text(msg);
+    return PCL_ERR_CUDA;
+  }
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   TmapEntry& e = g_tmaps[g_tmap_next++ % 16];
   e.k = TmapKey{base, rows, box_rows};
   e.m = *m;
   e.used = true;
   return PCL_OK;
+}
+
+int pcl::tc_make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t box_rows) {
+  return make_tmap(m, base, rows, box_rows);
 }
 
 struct TcPlan {

@@ -10,8 +10,11 @@
 //   k_scatter dense-gradient writer (after a memset): one warp per anchor row
 #include "pcl_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace pcl {
+
+__device__ __forceinline__ void plan_body(const pcl_geom& g, const int32_t* counts, int32_t* plan);   // below (k_plan)
 
 // ------------------------------------------------------------------------------------------------
 // k_keys
@@ -19,7 +22,7 @@ namespace pcl {
 __global__ void __launch_bounds__(PCL_CHUNK)
 k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __restrict__ labels,
        const float* __restrict__ seg, const int64_t* __restrict__ predict, uint16_t* __restrict__ keys,
-       int32_t* __restrict__ chunk_hist, int32_t* __restrict__ counts) {
+       int32_t* chunk_hist, int32_t* counts, int32_t* plan, unsigned int* done_ctr) {
   extern __shared__ int s_hist[];                 // 2K+1 bins
   const int K = g.K, NK = 2 * K;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -59,8 +62,30 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
   for (int i = threadIdx.x; i < NK; i += blockDim.x) {
     const int v = s_hist[i];
     chunk_hist[((int64_t)b * NK + i) * nchunk + chunk] = v;
-    if (v) atomicAdd(&counts[b * NK + i], v);     // integer totals: order-independent
+    if (v && done_ctr == nullptr) atomicAdd(&counts[b * NK + i], v);     // integer totals: order-independent
   }
+  if (done_ctr == nullptr) return;
+  // ---- fused tail (step path): the LAST block to finish sums the per-chunk histograms into the totals (no atomics, no
+  //      memset) and computes the sampling plan — saves the single-CTA k_plan launch and the counts memset ----
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    s_last = (atomicAdd(done_ctr, 1u) == total - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < g.B * NK; i += blockDim.x) {
+    const int32_t* hrow = chunk_hist + (int64_t)i * nchunk;
+    int t = 0;
+    for (int ch = 0; ch < nchunk; ++ch) t += __ldcg(hrow + ch);
+    counts[i] = t;
+  }
+  if (threadIdx.x == 0) *done_ctr = 0u;           // re-armed for the next launch
+  __syncthreads();
+  plan_body(g, counts, plan);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,32 +95,34 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
 // ------------------------------------------------------------------------------------------------
 constexpr int PLAN_THREADS = 256;
 
-__global__ void __launch_bounds__(PLAN_THREADS)
-k_plan(pcl_geom g, int nchunk, const int32_t* __restrict__ counts, int32_t* __restrict__ plan) {
+// Executed by the first PLAN_THREADS threads of a block whose ALL threads call it (it contains block barriers).
+// (no __restrict__ / read-only path on `counts`: the fused scan's last block writes the totals itself just before)
+__device__ __forceinline__ void plan_body(const pcl_geom& g, const int32_t* counts, int32_t* plan) {
   __shared__ int s_scan[PLAN_THREADS];
   __shared__ int s_cls_cnt[PCL_MAX_CLASSES];
   __shared__ int s_cls_start[PCL_MAX_CLASSES];
   __shared__ int s_TC, s_V, s_err;
   const int K = g.K, NK = 2 * K, B = g.B;
   const int tid = threadIdx.x;
+  const bool act = tid < PLAN_THREADS;                 // the other threads of a larger block only take part in barriers
   if (tid == 0) s_err = 0;
 
-  // 1. per-image key totals were accumulated by k_keys (integer atomics); chunk_pref keeps the raw per-chunk
+  // 1. per-image key totals were accumulated by k_keys; chunk_pref keeps the raw per-chunk
   //    histograms — k_select scans the 32-entry row it needs with warp shuffles
-  for (int c = tid; c < K; c += PLAN_THREADS) s_cls_cnt[c] = 0;
+  if (act) for (int c = tid; c < K; c += PLAN_THREADS) s_cls_cnt[c] = 0;
   __syncthreads();
 
   // 2. compact kept (image,class) pairs in (image asc, class asc) order
   const int E = B * K;
   const int per = (E + PLAN_THREADS - 1) / PLAN_THREADS;
-  const int e0 = tid * per, e1 = min(E, e0 + per);
+  const int e0 = act ? tid * per : E, e1 = act ? min(E, e0 + per) : E;
   int local = 0;
   for (int e = e0; e < e1; ++e) {
     int b = e / K, c = e - b * K;
     int n = counts[b * NK + 2 * c] + counts[b * NK + 2 * c + 1];
     local += (n > g.max_views) ? 1 : 0;
   }
-  s_scan[tid] = local;
+  if (act) s_scan[tid] = local;
   __syncthreads();
   if (tid == 0) {
     int run = 0;
@@ -106,7 +133,7 @@ k_plan(pcl_geom g, int nchunk, const int32_t* __restrict__ counts, int32_t* __re
   __syncthreads();
   const int TC = s_TC, V = s_V;
   int32_t* pairs = plan + PCL_PLAN_HEADER;
-  int t = s_scan[tid];
+  int t = act ? s_scan[tid] : 0;
   int split_err = 0;
   for (int e = e0; e < e1; ++e) {
     int b = e / K, c = e - b * K;
@@ -146,7 +173,7 @@ k_plan(pcl_geom g, int nchunk, const int32_t* __restrict__ counts, int32_t* __re
   }
   __syncthreads();
   // 3. sorted base per pair: V * (class start + number of earlier images that kept the class)
-  for (int p = tid; p < TC; p += PLAN_THREADS) {
+  for (int p = act ? tid : TC; p < TC; p += PLAN_THREADS) {
     int32_t* q = pairs + (int64_t)p * 8;
     int b = q[0], c = q[1];
     int before = 0;
@@ -158,6 +185,11 @@ k_plan(pcl_geom g, int nchunk, const int32_t* __restrict__ counts, int32_t* __re
   }
 }
 
+__global__ void __launch_bounds__(PLAN_THREADS)
+k_plan(pcl_geom g, int nchunk, const int32_t* __restrict__ counts, int32_t* __restrict__ plan) {
+  plan_body(g, counts, plan);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_select: one warp per anchor row
 // ------------------------------------------------------------------------------------------------
@@ -167,7 +199,9 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
          const int32_t* __restrict__ ranks, uint64_t seed, int normalize, int32_t* __restrict__ meta,
          float* __restrict__ anchors, __nv_bfloat16* __restrict__ anchors_bf16, float* __restrict__ inv_norm,
          float* __restrict__ norm_max, float* __restrict__ row_m2, float m2_scale, float* __restrict__ partials,
-         int64_t n_slot_rows) {
+         int64_t n_slot_rows, const unsigned long long* __restrict__ seed_ctr) {
+  // captured launch sequences: the per-step part of the seed lives in device memory (same formula as pcl_step_ranks)
+  if (seed_ctr != nullptr) seed = seed * 0x9E3779B97F4A7C15ull + *seed_ctr + 1ull;
   // tensor-path fusion: initialise the partial-statistic slots (m = -inf, sums = 0) while we are here
   if (partials != nullptr) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_slot_rows; k += (int64_t)gridDim.x * blockDim.x) {
@@ -391,9 +425,76 @@ k_zero_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_
   }
 }
 
+// Scatter of the A gradient rows into an ALREADY zero-filled dense gradient, with the fixed-order sum of the per-split
+// (per-column-tile) partial rows folded in: one warp per anchor row.  Also advances the step counter of a captured
+// sequence (last kernel of the step).
+__global__ void __launch_bounds__(256)
+k_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restrict__ meta,
+                 const float* __restrict__ dpartials, int splits, int split_cols, int a_pad, float inv_T,
+                 const float* __restrict__ grad_scale, float* __restrict__ grad, unsigned long long* step_counter) {
+  if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1ull;
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int A = min(plan[PCL_PLAN_A], g.max_samples);
+  if (s >= A) return;
+  // partial p covers the contrast columns [p * split_cols, (p+1) * split_cols): only the live ones were written
+  if (split_cols > 0) splits = min(splits, (A + split_cols - 1) / split_cols);
+  const int ms = g.max_samples, D = g.D;
+  const int64_t HW = (int64_t)g.h * g.w;
+  const int pix = meta[s], b = meta[ms + s];
+  const float scale = inv_T * (grad_scale ? grad_scale[0] : 1.f);
+  float* dst = grad + (int64_t)b * D * HW + pix;
+  for (int d = lane; d < D; d += 32) {
+    float v = 0.f;
+    for (int p = 0; p < splits; ++p) v += dpartials[((int64_t)p * a_pad + s) * D + d];      // fixed order
+    dst[(int64_t)d * HW] = v * scale;
+  }
+}
+
+// Zero-fill with 16-byte stores (the dense gradient: B*D*h*w*4 bytes, the HBM floor of the step).  Small footprint
+// (256 threads, no shared memory) so that its CTAs share the SMs with the latency-bound kernels of the step.
+__global__ void __launch_bounds__(256)
+k_fill_zero(uint4* __restrict__ p, uint64_t n16) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // four independent stores per iteration
+  for (; i + 3 * stride < n16; i += 4 * stride) { p[i] = z; p[i + stride] = z; p[i + 2 * stride] = z; p[i + 3 * stride] = z; }
+  for (; i < n16; i += stride) p[i] = z;
+}
+
 }  // namespace pcl
 
 using namespace pcl;
+
+extern "C" int pcl_fill_zero(void* ptr, uint64_t bytes, void* stream) {
+  PCL_REQUIRE(ptr && (bytes & 15) == 0 && ((uintptr_t)ptr & 15) == 0);
+  if (bytes == 0) return PCL_OK;
+  const uint64_t n16 = bytes >> 4;
+  uint64_t blocks = (n16 + 255) / 256;
+  // CTAs per SM: the fill is a long-running branch that shares the SMs with the latency-bound kernels of the step; a
+  // few resident warps per SM saturate the HBM write path (stores do not wait), more would only crowd the others out
+  // (8 CTAs/SM = all 2048 thread slots: the step's kernels then queue behind the whole fill — measured 137 us vs
+  // profiles/r2_06_fill_occupancy.log).  PCL_FILL_CTAS_PER_SM overrides (tuning runs).
+  int per_sm = 2;
+  if (const char* e = getenv("PCL_FILL_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
+  const uint64_t cap = (uint64_t)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  k_fill_zero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint4*)ptr, n16);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+int pcl::scatter_reduce_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
+                             int splits, int split_cols, int a_pad, float inv_T, const float* grad_scale, float* grad_embed,
+                             unsigned long long* step_counter, void* stream) {
+  if (!g || !plan || !anchor_meta || !dpartials || !grad_embed || splits < 1) return PCL_ERR_ARG;
+  const int warps = 8;
+  k_scatter_reduce<<<ceil_div(g->max_samples, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      *g, plan, anchor_meta, dpartials, splits, split_cols, a_pad, inv_T, grad_scale, grad_embed, step_counter);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
 
 int pcl::zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
                              int splits, int a_pad, float inv_T, const float* grad_loss, float* grad_embed, void* stream) {
@@ -455,7 +556,26 @@ extern "C" int pcl_class_stats(const pcl_geom* g, const int64_t* labels, const f
   PCL_CUDA(cudaMemsetAsync(counts, 0, (size_t)g->B * 2 * g->K * sizeof(int32_t), s));
   dim3 grid(nchunk, g->B);
   size_t smem = (2 * g->K + 1) * sizeof(int);
-  k_keys<<<grid, PCL_CHUNK, smem, s>>>(*g, nchunk, scale_h, scale_w, labels, seg, predict, keys, chunk_pref, counts);
+  k_keys<<<grid, PCL_CHUNK, smem, s>>>(*g, nchunk, scale_h, scale_w, labels, seg, predict, keys, chunk_pref, counts,
+                                       nullptr, nullptr);
+  PCL_LAUNCH_CHECK();
+  return PCL_OK;
+}
+
+// Step path: scan + totals + plan in ONE launch (the last block to finish runs the plan; done_ctr: one zeroed word).
+int pcl::class_stats_plan(const pcl_geom* g, const int64_t* labels, const float* seg, const int64_t* predict, uint16_t* keys,
+                          int32_t* chunk_pref, int32_t* counts, int32_t* plan, unsigned int* done_ctr, void* stream) {
+  int st = check_geom(g);
+  if (st != PCL_OK) return st;
+  PCL_REQUIRE(labels && keys && chunk_pref && counts && plan && done_ctr && (seg || predict));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t HW = (int64_t)g->h * g->w;
+  const int nchunk = (int)ceil_div64(HW, PCL_CHUNK);
+  const float scale_h = (float)g->Himg / (float)g->h, scale_w = (float)g->Wimg / (float)g->w;
+  dim3 grid(nchunk, g->B);
+  size_t smem = (2 * g->K + 1) * sizeof(int);
+  k_keys<<<grid, PCL_CHUNK, smem, s>>>(*g, nchunk, scale_h, scale_w, labels, seg, predict, keys, chunk_pref, counts, plan,
+                                       done_ctr);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
@@ -474,7 +594,8 @@ extern "C" int pcl_plan_anchors(const pcl_geom* g, const int32_t* counts, int32_
 int pcl::select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t* keys, const int32_t* chunk_pref,
                           const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize, int32_t* anchor_meta,
                           float* anchors_f32, void* anchors_bf16, float* inv_norm, float* norm_max, float* row_m2,
-                          float m2_scale, float* partials, int64_t n_slot_rows, void* stream) {
+                          float m2_scale, float* partials, int64_t n_slot_rows, void* stream,
+                          const unsigned long long* seed_ctr) {
   int st = check_geom(g);
   if (st != PCL_OK) return st;
   PCL_REQUIRE(embed && keys && chunk_pref && plan && anchor_meta && anchors_f32 && inv_norm);
@@ -489,7 +610,7 @@ int pcl::select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t*
   k_select<<<ceil_div(rows, warps), warps * 32, 0, s>>>(*g, nchunk, embed, keys, chunk_pref, plan, ranks, seed,
                                                        normalize, anchor_meta, anchors_f32,
                                                        (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max, row_m2, m2_scale,
-                                                       partials, n_slot_rows);
+                                                       partials, n_slot_rows, seed_ctr);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

@@ -41,6 +41,9 @@ static void fill_tc(const pcl_step_desc* d, pcl_tc_desc* t) {
 
 extern "C" int pcl_step_stats(const pcl_step_desc* d, void* stream) {
   if (!d) return PCL_ERR_ARG;
+  if (d->sync != nullptr)        // one launch: the scan's last block computes totals and plan (sync[4] = its counter)
+    return pcl::class_stats_plan(&d->g, d->labels, d->seg, d->predict, d->keys, d->chunk_pref, d->counts, d->plan,
+                                 d->sync + 4, stream);
   int st = pcl_class_stats(&d->g, d->labels, d->seg, d->predict, d->keys, d->chunk_pref, d->counts, stream);
   if (st != PCL_OK) return st;
   return pcl_plan_anchors(&d->g, d->counts, d->plan, stream);
@@ -114,4 +117,39 @@ extern "C" int pcl_step_backward_prezeroed(const pcl_step_desc* d, const float* 
   if (st != PCL_OK) return st;
   return pcl::scatter_rows(&d->g, d->plan, d->anchor_meta, d->dA, d->anchors_f32, d->inv_norm, d->normalize,
                            d->grad_embed, stream);
+}
+
+// ---- fused small-anchor step (include/pcl.h: pcl_step_fused_*) ----
+extern "C" int pcl_step_fused_supported(const pcl_step_desc* d) {
+  if (!d || d->mode != 0 || d->precision != 1 || d->normalize != 0 || d->sync == nullptr) return 0;
+  if (d->g.D != 256 || d->g.max_samples < 1 || d->g.max_samples > 1024) return 0;
+  return 1;
+}
+
+extern "C" int pcl_step_fused_loss(const pcl_step_desc* d, const uint64_t* step_counter, void* stream) {
+  if (!pcl_step_fused_supported(d)) return PCL_ERR_UNSUPPORTED;
+  if (!d->anchors_bf16 || !d->row_m2) return PCL_ERR_ARG;
+  int st = pcl_step_stats(d, stream);
+  if (st != PCL_OK) return st;
+  pcl_tc_desc t;
+  fill_tc(d, &t);
+  int64_t n_slot_rows = 0;
+  float m2_scale = 0.f;
+  st = pcl::tc_query(&t, &n_slot_rows, &m2_scale);
+  if (st != PCL_OK) return st;
+  // selection + gather; the fused kernel writes every partial slot it reads: no slot initialisation
+  st = pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, step_counter ? nullptr : d->ranks, d->seed,
+                             0, d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, nullptr, d->row_m2, m2_scale,
+                             nullptr, 0, stream, reinterpret_cast<const unsigned long long*>(step_counter));
+  if (st != PCL_OK) return st;
+  return pcl::self_fused(&t, d->row_m2, d->partials, d->rowstats, d->loss, d->dpartials, d->sync, stream);
+}
+
+extern "C" int pcl_step_fused_scatter(const pcl_step_desc* d, const float* grad_scale, uint64_t* step_counter, void* stream) {
+  if (!pcl_step_fused_supported(d)) return PCL_ERR_UNSUPPORTED;
+  if (!d->grad_embed) return PCL_ERR_ARG;
+  const int a_pad = ((d->g.max_samples + 127) / 128) * 128;
+  const int splits = (a_pad + 255) / 256;
+  return pcl::scatter_reduce_rows(&d->g, d->plan, d->anchor_meta, d->dpartials, splits, 256, a_pad, 1.f / d->temperature, grad_scale,
+                                  d->grad_embed, reinterpret_cast<unsigned long long*>(step_counter), stream);
 }

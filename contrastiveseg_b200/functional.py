@@ -114,6 +114,7 @@ class ContrastWorkspace:
         self.loss = torch.zeros(1, **f32)
         self.ranks = torch.zeros(ms, **i32)
         self.ranks_host = torch.zeros(ms, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
+        self.sync = torch.zeros(8, **i32)      # inter-CTA counters of the fused kernels (re-armed by the kernels themselves)
         self.busy = False
         self.token = 0               # generation counter: a stale autograd node must not release a re-used workspace
         self.bank_key = None         # (device index, segment_queue address) while a backward that re-reads that bank is pending
@@ -122,7 +123,7 @@ class ContrastWorkspace:
         d.g = geom
         d.mode, d.bank_K, d.bank_M0, d.bank_M1 = mode, bank_K, bank_M0, bank_M1
         for name in ("keys", "chunk_pref", "counts", "plan", "anchor_meta", "anchors_f32", "anchors_bf16", "inv_norm",
-                     "partials", "rowstats", "dpartials", "dA", "loss", "row_m2"):      # norm_max: optional, unused
+                     "partials", "rowstats", "dpartials", "dA", "loss", "row_m2", "sync"):   # norm_max: optional, unused
             setattr(d, name, getattr(self, name).data_ptr())
         self.desc = d
 

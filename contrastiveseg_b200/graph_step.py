@@ -57,7 +57,8 @@ class GraphedContrastStep:
                  predict: Optional[torch.Tensor] = None, segment_queue: Optional[torch.Tensor] = None,
                  pixel_queue: Optional[torch.Tensor] = None, bank_shadow: Optional[torch.Tensor] = None,
                  options: Optional[ContrastOptions] = None, grad_scale: float = 1.0, capture: bool = True,
-                 warmup: int = 2, overlap_zero_fill: bool = True, enqueue: Optional[dict] = None):
+                 warmup: int = 2, overlap_zero_fill: bool = True, enqueue: Optional[dict] = None,
+                 fused: Optional[bool] = None):
         """enqueue (bank steps): dict(bank=MemoryBank, keys=(B,D,h,w) fp32 [default: embed], labels=(B,Himg,Wimg) int64
         [default: labels], network_stride=int, pixel_update_freq=int, seed=int, group=process group or None)."""
         self.lib = _abi.load()
@@ -122,6 +123,14 @@ class GraphedContrastStep:
         d.seed = int(opts.seed) & 0xFFFFFFFFFFFFFFFF          # base seed; the per-replay part is the device counter
         d.ranks = self.ws.ranks.data_ptr()
         d.loss, d.grad_embed = self.loss.data_ptr(), self.grad.data_ptr()
+        # Small-anchor shape (no bank, tensor path, D = 256, max_samples <= 1024: BASELINE configs[1]): four launches
+        # instead of eleven — scan+plan, selection, ONE kernel for the InfoNCE forward and backward (logits stay in tensor
+        # memory), scatter — with the engine's own zero-fill of the dense gradient on a parallel branch.
+        ok = bool(self.lib.pcl_step_fused_supported(C.byref(d))) and enqueue is None
+        if fused and not ok:
+            raise _abi.PclError("fused=True: the step does not qualify (needs no bank, precision='bf16', D=256, "
+                                "max_samples<=1024, normalize=False)")
+        self.fused = ok if fused is None else bool(fused)
         self.graph = None
         self.graph_b = None
         self.replays = 0
@@ -189,7 +198,11 @@ class GraphedContrastStep:
             self.side = torch.cuda.Stream(self.device)
         self.side.wait_stream(main)                  # the previous consumer of `grad` is ordered before the fill
         with torch.cuda.stream(self.side):
-            self.grad.zero_()
+            if self.fused:       # the engine's own fill kernel (small CTAs that share the SMs with the loss kernels)
+                _abi.check(self.lib.pcl_fill_zero(self.grad.data_ptr(), self.grad.numel() * 4, self.side.cuda_stream),
+                           "pcl_fill_zero")
+            else:
+                self.grad.zero_()
 
     def _join_zero_fill(self) -> None:
         torch.cuda.current_stream(self.device).wait_stream(self.side)
@@ -198,6 +211,11 @@ class GraphedContrastStep:
     def _enqueue_a(self, stream: int) -> None:
         """First half: (zero-fill branch ||) stats -> ranks -> forward -> this rank's enqueue packet."""
         lib, d = self.lib, self.ws.desc
+        if self.fused:
+            self._fork_zero_fill()
+            _abi.check(lib.pcl_step_fused_loss(C.byref(d), self.counter.data_ptr(), stream), "pcl_step_fused_loss")
+            self._join_zero_fill()
+            return
         if self.overlap_zero_fill:
             self._fork_zero_fill()
         _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
@@ -211,6 +229,10 @@ class GraphedContrastStep:
     def _enqueue_b(self, stream: int) -> None:
         """Second half: backward -> dense gradient -> (after the sweep that re-reads the bank) the bank write."""
         lib, d = self.lib, self.ws.desc
+        if self.fused:
+            _abi.check(lib.pcl_step_fused_scatter(C.byref(d), self.scale.data_ptr(), self.counter.data_ptr(), stream),
+                       "pcl_step_fused_scatter")
+            return
         if self.overlap_zero_fill:
             _abi.check(lib.pcl_step_backward_prezeroed(C.byref(d), self.scale.data_ptr(), stream),
                        "pcl_step_backward_prezeroed")

@@ -325,6 +325,9 @@ typedef struct {
   /* outputs */
   float* loss;                   /* 1 float                                                          */
   float* grad_embed;             /* (B,D,h,w), written by pcl_step_backward                          */
+  uint32_t* sync;                /* optional: 8 words of device memory, ZERO before the first call, owned by this step:
+                                  * inter-CTA counters of the fused kernels (re-armed by the kernels themselves).
+                                  * Non-NULL: pcl_step_stats runs as ONE launch (plan folded into the scan's last block) */
 } pcl_step_desc;
 
 int pcl_step_stats(const pcl_step_desc* d, void* stream);      /* pcl_class_stats + pcl_plan_anchors      */
@@ -345,6 +348,21 @@ int pcl_step_backward_prezeroed(const pcl_step_desc* d, const float* grad_loss, 
  *   step_counter  1 uint64 in device memory (caller-initialised, e.g. 0), read and incremented on the stream
  *   ranks         max_samples int32 */
 int pcl_step_ranks(const pcl_step_desc* d, uint64_t* step_counter, int32_t* ranks, void* stream);
+
+/* Fused small-anchor step (self-contrast, no bank, tensor path, D = 256, max_samples <= 1024, no in-kernel normalise:
+ * the shape of BASELINE configs[1]).  Four launches for the whole loss step instead of eleven:
+ *   pcl_step_fused_loss     label/argmax scan + plan (last block) -> selection + gather (anchor ranks drawn from
+ *                           *step_counter, or from d->seed when step_counter is NULL) -> ONE kernel for the InfoNCE
+ *                           forward and backward (logits stay in tensor memory; csrc/pcl_infonce_fused.cu)
+ *   pcl_step_fused_scatter  sum of the per-column-tile gradient partials + scatter of the A sampled rows into
+ *                           d->grad_embed, which the caller has zero-filled (pcl_fill_zero, e.g. concurrently on a second
+ *                           stream: the 268 MB fill is the HBM floor of the step); advances *step_counter.
+ * d->sync is required.  pcl_step_fused_supported: 1 if the descriptor qualifies, else 0. */
+int pcl_step_fused_supported(const pcl_step_desc* d);
+int pcl_step_fused_loss(const pcl_step_desc* d, const uint64_t* step_counter, void* stream);
+int pcl_step_fused_scatter(const pcl_step_desc* d, const float* grad_scale, uint64_t* step_counter, void* stream);
+/* Zero-fill `bytes` (multiple of 16, 16-byte aligned) with 16-byte stores on the engine's own fill kernel. */
+int pcl_fill_zero(void* ptr, uint64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

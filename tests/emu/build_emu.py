@@ -21,7 +21,7 @@ CSRC = os.path.join(ROOT, "contrastiveseg_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libpcl_emu.so")
 SOURCES = ["pcl_api.cu", "pcl_select.cu", "pcl_infonce_simt.cu", "pcl_topk.cu", "pcl_graph.cu", "pcl_bank.cu",
-           "pcl_norm.cu", "pcl_segce.cu", "pcl_step.cu", "pcl_infonce_tc.cu"]
+           "pcl_norm.cu", "pcl_segce.cu", "pcl_step.cu", "pcl_infonce_tc.cu", "pcl_infonce_fused.cu"]
 
 LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>", re.S)
 NAMED_BARRIER = re.compile(r'asm volatile\("bar\.sync (\d+), %0;" ::"n"\((\w+)\) : "memory"\);')

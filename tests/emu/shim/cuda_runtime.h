@@ -369,5 +369,8 @@ static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x)
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) {}
 template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }

@@ -86,7 +86,7 @@ def test_graphed_step_equals_eager_step(precision, mem, overlap):
         kw = dict(segment_queue=bank.segment_queue, pixel_queue=bank.pixel_queue, bank_shadow=bank.shadow)
     opts = cs.ContrastOptions(temperature=0.07, base_temperature=0.07, max_samples=128, max_views=8, seed=5,
                               precision=precision, num_classes=K)
-    step = cs.GraphedContrastStep(embed, tgt, seg=seg, options=opts, overlap_zero_fill=overlap, **kw)
+    step = cs.GraphedContrastStep(embed, tgt, seg=seg, options=opts, overlap_zero_fill=overlap, fused=False, **kw)
     metas, losses, grads = [], [], []
     for r in range(3):
         loss, grad = step.replay()
@@ -118,6 +118,64 @@ def test_graphed_step_equals_eager_step(precision, mem, overlap):
     out = step2.apply(e)
     out.backward()
     assert torch.equal(e.grad, step2.grad)
+
+
+@pytest.mark.parametrize("geom", [dict(B=2, h=32, w=32, K=7, ms=128, mv=8), dict(B=3, h=32, w=48, K=9, ms=700, mv=40),
+                                  dict(B=4, h=64, w=64, K=19, ms=1024, mv=100)])
+def test_fused_small_anchor_step_matches_the_streaming_path_and_the_oracle(geom):
+    """The fused step (scan+plan | selection | ONE kernel for InfoNCE forward+backward with the logits in tensor memory |
+    scatter; csrc/pcl_infonce_fused.cu) draws the same anchors as the eager step with the same counter (bit-exact
+    anchor_meta) and computes the same loss / gradient as the streaming tensor sweeps up to summation order (loss 2e-6
+    rel, gradient 2e-3 max|g|: bf16 rounding of the gradient tile flips on last-bit differences of its fp32 inputs), and
+    the float64 oracle's within the tensor-path tolerances (loss 1e-4, gradient 4e-3 max|g|).  Covers 1 (128 anchors),
+    partial (A < max_samples, several row/column tiles) and 8 x 4 tiles."""
+    from oracle import ref_port as P
+    B, h, w, K, ms, mv = (geom[k] for k in ("B", "h", "w", "K", "ms", "mv"))
+    D = 256
+    data = make_contrast_batch(B=B, D=D, h=h, w=w, num_classes=K, img_stride=4, block=16, seed=33)
+    embed, tgt, seg = data["embed"].to(DEV), data["target"].to(DEV), data["seg"].to(DEV)
+    opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=ms, max_views=mv, seed=5,
+                              precision="bf16", num_classes=K)
+    step = cs.GraphedContrastStep(embed, tgt, seg=seg, options=opts, grad_scale=0.5)
+    assert step.fused
+    for r in range(3):
+        loss, grad = step.replay()
+        torch.cuda.synchronize()
+        meta, loss, grad = step.ws.anchor_meta.clone(), loss.clone(), grad.clone()
+        A = int(step.ws.plan[2].item())
+        assert A > 0 and (ms < 1024 or A >= 512)
+        Fn._step_counter[0] = r
+        e = embed.clone().requires_grad_(True)
+        l = cs.pixel_contrast_loss(e, tgt, seg=seg, options=opts)
+        ws = Fn.last_workspace(e.device)
+        l.backward()
+        torch.cuda.synchronize()
+        assert torch.equal(ws.anchor_meta, meta)
+        assert abs(l.item() - loss.item()) <= 2e-6 * abs(l.item())
+        gmax = e.grad.abs().max().item()
+        assert (0.5 * e.grad - grad).abs().max().item() <= 2e-3 * 0.5 * gmax
+        # float64 oracle on the anchors the step drew (self-contrast, class-sorted rows: diagonal = own row)
+        m = meta.view(4, ms)[:, :A].long().cpu()
+        rows = data["embed"].permute(0, 2, 3, 1).reshape(B, h * w, D)[m[1], m[0]].double()
+        cf = P.infonce_closed_form(rows, m[2].double(), rows, m[2].double(), 0.1, 0.07, True)
+        assert abs(loss.item() - cf["loss"].item()) <= 1e-4 * abs(cf["loss"].item())
+        g_rows = grad.permute(0, 2, 3, 1).reshape(B, h * w, D)[m[1].to(DEV), m[0].to(DEV)].double().cpu() / 0.5
+        assert (g_rows - cf["dA"]).abs().max().item() <= 4e-3 * cf["dA"].abs().max().item()
+        assert int((grad != 0).sum().item()) <= A * D
+    assert int(step.counter.item()) == 3
+    assert int(step.ws.sync.abs().sum().item()) == 0             # the kernels re-armed their counters
+
+
+def test_fused_step_with_no_qualifying_class_gives_zero_loss():
+    """TC == 0 (every class has <= max_views pixels): zero loss, zero gradient, no hang of the inter-CTA barriers."""
+    data = make_contrast_batch(B=2, D=256, h=16, w=16, num_classes=5, img_stride=4, block=16, seed=3)
+    opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=64, max_views=100000, seed=5,
+                              precision="bf16", num_classes=5)
+    step = cs.GraphedContrastStep(data["embed"].to(DEV), data["target"].to(DEV), seg=data["seg"].to(DEV), options=opts)
+    assert step.fused
+    loss, grad = step.replay()
+    torch.cuda.synchronize()
+    assert loss.item() == 0.0 and float(grad.abs().sum().item()) == 0.0
 
 
 def test_smem_opt_in_survives_a_smaller_launch():
