@@ -40,7 +40,8 @@ int select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t* keys
                      const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize, int32_t* anchor_meta,
                      float* anchors_f32, void* anchors_bf16, float* inv_norm, float* norm_max, float* row_m2,
                      float m2_scale, float* partials, int64_t n_slot_rows, void* stream,
-                     const unsigned long long* seed_ctr = nullptr);
+                     const unsigned long long* seed_ctr = nullptr, unsigned int* dbg = nullptr,
+                     const int32_t* prev_rows = nullptr, float* grad_clear = nullptr);
 int tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
               bool skip_prep);
 int tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale);
@@ -56,7 +57,8 @@ int class_stats_plan(const pcl_geom* g, const int64_t* labels, const float* seg,
                      int32_t* chunk_pref, int32_t* counts, int32_t* plan, unsigned int* done_ctr, void* stream);
 int scatter_reduce_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials, int splits,
                         int split_cols, int a_pad, float inv_T, const float* grad_scale, float* grad_embed, unsigned long long* step_counter,
-                        void* stream);
+                        void* stream, unsigned int* dbg = nullptr, int32_t* prev_rows = nullptr);
+int fill_zero(void* ptr, uint64_t bytes, void* stream, unsigned int* dbg, int reserve_sms);
 int scatter_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dA,
                  const float* anchors_f32, const float* inv_norm, int normalize, float* grad_embed, void* stream);
 
@@ -88,6 +90,29 @@ int num_sms();
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- optional in-graph timeline (diagnostics) ----------------------------------------------------------
+// The step's `sync` buffer (pcl_step_desc.sync, >= 1024 words) doubles as a timeline when word 7 is non-zero: words
+// [16, 16 + 4*16) hold, per kernel slot k, {min block start, max block end} of %globaltimer (ns) — the only way to see
+// how the kernels of a captured graph actually overlap (ncu serialises them).  Costs one predicated load per block when off.
+enum { PCL_TL_KEYS = 0, PCL_TL_SELECT = 1, PCL_TL_FUSED = 2, PCL_TL_SCATTER = 3, PCL_TL_FILL = 4 };
+__device__ __forceinline__ unsigned long long pcl_globaltimer() {
+#ifdef PCL_EMULATION
+  return 0ull;
+#else
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
+__device__ __forceinline__ void tl_begin(unsigned int* dbg, int slot) {
+  if (dbg != nullptr && dbg[7] != 0u && threadIdx.x == 0)
+    atomicMin(reinterpret_cast<unsigned long long*>(dbg + 16) + 2 * slot, pcl_globaltimer());
+}
+__device__ __forceinline__ void tl_end(unsigned int* dbg, int slot) {
+  if (dbg != nullptr && dbg[7] != 0u && threadIdx.x == 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(dbg + 16) + 2 * slot + 1, pcl_globaltimer());
+}
 
 // ---- device helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -55,6 +55,9 @@ struct Smem {
   uint32_t tmem_base;
   float comb[3][2][BM];
   float red[BM];
+  float4 colstat[BN];                // phase 3: per column j of tile c: {m2_j, Neg_j, c_j S_j, -c_j Neg_j}
+  float2 colneg[BN];                 // {m2_j, c_j S_j}: all an all-negative chunk needs
+  int collab[BN];                    // label of column j (-2: beyond the live anchors)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -89,6 +92,11 @@ __device__ __forceinline__ void cta_group_barrier(unsigned int* ctr, unsigned in
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 }
 
+// Scheduling note (measured with the in-graph timeline, profiles/r2_1*_timeline_*): next to the 268 MB zero-fill of the
+// dense gradient every global access of this kernel (labels, TMA loads, the two partial exchanges, the barrier atomics)
+// takes 4-8x longer — co-resident with the fill (144 registers: 3 warps + 2 fill warps fit a 16 K sub-partition) it needs
+// 70 us instead of 35.  At 168 registers its CTAs cannot be placed next to fill CTAs, start when the first fill CTAs
+// retire and run at full speed: the step is 5-10 us shorter that way, so the register count is left alone.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -107,6 +115,10 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (A <= 0 || r >= R_live || c >= S_live) return;
   const unsigned int n_live = (unsigned int)(R_live * S_live);
   const int row0 = r * BM, col0 = c * BN;
+  tl_begin(a.sync, PCL_TL_FUSED);
+  // per-CTA phase stamps (diagnostics, when the timeline is on): words [64 + 16 * cta, +16) = 8 x uint64
+  unsigned long long* stamps = (a.sync[7] != 0u) ? reinterpret_cast<unsigned long long*>(a.sync + 64) + 8 * (r * a.s_max + c) : nullptr;
+#define PCL_STAMP(i) do { if (stamps != nullptr && threadIdx.x == 64) stamps[i] = pcl_globaltimer(); } while (0)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -171,15 +183,15 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const float m2 = valid ? a.row_m2[row] : 0.f;
     const int cbase = col0 + half * (BN / 2);
     int clab[4];
-    float cm2[4];
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       const int cj = cbase + ch * 32 + lane;
       clab[ch] = cj < A ? a.acls[cj] : -2;
-      cm2[ch] = cj < A ? a.row_m2[cj] : 0.f;
     }
+    PCL_STAMP(0);
     ptx::mbar_wait(&sm.s_full, 0);
     ptx::tc_fence_after();
+    PCL_STAMP(1);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * (BN / 2);
     float* pn = a.partials + 1 * pstride;
     float* pp0 = a.partials + 2 * pstride;
@@ -207,7 +219,9 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       sm.comb[0][half][r_in] = acc0 + acc1;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       if (half == 0) pn[po] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
+      PCL_STAMP(2);
       if (a.phase_mask == 7) cta_group_barrier(&a.sync[0], n_live);
+      PCL_STAMP(3);
     }
 
     // ---------------- phase 2: positives ----------------
@@ -222,20 +236,34 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
+        // Anchors are grouped by class, so a 32-column chunk holds a few classes and most (warp, chunk) pairs contain no
+        // positive at all (19 classes: ~1 in 10 does): find out with a walk over the chunk's distinct labels (ballots)
+        // and skip the tensor-memory load and the element loop otherwise.
+        bool mine = false;
+        {
+          const int L = clab[ch];
+          unsigned remaining = 0xffffffffu;
+          while (remaining) {
+            const int lab = __shfl_sync(0xffffffffu, L, __ffs(remaining) - 1);
+            remaining &= ~__ballot_sync(0xffffffffu, L == lab);
+            mine |= (lab == rcls);
+          }
+        }
+        if (!__any_sync(0xffffffffu, mine && valid)) continue;
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
         ptx::tmem_ld_wait();
         const int cb = cbase + ch * 32;
+        // branch-free (a divergent branch around the three MUFU ops serialised their latencies: 9 us per CTA)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int lj = __shfl_sync(0xffffffffu, clab[ch], j);
-          if (valid && lj == rcls && cb + j != row) {
-            const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
-            const float t = ptx::ex2_approx(x) + neg_i;
-            q0 += x - ptx::lg2_approx(t);
-            q1 += ptx::rcp_approx(t);
-            q2 += 1.f;
-          }
+          const float keep = (valid && lj == rcls && cb + j != row) ? 1.f : 0.f;
+          const float x = fmaf(__uint_as_float(v[j]), a.k1, -m2);
+          const float t = ptx::ex2_approx(x) + neg_i;
+          q0 = fmaf(keep, x - ptx::lg2_approx(t), q0);
+          q1 = fmaf(keep, ptx::rcp_approx(t), q1);
+          q2 += keep;
         }
       }
       sm.comb[0][half][r_in] = q0 * LN2;
@@ -247,7 +275,9 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         pp1[po] = sm.comb[1][0][r_in] + sm.comb[1][1][r_in];
         pp2[po] = sm.comb[2][0][r_in] + sm.comb[2][1][r_in];
       }
+      PCL_STAMP(4);
       if (a.phase_mask == 7) cta_group_barrier(&a.sync[1], n_live);
+      PCL_STAMP(5);
     }
 
     // ---------------- phase 3: gradient tile, MMA2, dA partial ----------------
@@ -287,13 +317,13 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           a.partials[r] = t;                                              // k = 0 region: per-row-tile loss sums
         }
       }
-      // statistics of this lane's columns (every column is an anchor too: H = G + G^T)
-      float j_neg[4], j_cs[4], j_cn[4];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int cj = cbase + ch * 32 + lane;
-        float nj = 1.f, sj = 0.f, cntj = 1.f;
+      // statistics of the 256 columns of tile c (every column is an anchor too: H = G + G^T): one column per epilogue
+      // thread, into shared memory (the element loop reads them as broadcasts: no register copies, no shuffles)
+      {
+        const int t = threadIdx.x - 64;                                    // 0..255
+        const int cj = col0 + t;
         const bool cok = cj < A;
+        float nj = 1.f, sj = 0.f, cntj = 1.f;
         if (cok) {
           nj = 0.f; cntj = 0.f;
           for (int cc = 0; cc < S_live; ++cc) {
@@ -303,37 +333,66 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         float c_j = cok ? a.rs_scale / ((float)A * cntj) : 0.f;
         if (a.nan_safe && !(cntj > 0.f)) c_j = 0.f;
-        j_neg[ch] = nj; j_cs[ch] = c_j * sj; j_cn[ch] = -c_j * nj;
+        const float m2j = cok ? a.row_m2[cj] : 0.f;
+        sm.colstat[t] = make_float4(m2j, nj, c_j * sj, -c_j * nj);
+        sm.colneg[t] = make_float2(m2j, c_j * sj);
+        sm.collab[t] = cok ? a.acls[cj] : -2;
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       uint8_t* h_row = sm.a + r_in * 128;                                  // + kblock * 16 KB + swizzled 16-byte chunk
+      const float rv = valid ? 1.f : 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + ch * 32, v);
-        ptx::tmem_ld_wait();
         const int cb = cbase + ch * 32;
-        uint32_t packed[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float hv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int jj = j + u;
-            const int lj = __shfl_sync(0xffffffffu, clab[ch], jj);
-            const float m2j = __shfl_sync(0xffffffffu, cm2[ch], jj);
-            const float negj = __shfl_sync(0xffffffffu, j_neg[ch], jj);
-            const float csj = __shfl_sync(0xffffffffu, j_cs[ch], jj);
-            const float cnj = __shfl_sync(0xffffffffu, j_cn[ch], jj);
-            const float x = __uint_as_float(v[jj]) * a.k1;
-            const float e = ptx::ex2_approx(x - m2);
-            const float e2 = ptx::ex2_approx(x - m2j);
-            const bool same = lj == rcls;
-            const bool diag = (cb + jj == row);
-            const float g_ij = same ? (diag ? 0.f : cn_i * ptx::rcp_approx(e + neg_i)) : cs_i * e;
-            const float g_ji = same ? (diag ? 0.f : cnj * ptx::rcp_approx(e2 + negj)) : csj * e2;
-            hv[u] = (!valid || lj == -2) ? 0.f : (g_ij + g_ji);
+        const int sb = half * (BN / 2) + ch * 32;                          // column index inside the tile
+        // One vote per CHUNK: does any row of this warp share its class with any (live) column of the chunk?  (A vote per
+        // element is a convergence point that keeps the compiler from interleaving the elements' LDS -> MUFU chains:
+        // 6 us per CTA.)  Anchors are grouped by class, so ~9 of 10 (warp, chunk) pairs are all-negative.
+        bool mine = !(cb + 32 <= A);                                       // ragged chunks take the general path
+        {
+          const int L = clab[ch];
+          unsigned remaining = 0xffffffffu;
+          while (remaining) {
+            const int lab = __shfl_sync(0xffffffffu, L, __ffs(remaining) - 1);
+            remaining &= ~__ballot_sync(0xffffffffu, L == lab);
+            mine |= (lab == rcls);
           }
-          packed[j >> 1] = pack_bf16x2(hv[0], hv[1]);
+        }
+        const bool general = __any_sync(0xffffffffu, mine);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
+        if (!general) {
+          // all-negative chunk: H_ij = c_i S_i e_ij + c_j S_j e_ji, no class test, no reciprocal
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 c0 = sm.colneg[sb + j], c1 = sm.colneg[sb + j + 1];      // {m2_j, c_j S_j}: warp-uniform loads
+            const float x0 = __uint_as_float(v[j]) * a.k1, x1 = __uint_as_float(v[j + 1]) * a.k1;
+            const float h0 = fmaf(cs_i, ptx::ex2_approx(x0 - m2), rv * c0.y * ptx::ex2_approx(x0 - c0.x));
+            const float h1 = fmaf(cs_i, ptx::ex2_approx(x1 - m2), rv * c1.y * ptx::ex2_approx(x1 - c1.x));
+            packed[j >> 1] = pack_bf16x2(h0, h1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float hv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int jj = j + u;
+              const int lj = sm.collab[sb + jj];                           // uniform over the warp
+              const float4 cs = sm.colstat[sb + jj];
+              const float x = __uint_as_float(v[jj]) * a.k1;
+              const float e = ptx::ex2_approx(x - m2);
+              const float e2 = ptx::ex2_approx(x - cs.x);
+              const bool same = lj == rcls;
+              const bool diag = (cb + jj == row);
+              const float g_ij = same ? (diag ? 0.f : cn_i * ptx::rcp_approx(e + neg_i)) : cs_i * e;
+              const float g_ji = same ? (diag ? 0.f : cs.w * ptx::rcp_approx(e2 + cs.y)) : cs.z * e2;
+              hv[u] = (!valid || lj == -2) ? 0.f : (g_ij + g_ji);
+            }
+            packed[j >> 1] = pack_bf16x2(hv[0], hv[1]);
+          }
         }
         // this thread's 32 columns = half a K-block (64 j) of the H tile: 4 chunks of 16 B, 128B-swizzled by row
         const int kblock = half * 2 + (ch >> 1);
@@ -348,20 +407,24 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::fence_proxy_async();                   // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sm.g_full);
+      PCL_STAMP(6);
       // dA tile: TMEM -> the partial of this column tile
       ptx::mbar_wait(&sm.da_full, 0);
       ptx::tc_fence_after();
       float* dst = a.dpartials + ((int64_t)c * a.a_pad + row) * DDIM + half * 128;
       const uint32_t t_da = tmem_dA + ((uint32_t)(quarter * 32) << 16) + half * 128;
-#pragma unroll 1
+      uint32_t dbuf[2][32];
+      ptx::tmem_ld_32x32b_x32(t_da, dbuf[0]);
+#pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_da + ch * 32, v);
         ptx::tmem_ld_wait();
+        if (ch < 3) ptx::tmem_ld_32x32b_x32(t_da + (ch + 1) * 32, dbuf[(ch + 1) & 1]);       // next chunk in flight
+        uint32_t(&v)[32] = dbuf[ch & 1];
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<uint4*>(dst + ch * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
+      PCL_STAMP(7);
       // ---- last CTA: loss = fixed-order sum of the row tiles' sums / A; counters re-armed for the next launch ----
       __threadfence();
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -385,6 +448,8 @@ k_self_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  tl_end(a.sync, PCL_TL_FUSED);
+#undef PCL_STAMP
 }
 
 }  // namespace fused

@@ -24,6 +24,8 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
        const float* __restrict__ seg, const int64_t* __restrict__ predict, uint16_t* __restrict__ keys,
        int32_t* chunk_hist, int32_t* counts, int32_t* plan, unsigned int* done_ctr) {
   extern __shared__ int s_hist[];                 // 2K+1 bins
+  unsigned int* dbg = done_ctr ? done_ctr - 4 : nullptr;       // the step's sync buffer (timeline, diagnostics)
+  tl_begin(dbg, PCL_TL_KEYS);
   const int K = g.K, NK = 2 * K;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int HW = g.h * g.w;
@@ -75,7 +77,7 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
     s_last = (atomicAdd(done_ctr, 1u) == total - 1u) ? 1 : 0;
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) { tl_end(dbg, PCL_TL_KEYS); return; }
   __threadfence();
   for (int i = threadIdx.x; i < g.B * NK; i += blockDim.x) {
     const int32_t* hrow = chunk_hist + (int64_t)i * nchunk;
@@ -86,6 +88,7 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
   if (threadIdx.x == 0) *done_ctr = 0u;           // re-armed for the next launch
   __syncthreads();
   plan_body(g, counts, plan);
+  tl_end(dbg, PCL_TL_KEYS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -96,44 +99,59 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
 constexpr int PLAN_THREADS = 256;
 
 // Executed by the first PLAN_THREADS threads of a block whose ALL threads call it (it contains block barriers).
+// Exclusive prefix sum over the first PLAN_THREADS (= 8 full warps) threads of the block; every thread of the block must
+// call it (block barriers inside).  Returns the exclusive prefix of v (0 for the other threads), *total = the sum.
+__device__ __forceinline__ int plan_scan(int v, bool act, int* s_w, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+  if (act) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < PLAN_THREADS / 32; ++w) { const int t = s_w[w]; s_w[w] = run; run += t; }
+    s_w[PLAN_THREADS / 32] = run;
+  }
+  __syncthreads();
+  *total = s_w[PLAN_THREADS / 32];
+  const int excl = act ? incl - v + s_w[warp] : 0;
+  __syncthreads();                                     // s_w may be re-used by the next scan
+  return excl;
+}
+
 // (no __restrict__ / read-only path on `counts`: the fused scan's last block writes the totals itself just before)
 __device__ __forceinline__ void plan_body(const pcl_geom& g, const int32_t* counts, int32_t* plan) {
-  __shared__ int s_scan[PLAN_THREADS];
+  __shared__ int s_w[PLAN_THREADS / 32 + 1];
   __shared__ int s_cls_cnt[PCL_MAX_CLASSES];
   __shared__ int s_cls_start[PCL_MAX_CLASSES];
-  __shared__ int s_TC, s_V, s_err;
+  __shared__ int s_err;
   const int K = g.K, NK = 2 * K, B = g.B;
   const int tid = threadIdx.x;
   const bool act = tid < PLAN_THREADS;                 // the other threads of a larger block only take part in barriers
   if (tid == 0) s_err = 0;
-
-  // 1. per-image key totals were accumulated by k_keys; chunk_pref keeps the raw per-chunk
-  //    histograms — k_select scans the 32-entry row it needs with warp shuffles
   if (act) for (int c = tid; c < K; c += PLAN_THREADS) s_cls_cnt[c] = 0;
   __syncthreads();
 
-  // 2. compact kept (image,class) pairs in (image asc, class asc) order
+  // 1. kept (image,class) pairs in (image asc, class asc) order: thread t owns entries [t*per, (t+1)*per)
   const int E = B * K;
   const int per = (E + PLAN_THREADS - 1) / PLAN_THREADS;
-  const int e0 = act ? tid * per : E, e1 = act ? min(E, e0 + per) : E;
+  const int e0 = act ? min(E, tid * per) : E, e1 = act ? min(E, e0 + per) : E;
   int local = 0;
   for (int e = e0; e < e1; ++e) {
     int b = e / K, c = e - b * K;
     int n = counts[b * NK + 2 * c] + counts[b * NK + 2 * c + 1];
     local += (n > g.max_views) ? 1 : 0;
   }
-  if (act) s_scan[tid] = local;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int i = 0; i < PLAN_THREADS; ++i) { int v = s_scan[i]; s_scan[i] = run; run += v; }
-    s_TC = run;
-    s_V = run > 0 ? min(g.max_samples / run, g.max_views) : 0;
-  }
-  __syncthreads();
-  const int TC = s_TC, V = s_V;
+  int TC = 0;
+  int t = plan_scan(local, act, s_w, &TC);
+  const int V = TC > 0 ? min(g.max_samples / TC, g.max_views) : 0;
   int32_t* pairs = plan + PCL_PLAN_HEADER;
-  int t = act ? s_scan[tid] : 0;
   int split_err = 0;
   for (int e = e0; e < e1; ++e) {
     int b = e / K, c = e - b * K;
@@ -153,14 +171,16 @@ __device__ __forceinline__ void plan_body(const pcl_geom& g, const int32_t* coun
   }
   if (split_err) atomicOr(&s_err, 1);
   __syncthreads();
+  // 2. class-sorted start rows, rank order 1,2,...,K-1,0 (K <= 256 = PLAN_THREADS: one rank per thread)
+  {
+    const int rnk = tid;
+    const int c = (rnk == K - 1) ? 0 : rnk + 1;
+    const int v = (act && rnk < K) ? s_cls_cnt[c] : 0;
+    int tot = 0;
+    const int start = plan_scan(v, act, s_w, &tot);
+    if (act && rnk < K) s_cls_start[c] = start;
+  }
   if (tid == 0) {
-    // class-sorted start rows, rank order 1,2,...,K-1,0
-    int run = 0;
-    for (int r = 0; r < K; ++r) {
-      int c = (r == K - 1) ? 0 : r + 1;
-      s_cls_start[c] = run;
-      run += s_cls_cnt[c];
-    }
     plan[PCL_PLAN_TC] = TC;
     plan[PCL_PLAN_V] = V;
     plan[PCL_PLAN_A] = TC * V;
@@ -199,7 +219,22 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
          const int32_t* __restrict__ ranks, uint64_t seed, int normalize, int32_t* __restrict__ meta,
          float* __restrict__ anchors, __nv_bfloat16* __restrict__ anchors_bf16, float* __restrict__ inv_norm,
          float* __restrict__ norm_max, float* __restrict__ row_m2, float m2_scale, float* __restrict__ partials,
-         int64_t n_slot_rows, const unsigned long long* __restrict__ seed_ctr) {
+         int64_t n_slot_rows, const unsigned long long* __restrict__ seed_ctr, unsigned int* dbg,
+         const int32_t* __restrict__ prev_rows, float* __restrict__ grad_clear) {
+  tl_begin(dbg, PCL_TL_SELECT);
+  struct TlEnd { unsigned int* d; __device__ ~TlEnd() { tl_end(d, PCL_TL_SELECT); } } tl_guard{dbg};
+  // Sparse reset (persistent dense-gradient buffer of a captured step): instead of re-filling B*D*h*w zeros every step,
+  // clear exactly the entries the PREVIOUS step scattered (prev_rows: [0] = A_prev, then pixel[ms], image[ms]); the
+  // buffer is zero everywhere else by induction.  Runs before this step's scatter (stream order).
+  if (prev_rows != nullptr) {
+    const int ip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int msp = g.max_samples;
+    if (ip < min(prev_rows[0], msp)) {
+      const int64_t HWp = (int64_t)g.h * g.w;
+      float* dstp = grad_clear + (int64_t)prev_rows[1 + msp + ip] * g.D * HWp + prev_rows[1 + ip];
+      for (int d = threadIdx.x & 31; d < g.D; d += 32) dstp[(int64_t)d * HWp] = 0.f;
+    }
+  }
   // captured launch sequences: the per-step part of the seed lives in device memory (same formula as pcl_step_ranks)
   if (seed_ctr != nullptr) seed = seed * 0x9E3779B97F4A7C15ull + *seed_ctr + 1ull;
   // tensor-path fusion: initialise the partial-statistic slots (m = -inf, sums = 0) while we are here
@@ -431,17 +466,22 @@ k_zero_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_
 __global__ void __launch_bounds__(256)
 k_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restrict__ meta,
                  const float* __restrict__ dpartials, int splits, int split_cols, int a_pad, float inv_T,
-                 const float* __restrict__ grad_scale, float* __restrict__ grad, unsigned long long* step_counter) {
+                 const float* __restrict__ grad_scale, float* __restrict__ grad, unsigned long long* step_counter,
+                 unsigned int* dbg, int32_t* __restrict__ prev_rows) {
+  tl_begin(dbg, PCL_TL_SCATTER);
+  struct TlEnd { unsigned int* d; __device__ ~TlEnd() { tl_end(d, PCL_TL_SCATTER); } } tl_guard{dbg};
   if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1ull;
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int A = min(plan[PCL_PLAN_A], g.max_samples);
+  if (prev_rows != nullptr && s == 0 && lane == 0) prev_rows[0] = A;           // what the next step has to clear
   if (s >= A) return;
   // partial p covers the contrast columns [p * split_cols, (p+1) * split_cols): only the live ones were written
   if (split_cols > 0) splits = min(splits, (A + split_cols - 1) / split_cols);
   const int ms = g.max_samples, D = g.D;
   const int64_t HW = (int64_t)g.h * g.w;
   const int pix = meta[s], b = meta[ms + s];
+  if (prev_rows != nullptr && lane == 0) { prev_rows[1 + s] = pix; prev_rows[1 + ms + s] = b; }
   const float scale = inv_T * (grad_scale ? grad_scale[0] : 1.f);
   float* dst = grad + (int64_t)b * D * HW + pix;
   for (int d = lane; d < D; d += 32) {
@@ -454,44 +494,52 @@ k_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __
 // Zero-fill with 16-byte stores (the dense gradient: B*D*h*w*4 bytes, the HBM floor of the step).  Small footprint
 // (256 threads, no shared memory) so that its CTAs share the SMs with the latency-bound kernels of the step.
 __global__ void __launch_bounds__(256)
-k_fill_zero(uint4* __restrict__ p, uint64_t n16) {
+k_fill_zero(uint4* __restrict__ p, uint64_t n16, unsigned int* dbg) {
+  tl_begin(dbg, PCL_TL_FILL);
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // four independent stores per iteration
   for (; i + 3 * stride < n16; i += 4 * stride) { p[i] = z; p[i + stride] = z; p[i + 2 * stride] = z; p[i + 3 * stride] = z; }
   for (; i < n16; i += stride) p[i] = z;
+  tl_end(dbg, PCL_TL_FILL);
 }
 
 }  // namespace pcl
 
 using namespace pcl;
 
-extern "C" int pcl_fill_zero(void* ptr, uint64_t bytes, void* stream) {
+extern "C" int pcl_fill_zero(void* ptr, uint64_t bytes, void* stream) { return pcl::fill_zero(ptr, bytes, stream, nullptr, 0); }
+
+// reserve_sms: SMs to leave free of fill CTAs (the fused InfoNCE kernel's CTAs run there: next to a fill CTA their
+// shuffles and shared-memory accesses queue behind the fill's stores in the SM's memory pipeline — NEG phase 2 -> 20 us)
+int pcl::fill_zero(void* ptr, uint64_t bytes, void* stream, unsigned int* dbg, int reserve_sms) {
   PCL_REQUIRE(ptr && (bytes & 15) == 0 && ((uintptr_t)ptr & 15) == 0);
   if (bytes == 0) return PCL_OK;
   const uint64_t n16 = bytes >> 4;
   uint64_t blocks = (n16 + 255) / 256;
   // CTAs per SM: the fill is a long-running branch that shares the SMs with the latency-bound kernels of the step; a
   // few resident warps per SM saturate the HBM write path (stores do not wait), more would only crowd the others out
-  // (8 CTAs/SM = all 2048 thread slots: the step's kernels then queue behind the whole fill — measured 137 us vs
-  // profiles/r2_06_fill_occupancy.log).  PCL_FILL_CTAS_PER_SM overrides (tuning runs).
-  int per_sm = 2;
+  // (1, 2, 4 or 8 CTAs per SM: the fill takes 43-47 us either way, profiles/r2_1*_probe.log).
+  // PCL_FILL_CTAS_PER_SM overrides (tuning runs).
+  int per_sm = 1;
   if (const char* e = getenv("PCL_FILL_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
-  const uint64_t cap = (uint64_t)num_sms() * per_sm;
+  int sms = num_sms() - reserve_sms;
+  if (sms < num_sms() / 2) sms = num_sms() / 2;
+  const uint64_t cap = (uint64_t)sms * per_sm;
   if (blocks > cap) blocks = cap;
-  k_fill_zero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint4*)ptr, n16);
+  k_fill_zero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint4*)ptr, n16, dbg);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
 
 int pcl::scatter_reduce_rows(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
                              int splits, int split_cols, int a_pad, float inv_T, const float* grad_scale, float* grad_embed,
-                             unsigned long long* step_counter, void* stream) {
+                             unsigned long long* step_counter, void* stream, unsigned int* dbg, int32_t* prev_rows) {
   if (!g || !plan || !anchor_meta || !dpartials || !grad_embed || splits < 1) return PCL_ERR_ARG;
   const int warps = 8;
   k_scatter_reduce<<<ceil_div(g->max_samples, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      *g, plan, anchor_meta, dpartials, splits, split_cols, a_pad, inv_T, grad_scale, grad_embed, step_counter);
+      *g, plan, anchor_meta, dpartials, splits, split_cols, a_pad, inv_T, grad_scale, grad_embed, step_counter, dbg, prev_rows);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }
@@ -595,7 +643,7 @@ int pcl::select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t*
                           const int32_t* plan, const int32_t* ranks, uint64_t seed, int normalize, int32_t* anchor_meta,
                           float* anchors_f32, void* anchors_bf16, float* inv_norm, float* norm_max, float* row_m2,
                           float m2_scale, float* partials, int64_t n_slot_rows, void* stream,
-                          const unsigned long long* seed_ctr) {
+                          const unsigned long long* seed_ctr, unsigned int* dbg, const int32_t* prev_rows, float* grad_clear) {
   int st = check_geom(g);
   if (st != PCL_OK) return st;
   PCL_REQUIRE(embed && keys && chunk_pref && plan && anchor_meta && anchors_f32 && inv_norm);
@@ -610,7 +658,7 @@ int pcl::select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t*
   k_select<<<ceil_div(rows, warps), warps * 32, 0, s>>>(*g, nchunk, embed, keys, chunk_pref, plan, ranks, seed,
                                                        normalize, anchor_meta, anchors_f32,
                                                        (__nv_bfloat16*)anchors_bf16, inv_norm, norm_max, row_m2, m2_scale,
-                                                       partials, n_slot_rows, seed_ctr);
+                                                       partials, n_slot_rows, seed_ctr, dbg, prev_rows, grad_clear);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

@@ -1,5 +1,6 @@
 // One loss step chained on a stream behind a single descriptor (include/pcl.h: pcl_step_*).
 #include "pcl_common.cuh"
+#include <stdlib.h>
 
 static void fill_sweep(const pcl_step_desc* d, pcl_sweep_desc* w) {
   memset(w, 0, sizeof(*w));
@@ -126,30 +127,47 @@ extern "C" int pcl_step_fused_supported(const pcl_step_desc* d) {
   return 1;
 }
 
-extern "C" int pcl_step_fused_loss(const pcl_step_desc* d, const uint64_t* step_counter, void* stream) {
+extern "C" int pcl_step_fused_select(const pcl_step_desc* d, const uint64_t* step_counter, const int32_t* prev_rows,
+                                     void* stream) {
   if (!pcl_step_fused_supported(d)) return PCL_ERR_UNSUPPORTED;
-  if (!d->anchors_bf16 || !d->row_m2) return PCL_ERR_ARG;
-  int st = pcl_step_stats(d, stream);
-  if (st != PCL_OK) return st;
+  if (!d->anchors_bf16 || !d->row_m2 || (prev_rows && !d->grad_embed)) return PCL_ERR_ARG;
   pcl_tc_desc t;
   fill_tc(d, &t);
   int64_t n_slot_rows = 0;
   float m2_scale = 0.f;
-  st = pcl::tc_query(&t, &n_slot_rows, &m2_scale);
+  int st = pcl::tc_query(&t, &n_slot_rows, &m2_scale);
   if (st != PCL_OK) return st;
   // selection + gather; the fused kernel writes every partial slot it reads: no slot initialisation
-  st = pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, step_counter ? nullptr : d->ranks, d->seed,
-                             0, d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, nullptr, d->row_m2, m2_scale,
-                             nullptr, 0, stream, reinterpret_cast<const unsigned long long*>(step_counter));
-  if (st != PCL_OK) return st;
+  return pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, step_counter ? nullptr : d->ranks, d->seed,
+                               0, d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, nullptr, d->row_m2, m2_scale,
+                               nullptr, 0, stream, reinterpret_cast<const unsigned long long*>(step_counter), d->sync,
+                               prev_rows, d->grad_embed);
+}
+
+extern "C" int pcl_step_fused_loss(const pcl_step_desc* d, void* stream) {
+  if (!pcl_step_fused_supported(d)) return PCL_ERR_UNSUPPORTED;
+  if (!d->anchors_bf16 || !d->row_m2) return PCL_ERR_ARG;
+  pcl_tc_desc t;
+  fill_tc(d, &t);
   return pcl::self_fused(&t, d->row_m2, d->partials, d->rowstats, d->loss, d->dpartials, d->sync, stream);
 }
 
-extern "C" int pcl_step_fused_scatter(const pcl_step_desc* d, const float* grad_scale, uint64_t* step_counter, void* stream) {
+extern "C" int pcl_step_fused_scatter(const pcl_step_desc* d, const float* grad_scale, uint64_t* step_counter,
+                                      int32_t* prev_rows, void* stream) {
   if (!pcl_step_fused_supported(d)) return PCL_ERR_UNSUPPORTED;
   if (!d->grad_embed) return PCL_ERR_ARG;
   const int a_pad = ((d->g.max_samples + 127) / 128) * 128;
   const int splits = (a_pad + 255) / 256;
   return pcl::scatter_reduce_rows(&d->g, d->plan, d->anchor_meta, d->dpartials, splits, 256, a_pad, 1.f / d->temperature, grad_scale,
-                                  d->grad_embed, reinterpret_cast<unsigned long long*>(step_counter), stream);
+                                  d->grad_embed, reinterpret_cast<unsigned long long*>(step_counter), stream, d->sync, prev_rows);
+}
+
+// zero-fill of the step's dense gradient on the engine's fill kernel (the caller picks the stream: a parallel branch)
+extern "C" int pcl_step_fused_fill(const pcl_step_desc* d, void* stream) {
+  if (!d || !d->grad_embed) return PCL_ERR_ARG;
+  const uint64_t bytes = (uint64_t)d->g.B * d->g.D * d->g.h * d->g.w * sizeof(float);
+  if ((bytes & 15) != 0 || ((uintptr_t)d->grad_embed & 15) != 0) return PCL_ERR_UNSUPPORTED;
+  int reserve = 0;                 // (reserving SMs for the fused kernel's CTAs changed nothing: profiles/r2_14_*)
+  if (const char* e = getenv("PCL_FILL_RESERVE_SMS")) reserve = atoi(e);
+  return pcl::fill_zero(d->grad_embed, bytes, stream, d->sync, reserve);
 }

@@ -114,7 +114,7 @@ class ContrastWorkspace:
         self.loss = torch.zeros(1, **f32)
         self.ranks = torch.zeros(ms, **i32)
         self.ranks_host = torch.zeros(ms, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else None
-        self.sync = torch.zeros(8, **i32)      # inter-CTA counters of the fused kernels (re-armed by the kernels themselves)
+        self.sync = torch.zeros(1024, **i32)      # inter-CTA counters of the fused kernels (re-armed by the kernels themselves)
         self.busy = False
         self.token = 0               # generation counter: a stale autograd node must not release a re-used workspace
         self.bank_key = None         # (device index, segment_queue address) while a backward that re-reads that bank is pending

@@ -58,7 +58,7 @@ class GraphedContrastStep:
                  pixel_queue: Optional[torch.Tensor] = None, bank_shadow: Optional[torch.Tensor] = None,
                  options: Optional[ContrastOptions] = None, grad_scale: float = 1.0, capture: bool = True,
                  warmup: int = 2, overlap_zero_fill: bool = True, enqueue: Optional[dict] = None,
-                 fused: Optional[bool] = None):
+                 fused: Optional[bool] = None, sparse_reset: bool = False):
         """enqueue (bank steps): dict(bank=MemoryBank, keys=(B,D,h,w) fp32 [default: embed], labels=(B,Himg,Wimg) int64
         [default: labels], network_stride=int, pixel_update_freq=int, seed=int, group=process group or None)."""
         self.lib = _abi.load()
@@ -67,8 +67,9 @@ class GraphedContrastStep:
         device = embed.device
         if opts.rng != "device" or opts.perm_fn is not None:
             raise _abi.PclError("a captured step draws its anchors on the device: rng must be 'device'")
-        if opts.topk_negatives:
-            raise _abi.PclError("topk_negatives is not wired into the captured step yet")
+        self.opts = opts
+        if opts.topk_negatives and opts.precision != "fp32":
+            raise _abi.PclError("topk_negatives runs on the exact fp32 sweep: use precision='fp32'")
         self.embed = _canonical(embed.detach(), torch.float32, "embed", device)
         self.labels = _canonical(labels, torch.int64, "labels", device)
         self.seg = _canonical(None if seg is None else seg.detach(), torch.float32, "seg", device)
@@ -126,11 +127,24 @@ class GraphedContrastStep:
         # Small-anchor shape (no bank, tensor path, D = 256, max_samples <= 1024: BASELINE configs[1]): four launches
         # instead of eleven — scan+plan, selection, ONE kernel for the InfoNCE forward and backward (logits stay in tensor
         # memory), scatter — with the engine's own zero-fill of the dense gradient on a parallel branch.
-        ok = bool(self.lib.pcl_step_fused_supported(C.byref(d))) and enqueue is None
+        ok = bool(self.lib.pcl_step_fused_supported(C.byref(d))) and enqueue is None and not opts.topk_negatives
+        self.topk = None
+        if opts.topk_negatives:
+            # a10 (per-anchor top-k hard negatives): the radix-select sweeps + weighted NEG sweep are part of the captured
+            # sequence; their backward writes the dense gradient itself (zero-fill + scatter), so no parallel fill branch
+            overlap_zero_fill = False
         if fused and not ok:
             raise _abi.PclError("fused=True: the step does not qualify (needs no bank, precision='bf16', D=256, "
                                 "max_samples<=1024, normalize=False)")
         self.fused = ok if fused is None else bool(fused)
+        # sparse_reset (fused steps): ``grad`` persists between replays, zero-filled once here; every replay clears exactly
+        # the A*D entries the previous one scattered instead of re-filling B*D*h*w zeros (268 MB at the Cityscapes shape).
+        # Contract: nobody else writes ``grad`` (call ``reset_grad()`` if that happened).
+        self.sparse_reset = bool(sparse_reset) and self.fused
+        self.prev_rows = None
+        if self.sparse_reset:
+            self.prev_rows = torch.zeros(1 + 2 * opts.max_samples, dtype=torch.int32, device=device)
+            self.grad.zero_()
         self.graph = None
         self.graph_b = None
         self.replays = 0
@@ -140,7 +154,7 @@ class GraphedContrastStep:
         # The zero-fill of the dense gradient (B*D*h*w*4 bytes, the HBM floor of the step) does not depend on anything
         # the step computes: run it on a second stream from the start of the step, behind the latency-bound selection
         # and sweep kernels, and let the backward scatter only the sampled columns (pcl_step_backward_prezeroed).
-        self.overlap_zero_fill = bool(overlap_zero_fill)
+        self.overlap_zero_fill = bool(overlap_zero_fill) and not opts.topk_negatives
         self.side = None
         if capture:
             self._capture(max(1, int(warmup)))
@@ -199,8 +213,7 @@ class GraphedContrastStep:
         self.side.wait_stream(main)                  # the previous consumer of `grad` is ordered before the fill
         with torch.cuda.stream(self.side):
             if self.fused:       # the engine's own fill kernel (small CTAs that share the SMs with the loss kernels)
-                _abi.check(self.lib.pcl_fill_zero(self.grad.data_ptr(), self.grad.numel() * 4, self.side.cuda_stream),
-                           "pcl_fill_zero")
+                _abi.check(self.lib.pcl_step_fused_fill(C.byref(self.ws.desc), self.side.cuda_stream), "pcl_step_fused_fill")
             else:
                 self.grad.zero_()
 
@@ -212,15 +225,25 @@ class GraphedContrastStep:
         """First half: (zero-fill branch ||) stats -> ranks -> forward -> this rank's enqueue packet."""
         lib, d = self.lib, self.ws.desc
         if self.fused:
-            self._fork_zero_fill()
-            _abi.check(lib.pcl_step_fused_loss(C.byref(d), self.counter.data_ptr(), stream), "pcl_step_fused_loss")
-            self._join_zero_fill()
+            _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
+            _abi.check(lib.pcl_step_fused_select(C.byref(d), self.counter.data_ptr(), _abi.ptr(self.prev_rows), stream),
+                       "pcl_step_fused_select")
+            # full-fill mode: the fill forks AFTER scan and selection — next to it every DRAM read is 3-4x slower (measured
+            # in-graph: scan 22 -> 60 us, selection 13 -> 54 us), only the L2-resident InfoNCE kernel hides behind it
+            if not self.sparse_reset:
+                self._fork_zero_fill()
+            _abi.check(lib.pcl_step_fused_loss(C.byref(d), stream), "pcl_step_fused_loss")
+            if not self.sparse_reset:
+                self._join_zero_fill()
             return
         if self.overlap_zero_fill:
             self._fork_zero_fill()
         _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
         _abi.check(lib.pcl_step_ranks(C.byref(d), self.counter.data_ptr(), self.ws.ranks.data_ptr(), stream), "pcl_step_ranks")
-        _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
+        if self.opts.topk_negatives:
+            self.topk = _fn._topk_step_forward(lib, self.ws, d, self.opts, stream)
+        else:
+            _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
         if self.enq is not None:
             self._enqueue_packet(stream)
         if self.overlap_zero_fill:
@@ -230,10 +253,12 @@ class GraphedContrastStep:
         """Second half: backward -> dense gradient -> (after the sweep that re-reads the bank) the bank write."""
         lib, d = self.lib, self.ws.desc
         if self.fused:
-            _abi.check(lib.pcl_step_fused_scatter(C.byref(d), self.scale.data_ptr(), self.counter.data_ptr(), stream),
-                       "pcl_step_fused_scatter")
+            _abi.check(lib.pcl_step_fused_scatter(C.byref(d), self.scale.data_ptr(), self.counter.data_ptr(),
+                                                  _abi.ptr(self.prev_rows), stream), "pcl_step_fused_scatter")
             return
-        if self.overlap_zero_fill:
+        if self.opts.topk_negatives:
+            _fn._topk_step_backward(lib, self.ws, d, self.topk, self.scale, stream)
+        elif self.overlap_zero_fill:
             _abi.check(lib.pcl_step_backward_prezeroed(C.byref(d), self.scale.data_ptr(), stream),
                        "pcl_step_backward_prezeroed")
         else:
@@ -292,6 +317,12 @@ class GraphedContrastStep:
             t.copy_(v)
         if b.shadow is not None:
             b.shadow.copy_(snap[4])
+
+    def reset_grad(self) -> None:
+        """sparse_reset steps: re-establish the all-zero state of ``grad`` after somebody else wrote into it."""
+        if self.sparse_reset:
+            self.grad.zero_()
+            self.prev_rows.zero_()
 
     def set_grad_scale(self, value: float) -> None:
         self.scale.fill_(float(value))

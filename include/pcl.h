@@ -325,9 +325,11 @@ typedef struct {
   /* outputs */
   float* loss;                   /* 1 float                                                          */
   float* grad_embed;             /* (B,D,h,w), written by pcl_step_backward                          */
-  uint32_t* sync;                /* optional: 8 words of device memory, ZERO before the first call, owned by this step:
+  uint32_t* sync;                /* optional: 1024 words of device memory, ZERO before the first call, owned by this step:
                                   * inter-CTA counters of the fused kernels (re-armed by the kernels themselves).
-                                  * Non-NULL: pcl_step_stats runs as ONE launch (plan folded into the scan's last block) */
+                                  * Non-NULL: pcl_step_stats runs as ONE launch (plan folded into the scan's last block).
+                                  * Words [0,8): counters; word 7 != 0 turns on the diagnostic timeline in words [16,1024)
+                                  * (csrc/pcl_common.cuh: per-kernel min start / max end of %globaltimer) */
 } pcl_step_desc;
 
 int pcl_step_stats(const pcl_step_desc* d, void* stream);      /* pcl_class_stats + pcl_plan_anchors      */
@@ -351,16 +353,27 @@ int pcl_step_ranks(const pcl_step_desc* d, uint64_t* step_counter, int32_t* rank
 
 /* Fused small-anchor step (self-contrast, no bank, tensor path, D = 256, max_samples <= 1024, no in-kernel normalise:
  * the shape of BASELINE configs[1]).  Four launches for the whole loss step instead of eleven:
- *   pcl_step_fused_loss     label/argmax scan + plan (last block) -> selection + gather (anchor ranks drawn from
- *                           *step_counter, or from d->seed when step_counter is NULL) -> ONE kernel for the InfoNCE
- *                           forward and backward (logits stay in tensor memory; csrc/pcl_infonce_fused.cu)
+ *   pcl_step_stats          label/argmax scan + totals + plan in one launch (d->sync != NULL)
+ *   pcl_step_fused_select   selection + gather; anchor ranks drawn from *step_counter (captured sequences), or from
+ *                           d->seed / d->ranks when step_counter is NULL
+ *   pcl_step_fused_loss     ONE kernel for the InfoNCE forward and backward (logits stay in tensor memory;
+ *                           csrc/pcl_infonce_fused.cu)
  *   pcl_step_fused_scatter  sum of the per-column-tile gradient partials + scatter of the A sampled rows into
- *                           d->grad_embed, which the caller has zero-filled (pcl_fill_zero, e.g. concurrently on a second
- *                           stream: the 268 MB fill is the HBM floor of the step); advances *step_counter.
+ *                           d->grad_embed; advances *step_counter.
+ * The dense gradient d->grad_embed must be zero outside the A sampled columns.  Two ways:
+ *   full fill     pcl_step_fused_fill before the scatter, e.g. on a second stream forked AFTER the selection: the 268 MB fill
+ *                 saturates HBM and multiplies the latency of every DRAM read issued next to it (scan 22 -> 60 us, selection
+ *                 13 -> 54 us, profiles/r2_07_*, r2_08_*), while the L2-resident InfoNCE kernel hides behind it;
+ *   sparse reset  prev_rows != NULL (1 + 2 * max_samples int32, zero before the first call, owned by the step): the buffer
+ *                 persists between steps, zero-filled ONCE by the caller; the selection kernel clears exactly the entries
+ *                 the previous step scattered and the scatter records its own.  The caller must not write the buffer.
  * d->sync is required.  pcl_step_fused_supported: 1 if the descriptor qualifies, else 0. */
 int pcl_step_fused_supported(const pcl_step_desc* d);
-int pcl_step_fused_loss(const pcl_step_desc* d, const uint64_t* step_counter, void* stream);
-int pcl_step_fused_scatter(const pcl_step_desc* d, const float* grad_scale, uint64_t* step_counter, void* stream);
+int pcl_step_fused_select(const pcl_step_desc* d, const uint64_t* step_counter, const int32_t* prev_rows, void* stream);
+int pcl_step_fused_loss(const pcl_step_desc* d, void* stream);
+int pcl_step_fused_scatter(const pcl_step_desc* d, const float* grad_scale, uint64_t* step_counter, int32_t* prev_rows,
+                           void* stream);
+int pcl_step_fused_fill(const pcl_step_desc* d, void* stream);   /* zero-fill of d->grad_embed (B*D*h*w floats) */
 /* Zero-fill `bytes` (multiple of 16, 16-byte aligned) with 16-byte stores on the engine's own fill kernel. */
 int pcl_fill_zero(void* ptr, uint64_t bytes, void* stream);
 

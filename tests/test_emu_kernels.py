@@ -116,6 +116,12 @@ def test_graphed_step_tensor_path_on_emulation(emu, monkeypatch, mem, overlap):
     PD.test_graphed_step_equals_eager_step("bf16", mem, overlap)
 
 
+def test_topk_inside_the_captured_step_on_emulation(emu, monkeypatch):
+    from contrastiveseg_b200 import graph_step
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
+    TK.test_topk_inside_the_captured_step_equals_the_eager_step()
+
+
 @pytest.mark.parametrize("geom", [dict(B=2, h=32, w=32, K=7, ms=128, mv=8), dict(B=3, h=32, w=48, K=9, ms=700, mv=40)])
 def test_fused_small_anchor_step_on_emulation(emu, monkeypatch, geom):
     """csrc/pcl_infonce_fused.cu on the functional tcgen05 model (one phase per launch: the emulator runs the blocks of a
@@ -125,12 +131,15 @@ def test_fused_small_anchor_step_on_emulation(emu, monkeypatch, geom):
     lib = _abi.load()
 
     def fill(self):                                          # the fill kernel runs on the emulator too
-        _abi.check(lib.pcl_fill_zero(self.grad.data_ptr(), self.grad.numel() * 4, 0), "pcl_fill_zero")
+        import ctypes as C
+        _abi.check(lib.pcl_step_fused_fill(C.byref(self.ws.desc), 0), "pcl_step_fused_fill")
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", fill)
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_fused_small_anchor_step_matches_the_streaming_path_and_the_oracle(geom)
     PD.test_fused_step_with_no_qualifying_class_gives_zero_loss()
+    if geom["ms"] == 700:
+        PD.test_fused_step_sparse_reset_equals_full_fill()
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])

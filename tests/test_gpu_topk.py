@@ -144,3 +144,32 @@ def test_topk_through_the_loss_module(name):
     assert rel_err(loss.item(), lo.item()) < 5e-6
     gerr = (embed.grad.cpu().double() - e64.grad).abs().max().item()
     assert gerr <= 2e-3 * e64.grad.abs().max().item()    # one near-tie swap moves one negative's share of a row
+
+
+def test_topk_inside_the_captured_step_equals_the_eager_step():
+    """a10 wired into GraphedContrastStep: the three histogram sweeps, the scans, the weighted NEG sweep, POS, finalize and
+    the top-k backward are part of the captured sequence; replay r == eager step with counter r+1 bit for bit."""
+    from contrastiveseg_b200.synth import make_contrast_batch
+    K, D = 6, 64
+    data = make_contrast_batch(B=2, D=D, h=32, w=32, num_classes=K, img_stride=4, block=16, seed=17)
+    embed, tgt, seg = data["embed"].to(DEV), data["target"].to(DEV), data["seg"].to(DEV)
+    opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=96, max_views=8, seed=2,
+                              precision="fp32", num_classes=K, topk_negatives=11)
+    step = cs.GraphedContrastStep(embed, tgt, seg=seg, options=opts)
+    assert not step.fused
+    for r in range(3):
+        loss, grad = step.replay()
+        torch.cuda.synchronize()
+        loss, grad = loss.clone(), grad.clone()
+        Fn._step_counter[0] = r
+        e = embed.clone().requires_grad_(True)
+        l = cs.pixel_contrast_loss(e, tgt, seg=seg, options=opts)
+        l.backward()
+        torch.cuda.synchronize()
+        assert torch.equal(l.detach(), loss) and torch.equal(e.grad, grad)
+    opts_all = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=96, max_views=8, seed=2,
+                                  precision="fp32", num_classes=K)
+    Fn._step_counter[0] = 2
+    e = embed.clone().requires_grad_(True)
+    l_all = cs.pixel_contrast_loss(e, tgt, seg=seg, options=opts_all)
+    assert l_all.item() > loss.item()                     # fewer negatives in the denominator -> smaller loss

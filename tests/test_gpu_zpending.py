@@ -166,6 +166,38 @@ def test_fused_small_anchor_step_matches_the_streaming_path_and_the_oracle(geom)
     assert int(step.ws.sync.abs().sum().item()) == 0             # the kernels re-armed their counters
 
 
+def test_fused_step_sparse_reset_equals_full_fill():
+    """sparse_reset=True: the dense gradient persists between replays and only the entries of the previous replay are
+    cleared.  Bit-identical to the full-fill step on every replay (different anchors every time), also after inputs
+    change, and after reset_grad() following an outside write."""
+    D, K = 256, 9
+    data = make_contrast_batch(B=3, D=D, h=32, w=48, num_classes=K, img_stride=4, block=16, seed=33)
+    tgt, seg = data["target"].to(DEV), data["seg"].to(DEV)
+    e1, e2 = data["embed"].to(DEV), data["embed"].to(DEV).clone()
+    opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=700, max_views=40, seed=5,
+                              precision="bf16", num_classes=K)
+    full = cs.GraphedContrastStep(e1, tgt, seg=seg, options=opts)
+    sparse = cs.GraphedContrastStep(e2, tgt, seg=seg, options=opts, sparse_reset=True)
+    assert full.fused and sparse.sparse_reset
+    for r in range(5):
+        if r == 3:                                             # new inputs in the static buffers
+            nxt = make_contrast_batch(B=3, D=D, h=32, w=48, num_classes=K, img_stride=4, block=16, seed=77)
+            for e in (e1, e2):
+                e.copy_(nxt["embed"].to(DEV))
+            tgt.copy_(nxt["target"].to(DEV)); seg.copy_(nxt["seg"].to(DEV))
+        lf, gf = full.replay()
+        ls, gs = sparse.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(full.ws.anchor_meta, sparse.ws.anchor_meta)
+        assert torch.equal(lf, ls) and torch.equal(gf, gs), r
+    sparse.grad.add_(1.0)                                      # somebody wrote into the buffer ...
+    sparse.reset_grad()                                        # ... and said so
+    lf, gf = full.replay()
+    ls, gs = sparse.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(lf, ls) and torch.equal(gf, gs)
+
+
 def test_fused_step_with_no_qualifying_class_gives_zero_loss():
     """TC == 0 (every class has <= max_views pixels): zero loss, zero gradient, no hang of the inter-CTA barriers."""
     data = make_contrast_batch(B=2, D=256, h=16, w=16, num_classes=5, img_stride=4, block=16, seed=3)

@@ -11,7 +11,7 @@ from contrastiveseg_b200 import _abi, functional as Fn
 
 HOST_ONLY = {"pcl_version", "pcl_strerror", "pcl_last_cuda_error", "pcl_abi_sizeof", "pcl_select_sizes",
              "pcl_sweep_sizes", "pcl_tc_sizes", "pcl_topk_scratch_u32", "pcl_seg_ce_scratch_floats",
-             "pcl_bank_packet_floats", "pcl_bank_scratch_floats"}
+             "pcl_bank_packet_floats", "pcl_bank_scratch_floats", "pcl_step_fused_supported", "pcl_launch_count"}
 
 
 class RecordingLib:
@@ -210,6 +210,37 @@ def test_workspace_cache_is_bounded(rec, monkeypatch):
     embed, labels, seg = _inputs(h=20, w=20)
     cs.pixel_contrast_loss(embed, labels, seg=seg, options=opts)
     assert len(Fn._WS_CACHE) <= 3
+
+
+def test_fused_graphed_step_launch_sequence(rec):
+    """No bank, precision bf16, D = 256, max_samples <= 1024: the step takes the fused path — zero-fill on the side
+    stream, pcl_step_fused_loss (scan+plan, selection seeded from the device counter, one InfoNCE fwd+bwd kernel), then
+    the reducing scatter that advances the counter."""
+    embed, labels, seg = _inputs(D=256)
+    opts = cs.ContrastOptions(max_samples=64, max_views=4, seed=77, precision="bf16")
+    step = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, grad_scale=0.1, capture=False)
+    assert step.fused
+    step._fork_zero_fill = lambda: rec.calls.append(("fill", []))
+    step._join_zero_fill = lambda: rec.calls.append(("join", []))
+    loss, grad = step.replay()
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_fused_select", "fill", "pcl_step_fused_loss", "join",
+                                         "pcl_step_fused_scatter"]
+    d = rec.calls[1][1][0]
+    assert d.sync == step.ws.sync.data_ptr() and d.precision == 1 and d.mode == 0 and d.seed == 77
+    assert rec.calls[1][1][1] == step.counter.data_ptr() and rec.calls[1][1][2] is None
+    sc = rec.calls[5][1]
+    assert sc[1] == step.scale.data_ptr() and sc[2] == step.counter.data_ptr()
+    assert sc[0].grad_embed == grad.data_ptr() and sc[0].loss == loss.data_ptr()
+    # sparse reset: no fill at all, the previous step's rows travel from the scatter to the next selection
+    rec.calls.clear()
+    sp = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, capture=False, sparse_reset=True)
+    sp.replay()
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_fused_select", "pcl_step_fused_loss", "pcl_step_fused_scatter"]
+    assert rec.calls[1][1][2] == sp.prev_rows.data_ptr() == rec.calls[3][1][3]
+    # a bank, fp32 sweeps or fused=False keep the streaming path
+    assert not cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, capture=False, fused=False).fused
+    o32 = cs.ContrastOptions(max_samples=64, max_views=4, precision="fp32")
+    assert not cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=o32, capture=False).fused
 
 
 def test_graphed_step_launch_sequence(rec):

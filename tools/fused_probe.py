@@ -17,11 +17,12 @@ crit = cs.PixelContrastLoss(bench.engine_configer(cfg, False, "bf16"))
 opts = crit.options(); opts.num_classes = cfg["K"]
 steps = int(os.environ.get("PROBE_STEPS", "200"))
 variants = [v for v in os.environ.get("PROBE_FILL", "1,2,3,4,8").split(",")]
-for fused in (True, False):
-    for per_sm in (variants if fused else ["-"]):
-        if fused:
+for fused in (True, "sparse", False):
+    for per_sm in (variants if fused is True else ["-"]):
+        if fused is True:
             os.environ["PCL_FILL_CTAS_PER_SM"] = per_sm
-        st = cs.GraphedContrastStep(inp["embed"], inp["target"], seg=inp["seg"], options=opts, fused=fused)
+        st = cs.GraphedContrastStep(inp["embed"], inp["target"], seg=inp["seg"], options=opts, fused=bool(fused),
+                                    sparse_reset=(fused == "sparse"))
         for _ in range(10):
             st.replay()
         torch.cuda.synchronize()
