@@ -158,8 +158,11 @@ k_bank_rows(BankDims d, const float* __restrict__ keys, const int32_t* __restric
 __global__ void __launch_bounds__(256)
 k_bank_apply(BankDims d, const float* __restrict__ packets, int world, int64_t packet_f32, float* __restrict__ segq,
              int64_t* __restrict__ seg_ptr, float* __restrict__ pixq, int64_t* __restrict__ pix_ptr,
-             __nv_bfloat16* __restrict__ shadow) {
+             __nv_bfloat16* __restrict__ shadow, unsigned long long* enqueue_counter) {
   const int c = blockIdx.x;
+  // captured sequences: the packet of this step was seeded from *enqueue_counter (pcl_bank_packet_dev); the apply is the
+  // last kernel of the step's enqueue, so it advances the counter
+  if (c == 0 && threadIdx.x == 0 && enqueue_counter != nullptr) *enqueue_counter += 1ull;
   if (c == 0) return;
   const int K = d.g.K, D = d.g.D, M = d.g.M, B = d.g.B;
   int sp = (int)seg_ptr[c], pp = (int)pix_ptr[c];
@@ -289,6 +292,13 @@ extern "C" int pcl_bank_packet_dev(const pcl_bank_geom* g, const float* keys, co
 extern "C" int pcl_bank_apply(const pcl_bank_geom* g, const float* packets, int32_t world, float* segment_queue,
                               int64_t* segment_queue_ptr, float* pixel_queue, int64_t* pixel_queue_ptr,
                               void* shadow_bf16, void* stream) {
+  return pcl_bank_apply_ctr(g, packets, world, segment_queue, segment_queue_ptr, pixel_queue, pixel_queue_ptr, shadow_bf16,
+                            nullptr, stream);
+}
+
+extern "C" int pcl_bank_apply_ctr(const pcl_bank_geom* g, const float* packets, int32_t world, float* segment_queue,
+                                  int64_t* segment_queue_ptr, float* pixel_queue, int64_t* pixel_queue_ptr,
+                                  void* shadow_bf16, uint64_t* enqueue_counter, void* stream) {
   BankDims d;
   int st = make_dims(g, &d);
   if (st != PCL_OK) return st;
@@ -296,7 +306,8 @@ extern "C" int pcl_bank_apply(const pcl_bank_geom* g, const float* packets, int3
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t packet_f32 = (int64_t)g->B * g->K * d.slot_f32;
   k_bank_apply<<<g->K, 256, 0, s>>>(d, packets, world, packet_f32, segment_queue, segment_queue_ptr, pixel_queue,
-                                   pixel_queue_ptr, (__nv_bfloat16*)shadow_bf16);
+                                   pixel_queue_ptr, (__nv_bfloat16*)shadow_bf16,
+                                   reinterpret_cast<unsigned long long*>(enqueue_counter));
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

@@ -43,7 +43,9 @@ int select_gather_ex(const pcl_geom* g, const float* embed, const uint16_t* keys
                      const unsigned long long* seed_ctr = nullptr, unsigned int* dbg = nullptr,
                      const int32_t* prev_rows = nullptr, float* grad_clear = nullptr);
 int tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
-              bool skip_prep);
+              bool skip_prep, unsigned long long* step_counter = nullptr);
+int simt_fwd_ex(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream,
+                unsigned long long* step_counter);
 int tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale);
 int tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss, float* dpartials,
               float* dA, void* stream, int* splits_out, int* a_pad_out);

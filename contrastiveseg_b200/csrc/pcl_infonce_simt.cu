@@ -345,6 +345,11 @@ extern "C" int pcl_sweep_sizes(const pcl_sweep_desc* d, pcl_sweep_sizes_t* out) 
 }
 
 extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream) {
+  return pcl::simt_fwd_ex(d, partials, rowstats, loss, stream, nullptr);
+}
+
+int pcl::simt_fwd_ex(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream,
+                     unsigned long long* step_counter) {
   SweepArgs a;
   int st = simt_make_args(d, &a);
   if (st != PCL_OK) return st;
@@ -362,7 +367,7 @@ extern "C" int pcl_infonce_fwd(const pcl_sweep_desc* d, float* partials, float* 
   PCL_LAUNCH_CHECK();
   k_sweep<MODE_POS><<<grid, SWEEP_THREADS, smem, s>>>(a, partials, rowstats, nullptr);
   PCL_LAUNCH_CHECK();
-  k_finalize<<<1, 1024, 0, s>>>(a, partials, rowstats, loss);
+  k_finalize<<<1, 1024, 0, s>>>(a, partials, rowstats, loss, step_counter);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

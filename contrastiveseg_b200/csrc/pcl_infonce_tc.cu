@@ -46,7 +46,25 @@ struct TcArgs {
   int tail_count;              // analytic all-zero columns of label 0 (bank mode: R)
   int neg_grid;                // CTAs of the persistent NEG sweep (bounds the partial slots a row tile can own)
   int persistent;              // 1: grid = CTAs, each walks a contiguous range of (row tile, column tile) pairs
+  uint32_t r_mul, r_sh;        // exact n / R for 32-bit n without a hardware divide: ((umulhi(n, r_mul) + n') >> r_sh), see div_R
 };
+
+// n / R by multiplication (Granlund-Montgomery round-up method, exact for every 32-bit n): the bank-mode column label
+// n / R + 1 is evaluated per 32-column chunk by every epilogue thread, and the integer divide (about 25 instructions)
+// showed up as 11-17 % of all warp-stall samples of the POS and backward sweeps (profiles/r2_06_bank_source_top.txt).
+__device__ __forceinline__ uint32_t div_R(const TcArgs& a, uint32_t n) {
+  const uint32_t t = __umulhi(n, a.r_mul);
+  return (t + ((n - t) >> 1)) >> a.r_sh;
+}
+static inline void make_div(uint32_t d, uint32_t* mul, uint32_t* sh) {
+  // d >= 1.  l = ceil(log2 d); m = floor(2^32 (2^l - d) / d) + 1; q = (t + ((n - t) >> 1)) >> (l - 1), t = umulhi(m, n)
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  if (l == 0) { *mul = 0u; *sh = 0u; return; }                  // d == 1: t = 0 -> (n >> 1) >> ... handled below
+  const unsigned long long m = ((1ull << 32) * ((1ull << l) - d)) / d + 1ull;
+  *mul = (uint32_t)m;
+  *sh = l - 1;
+}
 
 struct SmemLayout {
   uint8_t a[NKB * A_KB_BYTES];
@@ -57,7 +75,7 @@ struct SmemLayout {
 };
 
 __device__ __forceinline__ int col_label(const TcArgs& a, int n) {      // columns < 2^31
-  return a.ccls ? a.ccls[n] : (a.mode == 1 ? n / a.R + 1 : a.acls[n]);
+  return a.ccls ? a.ccls[n] : (a.mode == 1 ? (int)div_R(a, (uint32_t)n) + 1 : a.acls[n]);
 }
 
 enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2 };   // DUMP: raw logit tiles to global (descriptor self-test)
@@ -922,6 +940,8 @@ static int make_tc_plan(const pcl_tc_desc* d, TcPlan* p) {
   } else if (d->mode == 1) {
     if (d->bank_K < 1 || d->bank_R < 1) return PCL_ERR_ARG;
     a.K = d->bank_K; a.R = d->bank_R; a.n_cols = (int64_t)(d->bank_K - 1) * d->bank_R; a.sorted = 1; tail = d->bank_R;
+    if (d->bank_R < 2) return PCL_ERR_ARG;                      // (segment + pixel queue: R = 2M >= 2)
+    tc::make_div((uint32_t)d->bank_R, &a.r_mul, &a.r_sh);
   } else if (d->mode == 2) {
     if (!d->contrast_cls || d->n_cols <= 0) return PCL_ERR_ARG;
     a.ccls = d->contrast_cls; a.n_cols = d->n_cols; a.sorted = d->sorted ? 1 : 0; a.K = 0; a.R = 1;
@@ -998,11 +1018,11 @@ int pcl::tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale) {
 
 extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss,
                                   void* stream) {
-  return pcl::tc_fwd_ex(d, row_m2, partials, rowstats, loss, stream, false);
+  return pcl::tc_fwd_ex(d, row_m2, partials, rowstats, loss, stream, false, nullptr);
 }
 
 int pcl::tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
-                   bool skip_prep) {
+                   bool skip_prep, unsigned long long* step_counter) {
   TcPlan p;
   int st = make_tc_plan(d, &p);
   if (st != PCL_OK) return st;
@@ -1056,7 +1076,7 @@ int pcl::tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* 
   // (the NEG partials are combined by the POS sweep's row prologue: no separate pass)
   tc::k_tc_fwd<tc::TC_POS, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
   PCL_LAUNCH_CHECK();
-  k_finalize<<<1, 1024, 0, s>>>(p.sw, partials, rowstats, loss);
+  k_finalize<<<1, 1024, 0, s>>>(p.sw, partials, rowstats, loss, step_counter);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

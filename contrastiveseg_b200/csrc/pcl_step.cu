@@ -50,7 +50,19 @@ extern "C" int pcl_step_stats(const pcl_step_desc* d, void* stream) {
   return pcl_plan_anchors(&d->g, d->counts, d->plan, stream);
 }
 
-extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {
+static int step_forward(const pcl_step_desc* d, unsigned long long* ctr, void* stream);
+
+extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) { return step_forward(d, nullptr, stream); }
+
+// Captured sequences: the anchors are drawn by the selection kernel itself from *step_counter (same keyed bijection and
+// seed formula as pcl_step_ranks, whose single CTA needed 13-15 us for 1024 draws) and the forward's last kernel advances
+// the counter — no separate rank-draw launch.
+extern "C" int pcl_step_forward_ctr(const pcl_step_desc* d, uint64_t* step_counter, void* stream) {
+  if (!step_counter) return PCL_ERR_ARG;
+  return step_forward(d, reinterpret_cast<unsigned long long*>(step_counter), stream);
+}
+
+static int step_forward(const pcl_step_desc* d, unsigned long long* ctr, void* stream) {
   if (!d) return PCL_ERR_ARG;
   if (d->precision == 1) {
     // tensor path: the selection kernel also writes the row stabilisers and initialises the partial slots
@@ -61,18 +73,19 @@ extern "C" int pcl_step_forward(const pcl_step_desc* d, void* stream) {
     float m2_scale = 0.f;
     int st = pcl::tc_query(&t, &n_slot_rows, &m2_scale);
     if (st != PCL_OK) return st;
-    st = pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
-                               d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, nullptr, d->row_m2, m2_scale,
-                               d->partials, n_slot_rows, stream);
+    st = pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, ctr ? nullptr : d->ranks, d->seed,
+                               d->normalize, d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, nullptr, d->row_m2,
+                               m2_scale, d->partials, n_slot_rows, stream, ctr);
     if (st != PCL_OK) return st;
-    return pcl::tc_fwd_ex(&t, d->row_m2, d->partials, d->rowstats, d->loss, stream, true);
+    return pcl::tc_fwd_ex(&t, d->row_m2, d->partials, d->rowstats, d->loss, stream, true, ctr);
   }
-  int st = pcl_select_gather(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, d->ranks, d->seed, d->normalize,
-                             d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, d->norm_max, stream);
+  int st = pcl::select_gather_ex(&d->g, d->embed, d->keys, d->chunk_pref, d->plan, ctr ? nullptr : d->ranks, d->seed,
+                                 d->normalize, d->anchor_meta, d->anchors_f32, d->anchors_bf16, d->inv_norm, d->norm_max,
+                                 nullptr, 0.f, nullptr, 0, stream, ctr);
   if (st != PCL_OK) return st;
   pcl_sweep_desc w;
   fill_sweep(d, &w);
-  return pcl_infonce_fwd(&w, d->partials, d->rowstats, d->loss, stream);
+  return pcl::simt_fwd_ex(&w, d->partials, d->rowstats, d->loss, stream, ctr);
 }
 
 extern "C" int pcl_step_backward(const pcl_step_desc* d, const float* grad_loss, void* stream) {

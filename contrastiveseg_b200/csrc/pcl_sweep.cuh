@@ -48,7 +48,10 @@ static __global__ void k_combine_neg(SweepArgs a, const float* __restrict__ part
 
 // Combine the POS partials, add the zero-tail positives of class-0 anchors, row losses and the mean.
 static __global__ void __launch_bounds__(1024)
-k_finalize(SweepArgs a, const float* __restrict__ partials, float* __restrict__ rowstats, float* __restrict__ loss) {
+k_finalize(SweepArgs a, const float* __restrict__ partials, float* __restrict__ rowstats, float* __restrict__ loss,
+           unsigned long long* step_counter) {
+  // captured sequences: the selection (an earlier kernel) has drawn this step's anchors from *step_counter; advance it
+  if (step_counter != nullptr && threadIdx.x == 0) *step_counter += 1ull;
   __shared__ float s_red[1024];
   const int A = live_rows(a);
   float acc = 0.f;

@@ -467,7 +467,7 @@ extern "C" int pcl_infonce_topk_fwd(const pcl_sweep_desc* d, int32_t k, uint32_t
   PCL_LAUNCH_CHECK();
   st = simt_launch_pos(a, partials, rowstats, s);          // positives are untouched by the selection
   if (st != PCL_OK) return st;
-  k_finalize<<<1, 1024, 0, s>>>(a, partials, rowstats, loss);
+  k_finalize<<<1, 1024, 0, s>>>(a, partials, rowstats, loss, nullptr);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
 }

@@ -180,13 +180,17 @@ class GraphedContrastStep:
         scratch, packet, recv = _bank.enqueue_buffers(dev, int(n_scratch), int(n_packet), world, fresh=True)
         if bank.with_shadow and bank.shadow is None:
             bank.sync_shadow()
+        # the enqueue has its own device counter: its packet is built on a parallel branch of the graph (it depends on the
+        # inputs only), so it must not read the step counter the forward branch advances; replay r uses offset r + 1 like
+        # the eager enqueue (bank._enqueue_counter pre-increments)
+        self.enq_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.enq = dict(bank=bank, keys=keys, labels=labels, g=g, scratch=scratch, packet=packet, recv=recv, world=world,
-                        group=group, seed=_bank.enqueue_seed(int(e.get("seed", 304))))
+                        group=group, seed=(_bank.enqueue_seed(int(e.get("seed", 304))) + 1) & 0xFFFFFFFFFFFFFFFF)
 
     def _enqueue_packet(self, stream: int) -> None:
         q = self.enq
         _abi.check(self.lib.pcl_bank_packet_dev(C.byref(q["g"]), q["keys"].data_ptr(), q["labels"].data_ptr(), q["seed"],
-                                                self.counter.data_ptr(), q["scratch"].data_ptr(), q["packet"].data_ptr(),
+                                                self.enq_counter.data_ptr(), q["scratch"].data_ptr(), q["packet"].data_ptr(),
                                                 stream), "pcl_bank_packet_dev")
 
     def _gather(self) -> torch.Tensor:
@@ -201,9 +205,10 @@ class GraphedContrastStep:
         q = self.enq
         b = q["bank"]
         pk = q["recv"] if q["world"] > 1 else q["packet"]
-        _abi.check(self.lib.pcl_bank_apply(C.byref(q["g"]), pk.data_ptr(), q["world"], b.segment_queue.data_ptr(),
-                                           b.segment_queue_ptr.data_ptr(), b.pixel_queue.data_ptr(),
-                                           b.pixel_queue_ptr.data_ptr(), _abi.ptr(b.shadow), stream), "pcl_bank_apply")
+        _abi.check(self.lib.pcl_bank_apply_ctr(C.byref(q["g"]), pk.data_ptr(), q["world"], b.segment_queue.data_ptr(),
+                                               b.segment_queue_ptr.data_ptr(), b.pixel_queue.data_ptr(),
+                                               b.pixel_queue_ptr.data_ptr(), _abi.ptr(b.shadow),
+                                               self.enq_counter.data_ptr(), stream), "pcl_bank_apply_ctr")
 
     # fork / join of the overlapped zero-fill (torch streams + events; inside a capture these become graph edges)
     def _fork_zero_fill(self) -> None:
@@ -212,10 +217,18 @@ class GraphedContrastStep:
             self.side = torch.cuda.Stream(self.device)
         self.side.wait_stream(main)                  # the previous consumer of `grad` is ordered before the fill
         with torch.cuda.stream(self.side):
-            if self.fused:       # the engine's own fill kernel (small CTAs that share the SMs with the loss kernels)
-                _abi.check(self.lib.pcl_step_fused_fill(C.byref(self.ws.desc), self.side.cuda_stream), "pcl_step_fused_fill")
-            else:
-                self.grad.zero_()
+            self._side_branch(self.side.cuda_stream)
+
+    def _side_branch(self, stream: int) -> None:
+        """Work that depends on the step's inputs only: zero-fill of the dense gradient, enqueue packet."""
+        if self.fused:           # the engine's own fill kernel (small CTAs that share the SMs with the loss kernels)
+            _abi.check(self.lib.pcl_step_fused_fill(C.byref(self.ws.desc), stream), "pcl_step_fused_fill")
+        elif self.overlap_zero_fill:
+            self.grad.zero_()
+        if self.enq is not None:
+            # the enqueue packet (label counts, segment sums over the keys, pixel rows: ~70 us at the Cityscapes shape)
+            # runs on this branch, next to the forward sweeps
+            self._enqueue_packet(stream)
 
     def _join_zero_fill(self) -> None:
         torch.cuda.current_stream(self.device).wait_stream(self.side)
@@ -236,17 +249,16 @@ class GraphedContrastStep:
             if not self.sparse_reset:
                 self._join_zero_fill()
             return
-        if self.overlap_zero_fill:
+        side = self.overlap_zero_fill or self.enq is not None
+        if side:
             self._fork_zero_fill()
         _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
-        _abi.check(lib.pcl_step_ranks(C.byref(d), self.counter.data_ptr(), self.ws.ranks.data_ptr(), stream), "pcl_step_ranks")
         if self.opts.topk_negatives:
+            _abi.check(lib.pcl_step_ranks(C.byref(d), self.counter.data_ptr(), self.ws.ranks.data_ptr(), stream), "pcl_step_ranks")
             self.topk = _fn._topk_step_forward(lib, self.ws, d, self.opts, stream)
-        else:
-            _abi.check(lib.pcl_step_forward(C.byref(d), stream), "pcl_step_forward")
-        if self.enq is not None:
-            self._enqueue_packet(stream)
-        if self.overlap_zero_fill:
+        else:     # the selection kernel draws the anchors from the device counter itself (no separate rank-draw launch)
+            _abi.check(lib.pcl_step_forward_ctr(C.byref(d), self.counter.data_ptr(), stream), "pcl_step_forward_ctr")
+        if side:
             self._join_zero_fill()
 
     def _enqueue_b(self, stream: int) -> None:
@@ -292,6 +304,7 @@ class GraphedContrastStep:
         self.counter.zero_()
         if self.enq is not None:
             torch.cuda.synchronize(dev)
+            self.enq_counter.zero_()
             self._restore_bank()
         # thread_local: only this thread's CUDA calls are policed during the capture (the NCCL watchdog of a DDP job polls
         # events from another thread)

@@ -247,6 +247,12 @@ int pcl_bank_apply(const pcl_bank_geom* g, const float* packets, int32_t world, 
                    int64_t* segment_queue_ptr, float* pixel_queue, int64_t* pixel_queue_ptr,
                    void* shadow_bf16, void* stream);
 
+/* Same; additionally advances *enqueue_counter (device uint64, may be NULL) when done: the seed offset of the NEXT
+ * pcl_bank_packet_dev of a captured sequence. */
+int pcl_bank_apply_ctr(const pcl_bank_geom* g, const float* packets, int32_t world, float* segment_queue,
+                       int64_t* segment_queue_ptr, float* pixel_queue, int64_t* pixel_queue_ptr,
+                       void* shadow_bf16, uint64_t* enqueue_counter, void* stream);
+
 /* Rebuild the bf16 shadow from the fp32 queues (after a checkpoint load / external write). */
 int pcl_bank_shadow_rebuild(const float* segment_queue, const float* pixel_queue, int32_t K, int32_t M,
                             int32_t D, void* shadow_bf16, void* stream);
@@ -350,6 +356,9 @@ int pcl_step_backward_prezeroed(const pcl_step_desc* d, const float* grad_loss, 
  *   step_counter  1 uint64 in device memory (caller-initialised, e.g. 0), read and incremented on the stream
  *   ranks         max_samples int32 */
 int pcl_step_ranks(const pcl_step_desc* d, uint64_t* step_counter, int32_t* ranks, void* stream);
+/* pcl_step_forward for captured sequences without the separate rank draw: the selection kernel draws the anchors from
+ * *step_counter itself (same bijection and seed formula as pcl_step_ranks) and the forward's last kernel advances it. */
+int pcl_step_forward_ctr(const pcl_step_desc* d, uint64_t* step_counter, void* stream);
 
 /* Fused small-anchor step (self-contrast, no bank, tensor path, D = 256, max_samples <= 1024, no in-kernel normalise:
  * the shape of BASELINE configs[1]).  Four launches for the whole loss step instead of eleven:

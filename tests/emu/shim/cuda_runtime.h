@@ -372,6 +372,7 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline void __threadfence() {}
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
 static inline void __nanosleep(unsigned) {}
 template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }

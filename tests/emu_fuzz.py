@@ -356,7 +356,7 @@ def fuzz_graphed_step(seed: int, n: int):
     saved = (graph_step.GraphedContrastStep._capture, graph_step.GraphedContrastStep._fork_zero_fill,
              graph_step.GraphedContrastStep._join_zero_fill)
     graph_step.GraphedContrastStep._capture = lambda self, warmup: None            # no CUDA graphs on a CPU: run eagerly
-    graph_step.GraphedContrastStep._fork_zero_fill = lambda self: self.grad.zero_()
+    graph_step.GraphedContrastStep._fork_zero_fill = lambda self: self._side_branch(0)
     graph_step.GraphedContrastStep._join_zero_fill = lambda self: None
     try:
         for it in range(n):

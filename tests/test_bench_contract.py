@@ -59,7 +59,7 @@ def _run_engine_on_emulator(monkeypatch, workload="s1"):
     monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
-    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self._side_branch(0))
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     monkeypatch.setenv("PCL_BENCH_TINY", "1")
     orig_stage = bench.stage_timings

@@ -111,7 +111,7 @@ def test_tensor_path_on_the_functional_tcgen05_model(emu, fn, kw):
 def test_graphed_step_tensor_path_on_emulation(emu, monkeypatch, mem, overlap):
     from contrastiveseg_b200 import graph_step
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
-    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self._side_branch(0))
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_graphed_step_equals_eager_step("bf16", mem, overlap)
 
@@ -130,11 +130,8 @@ def test_fused_small_anchor_step_on_emulation(emu, monkeypatch, geom):
     from contrastiveseg_b200 import graph_step, _abi
     lib = _abi.load()
 
-    def fill(self):                                          # the fill kernel runs on the emulator too
-        import ctypes as C
-        _abi.check(lib.pcl_step_fused_fill(C.byref(self.ws.desc), 0), "pcl_step_fused_fill")
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
-    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", fill)
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self._side_branch(0))
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_fused_small_anchor_step_matches_the_streaming_path_and_the_oracle(geom)
     PD.test_fused_step_with_no_qualifying_class_gives_zero_loss()
@@ -147,7 +144,7 @@ def test_graphed_bank_step_on_emulation(emu, monkeypatch, precision):
     """The bank step's launch sequence incl. the device-seeded enqueue packet (pcl_bank_packet_dev) == the trainer order."""
     from contrastiveseg_b200 import graph_step
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
-    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self._side_branch(0))
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_graphed_bank_step_with_enqueue_equals_the_trainer_order(precision)
 
@@ -163,7 +160,7 @@ def test_graphed_step_sequence_on_emulation(emu, monkeypatch, overlap):
     (csrc/pcl_graph.cu) reproduces the eager sampling stream, the scatter-only backward equals the fused writer."""
     from contrastiveseg_b200 import graph_step
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
-    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self.grad.zero_())
+    monkeypatch.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self._side_branch(0))
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
     PD.test_graphed_step_equals_eager_step("fp32", False, overlap)
 

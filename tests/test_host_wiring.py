@@ -251,14 +251,13 @@ def test_graphed_step_launch_sequence(rec):
     step = cs.GraphedContrastStep(embed.detach(), labels, seg=seg, options=opts, grad_scale=0.1, capture=False,
                                   overlap_zero_fill=False)
     loss, grad = step.replay()
-    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_ranks", "pcl_step_forward", "pcl_step_backward"]
-    d = rec.calls[2][1][0]
-    assert d.ranks == step.ws.ranks.data_ptr() and d.seed == 77
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_step_forward_ctr", "pcl_step_backward"]
+    d = rec.calls[1][1][0]
+    assert d.seed == 77
     assert d.loss == loss.data_ptr() and d.grad_embed == grad.data_ptr() and grad.shape == embed.shape
     assert d.embed == embed.data_ptr() and d.labels == labels.data_ptr() and d.seg == seg.data_ptr()
-    rk = rec.calls[1][1]
-    assert rk[1] == step.counter.data_ptr() and rk[2] == step.ws.ranks.data_ptr()
-    assert rec.calls[3][1][1] == step.scale.data_ptr() and abs(step.scale.item() - 0.1) < 1e-7
+    assert rec.calls[1][1][1] == step.counter.data_ptr()
+    assert rec.calls[2][1][1] == step.scale.data_ptr() and abs(step.scale.item() - 0.1) < 1e-7
     l2, g2 = step.replay()
     assert l2.data_ptr() == loss.data_ptr() and g2.data_ptr() == grad.data_ptr() and step.replays == 2
     # autograd hand-off: the static gradient comes back for the captured tensor only
@@ -280,8 +279,7 @@ def test_graphed_step_launch_sequence(rec):
     step3._fork_zero_fill = lambda: rec.calls.append(("fork", []))
     step3._join_zero_fill = lambda: rec.calls.append(("join", []))
     step3.replay()
-    assert _names(rec) == ["fork", "pcl_step_stats", "pcl_step_ranks", "pcl_step_forward", "join",
-                           "pcl_step_backward_prezeroed"]
+    assert _names(rec) == ["fork", "pcl_step_stats", "pcl_step_forward_ctr", "join", "pcl_step_backward_prezeroed"]
     assert rec.calls[-1][1][0].grad_embed == step3.grad.data_ptr() and rec.calls[-1][1][1] == step3.scale.data_ptr()
 
 
