@@ -869,6 +869,10 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint32_t b
   }
   PFN_tmapEncodeTiled enc = get_encode();
   if (!enc) { pcl::set_error_text("cuTensorMapEncodeTiled entry point not found"); return PCL_ERR_CUDA; }
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on THIS thread.  A thread that has not made a
+  // runtime call yet (PyTorch's autograd worker on its first backward) has none -> CUDA_ERROR_INVALID_CONTEXT (201), seen
+  // in tools/dist_bank_check.py (profiles/r2_17_dist_bank_check_before_fix.log).  cudaFree(0) binds the primary context.
+  (void)cudaFree(nullptr);
   cuuint64_t gdim[2] = {(cuuint64_t)tc::DDIM, rows};
   cuuint64_t gstride[1] = {(cuuint64_t)tc::DDIM * 2};
   cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};

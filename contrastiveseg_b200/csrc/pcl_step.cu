@@ -122,6 +122,14 @@ extern "C" int pcl_step_backward_prezeroed(const pcl_step_desc* d, const float* 
   if (d->precision == 1) {
     pcl_tc_desc t;
     fill_tc(d, &t);
+    if (!d->normalize) {
+      // the scatter sums the per-split partial rows itself (fixed order): no (A, D) gradient round trip, one launch less
+      int splits = 0, a_pad = 0;
+      st = pcl::tc_bwd_ex(&t, d->row_m2, d->rowstats, grad_loss, d->dpartials, nullptr, stream, &splits, &a_pad);
+      if (st != PCL_OK) return st;
+      return pcl::scatter_reduce_rows(&d->g, d->plan, d->anchor_meta, d->dpartials, splits, 0, a_pad, 1.f / d->temperature,
+                                      grad_loss, d->grad_embed, nullptr, stream, d->sync);
+    }
     st = pcl_infonce_tc_bwd(&t, d->row_m2, d->rowstats, grad_loss, d->dpartials, d->dA, stream);
   } else {
     pcl_sweep_desc w;
