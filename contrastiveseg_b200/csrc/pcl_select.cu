@@ -461,30 +461,32 @@ k_zero_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_
 }
 
 // Scatter of the A gradient rows into an ALREADY zero-filled dense gradient, with the fixed-order sum of the per-split
-// (per-column-tile) partial rows folded in: one warp per anchor row.  Also advances the step counter of a captured
+// (per-column-tile) partial rows folded in: one block per anchor row.  Also advances the step counter of a captured
 // sequence (last kernel of the step).
 __global__ void __launch_bounds__(256)
 k_scatter_reduce(pcl_geom g, const int32_t* __restrict__ plan, const int32_t* __restrict__ meta,
                  const float* __restrict__ dpartials, int splits, int split_cols, int a_pad, float inv_T,
                  const float* __restrict__ grad_scale, float* __restrict__ grad, unsigned long long* step_counter,
                  unsigned int* dbg, int32_t* __restrict__ prev_rows) {
+  // one BLOCK per anchor row, one thread per channel: the sum over the splits (up to 18 for the bank sweeps) is a chain
+  // of dependent adds per element, so the parallelism has to come from the elements (a warp per row left 7 warps per SM
+  // and took 42 us at 18 splits; profiles/r2_19_*)
   tl_begin(dbg, PCL_TL_SCATTER);
   struct TlEnd { unsigned int* d; __device__ ~TlEnd() { tl_end(d, PCL_TL_SCATTER); } } tl_guard{dbg};
   if (step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_counter += 1ull;
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int s = blockIdx.x;
   const int A = min(plan[PCL_PLAN_A], g.max_samples);
-  if (prev_rows != nullptr && s == 0 && lane == 0) prev_rows[0] = A;           // what the next step has to clear
+  if (prev_rows != nullptr && s == 0 && threadIdx.x == 0) prev_rows[0] = A;           // what the next step has to clear
   if (s >= A) return;
   // partial p covers the contrast columns [p * split_cols, (p+1) * split_cols): only the live ones were written
   if (split_cols > 0) splits = min(splits, (A + split_cols - 1) / split_cols);
   const int ms = g.max_samples, D = g.D;
   const int64_t HW = (int64_t)g.h * g.w;
   const int pix = meta[s], b = meta[ms + s];
-  if (prev_rows != nullptr && lane == 0) { prev_rows[1 + s] = pix; prev_rows[1 + ms + s] = b; }
+  if (prev_rows != nullptr && threadIdx.x == 0) { prev_rows[1 + s] = pix; prev_rows[1 + ms + s] = b; }
   const float scale = inv_T * (grad_scale ? grad_scale[0] : 1.f);
   float* dst = grad + (int64_t)b * D * HW + pix;
-  for (int d = lane; d < D; d += 32) {
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float v = 0.f;
     for (int p = 0; p < splits; ++p) v += dpartials[((int64_t)p * a_pad + s) * D + d];      // fixed order
     dst[(int64_t)d * HW] = v * scale;
@@ -537,8 +539,7 @@ int pcl::scatter_reduce_rows(const pcl_geom* g, const int32_t* plan, const int32
                              int splits, int split_cols, int a_pad, float inv_T, const float* grad_scale, float* grad_embed,
                              unsigned long long* step_counter, void* stream, unsigned int* dbg, int32_t* prev_rows) {
   if (!g || !plan || !anchor_meta || !dpartials || !grad_embed || splits < 1) return PCL_ERR_ARG;
-  const int warps = 8;
-  k_scatter_reduce<<<ceil_div(g->max_samples, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+  k_scatter_reduce<<<g->max_samples, g->D <= 128 ? 128 : 256, 0, (cudaStream_t)stream>>>(
       *g, plan, anchor_meta, dpartials, splits, split_cols, a_pad, inv_T, grad_scale, grad_embed, step_counter, dbg, prev_rows);
   PCL_LAUNCH_CHECK();
   return PCL_OK;
