@@ -197,9 +197,8 @@ class GraphedContrastStep:
         q = self.enq
         if q["world"] == 1:
             return q["packet"].view(1, -1)
-        import torch.distributed as dist
-        dist.all_gather_into_tensor(q["recv"], q["packet"], group=q["group"])          # NCCL over NVLink
-        return q["recv"]
+        from . import bank as _bank
+        return _bank.gather_packets(q["packet"], q["group"], out=q["recv"])        # NCCL over NVLink (gloo in CPU tests)
 
     def _enqueue_apply(self, stream: int) -> None:
         q = self.enq

@@ -188,3 +188,59 @@ def test_ddp_training_iterations_with_the_hook_on_two_ranks(tmp_path):
     for a, b in zip(s0["bank"], s1["bank"]):
         assert torch.equal(a, b)                            # one all_gather per step kept the banks identical
     assert not torch.equal(s0["bank"][3], torch.zeros_like(s0["bank"][3]))     # and the bank advanced
+
+
+def _graphed_bank_worker(rank, world, port, out_dir):
+    """The captured bank step on several ranks (graph_step.py: first half | ONE all_gather of the enqueue packet | second
+    half) with the launch sequences run eagerly on the emulated kernels and the real gloo all_gather in between: replay r
+    equals the eager trainer order (loss -> enqueue -> backward with the held-back write) on every rank, and the banks
+    stay bit-identical across ranks."""
+    import pytest
+    import emu_harness
+    import contrastiveseg_b200 as cs
+    from contrastiveseg_b200 import bank as bank_mod, functional as Fn, graph_step
+    from contrastiveseg_b200.synth import make_contrast_batch
+    mp_ = pytest.MonkeyPatch()
+    emu_harness.use_emulation(mp_)
+    mp_.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
+    mp_.setattr(graph_step.GraphedContrastStep, "_fork_zero_fill", lambda self: self._side_branch(0))
+    mp_.setattr(graph_step.GraphedContrastStep, "_join_zero_fill", lambda self: None)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K, D, M = 6, 64, 24
+    data = make_contrast_batch(B=1, D=D, h=16, w=16, num_classes=K, img_stride=2, block=8, seed=300 + rank)
+    embed, tgt, seg = data["embed"], data["target"], data["seg"]
+    torch.manual_seed(0)
+    bank_g, bank_e = cs.MemoryBank(K, M, D), cs.MemoryBank(K, M, D)
+    bank_e.load_state_dict(bank_g.state_dict())
+    opts = cs.ContrastOptions(temperature=0.07, base_temperature=0.07, max_samples=64, max_views=6, seed=5,
+                              precision="fp32", num_classes=K)
+    step = cs.GraphedContrastStep(embed, tgt, seg=seg, segment_queue=bank_g.segment_queue, pixel_queue=bank_g.pixel_queue,
+                                  options=opts, enqueue=dict(bank=bank_g, network_stride=2, pixel_update_freq=4, seed=3))
+    assert step.split and step.enq["world"] == world
+    names = ("segment_queue", "pixel_queue", "segment_queue_ptr", "pixel_queue_ptr")
+    for r in range(3):
+        loss, grad = step.replay()
+        loss, grad = loss.clone(), grad.clone()
+        Fn._step_counter[0] = r
+        bank_mod._enqueue_counter[0] = r
+        e = embed.clone().requires_grad_(True)
+        l = cs.pixel_contrast_loss(e, tgt, seg=seg, segment_queue=bank_e.segment_queue, pixel_queue=bank_e.pixel_queue,
+                                   options=opts)
+        bank_e.enqueue(e.detach(), tgt, network_stride=2, pixel_update_freq=4, seed=3)
+        l.backward()
+        assert torch.equal(l.detach(), loss) and torch.allclose(e.grad, grad, rtol=2e-6, atol=0)
+        for n in names:
+            assert torch.equal(getattr(bank_g, n), getattr(bank_e, n)), (r, n)
+    torch.save([getattr(bank_g, n).clone() for n in names], os.path.join(out_dir, f"gb{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_graphed_bank_step_two_ranks_on_emulated_kernels(tmp_path):
+    port = _free_port()
+    mp.spawn(_graphed_bank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    b0, b1 = torch.load(tmp_path / "gb0.pt"), torch.load(tmp_path / "gb1.pt")
+    for x, y in zip(b0, b1):
+        assert torch.equal(x, y)
+    assert not torch.equal(b0[3], torch.zeros_like(b0[3]))
