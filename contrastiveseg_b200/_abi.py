@@ -114,6 +114,9 @@ SIGNATURES = {
     "pcl_to_bf16": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "pcl_infonce_tc_fwd": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_infonce_tc_bwd": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_tc_topk_scratch_u32": (c_i64, [C.POINTER(TcDesc)]),
+    "pcl_infonce_tc_topk_fwd": (c_i32, [C.POINTER(TcDesc), c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pcl_infonce_tc_topk_bwd": (c_i32, [C.POINTER(TcDesc), c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pcl_tc_dump_logits": (c_i32, [C.POINTER(TcDesc), c_vp, c_vp, c_vp]),
     "pcl_step_stats": (c_i32, [C.POINTER(StepDesc), c_vp]),
     "pcl_step_forward": (c_i32, [C.POINTER(StepDesc), c_vp]),

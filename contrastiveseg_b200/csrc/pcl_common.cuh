@@ -46,9 +46,11 @@ int tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowst
               bool skip_prep, unsigned long long* step_counter = nullptr);
 int simt_fwd_ex(const pcl_sweep_desc* d, float* partials, float* rowstats, float* loss, void* stream,
                 unsigned long long* step_counter);
+int tc_fwd_topk_ex(const pcl_tc_desc* d, int k, uint32_t* scratch, float* row_m2, float* partials, float* rowstats,
+                   float* loss, void* stream, bool skip_prep, unsigned long long* step_counter);
 int tc_query(const pcl_tc_desc* d, int64_t* n_slot_rows, float* m2_scale);
 int tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss, float* dpartials,
-              float* dA, void* stream, int* splits_out, int* a_pad_out);
+              float* dA, void* stream, int* splits_out, int* a_pad_out, const uint32_t* topk_scratch = nullptr);
 int zero_scatter_reduce(const pcl_geom* g, const int32_t* plan, const int32_t* anchor_meta, const float* dpartials,
                         int splits, int a_pad, float inv_T, const float* grad_loss, float* grad_embed, void* stream);
 

@@ -15,6 +15,7 @@
 #include "pcl_common.cuh"
 #include "pcl_sweep.cuh"
 #include "ptx_sm100.cuh"
+#include "pcl_topk.cuh"
 #include <stdlib.h>
 #include <mutex>
 
@@ -47,6 +48,11 @@ struct TcArgs {
   int neg_grid;                // CTAs of the persistent NEG sweep (bounds the partial slots a row tile can own)
   int persistent;              // 1: grid = CTAs, each walks a contiguous range of (row tile, column tile) pairs
   uint32_t r_mul, r_sh;        // exact n / R for 32-bit n without a hardware divide: ((umulhi(n, r_mul) + n') >> r_sh), see div_R
+  // a10 (top-k hard negatives on the tensor path): per-row radix bins [a_pad][2048] and the selection state [4][a_rows]
+  // (pcl_topk.cuh); NULL = all negatives (the reference).  The selection key is the float x = rn(s * k1) (log2 units),
+  // formed with the same instruction in every sweep and in the backward.
+  uint32_t* tk_hist;
+  const uint32_t* tk_sel;
 };
 
 // n / R by multiplication (Granlund-Montgomery round-up method, exact for every 32-bit n): the bank-mode column label
@@ -78,7 +84,11 @@ __device__ __forceinline__ int col_label(const TcArgs& a, int n) {      // colum
   return a.ccls ? a.ccls[n] : (a.mode == 1 ? (int)div_R(a, (uint32_t)n) + 1 : a.acls[n]);
 }
 
-enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2 };   // DUMP: raw logit tiles to global (descriptor self-test)
+enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2,     // DUMP: raw logit tiles to global (descriptor self-test)
+       TC_H1 = 3, TC_H2 = 4, TC_H3 = 5,         // a10: radix-select histogram sweeps (11 + 11 + 10 bits of the logit key)
+       TC_NEGW = 6 };                           // a10: negative sum with the selection weights
+// modes that walk ALL columns persistently and (NEG, NEGW) leave a partial negative sum per (slot, row)
+#define TC_IS_NEGLIKE(M) ((M) == TC_NEG || (M) == TC_NEGW || (M) == TC_H1 || (M) == TC_H2 || (M) == TC_H3)
 
 // A segment = consecutive column tiles [ct0, ct1) of one row tile, whose partial row sums go to slot `slot`.
 struct Seg { int r, ct0, ct1, slot; };
@@ -316,12 +326,27 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           const int used = (int)min((long long)a.slots, T_all / Un + 2);
           float n = 0.f;
           for (int pslot = 0; pslot < used; ++pslot) n += partials[stride + (int64_t)pslot * a.a_pad + row];
-          if (a.tail_count > 0 && rcls != 0) n += (float)a.tail_count * ptx::ex2_approx(-m2);
+          if (a.tail_count > 0 && rcls != 0) {
+            // the zero tail takes part in the a10 selection with the key of +0.0
+            const float wt = a.tk_sel ? topk_weight(KEY_ZERO, a.tk_sel[row], __uint_as_float(a.tk_sel[a.a_rows + row])) : 1.f;
+            n += wt * (float)a.tail_count * ptx::ex2_approx(-m2);
+          }
           neg_i = n;
           if (sg.slot == 0 && rowstats_out != nullptr) {
             rowstats_out[row] = m2 * LN2;
             rowstats_out[a.a_rows + row] = n;
           }
+        }
+      }
+      // a10 selection state of this row: key prefix (H2, H3) / tau key and tie weight (NEGW)
+      uint32_t tk_pref = TK_ALL;
+      float tk_tw = 0.f;
+      uint32_t* tk_hrow = nullptr;
+      if (MODE == TC_H1 || MODE == TC_H2 || MODE == TC_H3 || MODE == TC_NEGW) {
+        if (valid) {
+          if (MODE != TC_H1) tk_pref = a.tk_sel[row];
+          if (MODE == TC_NEGW) tk_tw = __uint_as_float(a.tk_sel[a.a_rows + row]);
+          tk_hrow = a.tk_hist + (int64_t)row * TK_BINS;
         }
       }
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
@@ -376,6 +401,40 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             const int64_t ld = (int64_t)T_all * BN;
 #pragma unroll
             for (int j = 0; j < 32; ++j) partials[(int64_t)row * ld + cb + j] = __uint_as_float(v[j]);
+          } else if (MODE == TC_H1 || MODE == TC_H2 || MODE == TC_H3 || MODE == TC_NEGW) {
+            // a10: every NEGATIVE logit of the row goes through its sortable key
+            const int mylab = uniform ? ulab : ((cb + lane < ncols) ? col_label(a, cb + lane) : -2);
+            if (MODE == TC_NEGW) {
+              // branch-free: one ex2 per logit like the plain NEG sweep, times the selection weight (0, 1 or the tie share);
+              // a branch on w > 0 diverged on almost every element (some lane of the warp keeps it): 568 us vs 86 for NEG
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const int l0 = uniform ? ulab : __shfl_sync(0xffffffffu, mylab, j);
+                const int l1 = uniform ? ulab : __shfl_sync(0xffffffffu, mylab, j + 1);
+                const float x0 = __fmul_rn(__uint_as_float(v[j]), a.k1), x1 = __fmul_rn(__uint_as_float(v[j + 1]), a.k1);
+                const float w0 = (valid && l0 != -2 && l0 != rcls) ? topk_weight(sortable_key(x0), tk_pref, tk_tw) : 0.f;
+                const float w1 = (valid && l1 != -2 && l1 != rcls) ? topk_weight(sortable_key(x1), tk_pref, tk_tw) : 0.f;
+                const float e0 = ptx::ex2_approx(x0 - m2), e1 = ptx::ex2_approx(x1 - m2);
+                acc0 = fmaf(w0, w0 > 0.f ? e0 : 0.f, acc0);       // (select, not multiply: an excluded logit may overflow)
+                acc1 = fmaf(w1, w1 > 0.f ? e1 : 0.f, acc1);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int lj = uniform ? ulab : __shfl_sync(0xffffffffu, mylab, j);
+                if (valid && lj != -2 && lj != rcls) {
+                  const float x = __fmul_rn(__uint_as_float(v[j]), a.k1);
+                  const uint32_t key = sortable_key(x);
+                  if (MODE == TC_H1) {
+                    atomicAdd(tk_hrow + (key >> 21), 1u);
+                  } else if (MODE == TC_H2) {
+                    if ((key >> 21) == tk_pref) atomicAdd(tk_hrow + ((key >> 10) & 0x7FFu), 1u);
+                  } else {
+                    if ((key >> 10) == tk_pref) atomicAdd(tk_hrow + (key & 0x3FFu), 1u);
+                  }
+                }
+              }
+            }
           } else if (MODE == TC_NEG) {
             if (uniform) {
               if (valid && ulab != rcls) {
@@ -432,8 +491,8 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         if (lane == 0) ptx::mbar_arrive(&sm.tmem_empty[accb]);
       }
       // ---- combine the two column halves, write the partials of this segment ----
-      if (MODE != TC_DUMP) {
-        if (MODE == TC_NEG) {
+      if (MODE != TC_DUMP && MODE != TC_H1 && MODE != TC_H2 && MODE != TC_H3) {
+        if (MODE == TC_NEG || MODE == TC_NEGW) {
           sm.comb[0][half][r_in] = (acc0 + acc1) + (acc2 + acc3);
         } else {
           sm.comb[0][half][r_in] = acc0 * LN2;
@@ -444,7 +503,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         if (half == 0) {
           const int64_t o = (int64_t)sg.slot * a.a_pad + row;
           const int64_t stride = (int64_t)a.slots * a.a_pad;
-          if (MODE == TC_NEG) {
+          if (MODE == TC_NEG || MODE == TC_NEGW) {
             partials[0 * stride + o] = m2 * LN2;                             // stabiliser in natural-log units
             partials[1 * stride + o] = sm.comb[0][0][r_in] + sm.comb[0][1][r_in];
           } else {
@@ -498,7 +557,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EPI_W epilogue warps (8 or 16).  The epilogue (one ex2 + a few ALU ops per logit, then the bf16 gradient tile) is a chain
+// of dependent instructions per element; with 8 warps (2 per scheduler) the issue slots were 29 % busy and the tensor
+// pipe 49 % (profiles/r2_06_bank_source_top.txt): 16 warps halve the columns per thread and double the latency hiding.
+template <int EPI_W, bool TOPK>
+__global__ void __launch_bounds__(64 + 32 * EPI_W, 1)
 k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC, TcBwdArgs ba,
          float* __restrict__ dpartials) {
   extern __shared__ uint8_t smem_raw[];
@@ -522,8 +585,8 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     ptx::prefetch_tmap(&tmC);
     ptx::mbar_init(&sm.a_full, 1);
     for (int s = 0; s < BWD_STAGES; ++s) { ptx::mbar_init(&sm.c_full[s], 1); ptx::mbar_init(&sm.c_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.s_full[i], 1); ptx::mbar_init(&sm.s_empty[i], EPI_THREADS / 32); }
-    ptx::mbar_init(&sm.g_full, EPI_THREADS / 32);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.s_full[i], 1); ptx::mbar_init(&sm.s_empty[i], EPI_W); }
+    ptx::mbar_init(&sm.g_full, EPI_W);
     ptx::mbar_init(&sm.g_empty, 1);
     ptx::mbar_init(&sm.da_full, 1);
     ptx::fence_barrier_init();
@@ -610,8 +673,11 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       ptx::mma_commit(&sm.da_full);
     }
   } else {
+    constexpr int SLICES = EPI_W / 4;             // column slices of the 128-column tile (one per warp of a lane quarter)
+    constexpr int CPS = BNB / SLICES;             // columns per slice: 64 (8 warps) or 32 (16 warps)
+    constexpr int NCH = CPS / 32;                 // 32-column chunks per thread
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;             // which 64 columns of the 128-column tile
+    const int half = (warp - 2) >> 2;             // which column slice of the 128-column tile
     const int r_in = quarter * 32 + lane;
     const int row = row0 + r_in;
     const bool valid = row < A;
@@ -629,11 +695,15 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     }
     const float cs_i = c_i * s_i;
     const float cn_i = -c_i * neg_i;
+    // a10: selection weights on the negatives (tau key, tie weight; pcl_topk.cuh); key = rn(s * k1) as in the forward
+    uint32_t tk_tau = 0u;
+    float tk_tw = 1.f;
+    if (TOPK && valid) { tk_tau = a.tk_sel[row]; tk_tw = __uint_as_float(a.tk_sel[a.a_rows + row]); }
     uint8_t* g_row = sm.g + r_in * 128;           // + kblock * 16 KB + swizzled 16-byte chunk
-    int nlab_lo[2], nlab_hi[2];
+    int nlab_lo[NCH], nlab_hi[NCH];
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int cb = my_lo * BNB + half * 64 + ch * 32;
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int cb = my_lo * BNB + half * CPS + ch * 32;
       const bool in = ntiles > 0 && a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
       nlab_lo[ch] = in ? col_label(a, cb) : -2;
       nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
@@ -641,19 +711,19 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     for (int it = 0; it < ntiles; ++it) {
       const int ct = my_lo + it * tstep;
       const uint32_t acc = it & 1, phase = (it >> 1) & 1;
-      const int col0 = ct * BNB + half * 64;
-      int clab[2];
-      bool cuni[2];
+      const int col0 = ct * BNB + half * CPS;
+      int clab[NCH];
+      bool cuni[NCH];
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
         const int cb = col0 + ch * 32;
         clab[ch] = nlab_lo[ch];
         cuni[ch] = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols && nlab_lo[ch] == nlab_hi[ch];
       }
       if (it + 1 < ntiles) {                       // labels of the next tile: loads fly while this tile is processed
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const int cb = (ct + tstep) * BNB + half * 64 + ch * 32;
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int cb = (ct + tstep) * BNB + half * CPS + ch * 32;
           const bool in = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
           nlab_lo[ch] = in ? col_label(a, cb) : -2;
           nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
@@ -661,21 +731,29 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       }
       ptx::mbar_wait(&sm.s_full[acc], phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BNB + half * 64;
-      uint32_t packed[2][16];
-      uint32_t vbuf[2][32];
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BNB + half * CPS;
+      uint32_t packed[NCH][16];
+      uint32_t vbuf[NCH][32];
       ptx::tmem_ld_32x32b_x32(t_row, vbuf[0]);
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
         ptx::tmem_ld_wait();
-        if (ch == 0) ptx::tmem_ld_32x32b_x32(t_row + 32, vbuf[1]);         // prefetch the second chunk
+        if (ch + 1 < NCH) ptx::tmem_ld_32x32b_x32(t_row + 32, vbuf[NCH - 1]);   // prefetch the second chunk
         uint32_t(&v)[32] = vbuf[ch];
         const int cb = col0 + ch * 32;
         float gv[32];
         if (cuni[ch] && clab[ch] != rcls) {
           // all-negative chunk: G = c S e   (cs_i == 0 for rows beyond A)
+          if (TOPK) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) gv[j] = cs_i * ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+            for (int j = 0; j < 32; ++j) {
+              const float x = __fmul_rn(__uint_as_float(v[j]), a.k1);
+              gv[j] = cs_i * topk_weight(sortable_key(x), tk_tau, tk_tw) * ptx::ex2_approx(x - m2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gv[j] = cs_i * ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+          }
         } else if (cuni[ch]) {
           // all-positive chunk: G = -c Neg / (e + Neg), zero on the masked (i,i) column
           const bool has_diag = rdiag >= cb && rdiag < cb + 32;
@@ -690,8 +768,9 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int lj = __shfl_sync(0xffffffffu, mylab, j);
-            const float e = ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
-            const float gneg = cs_i * e;
+            const float xq = __fmul_rn(__uint_as_float(v[j]), a.k1);
+            const float e = TOPK ? ptx::ex2_approx(xq - m2) : ptx::ex2_approx(fmaf(__uint_as_float(v[j]), a.k1, -m2));
+            const float gneg = TOPK ? cs_i * e * topk_weight(sortable_key(xq), tk_tau, tk_tw) : cs_i * e;
             const float gpos = (cb + j == rdiag) ? 0.f : cn_i * ptx::rcp_approx(e + neg_i);
             gv[j] = (!valid || lj == -2) ? 0.f : (lj == rcls ? gpos : gneg);
           }
@@ -702,6 +781,9 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           const bool cok = cj < (int)ncols;
           const int mylab = cok ? a.acls[cj] : -2;
           float my_m2 = 0.f, my_neg = 1.f, my_cs = 0.f, my_cn = 0.f;
+          uint32_t my_tau = 0u;
+          float my_tw = 1.f;
+          if (TOPK && cok) { my_tau = a.tk_sel[cj]; my_tw = __uint_as_float(a.tk_sel[a.a_rows + cj]); }
           if (cok) {
             const float np_j = st[4 * a.a_rows + cj];
             float c_j = ba.rs_scale / ((float)A * np_j);
@@ -718,13 +800,19 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             const float negj = __shfl_sync(0xffffffffu, my_neg, j);
             const float csj = __shfl_sync(0xffffffffu, my_cs, j);
             const float cnj = __shfl_sync(0xffffffffu, my_cn, j);
-            const float x = __uint_as_float(v[j]) * a.k1;
+            const float x = __fmul_rn(__uint_as_float(v[j]), a.k1);
             const float e = ptx::ex2_approx(x - m2);
             const float e2 = ptx::ex2_approx(x - m2j);
             const bool same = lj == rcls;
             const bool diag = (cb + j == rdiag);
-            const float g_ij = same ? (diag ? 0.f : cn_i * ptx::rcp_approx(e + neg_i)) : cs_i * e;
-            const float g_ji = same ? (diag ? 0.f : cnj * ptx::rcp_approx(e2 + negj)) : csj * e2;
+            float wi = 1.f, wj = 1.f;
+            if (TOPK) {
+              const uint32_t key = sortable_key(x);
+              wi = topk_weight(key, tk_tau, tk_tw);
+              wj = topk_weight(key, __shfl_sync(0xffffffffu, my_tau, j), __shfl_sync(0xffffffffu, my_tw, j));
+            }
+            const float g_ij = same ? (diag ? 0.f : cn_i * ptx::rcp_approx(e + neg_i)) : cs_i * e * wi;
+            const float g_ji = same ? (diag ? 0.f : cnj * ptx::rcp_approx(e2 + negj)) : csj * e2 * wj;
             gv[j] = (!valid || lj == -2) ? 0.f : (g_ij + g_ji);
           }
         }
@@ -737,14 +825,15 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       if (lane == 0) ptx::mbar_arrive(&sm.s_empty[acc]);
       // G buffer free once MMA2 of the previous tile retired
       ptx::mbar_wait(&sm.g_empty, (it & 1) ^ 1);
-      // this thread's 64 columns = K-block `half` of the G tile, 8 chunks of 16 B, 128B-swizzled by row
+      // this thread's columns inside the G tile: K-block (64 columns) kb, 16-byte chunks 128B-swizzled by row
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int c0 = half * CPS + ch * 32;          // first column of the chunk inside the tile
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ch * 4 + q;
+          const int chunk = ((c0 & 63) >> 3) + q;
           uint4 val = make_uint4(packed[ch][4 * q], packed[ch][4 * q + 1], packed[ch][4 * q + 2], packed[ch][4 * q + 3]);
-          *reinterpret_cast<uint4*>(g_row + half * (BM * 128) + ((chunk ^ (r_in & 7)) << 4)) = val;
+          *reinterpret_cast<uint4*>(g_row + (c0 >> 6) * (BM * 128) + ((chunk ^ (r_in & 7)) << 4)) = val;
         }
       }
       ptx::fence_proxy_async();                   // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -756,10 +845,11 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       ptx::mbar_wait(&sm.da_full, 0);
       ptx::tc_fence_after();
     }
-    float* dst = dpartials + ((int64_t)split * a.a_pad + row) * DDIM + half * 128;
-    const uint32_t t_da = tmem_dA + ((uint32_t)(quarter * 32) << 16) + half * 128;
+    constexpr int DCOLS = DDIM / SLICES;           // dA columns this thread stores: 128 or 64
+    float* dst = dpartials + ((int64_t)split * a.a_pad + row) * DDIM + half * DCOLS;
+    const uint32_t t_da = tmem_dA + ((uint32_t)(quarter * 32) << 16) + half * DCOLS;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < DCOLS / 32; ++ch) {
       uint32_t v[32];
       if (ntiles > 0) {
         ptx::tmem_ld_32x32b_x32(t_da + ch * 32, v);
@@ -1027,6 +1117,26 @@ extern "C" int pcl_infonce_tc_fwd(const pcl_tc_desc* d, float* row_m2, float* pa
 
 int pcl::tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* rowstats, float* loss, void* stream,
                    bool skip_prep, unsigned long long* step_counter) {
+  return tc_fwd_topk_ex(d, 0, nullptr, row_m2, partials, rowstats, loss, stream, skip_prep, step_counter);
+}
+
+extern "C" int64_t pcl_tc_topk_scratch_u32(const pcl_tc_desc* d) {
+  if (!d || d->a_rows <= 0) return PCL_ERR_ARG;
+  const int64_t a_pad = (int64_t)ceil_div(d->a_rows, tc::BM) * tc::BM;
+  return a_pad * TK_BINS + 4 * (int64_t)d->a_rows;
+}
+
+extern "C" int pcl_infonce_tc_topk_fwd(const pcl_tc_desc* d, int32_t k, uint32_t* scratch, float* row_m2, float* partials,
+                                       float* rowstats, float* loss, void* stream) {
+  if (k < 1 || !scratch) return PCL_ERR_ARG;
+  return pcl::tc_fwd_topk_ex(d, k, scratch, row_m2, partials, rowstats, loss, stream, false, nullptr);
+}
+
+// k == 0: all negatives (the reference).  k >= 1 (a10): the negative sum keeps the k hardest negatives of every anchor:
+// three histogram sweeps over the logit keys (per-row bins in global memory, red.global from the epilogue) with the
+// warp-per-row scans of pcl_topk.cuh in between, then the weighted negative sweep; POS and finalize as usual.
+int pcl::tc_fwd_topk_ex(const pcl_tc_desc* d, int k, uint32_t* scratch, float* row_m2, float* partials, float* rowstats,
+                        float* loss, void* stream, bool skip_prep, unsigned long long* step_counter) {
   TcPlan p;
   int st = make_tc_plan(d, &p);
   if (st != PCL_OK) return st;
@@ -1065,7 +1175,34 @@ int pcl::tc_fwd_ex(const pcl_tc_desc* d, float* row_m2, float* partials, float* 
   PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_POS, false>), smem);
   dim3 grid(p.row_tiles, a.splits);
   const int variant = tc_variant();
-  if (variant & 2) {                                   // tuning knob: 2-D grid instead of the persistent walk
+  if (k >= 1) {
+    PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_H1, false>), smem);
+    PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_H2, false>), smem);
+    PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_H3, false>), smem);
+    PCL_SMEM_OPT_IN((tc::k_tc_fwd<tc::TC_NEGW, false>), smem);
+    TopkArgs tk;
+    tk.k = k;
+    tk.hist = scratch;
+    tk.sel = scratch + (int64_t)a.a_pad * TK_BINS;
+    a.tk_hist = tk.hist;
+    a.tk_sel = tk.sel;
+    PCL_CUDA(cudaMemsetAsync(tk.hist, 0, (size_t)a.a_pad * TK_BINS * sizeof(uint32_t), s));
+    const int scan_blocks = ceil_div(d->a_rows, 8);          // 8 warps (rows) per 256-thread block
+    a.persistent = 1;
+    tc::k_tc_fwd<tc::TC_H1, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    PCL_LAUNCH_CHECK();
+    k_topk_scan<1><<<scan_blocks, 256, 0, s>>>(p.sw, tk);
+    PCL_LAUNCH_CHECK();
+    tc::k_tc_fwd<tc::TC_H2, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    PCL_LAUNCH_CHECK();
+    k_topk_scan<2><<<scan_blocks, 256, 0, s>>>(p.sw, tk);
+    PCL_LAUNCH_CHECK();
+    tc::k_tc_fwd<tc::TC_H3, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+    PCL_LAUNCH_CHECK();
+    k_topk_scan<3><<<scan_blocks, 256, 0, s>>>(p.sw, tk);
+    PCL_LAUNCH_CHECK();
+    tc::k_tc_fwd<tc::TC_NEGW, false><<<p.grid_persistent, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
+  } else if (variant & 2) {                            // tuning knob: 2-D grid instead of the persistent walk
     a.persistent = 0;
     if (variant & 1) tc::k_tc_fwd<tc::TC_NEG, true><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
     else             tc::k_tc_fwd<tc::TC_NEG, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, nullptr);
@@ -1118,9 +1255,16 @@ extern "C" int pcl_infonce_tc_bwd(const pcl_tc_desc* d, const float* row_m2, con
   return pcl::tc_bwd_ex(d, row_m2, rowstats, grad_loss, dpartials, dA, stream, nullptr, nullptr);
 }
 
+extern "C" int pcl_infonce_tc_topk_bwd(const pcl_tc_desc* d, int32_t k, const uint32_t* scratch, const float* row_m2,
+                                       const float* rowstats, const float* grad_loss, float* dpartials, float* dA,
+                                       void* stream) {
+  if (k < 1 || !scratch) return PCL_ERR_ARG;
+  return pcl::tc_bwd_ex(d, row_m2, rowstats, grad_loss, dpartials, dA, stream, nullptr, nullptr, scratch);
+}
+
 // dA == nullptr: leave the per-split partials for a fused consumer (splits_out / a_pad_out describe their layout)
 int pcl::tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowstats, const float* grad_loss,
-                   float* dpartials, float* dA, void* stream, int* splits_out, int* a_pad_out) {
+                   float* dpartials, float* dA, void* stream, int* splits_out, int* a_pad_out, const uint32_t* topk_scratch) {
   TcPlan p;
   int st = make_tc_plan(d, &p);
   if (st != PCL_OK) return st;
@@ -1130,6 +1274,7 @@ int pcl::tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowst
   tc::TcBwdArgs ba;
   ba.t = p.a;
   ba.t.row_m2 = row_m2;
+  if (topk_scratch != nullptr) ba.t.tk_sel = topk_scratch + (int64_t)ba.t.a_pad * TK_BINS;      // a10 selection of the forward
   ba.rowstats = rowstats;
   ba.rs_scale = d->temperature / d->base_temperature;
   ba.nan_safe = d->nan_safe;
@@ -1143,9 +1288,15 @@ int pcl::tc_bwd_ex(const pcl_tc_desc* d, const float* row_m2, const float* rowst
   else st = make_tmap(&tmC, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : ba.t.n_cols), tc::BNB);
   if (st != PCL_OK) return st;
   const size_t smem = sizeof(tc::SmemBwd) + 1024;
-  PCL_SMEM_OPT_IN(tc::k_tc_bwd, smem);
+  PCL_SMEM_OPT_IN((tc::k_tc_bwd<8, false>), smem);
+  PCL_SMEM_OPT_IN((tc::k_tc_bwd<16, false>), smem);
+  PCL_SMEM_OPT_IN((tc::k_tc_bwd<16, true>), smem);
   dim3 grid(p.row_tiles, splits);
-  tc::k_tc_bwd<<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmC, ba, dpartials);
+  static int epi_w = 0;                        // PCL_TC_BWD_EPI=8|16 (tuning runs); default 16
+  if (epi_w == 0) { const char* e = getenv("PCL_TC_BWD_EPI"); epi_w = (e && atoi(e) == 8) ? 8 : 16; }
+  if (ba.t.tk_sel != nullptr) tc::k_tc_bwd<16, true><<<grid, 64 + 32 * 16, smem, s>>>(tmA, tmC, ba, dpartials);
+  else if (epi_w == 8)        tc::k_tc_bwd<8, false><<<grid, 64 + 32 * 8, smem, s>>>(tmA, tmC, ba, dpartials);
+  else                        tc::k_tc_bwd<16, false><<<grid, 64 + 32 * 16, smem, s>>>(tmA, tmC, ba, dpartials);
   PCL_LAUNCH_CHECK();
   if (splits_out) *splits_out = splits;
   if (a_pad_out) *a_pad_out = ba.t.a_pad;

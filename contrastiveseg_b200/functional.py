@@ -235,14 +235,44 @@ def _step_sweep_desc(ws, d) -> "_abi.SweepDesc":
     return sw
 
 
+def _step_tc_desc(ws, d) -> "_abi.TcDesc":
+    """pcl_tc_desc of the step's tensor sweep (what pcl_step.cu:fill_tc builds on the C side)."""
+    ms = ws.geom.max_samples
+    t = _abi.TcDesc()
+    t.anchors_bf16 = ws.anchors_bf16.data_ptr()
+    t.anchor_cls = ws.anchor_meta.data_ptr() + 4 * 2 * ms
+    t.diag_col = ws.anchor_meta.data_ptr() + 4 * 3 * ms
+    t.plan = ws.plan.data_ptr()
+    t.a_rows, t.D, t.mode = ms, ws.geom.D, d.mode
+    t.contrast_bf16, t.contrast_rows_alloc = d.shadow_bf16, d.shadow_rows
+    t.bank_K, t.bank_R, t.sorted = d.bank_K, d.bank_M0 + d.bank_M1, 1
+    t.contrast_norm_bound = d.contrast_norm_bound
+    t.temperature, t.base_temperature, t.nan_safe = d.temperature, d.base_temperature, d.nan_safe
+    return t
+
+
 def _topk_step_forward(lib, ws, d, opts, stream):
-    """a10: selection + gather as usual, then the top-k InfoNCE sweep (exact fp32 path only)."""
-    if opts.precision != "fp32":
-        raise _abi.PclError("topk_negatives runs on the exact fp32 sweep: use precision='fp32'")
+    """a10: selection + gather as usual, then the top-k InfoNCE sweep (exact fp32 path, or the tensor path: the radix
+    select then runs in the tcgen05 sweep's epilogue on the fp32-accumulated logits of the bf16 operands)."""
     k = int(opts.topk_negatives)
     if k < 1:
         raise _abi.PclError("topk_negatives must be >= 1 (None disables the selection)")
     g = ws.geom
+    if opts.precision == "bf16":
+        _abi.check(lib.pcl_select_gather(C.byref(g), d.embed, ws.keys.data_ptr(), ws.chunk_pref.data_ptr(),
+                                         ws.plan.data_ptr(), d.ranks, d.seed, d.normalize, ws.anchor_meta.data_ptr(),
+                                         ws.anchors_f32.data_ptr(), ws.anchors_bf16.data_ptr(), ws.inv_norm.data_ptr(),
+                                         ws.norm_max.data_ptr(), stream), "pcl_select_gather")
+        t = _step_tc_desc(ws, d)
+        n = lib.pcl_tc_topk_scratch_u32(C.byref(t))
+        if n < 0:
+            _abi.check(int(n), "pcl_tc_topk_scratch_u32")
+        scratch = getattr(ws, "topk_scratch", None)
+        if scratch is None or scratch.numel() < n:
+            scratch = ws.topk_scratch = torch.empty(n, dtype=torch.int32, device=ws.device)
+        _abi.check(lib.pcl_infonce_tc_topk_fwd(C.byref(t), k, scratch.data_ptr(), ws.row_m2.data_ptr(), ws.partials.data_ptr(),
+                                               ws.rowstats.data_ptr(), d.loss, stream), "pcl_infonce_tc_topk_fwd")
+        return t, k, scratch
     _abi.check(lib.pcl_select_gather(C.byref(g), d.embed, ws.keys.data_ptr(), ws.chunk_pref.data_ptr(),
                                      ws.plan.data_ptr(), d.ranks, d.seed, d.normalize, ws.anchor_meta.data_ptr(),
                                      ws.anchors_f32.data_ptr(), ws.anchors_bf16.data_ptr(), ws.inv_norm.data_ptr(),
@@ -261,6 +291,14 @@ def _topk_step_forward(lib, ws, d, opts, stream):
 
 def _topk_step_backward(lib, ws, d, topk, go, stream):
     sw, k, scratch = topk
+    if isinstance(sw, _abi.TcDesc):
+        _abi.check(lib.pcl_infonce_tc_topk_bwd(C.byref(sw), k, scratch.data_ptr(), ws.row_m2.data_ptr(), ws.rowstats.data_ptr(),
+                                               go.data_ptr(), ws.dpartials.data_ptr(), ws.dA.data_ptr(), stream),
+                   "pcl_infonce_tc_topk_bwd")
+        _abi.check(lib.pcl_scatter_grad(C.byref(ws.geom), ws.plan.data_ptr(), ws.anchor_meta.data_ptr(), ws.dA.data_ptr(),
+                                        ws.anchors_f32.data_ptr(), ws.inv_norm.data_ptr(), d.normalize, d.grad_embed,
+                                        stream), "pcl_scatter_grad")
+        return
     _abi.check(lib.pcl_infonce_topk_bwd(C.byref(sw), k, scratch.data_ptr(), ws.rowstats.data_ptr(), go.data_ptr(),
                                         ws.dpartials.data_ptr(), ws.dA.data_ptr(), stream), "pcl_infonce_topk_bwd")
     _abi.check(lib.pcl_scatter_grad(C.byref(ws.geom), ws.plan.data_ptr(), ws.anchor_meta.data_ptr(), ws.dA.data_ptr(),
@@ -451,6 +489,8 @@ def infonce_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast
                     nan_safe: bool = False, topk: Optional[int] = None):
     """Returns (loss (1,), rowstats (6, A), desc-state) for the exact fp32 sweep.
     Modes: self-contrast (contrast None, queues None), explicit matrix (contrast given), bank (queues given).
+    Bank mode expects the anchors grouped by class in the engine's row order (class rank 1, 2, ..., K-1, 0 — what the
+    selection kernel produces): the positive sweep only visits the column range of a row tile's classes.
     topk=k keeps only the k hardest negatives of every anchor (a10 extension; None = all, the reference)."""
     lib = _abi.load()
     _require_cuda(anchors, "anchors")
@@ -505,7 +545,7 @@ def infonce_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast
 
 def topk_selection(state, a_rows: int):
     """Selection result of a topk forward (diagnostics/tests): (tau_key uint32 as int64, tie_weight f32, n_above, n_ties)."""
-    scratch = state[4]
+    scratch = state[-1]                      # (exact sweep: 5-tuple, tensor sweep: 6-tuple; the scratch comes last)
     sel = scratch[scratch.numel() - 4 * a_rows:].view(4, a_rows)
     key = sel[0].to(torch.int64) & 0xFFFFFFFF
     return key, sel[1].view(torch.float32), sel[2].to(torch.int64) & 0xFFFFFFFF, sel[3].to(torch.int64) & 0xFFFFFFFF
@@ -617,9 +657,11 @@ def _tc_desc(anchors, anchor_cls, contrast_bf16, contrast_cls, n_cols, bank, dia
 def infonce_tc_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contrast_bf16: Optional[torch.Tensor] = None,
                        contrast_cls: Optional[torch.Tensor] = None, n_cols: int = 0, bank=None,
                        diag_col: Optional[torch.Tensor] = None, temperature: float = 0.1, base_temperature: float = 0.07,
-                       nan_safe: bool = False, sorted_cols: bool = True, norm_bound: float = 1.0, neg_only: bool = False):
+                       nan_safe: bool = False, sorted_cols: bool = True, norm_bound: float = 1.0, neg_only: bool = False,
+                       topk: Optional[int] = None):
     """bf16 tcgen05 sweep.  Returns (loss (1,), rowstats (6, A), state).  neg_only=True runs just the similarity +
-    negative-sum sweep (roofline measurement of the dense contraction)."""
+    negative-sum sweep (roofline measurement of the dense contraction).  topk=k: a10, the k hardest negatives per anchor
+    (radix select in the sweep's epilogue)."""
     lib = _abi.load()
     _require_cuda(anchors, "anchors")
     dev = anchors.device
@@ -632,6 +674,16 @@ def infonce_tc_forward(anchors: torch.Tensor, anchor_cls: torch.Tensor, *, contr
     partials = torch.empty(5 * ss.partial_f32, dtype=torch.float32, device=dev)
     rowstats = torch.empty(6 * ss.rowstat_f32, dtype=torch.float32, device=dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    if topk is not None:
+        n = lib.pcl_tc_topk_scratch_u32(C.byref(d))
+        if n < 0:
+            _abi.check(int(n), "pcl_tc_topk_scratch_u32")
+        scratch = torch.empty(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _abi.check(lib.pcl_infonce_tc_topk_fwd(C.byref(d), int(topk), scratch.data_ptr(), row_m2.data_ptr(),
+                                                   partials.data_ptr(), rowstats.data_ptr(), loss.data_ptr(),
+                                                   _stream_ptr(dev)), "pcl_infonce_tc_topk_fwd")
+        return loss, rowstats.view(6, d.a_rows), (d, ss, keep, row_m2, int(topk), scratch)
     with torch.cuda.device(dev):
         _abi.check(lib.pcl_infonce_tc_fwd(C.byref(d), row_m2.data_ptr(), partials.data_ptr(), rowstats.data_ptr(),
                                           loss.data_ptr(), _stream_ptr(dev)), "pcl_infonce_tc_fwd")
@@ -660,10 +712,16 @@ def tc_dump_logits(anchors: torch.Tensor, contrast_bf16: Optional[torch.Tensor],
 def infonce_tc_backward(state, rowstats: torch.Tensor, grad_loss: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dA (A, 256) fp32 from the tcgen05 backward sweep (recompute S, G tile in shared memory, dA += G.C)."""
     lib = _abi.load()
-    d, ss, keep, row_m2 = state
+    d, ss, keep, row_m2 = state[:4]
     dev = row_m2.device
     dpart = torch.empty(ss.dpartial_f32, dtype=torch.float32, device=dev)
     dA = torch.empty((d.a_rows, d.D), dtype=torch.float32, device=dev)
+    if len(state) == 6:                          # forward ran with topk: same selection state in the backward
+        with torch.cuda.device(dev):
+            _abi.check(lib.pcl_infonce_tc_topk_bwd(C.byref(d), state[4], state[5].data_ptr(), row_m2.data_ptr(),
+                                                   rowstats.contiguous().data_ptr(), _abi.ptr(grad_loss), dpart.data_ptr(),
+                                                   dA.data_ptr(), _stream_ptr(dev)), "pcl_infonce_tc_topk_bwd")
+        return dA
     with torch.cuda.device(dev):
         _abi.check(lib.pcl_infonce_tc_bwd(C.byref(d), row_m2.data_ptr(), rowstats.contiguous().data_ptr(),
                                           _abi.ptr(grad_loss), dpart.data_ptr(), dA.data_ptr(), _stream_ptr(dev)),

@@ -68,8 +68,6 @@ class GraphedContrastStep:
         if opts.rng != "device" or opts.perm_fn is not None:
             raise _abi.PclError("a captured step draws its anchors on the device: rng must be 'device'")
         self.opts = opts
-        if opts.topk_negatives and opts.precision != "fp32":
-            raise _abi.PclError("topk_negatives runs on the exact fp32 sweep: use precision='fp32'")
         self.embed = _canonical(embed.detach(), torch.float32, "embed", device)
         self.labels = _canonical(labels, torch.int64, "labels", device)
         self.seg = _canonical(None if seg is None else seg.detach(), torch.float32, "seg", device)

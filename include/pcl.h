@@ -285,6 +285,14 @@ typedef struct {
 } pcl_tc_desc;
 
 int pcl_tc_sizes(const pcl_tc_desc* d, pcl_sweep_sizes_t* out);
+/* a10 on the tensor path (same semantics as pcl_infonce_topk_fwd/bwd, selection on the fp32-accumulated logits of the bf16
+ * operands): scratch = pcl_tc_topk_scratch_u32(d) uint32 (per-row radix bins + the selection state, kept for the
+ * backward); three extra similarity sweeps whose epilogue bins the logit keys (red.global), then the weighted sweep. */
+int64_t pcl_tc_topk_scratch_u32(const pcl_tc_desc* d);
+int pcl_infonce_tc_topk_fwd(const pcl_tc_desc* d, int32_t k, uint32_t* scratch, float* row_m2, float* partials,
+                            float* rowstats, float* loss, void* stream);
+int pcl_infonce_tc_topk_bwd(const pcl_tc_desc* d, int32_t k, const uint32_t* scratch, const float* row_m2,
+                            const float* rowstats, const float* grad_loss, float* dpartials, float* dA, void* stream);
 int pcl_to_bf16(const float* src, void* dst_bf16, int64_t n_real, int64_t n_total, void* stream);
 /* row_m2: (a_rows rounded up to 256) + 512 floats of scratch (per-row stabiliser, kept for the backward,
  * followed by the per-label column bounds of a sorted explicit contrast set). */

@@ -81,6 +81,14 @@ TOPK = (
 )
 
 
+TOPK += (
+    [_case(TK.test_tc_topk_explicit_exact_data, A=a, N=n, k=k) for a, n, k in ((70, 333, 9), (200, 600, 40))] +
+    [_case(TK.test_tc_topk_self_contrast_exact_data, k=3)] +
+    [_case(TK.test_tc_topk_bank_mode_with_zero_tail, k=k) for k in (5, 10 ** 6)] +
+    [_case(TK.test_tc_topk_through_the_loss_module, name=n) for n in ("nomem_d256", "mem_d256")]
+)
+
+
 @pytest.mark.parametrize("fn,kw", TOPK)
 def test_topk_kernels_on_emulation(emu, fn, kw):
     """a10: the radix-select / weighted-sweep kernels of csrc/pcl_topk.cu against the sort-based oracle."""
@@ -116,10 +124,11 @@ def test_graphed_step_tensor_path_on_emulation(emu, monkeypatch, mem, overlap):
     PD.test_graphed_step_equals_eager_step("bf16", mem, overlap)
 
 
-def test_topk_inside_the_captured_step_on_emulation(emu, monkeypatch):
+@pytest.mark.parametrize("precision,D", [("fp32", 64), ("bf16", 256)])
+def test_topk_inside_the_captured_step_on_emulation(emu, monkeypatch, precision, D):
     from contrastiveseg_b200 import graph_step
     monkeypatch.setattr(graph_step.GraphedContrastStep, "_capture", lambda self, warmup: None)
-    TK.test_topk_inside_the_captured_step_equals_the_eager_step()
+    TK.test_topk_inside_the_captured_step_equals_the_eager_step(precision, D)
 
 
 @pytest.mark.parametrize("geom", [dict(B=2, h=32, w=32, K=7, ms=128, mv=8), dict(B=3, h=32, w=48, K=9, ms=700, mv=40)])

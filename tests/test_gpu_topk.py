@@ -146,15 +146,17 @@ def test_topk_through_the_loss_module(name):
     assert gerr <= 2e-3 * e64.grad.abs().max().item()    # one near-tie swap moves one negative's share of a row
 
 
-def test_topk_inside_the_captured_step_equals_the_eager_step():
+@pytest.mark.parametrize("precision,D", [("fp32", 64), ("bf16", 256)])
+def test_topk_inside_the_captured_step_equals_the_eager_step(precision, D):
     """a10 wired into GraphedContrastStep: the three histogram sweeps, the scans, the weighted NEG sweep, POS, finalize and
-    the top-k backward are part of the captured sequence; replay r == eager step with counter r+1 bit for bit."""
+    the top-k backward are part of the captured sequence; replay r == eager step with counter r+1 bit for bit (exact
+    sweep and tensor sweep)."""
     from contrastiveseg_b200.synth import make_contrast_batch
-    K, D = 6, 64
+    K = 6
     data = make_contrast_batch(B=2, D=D, h=32, w=32, num_classes=K, img_stride=4, block=16, seed=17)
     embed, tgt, seg = data["embed"].to(DEV), data["target"].to(DEV), data["seg"].to(DEV)
     opts = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=96, max_views=8, seed=2,
-                              precision="fp32", num_classes=K, topk_negatives=11)
+                              precision=precision, num_classes=K, topk_negatives=11)
     step = cs.GraphedContrastStep(embed, tgt, seg=seg, options=opts)
     assert not step.fused
     for r in range(3):
@@ -168,8 +170,116 @@ def test_topk_inside_the_captured_step_equals_the_eager_step():
         torch.cuda.synchronize()
         assert torch.equal(l.detach(), loss) and torch.equal(e.grad, grad)
     opts_all = cs.ContrastOptions(temperature=0.1, base_temperature=0.07, max_samples=96, max_views=8, seed=2,
-                                  precision="fp32", num_classes=K)
+                                  precision=precision, num_classes=K)
     Fn._step_counter[0] = 2
     e = embed.clone().requires_grad_(True)
     l_all = cs.pixel_contrast_loss(e, tgt, seg=seg, options=opts_all)
     assert l_all.item() > loss.item()                     # fewer negatives in the denominator -> smaller loss
+
+
+# ---------------------------------------------------------------------------------------------------
+# a10 on the tensor path: the radix select runs in the tcgen05 sweep's epilogue (csrc/pcl_infonce_tc.cu TC_H1..H3, TC_NEGW)
+# on the fp32-accumulated logits of the bf16 operands.  Dyadic operands (multiples of 1/4, |x| <= 3/4) are exact in bf16 and
+# their 256-term dot products exact in fp32, so selection state, loss and gradient must equal the oracle's like on the
+# exact path; the key is in log2 units (x = s * log2(e) / T), so tau is compared through the ordering, not bitwise.
+# ---------------------------------------------------------------------------------------------------
+def _bf16_rows(x, rows_alloc):
+    return Fn.to_bf16_rows(x.float().to(DEV), rows_alloc)
+
+
+@pytest.mark.parametrize("A,N,k", [(70, 333, 9), (130, 1000, 1), (200, 600, 40), (300, 5000, 128)])
+def test_tc_topk_explicit_exact_data(A, N, k):
+    a, c, ya, yc = _dyadic(A, N, 256, 5, seed=A + N + k)
+    order = torch.argsort(yc, stable=True)                       # the tensor sweep wants class-grouped contrast rows
+    c, yc = c[order], yc[order]
+    T, bT = 0.125, 0.25
+    diag = torch.arange(A) % N
+    o = P.infonce_topk(a, ya, c, yc, T, bT, k, False, diag_cols=diag)
+    c16 = _bf16_rows(c, -(-N // 256) * 256)
+    loss, rowstats, st = Fn.infonce_tc_forward(a.float().to(DEV), ya.to(DEV), contrast_bf16=c16, contrast_cls=yc.to(DEV),
+                                               n_cols=N, diag_col=diag.to(DEV), temperature=T, base_temperature=bT, topk=k)
+    key, tw, G, E = Fn.topk_selection(st, A)
+    sel = (o["n_ties"] > 0).numpy()
+    assert np.array_equal(G.cpu().numpy()[sel], o["n_above"].numpy()[sel])
+    assert np.array_equal(E.cpu().numpy()[sel], o["n_ties"].numpy()[sel])
+    tau_nat = _key_to_float(key) / 1.4426950408889634            # log2 units -> natural-log logit
+    assert np.allclose(tau_nat[sel], o["tau"].numpy()[sel], rtol=2e-6, atol=1e-6)
+    assert rel_err(loss.item(), o["loss"].item()) < 2e-5
+    dA = Fn.infonce_tc_backward(st, rowstats).cpu().double()
+    assert (dA - o["dA"]).abs().max().item() <= 4e-3 * o["dA"].abs().max().item()      # bf16 gradient tile
+
+
+@pytest.mark.parametrize("k", [3, 50])
+def test_tc_topk_self_contrast_exact_data(k):
+    A = 300
+    a, _, ya, _ = _dyadic(A, 8, 256, 4, seed=k, zero_every=0)
+    order = torch.argsort(ya, stable=True)                       # class-grouped anchors (the engine's layout)
+    a, ya = a[order], ya[order]
+    o = P.infonce_topk(a, ya, a, ya, 0.125, 0.25, k, True)
+    loss, rowstats, st = Fn.infonce_tc_forward(a.float().to(DEV), ya.to(DEV), temperature=0.125, base_temperature=0.25, topk=k)
+    assert rel_err(loss.item(), o["loss"].item()) < 2e-5
+    dA = Fn.infonce_tc_backward(st, rowstats).cpu().double()
+    assert (dA - o["dA"]).abs().max().item() <= 4e-3 * o["dA"].abs().max().item()
+
+
+@pytest.mark.parametrize("k", [5, 37, 10 ** 6])
+def test_tc_topk_bank_mode_with_zero_tail(k):
+    """Bank mode on the tensor path: the analytic zero tail takes part in the selection (scan + weighted POS prologue)."""
+    from contrastiveseg_b200.bank import shadow_rows
+    K, M, D, A = 5, 12, 256, 90
+    g = torch.Generator().manual_seed(k)
+    segq = torch.randint(-3, 4, (K, M, D), generator=g).double() / 4
+    pixq = torch.randint(-3, 4, (K, M, D), generator=g).double() / 4
+    pixq[:, ::3] = 0
+    a = torch.randint(-3, 4, (A, D), generator=g).double() / 4
+    ya = torch.randint(0, K, (A,), generator=g)
+    ya = ya[torch.argsort(torch.where(ya == 0, K, ya), stable=True)]
+    contrast, yc = P.flatten_queue(torch.cat((segq, pixq), 1))
+    o = P.infonce_topk(a, ya, contrast, yc.long(), 0.125, 0.25, k if k < 10 ** 6 else None, False)
+    shadow = torch.zeros((shadow_rows(K, M), D), dtype=torch.bfloat16, device=DEV)
+    shadow[:(K - 1) * 2 * M] = contrast[:(K - 1) * 2 * M].to(torch.bfloat16).to(DEV)
+    loss, rowstats, st = Fn.infonce_tc_forward(a.float().to(DEV), ya.to(DEV), bank=(shadow, K, 2 * M),
+                                               diag_col=torch.arange(A).to(DEV), temperature=0.125, base_temperature=0.25,
+                                               norm_bound=1.0, topk=k)     # (stabiliser only: keeps exp2 in range)
+    assert rel_err(loss.item(), o["loss"].item()) < 2e-5
+    dA = Fn.infonce_tc_backward(st, rowstats).cpu().double()
+    assert (dA - o["dA"]).abs().max().item() <= 4e-3 * max(o["dA"].abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("name", ["nomem_d256", "mem_d256"])
+def test_tc_topk_through_the_loss_module(name):
+    """contrast.topk_negatives with contrast.precision = 'bf16' through PixelContrastLoss on the D = 256 goldens: loss
+    and dense gradient against the oracle's top-k on the bf16-rounded operands (same anchors)."""
+    g = load_golden(name)
+    T, bT, ms, mv, K, ign = g["params"].tolist()
+    k = 7
+    cfg = {"data": {"num_classes": int(K)},
+           "contrast": {"temperature": T, "base_temperature": bT, "max_samples": int(ms), "max_views": int(mv),
+                        "loss_weight": 0.1, "topk_negatives": k, "precision": "bf16"},
+           "loss": {"params": {"ce_ignore_index": -1}}, "network": {"stride": 8}}
+    crit = cs.PixelContrastLoss(cs.Configer(cfg))
+    crit.perm_fn = P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"]))
+    embed = torch.from_numpy(g["embed"]).to(DEV).requires_grad_(True)
+    queue = queue_o = None
+    if "segment_queue" in g:
+        queue = (torch.from_numpy(g["segment_queue"]).to(DEV), torch.from_numpy(g["pixel_queue"]).to(DEV))
+        queue_o = torch.cat((torch.from_numpy(g["segment_queue"]), torch.from_numpy(g["pixel_queue"])), 1)
+    loss = crit(embed, torch.from_numpy(g["target"]).to(DEV), torch.from_numpy(g["predict"]).to(DEV), queue)
+    loss.backward()
+    bf = lambda x: x.to(torch.bfloat16).double()
+    e64 = torch.from_numpy(g["embed"]).double()
+    _, det = P.pixel_contrast_loss(e64, torch.from_numpy(g["target"]), torch.from_numpy(g["predict"]),
+                                   temperature=T, base_temperature=bT, max_samples=int(ms), max_views=int(mv),
+                                   ignore_label=int(ign), queue=queue_o,
+                                   perm_fn=P.PermReplay(unpack_perms(g["perm_flat"], g["perm_lens"])), return_details=True)
+    anchors = bf(det["anchors"]).requires_grad_(True)
+    contrast = anchors if queue_o is None else bf(det["contrast"])
+    lo = P.infonce_dense_topk(anchors, det["ya"], contrast, det["yc"], T, bT, k)
+    lo.backward()
+    assert rel_err(loss.item(), lo.item()) < 1e-4
+    # gradient rows of the sampled pixels, in the oracle's (view-major) row order
+    B, D, h, w = g["embed"].shape
+    flat = embed.grad.permute(0, 2, 3, 1).reshape(B, h * w, D).cpu().double()
+    TC, V = det["idx"].shape
+    rows = torch.stack([flat[int(det["img"][t]), int(det["idx"][t, v])] for v in range(V) for t in range(TC)])
+    assert (rows - anchors.grad).abs().max().item() <= 6e-3 * anchors.grad.abs().max().item()

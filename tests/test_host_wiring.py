@@ -11,7 +11,8 @@ from contrastiveseg_b200 import _abi, functional as Fn
 
 HOST_ONLY = {"pcl_version", "pcl_strerror", "pcl_last_cuda_error", "pcl_abi_sizeof", "pcl_select_sizes",
              "pcl_sweep_sizes", "pcl_tc_sizes", "pcl_topk_scratch_u32", "pcl_seg_ce_scratch_floats",
-             "pcl_bank_packet_floats", "pcl_bank_scratch_floats", "pcl_step_fused_supported", "pcl_launch_count"}
+             "pcl_bank_packet_floats", "pcl_bank_scratch_floats", "pcl_step_fused_supported", "pcl_launch_count",
+             "pcl_tc_topk_scratch_u32"}
 
 
 class RecordingLib:
@@ -173,11 +174,21 @@ def test_topk_step_call_sequence(rec):
     assert sc[1] == ws.plan.data_ptr() and sc[3] == ws.dA.data_ptr() and sc[6] == 1 and sc[7] == embed.grad.data_ptr()
 
 
-def test_topk_rejects_tensor_precision_and_bad_k(rec):
+def test_topk_on_the_tensor_path_call_sequence_and_bad_k(rec):
+    """precision='bf16' + topk_negatives: selection, then the tensor-path top-k forward (radix select in the tcgen05 sweep's
+    epilogue) and its backward with the SAME scratch (selection state)."""
     embed, labels, seg = _inputs(D=256)
-    with pytest.raises(_abi.PclError):
-        cs.pixel_contrast_loss(embed, labels, seg=seg,
-                               options=cs.ContrastOptions(max_samples=64, max_views=4, topk_negatives=3, precision="bf16"))
+    loss = cs.pixel_contrast_loss(embed, labels, seg=seg,
+                                  options=cs.ContrastOptions(max_samples=64, max_views=4, topk_negatives=3, precision="bf16"))
+    ws = Fn.last_workspace(embed.device)
+    assert [c[0] for c in rec.calls] == ["pcl_step_stats", "pcl_select_gather", "pcl_infonce_tc_topk_fwd"]
+    fw = rec.calls[2][1]
+    assert fw[1] == 3 and fw[2] == ws.topk_scratch.data_ptr() and fw[3] == ws.row_m2.data_ptr()
+    assert fw[0].anchors_bf16 == ws.anchors_bf16.data_ptr() and fw[0].mode == 0 and fw[0].a_rows == 64
+    loss.backward()
+    assert [c[0] for c in rec.calls][3:] == ["pcl_infonce_tc_topk_bwd", "pcl_scatter_grad"]
+    assert rec.calls[3][1][1] == 3 and rec.calls[3][1][2] == ws.topk_scratch.data_ptr()
+    rec.calls.clear()
     with pytest.raises(_abi.PclError):
         cs.pixel_contrast_loss(embed, labels, seg=seg,
                                options=cs.ContrastOptions(max_samples=64, max_views=4, topk_negatives=-2))
