@@ -601,7 +601,9 @@ class Workload:
         if with_e2e:
             e_steps = max(3, min(a.steps, 50))
             ev, h2d = self.e2e(fn, e_steps)
-            out["e2e"] = {"value": ev, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e_steps}
+            out["e2e"] = {"value": ev, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e_steps,
+                          "h2d_gbs_per_gpu": h2d * ev / (self.world * self.cfg["B"]) / 1e9,
+                          "note": "PCIe-bound: pinned H2D copies reach 55 GB/s on this box (tools/h2d_probe.py), the step itself is 2 % of e2e"}
         if with_eager and self.steps:
             ems, ehost, _ = self.time_loop(self.eager, a.steps, a.warmup)
             out["eager"] = {"ms_per_step": ems, "value": self.world * self.cfg["B"] / (ems / 1e3), "host_ms_per_step": ehost}
