@@ -154,50 +154,92 @@ k_bank_rows(BankDims d, const float* __restrict__ keys, const int32_t* __restric
   }
 }
 
-// one CTA per class; slots applied in (rank, image) order
+// one CTA per class.  The reference applies the (rank, image) slots of a class one after another (ring-buffer quirks Q2,
+// Q4: the pixel pointer advances by ONE per slot, so successive windows overlap and a later slot overwrites rows of an
+// earlier one).  Nothing reads the bank during the apply, so the result only depends on WHO WRITES LAST: thread 0 replays
+// the pointer arithmetic of all slots (integers only), then every row is copied once, in parallel, by its last writer.
+// (The sequential version took 9.6 us per packet: 77 us of the 8-GPU bank step, profiles/r2_20_bench_n8.json.)
+constexpr int APPLY_MAX_SLOTS = 1024;            // world * B slots of one class handled in shared memory
+
 __global__ void __launch_bounds__(256)
 k_bank_apply(BankDims d, const float* __restrict__ packets, int world, int64_t packet_f32, float* __restrict__ segq,
              int64_t* __restrict__ seg_ptr, float* __restrict__ pixq, int64_t* __restrict__ pix_ptr,
              __nv_bfloat16* __restrict__ shadow, unsigned long long* enqueue_counter) {
+  __shared__ int s_src[APPLY_MAX_SLOTS];         // valid slots in application order: r * B + b
+  __shared__ int s_seg[APPLY_MAX_SLOTS];         // segment row written by the slot
+  __shared__ int s_dst[APPLY_MAX_SLOTS];         // first pixel row written by the slot
+  __shared__ short s_kp[APPLY_MAX_SLOTS];        // number of pixel rows of the slot
+  __shared__ int s_n;
   const int c = blockIdx.x;
   // captured sequences: the packet of this step was seeded from *enqueue_counter (pcl_bank_packet_dev); the apply is the
   // last kernel of the step's enqueue, so it advances the counter
   if (c == 0 && threadIdx.x == 0 && enqueue_counter != nullptr) *enqueue_counter += 1ull;
   if (c == 0) return;
   const int K = d.g.K, D = d.g.D, M = d.g.M, B = d.g.B;
-  int sp = (int)seg_ptr[c], pp = (int)pix_ptr[c];
-  sp = ((sp % M) + M) % M; pp = ((pp % M) + M) % M;
-  bool touched = false;
-  for (int r = 0; r < world; ++r) {
-    for (int b = 0; b < B; ++b) {
-      const float* in = packets + (int64_t)r * packet_f32 + (int64_t)(b * K + c) * d.slot_f32;
-      const int n = (int)in[0];
-      if (n <= 0) continue;
-      const int kp = (int)in[1];
-      touched = true;
-      // segment row -> segq[c][sp]          (trainer_contrastive.py:120-123)
-      float* srow = segq + ((int64_t)c * M + sp) * D;
-      for (int dd = threadIdx.x; dd < D; dd += blockDim.x) {
-        float v = in[2 + dd];
-        srow[dd] = v;
-        if (shadow) shadow[((int64_t)(c - 1) * 2 * M + sp) * D + dd] = __float2bfloat16(v);
+  if (threadIdx.x == 0) {
+    int sp = (int)seg_ptr[c], pp = (int)pix_ptr[c];
+    sp = ((sp % M) + M) % M; pp = ((pp % M) + M) % M;
+    int n = 0;
+    for (int r = 0; r < world; ++r) {
+      for (int b = 0; b < B; ++b) {
+        const float* in = packets + (int64_t)r * packet_f32 + (int64_t)(b * K + c) * d.slot_f32;
+        const int cnt = (int)in[0];
+        if (cnt <= 0) continue;
+        const int kp = (int)in[1];
+        if (n < APPLY_MAX_SLOTS) {
+          s_src[n] = r * B + b;
+          s_seg[n] = sp;                                     // trainer_contrastive.py:120-123
+          // pixel rows (trainer_contrastive.py:133-138, Q4)
+          if (pp + kp >= M) { s_dst[n] = M - kp; pp = 0; }
+          else              { s_dst[n] = pp;     pp = (pp + 1) % M; }
+          s_kp[n] = (short)kp;
+          sp = (sp + 1) % M;
+          ++n;
+        }
       }
-      sp = (sp + 1) % M;
-      // pixel rows                           (trainer_contrastive.py:133-138, Q4)
-      int dst0, pnew;
-      if (pp + kp >= M) { dst0 = M - kp; pnew = 0; }
-      else              { dst0 = pp;     pnew = (pp + 1) % M; }
-      for (int i = threadIdx.x; i < kp * D; i += blockDim.x) {
-        int row = i / D, dd = i - row * D;
-        float v = in[2 + D + i];
-        pixq[((int64_t)c * M + dst0 + row) * D + dd] = v;
-        if (shadow) shadow[((int64_t)(c - 1) * 2 * M + M + dst0 + row) * D + dd] = __float2bfloat16(v);
+    }
+    s_n = n;
+    if (n > 0) { seg_ptr[c] = sp; pix_ptr[c] = pp; }
+  }
+  __syncthreads();
+  const int n = s_n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  // work items: (slot i, row j) with j = -1 the segment row, j in [0, kp) a pixel row; one warp per item
+  int item = warp;
+  for (int i = 0; i < n; ++i) {
+    const int kp = s_kp[i];
+    const int src = s_src[i];
+    const float* in = packets + (int64_t)(src / B) * packet_f32 + (int64_t)((src % B) * K + c) * d.slot_f32;
+    for (int j = -1; j < kp; ++j, --item) {
+      if (item != 0) { if (item < 0) item += nwarp; continue; }
+      item = nwarp;                                           // next item of this warp
+      // is this row overwritten by a later slot?
+      bool dead = false;
+      if (j < 0) {
+        for (int t = i + 1; t < n && !dead; ++t) dead = s_seg[t] == s_seg[i];
+        if (!dead) {
+          float* srow = segq + ((int64_t)c * M + s_seg[i]) * D;
+          for (int dd = lane; dd < D; dd += 32) {
+            const float v = in[2 + dd];
+            srow[dd] = v;
+            if (shadow) shadow[((int64_t)(c - 1) * 2 * M + s_seg[i]) * D + dd] = __float2bfloat16(v);
+          }
+        }
+      } else {
+        const int q = s_dst[i] + j;
+        for (int t = i + 1; t < n && !dead; ++t) dead = q >= s_dst[t] && q < s_dst[t] + s_kp[t];
+        if (!dead) {
+          float* prow = pixq + ((int64_t)c * M + q) * D;
+          const float* irow = in + 2 + D + (int64_t)j * D;
+          for (int dd = lane; dd < D; dd += 32) {
+            const float v = irow[dd];
+            prow[dd] = v;
+            if (shadow) shadow[((int64_t)(c - 1) * 2 * M + M + q) * D + dd] = __float2bfloat16(v);
+          }
+        }
       }
-      pp = pnew;
-      __syncthreads();                         // later slots may overwrite these rows: keep the order
     }
   }
-  if (threadIdx.x == 0 && touched) { seg_ptr[c] = sp; pix_ptr[c] = pp; }
 }
 
 __global__ void k_shadow_rebuild(const float* __restrict__ segq, const float* __restrict__ pixq, int K, int M, int D,

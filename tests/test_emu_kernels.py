@@ -158,6 +158,12 @@ def test_graphed_bank_step_on_emulation(emu, monkeypatch, precision):
     PD.test_graphed_bank_step_with_enqueue_equals_the_trainer_order(precision)
 
 
+@pytest.mark.parametrize("world,M,B", [(5, 4, 2), (8, 7, 3), (3, 40, 2)])
+def test_bank_apply_of_many_ranks_on_emulation(emu, monkeypatch, world, M, B):
+    """Last-writer-wins apply of world * B slots per class == the reference applied image by image."""
+    PD.test_bank_apply_of_many_ranks_equals_the_sequential_reference(monkeypatch, world, M, B)
+
+
 def test_bank_write_waits_for_backward_on_emulation(emu):
     """Gradient bit-identical with / without an enqueue between loss and backward; final bank equals an immediate enqueue."""
     PD.test_enqueue_between_loss_and_backward_does_not_change_the_gradient("fp32")

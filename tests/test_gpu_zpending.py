@@ -296,3 +296,49 @@ def test_graphed_bank_step_with_enqueue_equals_the_trainer_order(precision):
         if shadow:
             assert torch.equal(bank_g.shadow, bank_e.shadow)
     assert not torch.equal(bank_g.pixel_queue_ptr, torch.zeros_like(bank_g.pixel_queue_ptr))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,M,B", [(5, 4, 2), (8, 7, 3), (3, 40, 2)])
+def test_bank_apply_of_many_ranks_equals_the_sequential_reference(monkeypatch, world, M, B):
+    """pcl_bank_apply writes every row once, by its LAST writer (thread 0 replays the pointer arithmetic of all slots,
+    csrc/pcl_bank.cu k_bank_apply).  world * B slots per class with a tiny ring: the segment ring wraps inside one apply
+    and the pixel windows overlap (Q4) — must equal the reference applied image by image, rank-major
+    (trainer_contrastive.py:96-139 after its all-gather)."""
+    from contrastiveseg_b200 import bank as bank_mod
+    from contrastiveseg_b200.synth import make_bank, make_contrast_batch
+    from oracle import ref_port as P
+    dev = torch.device(DEV)
+    K, D, Fq, stride = 6, 32, 3, 2
+    names = ("segment_queue", "segment_queue_ptr", "pixel_queue", "pixel_queue_ptr")
+    b0 = make_bank(K, M, D, 5)
+    ref = [b0[k].clone() for k in names]
+    mine = [b0[k].clone().to(dev) for k in names]
+    for step in range(3):
+        datas = [make_contrast_batch(B=B, D=D, h=12, w=14, num_classes=K, img_stride=2, block=4, seed=31 * step + r)
+                 for r in range(world)]
+        perms, packets = [], []
+        for r in range(world):
+            rec = P.PermRecorder(torch.Generator().manual_seed(9 * step + r))
+            P.dequeue_and_enqueue(datas[r]["embed"], datas[r]["target"], *ref, network_stride=stride, memory_size=M,
+                                  pixel_update_freq=Fq, perm_fn=rec)
+            perms.append(rec.draws)
+        # every rank's packet, computed on a throw-away bank ...
+        for r in range(world):
+            monkeypatch.setattr(bank_mod, "gather_packets", lambda pk, group=None, out=None: (packets.append(pk.clone()),
+                                                                                                pk.view(1, -1))[1])
+            monkeypatch.setattr(bank_mod, "world_size", lambda group=None: 1)
+            scratch = [b0[k].clone().to(dev) for k in names]
+            cs.dequeue_and_enqueue(datas[r]["embed"].to(dev), datas[r]["target"].to(dev), *scratch,
+                                   network_stride=stride, memory_size=M, pixel_update_freq=Fq,
+                                   perm_fn=P.PermReplay(perms[r]))
+        # ... then one apply of the rank-major stack on the bank under test
+        stack = torch.stack([p.view(-1) for p in packets])
+        monkeypatch.setattr(bank_mod, "gather_packets", lambda pk, group=None, out=None: stack)
+        monkeypatch.setattr(bank_mod, "world_size", lambda group=None: world)
+        cs.dequeue_and_enqueue(datas[0]["embed"].to(dev), datas[0]["target"].to(dev), *mine, network_stride=stride,
+                               memory_size=M, pixel_update_freq=Fq, perm_fn=P.PermReplay(perms[0]))
+    torch.cuda.synchronize()
+    assert torch.equal(mine[1].cpu(), ref[1]) and torch.equal(mine[3].cpu(), ref[3])
+    assert (mine[0].cpu() - ref[0]).abs().max().item() <= 2e-6
+    assert (mine[2].cpu() - ref[2]).abs().max().item() <= 2e-7
