@@ -380,9 +380,43 @@ def train_iter_bench(cfg, inp, dev, precision, iters=10):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / iters
     ok = bool(torch.isfinite(loss).item())
+    # The same iteration with the REFERENCE's loss step in place of the engine's ("the reference ATen path
+    # on the B200 itself"): the CPU port's torch ops follow their input's device, so on CUDA tensors they are the
+    # reference's own op sequence (per-(image, class) nonzero/randperm/index loop, dense A x N temporaries, one
+    # SelectBackward per pair).  A baseline leg like cpu_baseline: measured beside the engine, never part of it.
+    ref_ms, ref_err = None, None
+    try:
+        from oracle import ref_port as P
+        kw = dict(with_embed=True, loss_weight=0.1, temperature=cfg["T"], base_temperature=cfg["bT"],
+                  max_samples=cfg["max_samples"], max_views=cfg["max_views"], ignore_label=-1)
+
+        def it_ref():
+            out = net(x)
+            l = P.contrast_ce_loss(out, inp["target"], **kw)
+            opt.zero_grad(set_to_none=True)
+            l.backward()
+            opt.step()
+            return l
+        for _ in range(2):
+            it_ref()
+        n_ref = max(3, iters // 2)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(n_ref):
+            it_ref()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ref_ms = e0.elapsed_time(e1) / n_ref
+    except Exception as exc:                              # noqa: BLE001
+        ref_err = f"{type(exc).__name__}: {exc}"[:200]
     del net, opt, x
     torch.cuda.empty_cache()
+    ref_block = ({"ms_per_iter": ref_ms, "iters_per_s": 1e3 / ref_ms, "speedup_of_the_iteration": ref_ms / ms,
+                  "what": "same producer, optimiser and batch; loss step = the reference's op sequence (oracle port's "
+                          "torch ops on CUDA tensors: ATen kernels, host loop with device syncs), fp32"}
+                 if ref_ms else {"error": ref_err})
     return {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "global_batch": cfg["B"], "finite_loss": ok,
+            "with_reference_loss_step": ref_block,
             "producer": "stand-in conv stem -> 720ch stride-4 features -> 19-class head + 720-720-256 projection head "
                         "(engine L2-normalise); fp32, SGD momentum 0.9; not HRNet-W48",
             "loss": "ContrastCELoss (fused seg CE + pixel contrast, with_embed=True)"}

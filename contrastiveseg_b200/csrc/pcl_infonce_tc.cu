@@ -524,6 +524,256 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 }
 
 // =====================================================================================================
+// POS sweep of the bank mode for SMALL anchor sets, transposed: the bank's column tile is the M operand (TMEM lane =
+// bank column), a block of <= 64 anchors of ONE class the N operand.  The positives of an anchor are the R columns of
+// its class, so the work list is (class, anchor block, column split) and every element the epilogue touches is a
+// positive: all 128 lanes of all 4 schedulers work, whatever the class mix of the anchors.  (The row-tile POS sweep
+// above computes [128 anchors x 256 columns] tiles in which only the lanes of the tile's class do anything: with ~53
+// anchors per class — configs[2] — one or two of the eight epilogue warps carried a CTA, 53 us for 10 us of MUFU work,
+// profiles/r2_25_bank_source_top.txt.)  Per-anchor sums are reduced across the lanes once per work item.
+// Anchors must be in class-rank order (bank mode's contract, like the row-tile sweep's [rk_f, rk_l] range).
+// =====================================================================================================
+constexpr int PT_NB = 64;                          // anchors per block (N of the MMA)
+constexpr int PT_BM = 128;                         // bank columns per tile (M of the MMA)
+constexpr int PT_A_KB = PT_NB * BK * 2;            // 8 KB: [64 anchors x 64 K] box
+constexpr int PT_C_KB = PT_BM * BK * 2;            // 16 KB: [128 columns x 64 K] box
+constexpr int PT_STAGES = 8;                       // K-block stages of the bank stream (2 tiles in flight)
+constexpr int PT_MAX_ROWS = 4096;                  // class-boundary scan of the prologue
+
+struct SmemPosT {
+  uint8_t a[NKB * PT_A_KB];                        // 32 KB
+  uint8_t c[PT_STAGES * PT_C_KB];                  // 128 KB
+  uint64_t full[PT_STAGES], empty[PT_STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  int rk_first[PCL_MAX_CLASSES], rk_cnt[PCL_MAX_CLASSES], blk_pref[PCL_MAX_CLASSES + 1];
+  int total_blocks, S;
+  float4 par[PT_NB];                               // per anchor of the block: m2, Neg, diag column (int bits), -
+  float comb[2][4][32][2];                         // [anchor half][lane quarter][anchor][possum2, s]
+};
+
+struct PosItem { int r0, nv, t0, t1, c_lo, c_hi, split; };
+
+__device__ __forceinline__ PosItem pos_item(const SmemPosT& sm, const TcArgs& a, int item) {
+  const int S = sm.S;
+  const int blk = item / S, split = item - blk * S;
+  int rk = 0;
+  while (rk + 1 < a.K && sm.blk_pref[rk + 1] <= blk) ++rk;
+  const int b = blk - sm.blk_pref[rk];
+  PosItem it;
+  it.r0 = sm.rk_first[rk] + b * PT_NB;
+  it.nv = min(PT_NB, sm.rk_cnt[rk] - b * PT_NB);
+  it.split = split;
+  if (rk > a.K - 2) {                               // class-0 anchors: their positives are the analytic zero tail (k_finalize)
+    it.c_lo = it.c_hi = 0; it.t0 = it.t1 = 0;
+  } else {
+    it.c_lo = rk * a.R; it.c_hi = it.c_lo + a.R;
+    const int t_lo = it.c_lo / PT_BM, t_hi = (it.c_hi + PT_BM - 1) / PT_BM;
+    const int per = (t_hi - t_lo + S - 1) / S;
+    it.t0 = min(t_hi, t_lo + split * per);
+    it.t1 = min(t_hi, it.t0 + per);
+  }
+  return it;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmC128, TcArgs a,
+           float* __restrict__ partials, float* __restrict__ rowstats_out) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemPosT& sm = *reinterpret_cast<SmemPosT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = a.plan ? min(a.plan[PCL_PLAN_A], a.a_rows) : a.a_rows;
+  if (A <= 0) return;
+
+  // ---- class runs of the anchors (class-rank order) -> blocks of <= 64 anchors, S column splits per block ----
+  for (int i = threadIdx.x; i < PCL_MAX_CLASSES; i += blockDim.x) { sm.rk_first[i] = 0; sm.rk_cnt[i] = 0; }
+  __syncthreads();
+  for (int r = threadIdx.x; r < A; r += blockDim.x) {
+    const int rk = min(max(class_rank(a.acls[r], a.K), 0), PCL_MAX_CLASSES - 1);
+    if (r == 0 || class_rank(a.acls[r - 1], a.K) != class_rank(a.acls[r], a.K)) sm.rk_first[rk] = r;
+    atomicAdd(&sm.rk_cnt[rk], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int rk = 0; rk < a.K; ++rk) { sm.blk_pref[rk] = acc; acc += (sm.rk_cnt[rk] + PT_NB - 1) / PT_NB; }
+    sm.blk_pref[a.K] = acc;
+    sm.total_blocks = acc;
+    sm.S = max(1, min(a.splits, (int)gridDim.x / max(acc, 1)));
+    ptx::prefetch_tmap(&tmA64);
+    ptx::prefetch_tmap(&tmC128);
+    for (int s = 0; s < PT_STAGES; ++s) { ptx::mbar_init(&sm.full[s], 1); ptx::mbar_init(&sm.empty[s], 1); }
+    ptx::mbar_init(&sm.a_full, 1);
+    ptx::mbar_init(&sm.a_empty, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.tmem_full[i], 1); ptx::mbar_init(&sm.tmem_empty[i], EPI_THREADS / 32); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(&sm.tmem_base);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_base;
+  const int n_items = sm.total_blocks * sm.S;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int seq = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const PosItem it = pos_item(sm, a, item);
+        if (it.t1 <= it.t0) continue;
+        if (seq > 0) ptx::mbar_wait(&sm.a_empty, (seq - 1) & 1);             // previous block's MMAs retired
+        ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * PT_A_KB);
+        for (int kb = 0; kb < NKB; ++kb) ptx::tma_load_2d(sm.a + kb * PT_A_KB, &tmA64, &sm.a_full, kb * BK, it.r0);
+        for (int t = it.t0; t < it.t1; ++t) {
+          for (int kb = 0; kb < NKB; ++kb) {
+            ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&sm.full[stage], PT_C_KB);
+            ptx::tma_load_2d(sm.c + stage * PT_C_KB, &tmC128, &sm.full[stage], kb * BK, t * PT_BM);
+            if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        ++seq;
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(PT_BM, PT_NB, 0, 0);
+      const uint32_t a_base = ptx::smem_u32(sm.a), c_base = ptx::smem_u32(sm.c);
+      uint32_t stage = 0, phase = 0;
+      int seq = 0, n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const PosItem it = pos_item(sm, a, item);
+        if (it.t1 <= it.t0) continue;
+        ptx::mbar_wait(&sm.a_full, seq & 1);
+        ptx::tc_fence_after();
+        for (int t = it.t0; t < it.t1; ++t, ++n) {
+          const uint32_t acc = n & 1, acc_phase = (n >> 1) & 1;
+          ptx::mbar_wait(&sm.tmem_empty[acc], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * PT_NB;
+          for (int kb = 0; kb < NKB; ++kb) {
+            ptx::mbar_wait(&sm.full[stage], phase);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t dc = ptx::make_desc_kmajor_sw128(c_base + stage * PT_C_KB + k * 32);    // M side: bank columns
+              const uint64_t da = ptx::make_desc_kmajor_sw128(a_base + kb * PT_A_KB + k * 32);       // N side: anchors
+              ptx::mma_f16_ss(d_tmem, dc, da, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::mma_commit(&sm.empty[stage]);
+            if (++stage == PT_STAGES) { stage = 0; phase ^= 1; }
+          }
+          ptx::mma_commit(&sm.tmem_full[acc]);
+        }
+        ptx::mma_commit(&sm.a_empty);
+        ++seq;
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+    const int ahalf = (warp - 2) >> 2;                // which 32 anchors of the block
+    const int et = threadIdx.x - 64;                  // 0..255 within the epilogue group
+    const int64_t stride = (int64_t)a.slots * a.a_pad;
+    int n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const PosItem it = pos_item(sm, a, item);
+      // ---- per-anchor constants of the block (the row prologue of the row-tile sweep, one thread per anchor) ----
+      if (et < PT_NB) {
+        float4 pr = make_float4(0.f, 1.f, __int_as_float(-1), 0.f);
+        if (et < it.nv && it.r0 + et < A) {
+          const int row = it.r0 + et;
+          const float m2 = a.row_m2[row];
+          const long long Pn = (long long)((A + BM - 1) / BM) * (long long)((a.n_cols + BN - 1) / BN);
+          const long long Un = max(1LL, Pn / max(1, a.neg_grid));
+          const int used = (int)min((long long)a.slots, (long long)((a.n_cols + BN - 1) / BN) / Un + 2);
+          float ng = 0.f;
+          for (int pslot = 0; pslot < used; ++pslot) ng += partials[stride + (int64_t)pslot * a.a_pad + row];
+          const int rcls = a.acls[row];
+          if (a.tail_count > 0 && rcls != 0) {
+            const float wt = a.tk_sel ? topk_weight(KEY_ZERO, a.tk_sel[row], __uint_as_float(a.tk_sel[a.a_rows + row])) : 1.f;
+            ng += wt * (float)a.tail_count * ptx::ex2_approx(-m2);
+          }
+          if (it.split == 0 && rowstats_out != nullptr) {
+            rowstats_out[row] = m2 * LN2;
+            rowstats_out[a.a_rows + row] = ng;
+          }
+          pr = make_float4(m2, ng, __int_as_float(a.diag ? a.diag[row] : -1), 0.f);
+        }
+        sm.par[et] = pr;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      float acc0[32], acc1[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+      const int nvh = min(32, max(0, it.nv - ahalf * 32));                  // valid anchors of this warp's half
+      for (int t = it.t0; t < it.t1; ++t, ++n) {
+        const uint32_t accb = n & 1, acc_phase = (n >> 1) & 1;
+        const int col = t * PT_BM + quarter * 32 + lane;
+        const bool colkeep = col >= it.c_lo && col < it.c_hi;
+        ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
+        ptx::tc_fence_after();
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * PT_NB + ahalf * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nvh) {                                                      // warp-uniform
+            const float4 pr = sm.par[ahalf * 32 + i];                         // broadcast read
+            const float x = fmaf(__uint_as_float(v[i]), a.k1, -pr.x);
+            const float tt = ptx::ex2_approx(x) + pr.y;
+            const bool keep = colkeep && col != __float_as_int(pr.z);
+            acc0[i] += keep ? x - ptx::lg2_approx(tt) : 0.f;
+            acc1[i] += keep ? ptx::rcp_approx(tt) : 0.f;
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sm.tmem_empty[accb]);
+      }
+      // ---- sum over the 128 lanes (columns): butterfly inside the warp, then the 4 quarters through shared memory ----
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          acc0[i] += __shfl_xor_sync(0xffffffffu, acc0[i], o);
+          acc1[i] += __shfl_xor_sync(0xffffffffu, acc1[i], o);
+        }
+        if (lane == i) { sm.comb[ahalf][quarter][i][0] = acc0[i]; sm.comb[ahalf][quarter][i][1] = acc1[i]; }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (et < it.nv && it.r0 + et < A) {
+        const int h = et >> 5, i = et & 31, row = it.r0 + et;
+        const float ps = (sm.comb[h][0][i][0] + sm.comb[h][1][i][0]) + (sm.comb[h][2][i][0] + sm.comb[h][3][i][0]);
+        const float ss = (sm.comb[h][0][i][1] + sm.comb[h][1][i][1]) + (sm.comb[h][2][i][1] + sm.comb[h][3][i][1]);
+        // positives counted analytically: the class columns inside this split's tile range, minus the masked (i, diag_i)
+        const int lo = max(it.c_lo, it.t0 * PT_BM), hi = min(it.c_hi, it.t1 * PT_BM);
+        const int dg = __float_as_int(sm.par[et].z);
+        const int cnt = max(0, hi - lo) - ((dg >= lo && dg < hi) ? 1 : 0);
+        const int64_t o = (int64_t)it.split * a.a_pad + row;
+        partials[2 * stride + o] = ps * LN2;
+        partials[3 * stride + o] = ss;
+        partials[4 * stride + o] = (float)cnt;
+        if (it.split == 0) {                                                  // slots this launch does not use: k_finalize sums a.splits of them
+          for (int sl = sm.S; sl < a.splits; ++sl) {
+            const int64_t oz = (int64_t)sl * a.a_pad + row;
+            partials[2 * stride + oz] = 0.f; partials[3 * stride + oz] = 0.f; partials[4 * stride + oz] = 0.f;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");       // par / comb reusable by the next item
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// =====================================================================================================
 // Backward: dA = G . C / T with G formed on the fly (closed form) — FlashAttention-backward
 // shaped: MMA1 S = A.C^T (128 x 128 tile, K = 256) -> epilogue turns S into the bf16 gradient tile G in shared
 // memory (128B-swizzled K-major) -> MMA2 dA(128 x 256, TMEM-resident across the whole column sweep) += G . C,
@@ -1215,7 +1465,19 @@ int pcl::tc_fwd_topk_ex(const pcl_tc_desc* d, int k, uint32_t* scratch, float* r
   a.persistent = 0;
   if ((variant & 8) || d->neg_only) return PCL_OK;     // similarity + negative-sum sweep only (roofline measurement)
   // (the NEG partials are combined by the POS sweep's row prologue: no separate pass)
-  tc::k_tc_fwd<tc::TC_POS, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
+  if (d->mode == 1 && d->a_rows <= tc::PT_MAX_ROWS && !(variant & 16)) {
+    // small anchor sets against the bank: the transposed POS sweep (work list by class, every epilogue lane busy)
+    CUtensorMap tmA64, tmC128;
+    st = make_tmap(&tmA64, d->anchors_bf16, (uint64_t)a.a_pad, tc::PT_NB);
+    if (st != PCL_OK) return st;
+    st = make_tmap(&tmC128, d->contrast_bf16, (uint64_t)(d->contrast_rows_alloc > 0 ? d->contrast_rows_alloc : a.n_cols), tc::PT_BM);
+    if (st != PCL_OK) return st;
+    const size_t smem_pt = sizeof(tc::SmemPosT) + 1024;
+    PCL_SMEM_OPT_IN(tc::k_tc_pos_t, smem_pt);
+    tc::k_tc_pos_t<<<num_sms(), tc::NUM_THREADS, smem_pt, s>>>(tmA64, tmC128, a, partials, rowstats);
+  } else {
+    tc::k_tc_fwd<tc::TC_POS, false><<<grid, tc::NUM_THREADS, smem, s>>>(tmA, tmB, a, partials, rowstats);
+  }
   PCL_LAUNCH_CHECK();
   k_finalize<<<1, 1024, 0, s>>>(p.sw, partials, rowstats, loss, step_counter);
   PCL_LAUNCH_CHECK();

@@ -124,8 +124,8 @@ def flatten_queue(queue: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(K,R,D) -> rows (K*R,D), labels (K*R,).  Class 0 is skipped, so classes 1..K-1 fill the
     first (K-1)*R rows and the last R rows stay zero with label 0."""
     K, R, D = queue.shape
-    rows = torch.zeros((K * R, D), dtype=queue.dtype)
-    labels = torch.zeros((K * R,), dtype=queue.dtype)
+    rows = torch.zeros((K * R, D), dtype=queue.dtype, device=queue.device)
+    labels = torch.zeros((K * R,), dtype=queue.dtype, device=queue.device)
     at = 0
     for c in range(1, K):
         rows[at:at + R] = queue[c]
@@ -291,12 +291,12 @@ def pixel_contrast_loss(feats: torch.Tensor, labels: torch.Tensor, predict: torc
     idx, cls, img, n_view = plan
     TC = idx.shape[0]
     if per_pair_gather:
-        X_ = torch.zeros((TC, n_view, D), dtype=feats.dtype)
+        X_ = torch.zeros((TC, n_view, D), dtype=feats.dtype, device=feats.device)   # loss_contrast.py:51 (.cuda())
         for t in range(TC):
             X_[t] = X[int(img[t]), idx[t], :]
     else:
-        X_ = X[img.view(-1, 1), idx]
-    y_ = cls.to(feats.dtype)
+        X_ = X[img.view(-1, 1).to(idx.device), idx]
+    y_ = cls.to(device=feats.device, dtype=feats.dtype)                              # loss_contrast.py:52 (.cuda())
 
     # view-major reordering: row r = v*TC + t (loss_contrast.py:98)
     anchors = torch.cat(torch.unbind(X_, dim=1), dim=0)
