@@ -507,14 +507,29 @@ k_fill_zero(uint4* __restrict__ p, uint64_t n16, unsigned int* dbg) {
   tl_end(dbg, PCL_TL_FILL);
 }
 
+// The same fill as a few CTAs that OWN their SM (1024 threads + a dynamic shared-memory request no other kernel of the
+// step fits next to): a CTA of another kernel that shares an SM with fill warps queues its loads, shuffles and shared-
+// memory accesses behind the fill's stores and becomes the straggler of its kernel (12 fill CTAs of 256 threads — 10 % of
+// the HBM write rate — took the 256-CTA scan from 20 to 45 us, profiles/r2_27_fill_throttle.log).
+__global__ void __launch_bounds__(1024, 1)
+k_fill_zero_excl(uint4* __restrict__ p, uint64_t n16, unsigned int* dbg) {
+  extern __shared__ uint8_t fill_smem_unused[];
+  tl_begin(dbg, PCL_TL_FILL);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) { p[i] = z; p[i + stride] = z; p[i + 2 * stride] = z; p[i + 3 * stride] = z; }
+  for (; i < n16; i += stride) p[i] = z;
+  tl_end(dbg, PCL_TL_FILL);
+}
+
 }  // namespace pcl
 
 using namespace pcl;
 
 extern "C" int pcl_fill_zero(void* ptr, uint64_t bytes, void* stream) { return pcl::fill_zero(ptr, bytes, stream, nullptr, 0); }
 
-// reserve_sms: SMs to leave free of fill CTAs (the fused InfoNCE kernel's CTAs run there: next to a fill CTA their
-// shuffles and shared-memory accesses queue behind the fill's stores in the SM's memory pipeline — NEG phase 2 -> 20 us)
+// reserve_sms: SMs to leave free of fill CTAs for a kernel that runs next to the fill (the fused InfoNCE kernel)
 int pcl::fill_zero(void* ptr, uint64_t bytes, void* stream, unsigned int* dbg, int reserve_sms) {
   PCL_REQUIRE(ptr && (bytes & 15) == 0 && ((uintptr_t)ptr & 15) == 0);
   if (bytes == 0) return PCL_OK;
@@ -528,7 +543,21 @@ int pcl::fill_zero(void* ptr, uint64_t bytes, void* stream, unsigned int* dbg, i
   if (const char* e = getenv("PCL_FILL_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 8) per_sm = v; }
   int sms = num_sms() - reserve_sms;
   if (sms < num_sms() / 2) sms = num_sms() / 2;
-  const uint64_t cap = (uint64_t)sms * per_sm;
+  // reserve_sms > 0: the caller runs a kernel of `reserve_sms` big CTAs next to the fill -> fill CTAs that own their SMs
+  // (k_fill_zero_excl), on all SMs but the reserved ones.  PCL_FILL_EXCL = n overrides the CTA count (tuning runs).
+  int excl = (reserve_sms > 0 && num_sms() - reserve_sms >= num_sms() / 2) ? num_sms() - reserve_sms : 0;
+  if (const char* e = getenv("PCL_FILL_EXCL")) excl = atoi(e);
+  if (excl >= 1) {
+    // ALL of the SM's shared memory (227 KB + the 1 KB the system reserves per CTA): no other CTA fits next to it
+    const size_t smem = 232448;
+    PCL_SMEM_OPT_IN(k_fill_zero_excl, smem);
+    k_fill_zero_excl<<<(unsigned)excl, 1024, smem, (cudaStream_t)stream>>>((uint4*)ptr, n16, dbg);
+    PCL_LAUNCH_CHECK();
+    return PCL_OK;
+  }
+  uint64_t cap = (uint64_t)sms * per_sm;
+  // PCL_FILL_GRID (tuning runs): absolute CTA count — a fill throttled to a fraction of the HBM write rate
+  if (const char* e = getenv("PCL_FILL_GRID")) { int v = atoi(e); if (v >= 1) cap = (uint64_t)v; }
   if (blocks > cap) blocks = cap;
   k_fill_zero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint4*)ptr, n16, dbg);
   PCL_LAUNCH_CHECK();

@@ -28,6 +28,7 @@ gradient and final bank equal the reference's (same property as the eager deferr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -235,12 +236,15 @@ class GraphedContrastStep:
         """First half: (zero-fill branch ||) stats -> ranks -> forward -> this rank's enqueue packet."""
         lib, d = self.lib, self.ws.desc
         if self.fused:
+            early = bool(os.environ.get("PCL_FILL_FORK_EARLY")) and not self.sparse_reset      # tuning runs
+            if early:
+                self._fork_zero_fill()
             _abi.check(lib.pcl_step_stats(C.byref(d), stream), "pcl_step_stats")
             _abi.check(lib.pcl_step_fused_select(C.byref(d), self.counter.data_ptr(), _abi.ptr(self.prev_rows), stream),
                        "pcl_step_fused_select")
             # full-fill mode: the fill forks AFTER scan and selection — next to it every DRAM read is 3-4x slower (measured
             # in-graph: scan 22 -> 60 us, selection 13 -> 54 us), only the L2-resident InfoNCE kernel hides behind it
-            if not self.sparse_reset:
+            if not self.sparse_reset and not early:
                 self._fork_zero_fill()
             _abi.check(lib.pcl_step_fused_loss(C.byref(d), stream), "pcl_step_fused_loss")
             if not self.sparse_reset:
