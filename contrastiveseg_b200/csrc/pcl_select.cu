@@ -19,7 +19,7 @@ __device__ __forceinline__ void plan_body(const pcl_geom& g, const int32_t* coun
 // ------------------------------------------------------------------------------------------------
 // k_keys
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PCL_CHUNK)
+__global__ void __launch_bounds__(PCL_CHUNK, 2)
 k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __restrict__ labels,
        const float* __restrict__ seg, const int64_t* __restrict__ predict, uint16_t* __restrict__ keys,
        int32_t* chunk_hist, int32_t* counts, int32_t* plan, unsigned int* done_ctr) {
@@ -37,9 +37,32 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
     const int sy = nearest_src(py, scale_h, g.Himg), sx = nearest_src(px, scale_w, g.Wimg);
     const int64_t lab = labels[(int64_t)b * g.Himg * g.Wimg + (int64_t)sy * g.Wimg + sx];
     int key = NK;
+    // K <= 32 (every configuration of the reference): the class-plane loads do not wait for the label — the label load
+    // and the first 16 planes are one DRAM round trip, the remaining planes a second (was: label, then one round trip
+    // per group of 8 planes behind the label test; the scan is a chain of dependent round trips: 10.8 us for ONE image,
+    // profiles/r2_32_timeline_b1.log).  16 at a time: 1024 threads x 32 registers keeps two CTAs per SM.
+    int pred32 = -1;
+    if (seg != nullptr && K <= 32) {
+      const float* sp = seg + (int64_t)b * K * HW + p;
+      float best = -CUDART_INF_F;
+      pred32 = 0;
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 16) {
+        if (c0 < K) {
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = (c0 + u < K) ? __ldg(sp + (int64_t)(c0 + u) * HW) : -CUDART_INF_F;
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            if (v[u] > best) { best = v[u]; pred32 = c0 + u; }        // first maximum wins, like torch.max
+        }
+      }
+    }
     if (lab >= 0 && lab < K && lab != (int64_t)g.ignore_label) {
       int pred;
-      if (seg != nullptr) {
+      if (seg != nullptr && K <= 32) {
+        pred = pred32;
+      } else if (seg != nullptr) {
         const float* sp = seg + (int64_t)b * K * HW + p;
         float best = -CUDART_INF_F;
         pred = 0;
@@ -79,11 +102,14 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
   __syncthreads();
   if (!s_last) { tl_end(dbg, PCL_TL_KEYS); return; }
   __threadfence();
-  for (int i = threadIdx.x; i < g.B * NK; i += blockDim.x) {
+  // one warp per (image, key) row, one chunk per lane: independent coalesced loads + a shuffle sum (integer: exact)
+  for (int i = threadIdx.x >> 5; i < g.B * NK; i += blockDim.x >> 5) {
     const int32_t* hrow = chunk_hist + (int64_t)i * nchunk;
     int t = 0;
-    for (int ch = 0; ch < nchunk; ++ch) t += __ldcg(hrow + ch);
-    counts[i] = t;
+    for (int ch = threadIdx.x & 31; ch < nchunk; ch += 32) t += __ldcg(hrow + ch);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) counts[i] = t;
   }
   if (threadIdx.x == 0) *done_ctr = 0u;           // re-armed for the next launch
   __syncthreads();
@@ -309,11 +335,25 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
   // ordered scan of the chunk: lane L owns pixels [32L, 32L+32)
   const int p0 = chunk * PCL_CHUNK + lane * 32;
   const uint16_t* kb = keys + (int64_t)b * HW;
-  int cnt = 0;
-  for (int u = 0; u < 32; ++u) {
-    int p = p0 + u;
-    cnt += (p < HW && kb[p] == (uint16_t)key) ? 1 : 0;
+  // the lane's 32 keys (64 bytes) in four 16-byte loads when the row base allows it (HW % 8 == 0: always for the step's
+  // geometries), kept in registers for both passes below
+  uint16_t kv[32];
+  if ((HW & 7) == 0 && p0 + 32 <= HW) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(kb + p0);
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+      const uint4 x = __ldg(k4 + w4);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { kv[w4 * 8 + 2 * e] = (uint16_t)(xs[e] & 0xFFFFu); kv[w4 * 8 + 2 * e + 1] = (uint16_t)(xs[e] >> 16); }
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 32; ++u) kv[u] = (p0 + u < HW) ? kb[p0 + u] : (uint16_t)0xFFFFu;
   }
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < 32; ++u) cnt += (p0 + u < HW && kv[u] == (uint16_t)key) ? 1 : 0;
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -324,10 +364,10 @@ k_select(pcl_geom g, int nchunk, const float* __restrict__ embed, const uint16_t
   int pix = -1;
   if (local >= excl && local < incl) {
     int need = local - excl;
+#pragma unroll
     for (int u = 0; u < 32; ++u) {
-      int p = p0 + u;
-      if (p < HW && kb[p] == (uint16_t)key) {
-        if (need == 0) { pix = p; break; }
+      if (p0 + u < HW && kv[u] == (uint16_t)key) {
+        if (need == 0 && pix < 0) pix = p0 + u;
         --need;
       }
     }
