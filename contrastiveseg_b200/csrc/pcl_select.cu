@@ -93,6 +93,7 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
   // ---- fused tail (step path): the LAST block to finish sums the per-chunk histograms into the totals (no atomics, no
   //      memset) and computes the sampling plan — saves the single-CTA k_plan launch and the counts memset ----
   __shared__ int s_last;
+  tl_end(dbg, 5);                                  // (diagnostics: end of the scan part of the last-arriving block)
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -102,18 +103,38 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
   __syncthreads();
   if (!s_last) { tl_end(dbg, PCL_TL_KEYS); return; }
   __threadfence();
-  // one warp per (image, key) row, one chunk per lane: independent coalesced loads + a shuffle sum (integer: exact)
-  for (int i = threadIdx.x >> 5; i < g.B * NK; i += blockDim.x >> 5) {
-    const int32_t* hrow = chunk_hist + (int64_t)i * nchunk;
-    int t = 0;
-    for (int ch = threadIdx.x & 31; ch < nchunk; ch += 32) t += __ldcg(hrow + ch);
+  // Totals: one warp per (image, key) row, one chunk per lane, FOUR rows per pass so that a warp has four loads in
+  // flight (a row-at-a-time loop cost one L2 round trip per row: 10 rows per warp = 7 of the scan's 21 us at B = 8,
+  // profiles/r2_35_timeline_full.log).  The totals also stay in shared memory for the plan (its loops re-read them).
+  __shared__ int s_counts[4096];
+  const int rows = g.B * NK;
+  const bool in_smem = rows <= 4096;
+  {
+    const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int base = wid; base < rows; base += 4 * nw) {
+      int t[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0) counts[i] = t;
+      for (int q = 0; q < 4; ++q) {
+        const int i = base + q * nw;
+        t[q] = 0;
+        if (i < rows) {
+          const int32_t* hrow = chunk_hist + (int64_t)i * nchunk;
+          for (int ch = ln; ch < nchunk; ch += 32) t[q] += __ldcg(hrow + ch);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
+        const int i = base + q * nw;
+        if (ln == 0 && i < rows) { counts[i] = t[q]; if (in_smem) s_counts[i] = t[q]; }
+      }
+    }
   }
   if (threadIdx.x == 0) *done_ctr = 0u;           // re-armed for the next launch
   __syncthreads();
-  plan_body(g, counts, plan);
+  tl_end(dbg, 6);                                  // (diagnostics: totals done)
+  plan_body(g, in_smem ? s_counts : counts, plan);
   tl_end(dbg, PCL_TL_KEYS);
 }
 

@@ -40,6 +40,7 @@ for rep in range(3):
     print(f"--- replay {rep}: event time {e0.elapsed_time(e1) * 1e3:.1f} us")
     for k, n in enumerate(names):
         print(f"  {n:10s} start {(t[2 * k] - t0) / 1e3:7.1f} us   end {(t[2 * k + 1] - t0) / 1e3:7.1f} us   dur {(t[2 * k + 1] - t[2 * k]) / 1e3:7.1f}")
+    print(f"    scan part ends (last block) {(t[2 * 5 + 1] - t0) / 1e3:7.1f} us   totals done {(t[2 * 6 + 1] - t0) / 1e3:7.1f} us")
     stamps = sync[64:64 + 16 * 32].view(torch.int64).view(32, 8).cpu()
     live = stamps[:, 0] > 0
     if live.any():
