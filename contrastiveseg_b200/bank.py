@@ -127,9 +127,12 @@ def enqueue_buffers(dev: torch.device, n_scratch: int, n_packet: int, world: int
     key = (dev.index, n_scratch, n_packet, world)
     bufs = None if fresh else _ENQ_BUFFERS.get(key)
     if bufs is None:
+        # the packet is zero-filled ONCE: slots of absent (image, class) pairs carry only their count header, the rest of
+        # their rows is never written — the all_gather ships the whole packet, so it must not be uninitialised memory
+        # (compute-sanitizer initcheck, profiles/r2_36_initcheck_packet_copy.log)
         bufs = (torch.empty(n_scratch, dtype=torch.float32, device=dev),
-                torch.empty(n_packet, dtype=torch.float32, device=dev),
-                torch.empty((world, n_packet), dtype=torch.float32, device=dev) if world > 1 else None)
+                torch.zeros(n_packet, dtype=torch.float32, device=dev),
+                torch.zeros((world, n_packet), dtype=torch.float32, device=dev) if world > 1 else None)
         if not fresh:
             if len(_ENQ_BUFFERS) >= 8:
                 _ENQ_BUFFERS.pop(next(iter(_ENQ_BUFFERS)))

@@ -540,40 +540,62 @@ constexpr int PT_C_KB = PT_BM * BK * 2;            // 16 KB: [128 columns x 64 K
 constexpr int PT_STAGES = 8;                       // K-block stages of the bank stream (2 tiles in flight)
 constexpr int PT_MAX_ROWS = 4096;                  // class-boundary scan of the prologue
 
+constexpr int PT_MAX_BLOCKS = PT_MAX_ROWS / PT_NB + PCL_MAX_CLASSES;      // blocks of <= 64 anchors of one class
+
 struct SmemPosT {
   uint8_t a[NKB * PT_A_KB];                        // 32 KB
   uint8_t c[PT_STAGES * PT_C_KB];                  // 128 KB
   uint64_t full[PT_STAGES], empty[PT_STAGES], a_full, a_empty, tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
-  int rk_first[PCL_MAX_CLASSES], rk_cnt[PCL_MAX_CLASSES], blk_pref[PCL_MAX_CLASSES + 1];
-  int total_blocks, S;
+  int rk_first[PCL_MAX_CLASSES], rk_cnt[PCL_MAX_CLASSES];
+  // work list: anchor blocks (first row, rows, class rank), exclusive prefix of their column tiles, blocks without tiles
+  int blk_r0[PT_MAX_BLOCKS], blk_rk[PT_MAX_BLOCKS], tile_pref[PT_MAX_BLOCKS + 1], zlist[PT_MAX_BLOCKS];
+  short blk_nv[PT_MAX_BLOCKS];
+  int total_blocks, n_zero, P, U;
   float4 par[PT_NB];                               // per anchor of the block: m2, Neg, diag column (int bits), -
   float comb[2][4][32][2];                         // [anchor half][lane quarter][anchor][possum2, s]
 };
 
-struct PosItem { int r0, nv, t0, t1, c_lo, c_hi, split; };
+// One segment = consecutive column tiles [t0, t1) of one anchor block; its partial sums go to slot `split`; the block
+// is covered by `nslots` segments (of consecutive CTAs).
+struct PosItem { int r0, nv, t0, t1, c_lo, c_hi, split, nslots; };
 
-__device__ __forceinline__ PosItem pos_item(const SmemPosT& sm, const TcArgs& a, int item) {
-  const int S = sm.S;
-  const int blk = item / S, split = item - blk * S;
-  int rk = 0;
-  while (rk + 1 < a.K && sm.blk_pref[rk + 1] <= blk) ++rk;
-  const int b = blk - sm.blk_pref[rk];
-  PosItem it;
-  it.r0 = sm.rk_first[rk] + b * PT_NB;
-  it.nv = min(PT_NB, sm.rk_cnt[rk] - b * PT_NB);
-  it.split = split;
-  if (rk > a.K - 2) {                               // class-0 anchors: their positives are the analytic zero tail (k_finalize)
-    it.c_lo = it.c_hi = 0; it.t0 = it.t1 = 0;
-  } else {
-    it.c_lo = rk * a.R; it.c_hi = it.c_lo + a.R;
-    const int t_lo = it.c_lo / PT_BM, t_hi = (it.c_hi + PT_BM - 1) / PT_BM;
-    const int per = (t_hi - t_lo + S - 1) / S;
-    it.t0 = min(t_hi, t_lo + split * per);
-    it.t1 = min(t_hi, it.t0 + per);
+// All tile units (block, tile) form one list of P entries; CTA k owns units [k U, (k+1) U) — a balanced walk whatever
+// the class mix (K = 171 classes: 171 blocks on 148 CTAs would otherwise make 23 CTAs do twice the work).  Every role
+// (TMA / MMA / epilogue) walks the same segments.  Blocks without tiles (class-0 anchors: their positives are the
+// analytic zero tail, k_finalize) are dealt round-robin and only write their rows.
+struct PosWalk {
+  int u, u1, blk, z, k, G;
+  __device__ __forceinline__ void init(const SmemPosT& sm, int cta, int grid) {
+    k = cta; G = grid;
+    u = min(sm.P, cta * sm.U); u1 = min(sm.P, u + sm.U);
+    blk = 0; z = cta;
   }
-  return it;
-}
+  __device__ __forceinline__ bool next(const SmemPosT& sm, const TcArgs& a, PosItem& it) {
+    if (u < u1) {
+      while (sm.tile_pref[blk + 1] <= u) ++blk;
+      const int b0 = sm.tile_pref[blk], b1 = sm.tile_pref[blk + 1];
+      const int e = min(u1, b1);
+      const int rk = sm.blk_rk[blk];
+      it.r0 = sm.blk_r0[blk]; it.nv = sm.blk_nv[blk];
+      it.c_lo = rk * a.R; it.c_hi = it.c_lo + a.R;
+      const int t_lo = it.c_lo / PT_BM;
+      it.t0 = t_lo + (u - b0); it.t1 = t_lo + (e - b0);
+      it.split = k - b0 / sm.U;
+      it.nslots = (b1 - 1) / sm.U - b0 / sm.U + 1;
+      u = e;
+      return true;
+    }
+    if (z < sm.n_zero) {
+      const int b = sm.zlist[z];
+      z += G;
+      it.r0 = sm.blk_r0[b]; it.nv = sm.blk_nv[b];
+      it.c_lo = it.c_hi = 0; it.t0 = it.t1 = 0; it.split = 0; it.nslots = 0;
+      return true;
+    }
+    return false;
+  }
+};
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmC128, TcArgs a,
@@ -594,11 +616,31 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int rk = 0; rk < a.K; ++rk) { sm.blk_pref[rk] = acc; acc += (sm.rk_cnt[rk] + PT_NB - 1) / PT_NB; }
-    sm.blk_pref[a.K] = acc;
-    sm.total_blocks = acc;
-    sm.S = max(1, min(a.splits, (int)gridDim.x / max(acc, 1)));
+    int nb = 0, nz = 0, P = 0, tmax = 1;
+    for (int rk = 0; rk < a.K && rk < PCL_MAX_CLASSES; ++rk) {
+      const int cnt = sm.rk_cnt[rk];
+      int tiles = 0;
+      if (rk <= a.K - 2) {
+        const int c_lo = rk * a.R;
+        tiles = (c_lo + a.R + PT_BM - 1) / PT_BM - c_lo / PT_BM;
+      }
+      for (int b = 0; b * PT_NB < cnt && nb < PT_MAX_BLOCKS; ++b) {
+        sm.blk_r0[nb] = sm.rk_first[rk] + b * PT_NB;
+        sm.blk_nv[nb] = (short)min(PT_NB, cnt - b * PT_NB);
+        sm.blk_rk[nb] = rk;
+        sm.tile_pref[nb] = P;
+        P += tiles;
+        if (tiles == 0) sm.zlist[nz++] = nb;
+        tmax = max(tmax, tiles);
+        ++nb;
+      }
+    }
+    sm.tile_pref[nb] = P;
+    sm.total_blocks = nb; sm.n_zero = nz; sm.P = P;
+    // units per CTA: even share, but a block must not be cut into more segments than there are partial slots
+    int U = (P + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int u_slots = a.splits >= 2 ? (tmax + a.splits - 2) / (a.splits - 1) : max(P, 1);
+    sm.U = max(1, max(U, u_slots));
     ptx::prefetch_tmap(&tmA64);
     ptx::prefetch_tmap(&tmC128);
     for (int s = 0; s < PT_STAGES; ++s) { ptx::mbar_init(&sm.full[s], 1); ptx::mbar_init(&sm.empty[s], 1); }
@@ -612,15 +654,16 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = sm.tmem_base;
-  const int n_items = sm.total_blocks * sm.S;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       int seq = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const PosItem it = pos_item(sm, a, item);
+      PosWalk w;
+      PosItem it;
+      w.init(sm, blockIdx.x, gridDim.x);
+      while (w.next(sm, a, it)) {
         if (it.t1 <= it.t0) continue;
         if (seq > 0) ptx::mbar_wait(&sm.a_empty, (seq - 1) & 1);             // previous block's MMAs retired
         ptx::mbar_arrive_expect_tx(&sm.a_full, NKB * PT_A_KB);
@@ -643,8 +686,10 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
       const uint32_t a_base = ptx::smem_u32(sm.a), c_base = ptx::smem_u32(sm.c);
       uint32_t stage = 0, phase = 0;
       int seq = 0, n = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const PosItem it = pos_item(sm, a, item);
+      PosWalk w;
+      PosItem it;
+      w.init(sm, blockIdx.x, gridDim.x);
+      while (w.next(sm, a, it)) {
         if (it.t1 <= it.t0) continue;
         ptx::mbar_wait(&sm.a_full, seq & 1);
         ptx::tc_fence_after();
@@ -678,8 +723,10 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
     const int et = threadIdx.x - 64;                  // 0..255 within the epilogue group
     const int64_t stride = (int64_t)a.slots * a.a_pad;
     int n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const PosItem it = pos_item(sm, a, item);
+    PosWalk w;
+    PosItem it;
+    w.init(sm, blockIdx.x, gridDim.x);
+    while (w.next(sm, a, it)) {
       // ---- per-anchor constants of the block (the row prologue of the row-tile sweep, one thread per anchor) ----
       if (et < PT_NB) {
         float4 pr = make_float4(0.f, 1.f, __int_as_float(-1), 0.f);
@@ -718,15 +765,22 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + accb * PT_NB + ahalf * 32, v);
         ptx::tmem_ld_wait();
+        // groups of 8 anchors behind ONE warp-uniform test: inside a group the 8 LDS -> FMA -> EX2 -> LG2 / RCP chains
+        // are independent and interleave (a test per anchor made 32 basic blocks, i.e. 32 serial ~100-cycle chains per
+        // tile: 3000 cycles per tile instead of the ~1500 the MUFU pipe needs, profiles/r2_36 ncu: XU 20 %).  Anchors
+        // past the block's end inside a group carry neutral constants (m2 = 0, Neg = 1) and are never written.
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nvh) {                                                      // warp-uniform
-            const float4 pr = sm.par[ahalf * 32 + i];                         // broadcast read
-            const float x = fmaf(__uint_as_float(v[i]), a.k1, -pr.x);
-            const float tt = ptx::ex2_approx(x) + pr.y;
-            const bool keep = colkeep && col != __float_as_int(pr.z);
-            acc0[i] += keep ? x - ptx::lg2_approx(tt) : 0.f;
-            acc1[i] += keep ? ptx::rcp_approx(tt) : 0.f;
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          if (i0 < nvh) {
+#pragma unroll
+            for (int i = i0; i < i0 + 8; ++i) {
+              const float4 pr = sm.par[ahalf * 32 + i];                       // broadcast read
+              const float x = fmaf(__uint_as_float(v[i]), a.k1, -pr.x);
+              const float tt = ptx::ex2_approx(x) + pr.y;
+              const bool keep = colkeep && col != __float_as_int(pr.z);
+              acc0[i] += keep ? x - ptx::lg2_approx(tt) : 0.f;
+              acc1[i] += keep ? ptx::rcp_approx(tt) : 0.f;
+            }
           }
         }
         ptx::tc_fence_before();
@@ -756,8 +810,8 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
         partials[2 * stride + o] = ps * LN2;
         partials[3 * stride + o] = ss;
         partials[4 * stride + o] = (float)cnt;
-        if (it.split == 0) {                                                  // slots this launch does not use: k_finalize sums a.splits of them
-          for (int sl = sm.S; sl < a.splits; ++sl) {
+        if (it.split == 0) {                                                  // slots no segment of this block writes: k_finalize sums a.splits of them
+          for (int sl = it.nslots; sl < a.splits; ++sl) {
             const int64_t oz = (int64_t)sl * a.a_pad + row;
             partials[2 * stride + oz] = 0.f; partials[3 * stride + oz] = 0.f; partials[4 * stride + oz] = 0.f;
           }

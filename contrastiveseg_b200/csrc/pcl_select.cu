@@ -94,15 +94,17 @@ k_keys(pcl_geom g, int nchunk, float scale_h, float scale_w, const int64_t* __re
   //      memset) and computes the sampling plan — saves the single-CTA k_plan launch and the counts memset ----
   __shared__ int s_last;
   tl_end(dbg, 5);                                  // (diagnostics: end of the scan part of the last-arriving block)
-  __threadfence();
+  // release: the block barrier orders every thread's writes before thread 0, whose device-scope fence is cumulative —
+  // ONE fence per block instead of 1024 (the grid-barrier idiom); acquire on the other side the same way
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int total = gridDim.x * gridDim.y;
+    __threadfence();
     s_last = (atomicAdd(done_ctr, 1u) == total - 1u) ? 1 : 0;
+    __threadfence();
   }
   __syncthreads();
   if (!s_last) { tl_end(dbg, PCL_TL_KEYS); return; }
-  __threadfence();
   // Totals: one warp per (image, key) row, one chunk per lane, FOUR rows per pass so that a warp has four loads in
   // flight (a row-at-a-time loop cost one L2 round trip per row: 10 rows per warp = 7 of the scan's 21 us at B = 8,
   // profiles/r2_35_timeline_full.log).  The totals also stay in shared memory for the plan (its loops re-read them).

@@ -457,6 +457,37 @@ def test_bank_shadow_tracks_enqueue_and_tensor_path_uses_it():
     assert rel_err(l16.item(), l32.item()) < 1e-4
 
 
+@pytest.mark.parametrize("K,M,A,seed", [(5, 300, 200, 1), (7, 200, 333, 2), (12, 70, 150, 3), (3, 500, 100, 4), (40, 130, 260, 5)])
+def test_tensor_path_bank_positives_by_class_blocks(K, M, A, seed):
+    """The transposed POS sweep of the bank mode (csrc/pcl_infonce_tc.cu k_tc_pos_t): anchor blocks of one class x that
+    class's bank columns, tile units dealt evenly to the CTAs.  Sizes where a class has several column tiles (so a block
+    is cut into several partial slots), several 64-anchor blocks, class-0 anchors (no columns: analytic zero tail) and
+    more blocks than a class has tiles.  Loss and positive counts vs the float64 closed form on the bf16-rounded
+    operands (loss_contrast_mem.py:107-152), gradient within the bf16 tolerance of the path."""
+    from contrastiveseg_b200 import _abi
+    from contrastiveseg_b200.bank import shadow_rows
+    lib = _abi.load()
+    g = torch.Generator().manual_seed(seed)
+    ya = torch.randint(0, K, (A,), generator=g)
+    ya = ya[torch.argsort(torch.where(ya == 0, K, ya), stable=True)]           # class-rank order: 1..K-1, 0
+    a = F.normalize(torch.randn(A, 256, generator=g), dim=1)
+    segq = F.normalize(torch.randn(K, M, 256, generator=g), dim=2)
+    pixq = F.normalize(torch.randn(K, M, 256, generator=g), dim=2)
+    shadow = torch.empty((shadow_rows(K, M), 256), dtype=torch.bfloat16, device=DEV)
+    segq_d, pixq_d = segq.to(DEV), pixq.to(DEV)
+    _abi.check(lib.pcl_bank_shadow_rebuild(segq_d.data_ptr(), pixq_d.data_ptr(), K, M, 256, shadow.data_ptr(), None))
+    torch.cuda.synchronize()
+    loss, st, state = Fn.infonce_tc_forward(a.to(DEV), ya.to(DEV), bank=(shadow, K, 2 * M), diag_col=torch.arange(A).to(DEV),
+                                            temperature=0.1, base_temperature=0.07)
+    dA = Fn.infonce_tc_backward(state, st).double().cpu()
+    contrast, yc = P.flatten_queue(torch.cat((_bf(segq), _bf(pixq)), 1).double())
+    cf = P.infonce_closed_form(_bf(a).double(), ya, contrast, yc.long(), 0.1, 0.07, self_contrast=False)
+    assert torch.equal(st[4].double().cpu(), cf["npos"])
+    assert abs(loss.item() - cf["loss"].item()) <= 5e-5 * abs(cf["loss"].item())
+    gmax = cf["dA"].abs().max().item()
+    assert (dA - cf["dA"]).abs().max().item() <= 6e-3 * gmax
+
+
 def test_torch_cpu_rng_mode_draws_the_reference_stream():
     """rng='torch_cpu': same torch CPU seed -> the engine samples exactly what the reference code path samples."""
     g = load_golden("nomem_small")
