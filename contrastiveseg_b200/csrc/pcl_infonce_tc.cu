@@ -737,7 +737,8 @@ k_tc_pos_t(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CU
           const long long Un = max(1LL, Pn / max(1, a.neg_grid));
           const int used = (int)min((long long)a.slots, (long long)((a.n_cols + BN - 1) / BN) / Un + 2);
           float ng = 0.f;
-          for (int pslot = 0; pslot < used; ++pslot) ng += partials[stride + (int64_t)pslot * a.a_pad + row];
+#pragma unroll 8
+          for (int pslot = 0; pslot < used; ++pslot) ng += __ldcg(partials + stride + (int64_t)pslot * a.a_pad + row);
           const int rcls = a.acls[row];
           if (a.tail_count > 0 && rcls != 0) {
             const float wt = a.tk_sel ? topk_weight(KEY_ZERO, a.tk_sel[row], __uint_as_float(a.tk_sel[a.a_rows + row])) : 1.f;
