@@ -84,6 +84,34 @@ __device__ __forceinline__ int col_label(const TcArgs& a, int n) {      // colum
   return a.ccls ? a.ccls[n] : (a.mode == 1 ? (int)div_R(a, (uint32_t)n) + 1 : a.acls[n]);
 }
 
+// First / last label of N consecutive 32-column chunks starting at column `base` (lo = -2 / hi = -3: chunk not complete
+// or test disabled).  Bank mode with class blocks of R >= 32 N rows: the N chunks meet at most ONE class boundary, so one
+// n / R for `base` and comparisons against the next block start replace 2 N multiply-shift divisions.  (Fewer
+// instructions, no measurable change of the sweep times: the label lines were 26 % of the NEG sweep's warp-stall samples,
+// profiles/r2_25_bank_source_top.txt, but they are evaluated one tile ahead, inside the wait for the accumulator.)
+template <int N>
+__device__ __forceinline__ void chunk_labels(const TcArgs& a, int base, bool en, int64_t ncols, int (&lo)[N], int (&hi)[N]) {
+  if (a.ccls == nullptr && a.mode == 1 && a.R >= 32 * N) {
+    const int q = (int)div_R(a, (uint32_t)base);
+    const long long nb = (long long)(q + 1) * a.R;                 // first column of the next class block
+#pragma unroll
+    for (int ch = 0; ch < N; ++ch) {
+      const int cb = base + ch * 32;
+      const bool in = en && cb + 32 <= ncols;
+      lo[ch] = in ? q + 1 + (cb >= nb ? 1 : 0) : -2;
+      hi[ch] = in ? q + 1 + (cb + 31 >= nb ? 1 : 0) : -3;
+    }
+  } else {
+#pragma unroll
+    for (int ch = 0; ch < N; ++ch) {
+      const int cb = base + ch * 32;
+      const bool in = en && cb + 32 <= ncols;
+      lo[ch] = in ? col_label(a, cb) : -2;
+      hi[ch] = in ? col_label(a, cb + 31) : -3;
+    }
+  }
+}
+
 enum { TC_NEG = 0, TC_POS = 1, TC_DUMP = 2,     // DUMP: raw logit tiles to global (descriptor self-test)
        TC_H1 = 3, TC_H2 = 4, TC_H3 = 5,         // a10: radix-select histogram sweeps (11 + 11 + 10 bits of the logit key)
        TC_NEGW = 6 };                           // a10: negative sum with the selection weights
@@ -351,13 +379,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       }
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;     // NEG: 4 partial sums; POS: possum2, s, cnt
       int nlab_lo[4], nlab_hi[4];                              // first / last label of the 4 chunks of the next tile
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int cb = sg.ct0 * BN + half * (BN / 2) + ch * 32;
-        const bool in = sg.ct0 < sg.ct1 && a.sorted && cb + 32 <= ncols;
-        nlab_lo[ch] = in ? col_label(a, cb) : -2;
-        nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
-      }
+      chunk_labels<4>(a, sg.ct0 * BN + half * (BN / 2), sg.ct0 < sg.ct1 && a.sorted, ncols, nlab_lo, nlab_hi);
       for (int ct = sg.ct0; ct < sg.ct1; ++ct, ++it) {
         const uint32_t accb = it & 1, acc_phase = (it >> 1) & 1;
         const int col0 = ct * BN + half * (BN / 2);
@@ -374,14 +396,7 @@ k_tc_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
           cuni[ch] = a.sorted && cb + 32 <= ncols && nlab_lo[ch] == nlab_hi[ch];
         }
         if (ct + 1 < sg.ct1) {
-          const int ncol0 = (ct + 1) * BN + half * (BN / 2);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const int cb = ncol0 + ch * 32;
-            const bool in = a.sorted && cb + 32 <= ncols;
-            nlab_lo[ch] = in ? col_label(a, cb) : -2;
-            nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
-          }
+          chunk_labels<4>(a, (ct + 1) * BN + half * (BN / 2), a.sorted != 0, ncols, nlab_lo, nlab_hi);
         }
         ptx::mbar_wait(&sm.tmem_full[accb], acc_phase);
         ptx::tc_fence_after();
@@ -1006,13 +1021,7 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (TOPK && valid) { tk_tau = a.tk_sel[row]; tk_tw = __uint_as_float(a.tk_sel[a.a_rows + row]); }
     uint8_t* g_row = sm.g + r_in * 128;           // + kblock * 16 KB + swizzled 16-byte chunk
     int nlab_lo[NCH], nlab_hi[NCH];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int cb = my_lo * BNB + half * CPS + ch * 32;
-      const bool in = ntiles > 0 && a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
-      nlab_lo[ch] = in ? col_label(a, cb) : -2;
-      nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
-    }
+    chunk_labels<NCH>(a, my_lo * BNB + half * CPS, ntiles > 0 && a.sorted && a.mode != 0, (int64_t)ncols, nlab_lo, nlab_hi);
     for (int it = 0; it < ntiles; ++it) {
       const int ct = my_lo + it * tstep;
       const uint32_t acc = it & 1, phase = (it >> 1) & 1;
@@ -1026,13 +1035,7 @@ k_tc_bwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         cuni[ch] = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols && nlab_lo[ch] == nlab_hi[ch];
       }
       if (it + 1 < ntiles) {                       // labels of the next tile: loads fly while this tile is processed
-#pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          const int cb = (ct + tstep) * BNB + half * CPS + ch * 32;
-          const bool in = a.sorted && a.mode != 0 && cb + 32 <= (int)ncols;
-          nlab_lo[ch] = in ? col_label(a, cb) : -2;
-          nlab_hi[ch] = in ? col_label(a, cb + 31) : -3;
-        }
+        chunk_labels<NCH>(a, (ct + tstep) * BNB + half * CPS, a.sorted && a.mode != 0, (int64_t)ncols, nlab_lo, nlab_hi);
       }
       ptx::mbar_wait(&sm.s_full[acc], phase);
       ptx::tc_fence_after();

@@ -59,13 +59,10 @@ k_finalize(SweepArgs a, const float* __restrict__ partials, float* __restrict__ 
     float ps = 0.f, s = 0.f, c = 0.f, rl = 0.f;
     if (r < A) {
       const int npos = a.pos_splits > 0 ? a.pos_splits : a.splits;
-      // (fixed summation order; unrolled so that the 3 x 6 loads of a pass are in flight together: one thread walks
-      //  up to 3 x 18 slots, and a load-per-iteration loop made this single-CTA kernel 12 us of L2 round trips)
-#pragma unroll 6
-      for (int p = 0; p < npos; ++p) {
-        ps += __ldcg(partials + ((int64_t)2 * a.splits + p) * a.a_pad + r);
-        s += __ldcg(partials + ((int64_t)3 * a.splits + p) * a.a_pad + r);
-        c += __ldcg(partials + ((int64_t)4 * a.splits + p) * a.a_pad + r);
+      for (int p = 0; p < npos; ++p) {                 // fixed summation order
+        ps += partials[((int64_t)2 * a.splits + p) * a.a_pad + r];
+        s += partials[((int64_t)3 * a.splits + p) * a.a_pad + r];
+        c += partials[((int64_t)4 * a.splits + p) * a.a_pad + r];
       }
       if (a.tail_count > 0 && a.acls[r] == 0) {
         const float m = rowstats[r], neg = rowstats[a.a_rows + r];

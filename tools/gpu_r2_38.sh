@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, visit 38 (1 GPU): POS' with 8 independent chains per uniform test — timing and parity
+# round 2, visit 38-39 (1 GPU): POS sweep ILP; chunk labels from one division per tile — timing and parity
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
