@@ -345,6 +345,8 @@ extern "C" int pcl_bank_apply_ctr(const pcl_bank_geom* g, const float* packets, 
   int st = make_dims(g, &d);
   if (st != PCL_OK) return st;
   PCL_REQUIRE(packets && world >= 1 && segment_queue && segment_queue_ptr && pixel_queue && pixel_queue_ptr);
+  // the slots of one class (world * B of them) are replayed in shared memory
+  if ((int64_t)world * g->B > APPLY_MAX_SLOTS) return PCL_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t packet_f32 = (int64_t)g->B * g->K * d.slot_f32;
   k_bank_apply<<<g->K, 256, 0, s>>>(d, packets, world, packet_f32, segment_queue, segment_queue_ptr, pixel_queue,

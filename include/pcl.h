@@ -241,8 +241,11 @@ int pcl_bank_packet(const pcl_bank_geom* g, const float* keys, const int64_t* la
 int pcl_bank_packet_dev(const pcl_bank_geom* g, const float* keys, const int64_t* labels, uint64_t seed,
                         const uint64_t* seed_offset, float* scratch, float* packet, void* stream);
 
-/* Apply `world` packets (contiguous, rank-major) to the queues in place.  shadow_bf16 (optional,
- * ((K-1)*2M rounded up to 256, D) bf16) is the engine's class-blocked bf16 copy used by the tensor path. */
+/* Apply `world` packets (contiguous, rank-major) to the queues in place, with the result of the reference's sequential
+ * per-image loop over the gathered batch (trainer_contrastive.py:96-139): every queue row is written once, by the LAST
+ * of the world * B slots that would have written it.  world * B <= 1024 (PCL_ERR_UNSUPPORTED otherwise).
+ * shadow_bf16 (optional, ((K-1)*2M rounded up to 256, D) bf16) is the engine's class-blocked bf16 copy used by the
+ * tensor path. */
 int pcl_bank_apply(const pcl_bank_geom* g, const float* packets, int32_t world, float* segment_queue,
                    int64_t* segment_queue_ptr, float* pixel_queue, int64_t* pixel_queue_ptr,
                    void* shadow_bf16, void* stream);
