@@ -189,6 +189,49 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const int i00 = ly0 * xs_n + lx0, i01 = ly0 * xs_n + lx1, i10 = ly1 * xs_n + lx0, i11 = ly1 * xs_n + lx1;
   const float inv_rx = a.rx > 0.f ? 1.f / a.rx : 0.f, inv_ry = a.ry > 0.f ? 1.f / a.ry : 0.f;
+  // The transposed bilinear map of the tile, once per CTA (it is the same for every class and row): weight of label
+  // column k in source column xs (s_wx), of label row k in source row ys (s_wy), and the label range [klo, khi] inside
+  // a source cell's footprint.  Phases B and C below were evaluating these (two compares, floorf / ceilf) per class, per
+  // row and per k: 152 times each.  Row stride 33 / 9: different source cells of one k fall into different banks.
+  __shared__ float s_wx[SRC_MAX * (BT + 1)], s_wy[SRC_MAX * (BTY + 1)];
+  __shared__ short s_xlo[SRC_MAX], s_xhi[SRC_MAX], s_ylo[SRC_MAX], s_yhi[SRC_MAX];
+  for (int i = threadIdx.x; i < xs_n * BT; i += BT * BTY) {
+    const int xs = i / BT, k = i - xs * BT, xg = xs_base + xs;
+    float wgt = 0.f;
+    if (k < nx) {
+      if (s_x0[k] == xg) wgt += 1.f - s_lx[k];
+      if (s_x1[k] == xg) wgt += s_lx[k];
+    }
+    s_wx[xs * (BT + 1) + k] = wgt;
+  }
+  for (int i = threadIdx.x; i < ys_n * BTY; i += BT * BTY) {
+    const int ysl = i / BTY, k = i - ysl * BTY, yg = ys_base + ysl;
+    float wgt = 0.f;
+    if (k < ny) {
+      if (s_y0[k] == yg) wgt += 1.f - s_ly[k];
+      if (s_y1[k] == yg) wgt += s_ly[k];
+    }
+    s_wy[ysl * (BTY + 1) + k] = wgt;
+  }
+  if (threadIdx.x < xs_n) {
+    const int xg = xs_base + threadIdx.x;
+    int klo = 0, khi = nx - 1;
+    if (a.rx > 0.f) {
+      klo = max(0, (int)floorf(((float)xg - 1.f) * inv_rx) - 1 - X0);
+      khi = min(nx - 1, (int)ceilf(((float)xg + 1.f) * inv_rx) + 1 - X0);
+    }
+    s_xlo[threadIdx.x] = (short)klo; s_xhi[threadIdx.x] = (short)khi;
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + ys_n) {
+    const int ysl = threadIdx.x - 64, yg = ys_base + ysl;
+    int klo = 0, khi = ny - 1;
+    if (a.ry > 0.f) {
+      klo = max(0, (int)floorf(((float)yg - 1.f) * inv_ry) - 1 - Y0);
+      khi = min(ny - 1, (int)ceilf(((float)yg + 1.f) * inv_ry) + 1 - Y0);
+    }
+    s_ylo[ysl] = (short)klo; s_yhi[ysl] = (short)khi;
+  }
+  __syncthreads();
   for (int c0 = 0; c0 < a.K; c0 += kc) {
     const int cn = min(kc, a.K - c0);
     for (int i = threadIdx.x; i < cn * patch; i += BT * BTY) {
@@ -211,20 +254,11 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
     // ---- B: x direction (only the label columns whose footprint touches source column xg) ----
     for (int i = threadIdx.x; i < cn * BTY * xs_n; i += BT * BTY) {
       const int xs = i % xs_n, row = (i / xs_n) % BTY, cc = i / (xs_n * BTY);
-      const int xg = xs_base + xs;
-      int klo = 0, khi = nx - 1;
-      if (a.rx > 0.f) {
-        klo = max(0, (int)floorf(((float)xg - 1.f) * inv_rx) - 1 - X0);
-        khi = min(nx - 1, (int)ceilf(((float)xg + 1.f) * inv_rx) + 1 - X0);
-      }
+      const int klo = s_xlo[xs], khi = s_xhi[xs];
       const float* gr = G + ((size_t)cc * BTY + row) * BT;
+      const float* wr = s_wx + xs * (BT + 1);
       float acc = 0.f;
-      for (int k = klo; k <= khi; ++k) {
-        float wgt = 0.f;
-        if (s_x0[k] == xg) wgt += 1.f - s_lx[k];
-        if (s_x1[k] == xg) wgt += s_lx[k];
-        acc += wgt * gr[k];
-      }
+      for (int k = klo; k <= khi; ++k) acc += wr[k] * gr[k];
       Hx[((size_t)cc * BTY + row) * SRC_MAX + xs] = acc;
     }
     __syncthreads();
@@ -232,18 +266,10 @@ k_segce_bwd_tile(SegCeArgs a, const float* __restrict__ lse, const float* __rest
     for (int i = threadIdx.x; i < cn * ys_n * xs_n; i += BT * BTY) {
       const int xs = i % xs_n, ysl = (i / xs_n) % ys_n, cc = i / (xs_n * ys_n);
       const int yg = ys_base + ysl;
-      int klo = 0, khi = ny - 1;
-      if (a.ry > 0.f) {
-        klo = max(0, (int)floorf(((float)yg - 1.f) * inv_ry) - 1 - Y0);
-        khi = min(ny - 1, (int)ceilf(((float)yg + 1.f) * inv_ry) + 1 - Y0);
-      }
+      const int klo = s_ylo[ysl], khi = s_yhi[ysl];
+      const float* wr = s_wy + ysl * (BTY + 1);
       float acc = 0.f;
-      for (int k = klo; k <= khi; ++k) {
-        float wgt = 0.f;
-        if (s_y0[k] == yg) wgt += 1.f - s_ly[k];
-        if (s_y1[k] == yg) wgt += s_ly[k];
-        acc += wgt * Hx[((size_t)cc * BTY + k) * SRC_MAX + xs];
-      }
+      for (int k = klo; k <= khi; ++k) acc += wr[k] * Hx[((size_t)cc * BTY + k) * SRC_MAX + xs];
       if (acc != 0.f) atomicAdd(&dseg[((int64_t)b * a.K + c0 + cc) * hw + (int64_t)yg * a.w + xs_base + xs], acc);
     }
     __syncthreads();
