@@ -146,6 +146,8 @@ class GraphedContrastStep:
             self.grad.zero_()
         self.graph = None
         self.graph_b = None
+        self.graph_c = None                    # split steps: the bank write as a graph of its own (see replay)
+        self._gather_stream = None
         self.replays = 0
         self.enq = None
         if enqueue is not None:
@@ -276,7 +278,7 @@ class GraphedContrastStep:
                        "pcl_step_backward_prezeroed")
         else:
             _abi.check(lib.pcl_step_backward(C.byref(d), self.scale.data_ptr(), stream), "pcl_step_backward")
-        if self.enq is not None:
+        if self.enq is not None and not self._apply_separately:
             self._enqueue_apply(stream)
 
     @property
@@ -284,11 +286,19 @@ class GraphedContrastStep:
         """Two graphs with the all_gather between them (bank step on several ranks)."""
         return self.enq is not None and self.enq["world"] > 1
 
+    @property
+    def _apply_separately(self) -> bool:
+        """Split steps launch the bank write on its own (third graph) so that the all_gather can run under the backward
+        sweep; PCL_GATHER_OVERLAP=0 restores the two-graph sequence with the all_gather between them."""
+        return self.split and os.environ.get("PCL_GATHER_OVERLAP", "1") != "0"
+
     def _enqueue(self, stream: int) -> None:
         self._enqueue_a(stream)
         if self.split:
             self._gather()
         self._enqueue_b(stream)
+        if self._apply_separately:
+            self._enqueue_apply(stream)
 
     def _capture(self, warmup: int) -> None:
         dev = self.device
@@ -322,6 +332,12 @@ class GraphedContrastStep:
                 self._enqueue_a(torch.cuda.current_stream(dev).cuda_stream)
             with torch.cuda.device(dev), torch.cuda.graph(graph_b, stream=cap, capture_error_mode="thread_local"):
                 self._enqueue_b(torch.cuda.current_stream(dev).cuda_stream)
+            if self._apply_separately:         # third graph: the bank write, after the all_gather that ran under graph_b
+                graph_c = torch.cuda.CUDAGraph()
+                with torch.cuda.device(dev), torch.cuda.graph(graph_c, stream=cap, capture_error_mode="thread_local"):
+                    self._enqueue_apply(torch.cuda.current_stream(dev).cuda_stream)
+                self.graph_c = graph_c
+                self._gather_stream = torch.cuda.Stream(dev)
             self.graph, self.graph_b = graph, graph_b
 
     def _restore_bank(self) -> None:
@@ -346,7 +362,17 @@ class GraphedContrastStep:
         replay; grad_embed = grad_scale * d loss / d embed."""
         if self.graph is not None:
             self.graph.replay()
-            if self.graph_b is not None:
+            if self.graph_c is not None:
+                # Only the bank WRITE needs the other ranks' packets: the all_gather runs on its own stream UNDER the
+                # backward sweep (graph_b), the write (graph_c) waits for both.
+                cur = torch.cuda.current_stream(self.device)
+                self._gather_stream.wait_stream(cur)
+                with torch.cuda.stream(self._gather_stream):
+                    self._gather()
+                self.graph_b.replay()
+                cur.wait_stream(self._gather_stream)
+                self.graph_c.replay()
+            elif self.graph_b is not None:
                 self._gather()
                 self.graph_b.replay()
         else:

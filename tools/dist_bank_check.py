@@ -77,11 +77,33 @@ for r in range(3):
     for name in names:
         gok &= torch.equal(getattr(bank_g, name), getattr(bank_e, name))
     gok &= torch.equal(bank_g.shadow, bank_e.shadow)
+# back-to-back replays (no host synchronisation between the steps: the all_gather of step r runs on its own stream under
+# the backward sweep, the bank write and the next step's packet must still be ordered around it)
+import os
+for r in range(3, 9):
+    step.replay()
+torch.cuda.synchronize()
+for r in range(3, 9):
+    Fn._step_counter[0] = r
+    bank_mod._enqueue_counter[0] = r
+    e = embed.clone().requires_grad_(True)
+    l = cs.pixel_contrast_loss(e, tgt, seg=seg, segment_queue=bank_e.segment_queue, pixel_queue=bank_e.pixel_queue,
+                               bank_shadow=bank_e.shadow, options=opts)
+    bank_e.enqueue(e.detach(), tgt, network_stride=4, pixel_update_freq=5, seed=3)
+    l.backward()
+torch.cuda.synchronize()
+gok &= torch.equal(l.detach(), step.loss) and torch.allclose(e.grad, step.grad, rtol=2e-6, atol=0)
+for name in names:
+    gok &= torch.equal(getattr(bank_g, name), getattr(bank_e, name))
+gok &= torch.equal(bank_g.shadow, bank_e.shadow)
+overlap = os.environ.get("PCL_GATHER_OVERLAP", "1") != "0"
+gok &= (step.graph_c is not None) == overlap
 for name in names:
     a = getattr(bank_g, name)
     g = [torch.empty_like(a) for _ in range(world)]
     dist.all_gather(g, a)
     gok &= all(torch.equal(g[0], x) for x in g)
+print(f"rank {rank} graphed bank step ({'3 graphs, all_gather under the backward' if overlap else '2 graphs + 1 all_gather'}; 9 steps)", flush=True)
 print(f"rank {rank} graphed bank step (2 graphs + 1 all_gather) {'OK' if gok else 'FAILED'}", flush=True)
 ok &= bool(gok)
 print(f"rank {rank} dist bank check {'OK' if ok else 'FAILED'}", flush=True)
