@@ -21,9 +21,11 @@ The reference RNG stream (``rng='torch_cpu'`` / injected permutations) needs a h
 
 Memory-bank steps (``enqueue=``): the trainer's order loss -> enqueue -> backward (trainer_contrastive.py:241-255) is part
 of the captured sequence: stats -> ranks -> forward -> enqueue packet | all_gather | backward -> bank write.  One rank: a
-single graph.  Several ranks: two graphs with ONE NCCL all_gather of the packet between them (three host calls per step,
-nothing allocated, no host synchronisation); the bank write comes after the backward sweep that re-reads the bank, so
-gradient and final bank equal the reference's (same property as the eager deferred write).
+single graph.  Several ranks: three graphs and ONE NCCL all_gather of the packet — forward + packet, then the backward
+sweep with the all_gather next to it on its own stream, then the bank write (four host calls per step, nothing
+allocated, no host synchronisation; ``PCL_GATHER_OVERLAP=0``: two graphs with the all_gather between them); the bank
+write comes after the backward sweep that re-reads the bank, so gradient and final bank equal the reference's (same
+property as the eager deferred write).
 """
 from __future__ import annotations
 
