@@ -158,7 +158,7 @@ def test_graphed_bank_step_on_emulation(emu, monkeypatch, precision):
     PD.test_graphed_bank_step_with_enqueue_equals_the_trainer_order(precision)
 
 
-@pytest.mark.parametrize("K,M,A,seed", [(5, 300, 200, 1), (12, 70, 150, 3), (40, 130, 260, 5)])
+@pytest.mark.parametrize("K,M,A,seed", [(5, 300, 200, 1), (12, 70, 150, 3), (40, 130, 260, 5), (171, 8, 400, 6)])
 def test_tensor_path_bank_positives_by_class_blocks_on_emulation(emu, K, M, A, seed):
     """k_tc_pos_t on the functional tcgen05 / TMA model: blocks cut into several partial slots, several blocks per class."""
     G.test_tensor_path_bank_positives_by_class_blocks(K, M, A, seed)

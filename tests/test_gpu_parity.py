@@ -457,7 +457,8 @@ def test_bank_shadow_tracks_enqueue_and_tensor_path_uses_it():
     assert rel_err(l16.item(), l32.item()) < 1e-4
 
 
-@pytest.mark.parametrize("K,M,A,seed", [(5, 300, 200, 1), (7, 200, 333, 2), (12, 70, 150, 3), (3, 500, 100, 4), (40, 130, 260, 5)])
+@pytest.mark.parametrize("K,M,A,seed", [(5, 300, 200, 1), (7, 200, 333, 2), (12, 70, 150, 3), (3, 500, 100, 4), (40, 130, 260, 5),
+                                         (171, 8, 400, 6)])
 def test_tensor_path_bank_positives_by_class_blocks(K, M, A, seed):
     """The transposed POS sweep of the bank mode (csrc/pcl_infonce_tc.cu k_tc_pos_t): anchor blocks of one class x that
     class's bank columns, tile units dealt evenly to the CTAs.  Sizes where a class has several column tiles (so a block
