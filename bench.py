@@ -238,7 +238,22 @@ def run_reference(args, cfg, bank, rank):
     step = real_reference_step if kind == "reference" else cpu_port_step
     threads, t1 = calibrate_cpu(cfg, bank)
     inp = make_inputs(cfg, 304, None, bank)
-    for _ in range(args.warmup):
+    # Bounded run: one probe step at the full batch (it doubles as the first warm-up step); if --steps/--warmup of those
+    # would take longer than REF_BUDGET_S, every step becomes a smaller sample of the same workload (fewer images of the
+    # batch: the reference's backward is super-linear in the batch, one dense (B,HW,D) SelectBackward per (image, class)).
+    full_b, cfg_full = cfg["B"], cfg
+    tp = time.perf_counter()
+    step(inp, cfg, bank)
+    probe = time.perf_counter() - tp
+    n_total = args.steps + max(args.warmup - 1, 0)
+    budget = float(os.environ.get("PCL_BENCH_REF_BUDGET_S", "400"))
+    if probe * n_total > budget and full_b > 1:
+        b_s = full_b
+        while b_s > 1 and probe * (b_s / full_b) ** 1.5 * n_total > budget:
+            b_s //= 2
+        cfg = dict(cfg, B=b_s)
+        inp = make_inputs(cfg, 304, None, bank)
+    for _ in range(max(args.warmup - 1, 0)):
         step(inp, cfg, bank)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -246,14 +261,16 @@ def run_reference(args, cfg, bank, rank):
     dt = time.perf_counter() - t0
     ms = dt / args.steps * 1e3
     val = cfg["B"] * args.steps / dt
-    sample = (f"{args.steps} steps of the full workload (batch {cfg['B']}) after {args.warmup} warm-up on {threads} of "
+    what = (f"the full workload (batch {full_b})" if cfg["B"] == full_b else
+            f"a {cfg['B']}-image sample of the batch of {full_b} (a full-batch step takes {probe:.1f} s here)")
+    sample = (f"{args.steps} steps of {what} after {args.warmup} warm-up on {threads} of "
               f"{os.cpu_count()} host threads (fastest of 8/16/32/64/all, calibrated on one image), fp32 torch CPU, "
               + ("the unmodified reference modules" if kind == "reference" else
                  "per-(image,class) gather + autograd backward like the reference (oracle/ref_port.py)"))
     return {"impl": "reference", "metric": "contrast-loss fwd+bwd throughput", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, bank),
+            "config": workload_config(cfg_full, bank),
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
