@@ -479,3 +479,41 @@ def test_loss_step_timer_never_blocks(rec, monkeypatch):
     assert timer.read() == 1.5                           # complete now
     hook.loss_step({"seg": seg, "embed": embed}, labels, iters=2)
     assert timer.read() == 1.5                           # the newest step is still in flight: last completed value
+
+
+def test_three_graph_replay_order_of_the_bank_step_on_several_ranks(monkeypatch):
+    """world > 1 (graph_step.GraphedContrastStep.replay): graph A (forward + packet) -> the all_gather on ITS OWN stream,
+    ordered after A -> graph B (backward sweep) on the caller's stream, not waiting for the all_gather -> the caller's
+    stream waits for the all_gather -> graph C (bank write).  PCL_GATHER_OVERLAP=0 / no third graph: A, all_gather, B."""
+    from contrastiveseg_b200 import graph_step
+    log = []
+
+    class FakeGraph:
+        def __init__(self, name): self.name = name
+        def replay(self): log.append(f"replay {self.name} on {cur_name[0]}")
+
+    class FakeStream:
+        def __init__(self, name): self.name = name
+        def wait_stream(self, other): log.append(f"{self.name} waits for {other.name}")
+
+    class Ctx:
+        def __init__(self, s): self.s = s
+        def __enter__(self): self.prev = cur_name[0]; cur_name[0] = self.s.name
+        def __exit__(self, *a): cur_name[0] = self.prev
+
+    cur_name = ["main"]
+    main, side = FakeStream("main"), FakeStream("gather")
+    monkeypatch.setattr(graph_step.torch.cuda, "current_stream", lambda dev=None: main)
+    monkeypatch.setattr(graph_step.torch.cuda, "stream", lambda s: Ctx(s))
+    st = object.__new__(graph_step.GraphedContrastStep)
+    st.device, st.replays, st.loss, st.grad = None, 0, "loss", "grad"
+    st.graph, st.graph_b, st.graph_c, st._gather_stream = FakeGraph("A"), FakeGraph("B"), FakeGraph("C"), side
+    st._gather = lambda: log.append(f"all_gather on {cur_name[0]}")
+    assert st.replay() == ("loss", "grad")
+    assert log == ["replay A on main", "gather waits for main", "all_gather on gather", "replay B on main",
+                   "main waits for gather", "replay C on main"]
+    del log[:]
+    st.graph_c = None
+    st.replay()
+    assert log == ["replay A on main", "all_gather on main", "replay B on main"]
+    assert st.replays == 2
