@@ -170,6 +170,15 @@ def test_bank_apply_of_many_ranks_on_emulation(emu, monkeypatch, world, M, B):
     PD.test_bank_apply_of_many_ranks_equals_the_sequential_reference(monkeypatch, world, M, B)
 
 
+def test_fuzz_bank_apply_of_many_ranks_on_emulation(emu, monkeypatch):
+    """Random (ranks, ring size, images per rank): the last-writer-wins apply == the reference applied image by image."""
+    import random
+    rng = random.Random(20)
+    for _ in range(10):
+        world, M, B = rng.randint(1, 9), rng.randint(3, 30), rng.randint(1, 3)
+        PD.test_bank_apply_of_many_ranks_equals_the_sequential_reference(monkeypatch, world, M, B)
+
+
 def test_bank_write_waits_for_backward_on_emulation(emu):
     """Gradient bit-identical with / without an enqueue between loss and backward; final bank equals an immediate enqueue."""
     PD.test_enqueue_between_loss_and_backward_does_not_change_the_gradient("fp32")
